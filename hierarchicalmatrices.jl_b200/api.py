@@ -1,0 +1,642 @@
+"""Host-side mirror of the HierarchicalMatrices.jl API for the `mul!` hot path.
+
+Julia is not available in the build image, so the host side that the reference
+keeps in Julia is mirrored here in Python with the reference's names, argument
+meaning (1-based `Block`, `istart`/`jstart`, `INCX`/`INCY`) and error behaviour.
+The Julia shim that binds the same C ABI with `ccall` is in julia/.
+
+    reference (file:line under /root/reference)              here
+    -------------------------------------------------------  -------------------------
+    BLOCKRANK, BLOCKSIZE      src/HierarchicalMatrices.jl:5-7   BLOCKRANK, BLOCKSIZE
+    Block                     src/block.jl:8-10                 Block
+    LowRankMatrix             src/LowRankMatrix.jl:28-38        LowRankMatrix
+    BarycentricMatrix2D       src/BarycentricMatrix.jl:208-218  BarycentricMatrix2D
+    @hierarchical             src/hierarchical.jl:4-232         hierarchical()
+    HierarchicalMatrix        src/HierarchicalMatrix.jl:1       HierarchicalMatrix
+    KernelMatrix              src/KernelMatrix.jl:1,47          KernelMatrix
+    blocksize, size           src/hierarchical.jl:31-47,76-97   blocksize, size
+    mul!, *                   src/KernelMatrix.jl:5-45,         mul_, H * x, H @ x
+                              src/HierarchicalMatrix.jl:5-52
+
+All arithmetic of `mul_` / `*` runs in the CUDA library (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import HmError, Stats
+
+_dp = C.POINTER(C.c_double)
+
+__all__ = [
+    "BLOCKRANK", "BLOCKSIZE", "Block", "LowRankMatrix", "BarycentricMatrix2D", "Matrix",
+    "hierarchical", "HierarchicalMatrix", "KernelMatrix", "blocksize", "size", "mul_",
+    "cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel", "Plan", "flatten",
+    "chebyshevpoints", "HmError",
+]
+
+Matrix = np.ndarray  # the dense leaf type of the reference
+
+
+# --------------------------------------------------------------------------- constants
+def BLOCKRANK(T=np.float64) -> int:
+    """2round(Int, half(T)*log(3+sqrt(T(8)), inv(eps(T)))) -- HierarchicalMatrices.jl:5."""
+    T = np.dtype(T)
+    if T.kind == "c":
+        T = np.dtype(f"f{T.itemsize // 2}")
+    if T == np.float64:
+        return int(_lib.lib().hm_blockrank_f64())
+    eps = T.type(np.finfo(T).eps)
+    v = T.type(0.5) * (np.log(T.type(1) / eps) / np.log(T.type(3) + np.sqrt(T.type(8))))
+    return 2 * int(np.rint(v))
+
+
+def BLOCKSIZE(T=np.float64) -> int:
+    """4BLOCKRANK(T) -- HierarchicalMatrices.jl:7."""
+    return 4 * BLOCKRANK(T)
+
+
+def chebyshevpoints(n: int, kind: int = 1) -> np.ndarray:
+    """chebyshevpoints(Float64, n; kind) -- BarycentricMatrix.jl:92-111 (sinpi in long double)."""
+    k = np.arange(1, n // 2 + 1, dtype=np.float64)
+    q = (n - 2 * k + 1.0) / (2.0 * n) if kind == 1 else (n - 2 * k + 1.0) / (2.0 * (n - 1))
+    ql = q.astype(np.longdouble)
+    pi = np.longdouble("3.14159265358979323846264338327950288")
+    v = np.where(q <= 0.25, np.sin(pi * ql), np.cos(pi * (np.longdouble(0.5) - ql))).astype(np.float64)
+    x = np.zeros(n)
+    x[: n // 2] = v
+    x[n - (n // 2):] = -v[::-1]
+    return x
+
+
+class Block:
+    """`Block(K)`, 1-based block index -- block.jl:8-10."""
+
+    __slots__ = ("K",)
+
+    def __init__(self, K: int):
+        self.K = int(K)
+
+    def __int__(self):
+        return self.K
+
+    def __eq__(self, o):
+        return isinstance(o, Block) and o.K == self.K
+
+    def __hash__(self):
+        return hash(("Block", self.K))
+
+    def __repr__(self):
+        return f"Block({self.K})"
+
+
+# --------------------------------------------------------------------------- kernels
+class _Kernel:
+    """One of the four kernels of examples/Kernel.jl:34-37; callable on the host
+    (scalars or broadcastable arrays) and known to the device assembler by id."""
+
+    def __init__(self, name, kid, fn):
+        self.__name__ = name
+        self.id = kid
+        self._fn = fn
+
+    def __call__(self, x, y):
+        return self._fn(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64))
+
+    def __repr__(self):
+        return self.__name__
+
+
+cauchykernel = _Kernel("cauchykernel", 0, lambda x, y: 1.0 / (x - y))
+coulombkernel = _Kernel("coulombkernel", 1, lambda x, y: 1.0 / ((x - y) * (x - y)))
+coulombprimekernel = _Kernel("coulombprimekernel", 2, lambda x, y: 1.0 / ((x - y) * (x - y) * (x - y)))
+logkernel = _Kernel("logkernel", 3, lambda x, y: np.log(np.abs(x - y)))
+
+
+# --------------------------------------------------------------------------- leaf types
+def _fmat(a, name):
+    a = np.asarray(a)
+    if a.ndim != 2:
+        raise TypeError(f"{name} must be a matrix")
+    return a
+
+
+class LowRankMatrix:
+    """A = U Σ V' (no conjugation in mul!, algebra.jl:118) -- LowRankMatrix.jl:28-38."""
+
+    def __init__(self, U, S, V):
+        self.U = _fmat(U, "U")
+        self.V = _fmat(V, "V")
+        S = np.asarray(S)
+        self.S = np.diag(S).copy() if S.ndim == 2 else S  # accepts Diagonal-as-matrix
+        if not (self.U.shape[1] == self.V.shape[1] == self.S.shape[0]):
+            raise ValueError("LowRankMatrix: rank mismatch between U, Σ and V")
+        if not (self.U.dtype == self.V.dtype == self.S.dtype):
+            raise TypeError("LowRankMatrix: U, Σ, V must share one element type")
+
+    Σ = property(lambda self: self.S)
+    dtype = property(lambda self: self.U.dtype)
+    shape = property(lambda self: (self.U.shape[0], self.V.shape[0]))
+
+    def rank(self):
+        return self.S.shape[0]
+
+
+class BarycentricMatrix2D:
+    """U F V' with U m×r, F r×r, V n×r -- BarycentricMatrix.jl:208-218 (factors as
+    produced by update!, :248-297; B.B.F is `F` here)."""
+
+    def __init__(self, U, F, V):
+        self.U = _fmat(U, "U")
+        self.F = _fmat(F, "F")
+        self.V = _fmat(V, "V")
+        r = self.F.shape[0]
+        if not (self.F.shape[1] == r == self.U.shape[1] == self.V.shape[1]):
+            raise ValueError("BarycentricMatrix2D: rank mismatch between U, F and V")
+        if not (self.U.dtype == self.V.dtype == self.F.dtype):
+            raise TypeError("BarycentricMatrix2D: U, F, V must share one element type")
+
+    dtype = property(lambda self: self.U.dtype)
+    shape = property(lambda self: (self.U.shape[0], self.V.shape[0]))
+
+
+# --------------------------------------------------------------------------- plan handle
+class Plan:
+    """Owning handle on an `hm_plan` (immutable packed operator on one GPU)."""
+
+    def __init__(self, handle, device):
+        self._h = C.c_void_p(handle)
+        self.device = device
+        self._stats = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib._lib is not None:
+            _lib._lib.hm_plan_destroy(h)
+
+    close = __del__
+
+    @property
+    def handle(self):
+        return self._h
+
+    def stats(self) -> dict:
+        if self._stats is None:
+            s = Stats()
+            _lib.check(_lib.lib().hm_plan_stats(self._h, C.byref(s)))
+            self._stats = s.asdict()
+        return self._stats
+
+    @property
+    def shape(self):
+        s = self.stats()
+        return (s["nrows"], s["ncols"])
+
+    @property
+    def launches_per_matvec(self) -> int:
+        return int(_lib.lib().hm_plan_launches_per_matvec(self._h))
+
+    # y[i*incy] (+)= (H x)[i]; host arrays, strides in elements
+    def matvec(self, x: np.ndarray, y: np.ndarray, incx=1, incy=1, accumulate=True, xoff=0, yoff=0):
+        for a, nm in ((x, "x"), (y, "y")):
+            if a.dtype != np.float64:
+                raise TypeError(f"{nm} must be Float64 (MethodError in the reference: all eltypes equal)")
+        isz = 8
+        px = C.cast(x.ctypes.data + xoff * isz, _dp)
+        py = C.cast(y.ctypes.data + yoff * isz, _dp)
+        _lib.check(_lib.lib().hm_matvec(self._h, px, incx, py, incy, 1 if accumulate else 0))
+        return y
+
+    def matmat(self, X: np.ndarray, Y: np.ndarray, accumulate=True):
+        assert X.flags.f_contiguous and Y.flags.f_contiguous and X.dtype == Y.dtype == np.float64
+        nrhs = X.shape[1]
+        _lib.check(_lib.lib().hm_matmat(
+            self._h, X.ctypes.data_as(_dp), max(X.shape[0], 1), Y.ctypes.data_as(_dp), max(Y.shape[0], 1),
+            nrhs, 1 if accumulate else 0))
+        return Y
+
+    # device pointers (ints), e.g. torch tensors' data_ptr(); enqueued on `stream`
+    def matvec_device(self, dx: int, dy: int, accumulate=False, stream: int = 0):
+        _lib.check(_lib.lib().hm_matvec_device(self._h, dx, dy, 1 if accumulate else 0, stream))
+
+    def matmat_device(self, dX: int, ldx: int, dY: int, ldy: int, nrhs: int, accumulate=False, stream: int = 0):
+        _lib.check(_lib.lib().hm_matmat_device(self._h, dX, ldx, dY, ldy, nrhs, 1 if accumulate else 0, stream))
+
+    def timing_begin(self, max_calls: int):
+        _lib.check(_lib.lib().hm_plan_timing_begin(self._h, max_calls))
+
+    def timing_end(self):
+        """(ms of stage 1, 2, 3 summed over the timed matvecs, number of matvecs)."""
+        ms = (C.c_double * 3)()
+        n = C.c_int64()
+        _lib.check(_lib.lib().hm_plan_timing_end(self._h, ms, C.byref(n)))
+        return [ms[0], ms[1], ms[2]], n.value
+
+    # test hooks
+    def num_leaves(self) -> int:
+        n = C.c_int64()
+        _lib.check(_lib.lib().hm_plan_num_leaves(self._h, C.byref(n)))
+        return n.value
+
+    def leaf_info(self, i: int) -> dict:
+        kind = C.c_int32()
+        v = [C.c_int64() for _ in range(5)]
+        _lib.check(_lib.lib().hm_plan_leaf_info(self._h, i, C.byref(kind), *[C.byref(a) for a in v]))
+        return dict(kind=kind.value, row0=v[0].value, col0=v[1].value, m=v[2].value, n=v[3].value, r=v[4].value)
+
+    def read_leaf(self, i: int, which: int) -> np.ndarray:
+        info = self.leaf_info(i)
+        m, n, r = info["m"], info["n"], info["r"]
+        dense = info["kind"] == 3
+        shape = {0: (m, r), 1: (r, r) if info["kind"] == 4 else (r, 1), 2: (n, r), 3: (m, n)}[which]
+        if dense != (which == 3):
+            raise ValueError("leaf kind has no such factor")
+        out = np.zeros(shape, order="F")
+        _lib.check(_lib.lib().hm_plan_read_leaf(self._h, i, which, out.ctypes.data_as(_dp), out.size))
+        return out
+
+
+def _current_device() -> int:
+    """The CUDA device of this process: LOCAL_RANK under torchrun, else 0."""
+    import os
+    return int(os.environ.get("HMB200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+# --------------------------------------------------------------------------- @hierarchical
+def _leaf_kind(A):
+    if isinstance(A, LowRankMatrix):
+        return 2
+    if isinstance(A, BarycentricMatrix2D):
+        return 4
+    if isinstance(A, np.ndarray):
+        return 3
+    return None
+
+
+class _HierarchicalBase:
+    """Common behaviour of the types `hierarchical()` generates (hierarchical.jl:18-232)."""
+
+    _name = ""
+    _types: tuple = ()
+
+    # $HierarchicalType(::Type{T}, M, N) / (M, N) -- hierarchical.jl:54-69
+    def __init__(self, *args):
+        if len(args) == 2:
+            T, (M, N) = np.float64, args
+        elif len(args) == 3:
+            T, M, N = args
+        else:
+            raise TypeError(f"{self._name}(T, M, N) or {self._name}(M, N)")
+        self.T = np.dtype(T)
+        self.M, self.N = int(M), int(N)
+        self._fields = [f"{self._name}blocks"] + [f"{_type_name(t)}blocks" for t in self._types]
+        for f in self._fields:
+            setattr(self, f, np.empty((self.M, self.N), dtype=object))  # "#undef" slots
+        self.assigned = np.zeros((self.M, self.N), dtype=np.int64)
+        self._plan = None
+
+    dtype = property(lambda self: self.T)
+
+    # setindex!(H, A, Block(m), Block(n)) -- hierarchical.jl:149-172: the field is
+    # picked by the exact type of A; no match is silently ignored, as in the reference.
+    def __setitem__(self, key, A):
+        B1, B2 = key
+        if not (isinstance(B1, Block) and isinstance(B2, Block)):
+            raise TypeError("only H[Block(m), Block(n)] = A is defined")
+        m, n = B1.K - 1, B2.K - 1
+        if not (0 <= m < self.M and 0 <= n < self.N):
+            raise IndexError("BoundsError: block index out of range")
+        code = self._code_for(A)
+        if code is None:
+            return
+        getattr(self, self._fields[code - 1])[m, n] = A
+        self.assigned[m, n] = code
+        self._plan = None
+
+    def _code_for(self, A):
+        if type(A) is type(self):
+            return 1 if A.T == self.T else None
+        for l, t in enumerate(self._types):
+            if t is Matrix:
+                if isinstance(A, np.ndarray) and A.ndim == 2 and A.dtype == self.T:
+                    return l + 2
+            elif type(A) is t and A.dtype == self.T:
+                return l + 2
+        return None
+
+    def _block(self, m, n):
+        code = self.assigned[m, n]
+        return None if code == 0 else getattr(self, self._fields[code - 1])[m, n]
+
+    # blocksize(H, m, n, k) -- hierarchical.jl:78-97 (1-based m, n; k = 1 rows, 2 columns)
+    def blocksize(self, m=None, n=None, k=None):
+        if m is None:
+            return (self.M, self.N)
+        if k is None:
+            return (self.blocksize(m, n, 1), self.blocksize(m, n, 2))
+        A = self._block(m - 1, n - 1)
+        if A is None:
+            return 0
+        return A.size(k) if isinstance(A, _HierarchicalBase) else A.shape[k - 1]
+
+    # size(H) -- hierarchical.jl:33-47: rows down the LAST block column, columns
+    # along the FIRST block row
+    def size(self, k=None):
+        if self.M == 0 or self.N == 0:
+            p = q = 0
+        else:
+            p = sum(self.blocksize(m, self.N, 1) for m in range(1, self.M + 1))
+            q = sum(self.blocksize(1, n, 2) for n in range(1, self.N + 1))
+        return (p, q) if k is None else (p, q)[k - 1]
+
+    shape = property(lambda self: self.size())
+
+    # getindex(H, i, j) -- hierarchical.jl:120-147 (1-based)
+    def __getitem__(self, key):
+        i, j = key
+        if isinstance(i, Block):
+            return self._block(i.K - 1, j.K - 1)
+        m = 1
+        while m <= self.M:
+            r = self.blocksize(m, self.N, 1)
+            if i > r:
+                i -= r
+                m += 1
+            else:
+                break
+        n = 1
+        while n <= self.N:
+            s = self.blocksize(1, n, 2)
+            if j > s:
+                j -= s
+                n += 1
+            else:
+                break
+        if m > self.M or n > self.N:
+            raise IndexError("BoundsError")
+        A = self._block(m - 1, n - 1)
+        if A is None:
+            return self.T.type(0)
+        if isinstance(A, _HierarchicalBase):
+            return A[i, j]
+        if isinstance(A, np.ndarray):
+            return A[i - 1, j - 1]
+        if isinstance(A, LowRankMatrix):  # LowRankMatrix.jl:50-58, k = r..1
+            ret = self.T.type(0)
+            for k in range(A.rank() - 1, -1, -1):
+                ret += A.U[i - 1, k] * A.S[k] * A.V[j - 1, k]
+            return ret
+        ret = self.T.type(0)  # BarycentricMatrix.jl:222-234
+        for k in range(A.F.shape[0]):
+            ret += A.U[i - 1, k] * np.dot(A.F[k, :], A.V[j - 1, :])
+        return ret
+
+    # ---- the planner's front end: walk `assigned` exactly as mul! does ----
+    def leaves(self, i0=0, j0=0, out=None):
+        """(kind, row0, col0, block) of every leaf in walk order with the offsets
+        KernelMatrix.jl:24-41 / HierarchicalMatrix.jl:30-48 pass to it (0-based)."""
+        out = [] if out is None else out
+        p = 0
+        for m in range(self.M):
+            q = 0
+            for n in range(self.N):
+                A = self._block(m, n)
+                if isinstance(A, _HierarchicalBase):
+                    A.leaves(i0 + p, j0 + q, out)
+                elif A is not None:
+                    out.append((_leaf_kind(A), i0 + p, j0 + q, A))
+                q += self.blocksize(1, n + 1, 2)
+            p += self.blocksize(m + 1, self.N, 1)
+        return out
+
+    def plan(self, device=None, part=0, nparts=1) -> Plan:
+        """Flatten the tree and pack it on the device.  The plan is a snapshot cached on
+        this object: `H[Block(m), Block(n)] = A` on it drops the cache; after mutating a
+        nested block or a leaf's arrays in place call `invalidate()`."""
+        key = (device, part, nparts)
+        if self._plan is not None and self._plan[0] == key:
+            return self._plan[1]
+        if self.T != np.float64:
+            raise HmError(8, "only Float64 operators are supported")
+        P = flatten(self, _current_device() if device is None else device, part, nparts)
+        self._plan = (key, P)
+        return P
+
+    def invalidate(self):
+        self._plan = None
+
+    def stats(self, part=0, nparts=1) -> dict:
+        """Planner only (no GPU needed): sizes of the packed layout."""
+        return _structure_stats(self, part, nparts)
+
+    # ---- *  (HierarchicalMatrix.jl:5-12, KernelMatrix.jl:5-12) ----
+    def __mul__(self, x):
+        x = np.asarray(x)
+        TS = np.result_type(self.T, x.dtype)
+        if TS != np.float64:
+            raise HmError(8, "only Float64 operators are supported")
+        if x.ndim == 1:
+            y = np.zeros(self.size(1), dtype=TS)
+            return mul_(y, self, np.ascontiguousarray(x, dtype=TS))
+        if x.ndim == 2:
+            # The reference has no usable matrix product here (HierarchicalMatrix fills
+            # column 1 only, KernelMatrix falls back to O(N^2) getindex); this is the
+            # column-wise product those methods are meant to compute.
+            X = np.asfortranarray(x, dtype=TS)
+            Y = np.zeros((self.size(1), X.shape[1]), dtype=TS, order="F")
+            if X.shape[0] != self.size(2):
+                raise ValueError("DimensionMismatch")
+            return self.plan().matmat(X, Y, accumulate=True)
+        raise TypeError("x must be a vector or a matrix")
+
+    __matmul__ = __mul__
+
+
+def _type_name(t):
+    return "Matrix" if t is Matrix else t.__name__
+
+
+def hierarchical(name: str, *types):
+    """`@hierarchical Name T1 T2 ...` -- hierarchical.jl:4: a block-matrix type whose
+    blocks are `Name` itself (code 1) or one of the listed leaf types (codes 2, 3, ...)."""
+    for t in types:
+        if t is not Matrix and t not in (LowRankMatrix, BarycentricMatrix2D):
+            raise HmError(8, f"leaf type {t!r} is not on the accelerated path")
+    return type(name, (_HierarchicalBase,), {"_name": name, "_types": tuple(types)})
+
+
+HierarchicalMatrix = hierarchical("HierarchicalMatrix", LowRankMatrix, Matrix)
+_KernelMatrixBlocks = hierarchical("KernelMatrix", BarycentricMatrix2D, Matrix)
+
+
+class KernelMatrix(_KernelMatrixBlocks):
+    """`@hierarchical KernelMatrix BarycentricMatrix2D Matrix` (KernelMatrix.jl:1).
+
+    KernelMatrix(T, M, N)            empty container, blocks set with H[Block(m), Block(n)] = A
+    KernelMatrix(f, x, y, a, b, c, d) the assembling constructor (KernelMatrix.jl:47-116):
+        the tree of index ranges is built on the host, U, V, F and the dense leaves
+        are evaluated on the GPU straight into the packed streams; `f` must be one
+        of the four kernels of examples/Kernel.jl.
+    """
+
+    _name = "KernelMatrix"
+
+    def __init__(self, *args, device=None, part=0, nparts=1):
+        if len(args) == 7:
+            f, x, y, a, b, c, d = args
+            if not isinstance(f, _Kernel):
+                raise HmError(8, "device assembly knows cauchykernel, coulombkernel, coulombprimekernel, logkernel")
+            super().__init__(np.float64, 0, 0)
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            y = np.ascontiguousarray(y, dtype=np.float64)
+            dev = _current_device() if device is None else device
+            h = C.c_void_p()
+            _lib.check(_lib.lib().hm_assemble_kernel(
+                x.ctypes.data_as(_dp), len(x), y.ctypes.data_as(_dp), len(y), a, b, c, d, f.id, dev,
+                part, nparts, C.byref(h)))
+            self._assembled = Plan(h.value, dev)
+            self.kernel = f
+        else:
+            super().__init__(*args)
+            self._assembled = None
+
+    def _code_for(self, A):
+        if isinstance(A, KernelMatrix):
+            return 1 if A.T == self.T and A._assembled is None else None
+        return super()._code_for(A)
+
+    def size(self, k=None):
+        if self._assembled is not None:
+            s = self._assembled.shape
+            return s if k is None else s[k - 1]
+        return super().size(k)
+
+    shape = property(lambda self: self.size())
+
+    def plan(self, device=None, part=0, nparts=1) -> Plan:
+        if self._assembled is not None:
+            return self._assembled
+        return super().plan(device, part, nparts)
+
+    def stats(self, part=0, nparts=1):
+        if self._assembled is not None:
+            return self._assembled.stats()
+        return super().stats(part, nparts)
+
+    @staticmethod
+    def layout_stats(x, y, a, b, c, d, part=0, nparts=1) -> dict:
+        """Planner only (no GPU): leaf counts and byte sizes of KernelMatrix(f,x,y,a,b,c,d)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        s = Stats()
+        _lib.check(_lib.lib().hm_assemble_kernel_stats(
+            x.ctypes.data_as(_dp), len(x), y.ctypes.data_as(_dp), len(y), a, b, c, d, part, nparts, C.byref(s)))
+        return s.asdict()
+
+
+# --------------------------------------------------------------------------- planner front end
+def _push_leaves(H, b):
+    L = _lib.lib()
+    keep = []  # keep converted arrays alive until the builder has copied them
+    for kind, row0, col0, A in H.leaves():
+        if kind == 3:
+            M = np.asfortranarray(A, dtype=np.float64)
+            keep.append(M)
+            _lib.check(L.hm_builder_add_dense(b, M.ctypes.data_as(_dp), M.shape[0], M.shape[1],
+                                              max(M.shape[0], 1), row0, col0))
+            continue
+        U = np.asfortranarray(A.U, dtype=np.float64)
+        V = np.asfortranarray(A.V, dtype=np.float64)
+        m, r = U.shape
+        n = V.shape[0]
+        if kind == 2:
+            S = np.ascontiguousarray(A.S, dtype=np.float64)
+            keep += [U, V, S]
+            _lib.check(L.hm_builder_add_lowrank(b, U.ctypes.data_as(_dp), max(m, 1), S.ctypes.data_as(_dp),
+                                                V.ctypes.data_as(_dp), max(n, 1), m, n, r, row0, col0))
+        else:
+            F = np.asfortranarray(A.F, dtype=np.float64)
+            keep += [U, V, F]
+            _lib.check(L.hm_builder_add_bary2d(b, U.ctypes.data_as(_dp), max(m, 1), F.ctypes.data_as(_dp),
+                                               max(r, 1), V.ctypes.data_as(_dp), max(n, 1), m, n, r, row0, col0))
+    return keep
+
+
+def flatten(H, device: int, part=0, nparts=1) -> Plan:
+    """Walk the block tree and pack it into device arrays (the planner)."""
+    L = _lib.lib()
+    nrows, ncols = H.size()
+    b = C.c_void_p()
+    _lib.check(L.hm_builder_create(C.byref(b), nrows, ncols, 0, device))
+    try:
+        _push_leaves(H, b)
+        h = C.c_void_p()
+        if nparts == 1:
+            dev = (C.c_int32 * 1)(device)
+            _lib.check(L.hm_plan_finalize(b, dev, 1, C.byref(h)))
+        else:
+            _lib.check(L.hm_plan_finalize_part(b, part, nparts, C.byref(h)))
+    finally:
+        L.hm_builder_destroy(b)
+    return Plan(h.value, device)
+
+
+def _structure_stats(H, part=0, nparts=1) -> dict:
+    L = _lib.lib()
+    nrows, ncols = H.size()
+    b = C.c_void_p()
+    _lib.check(L.hm_builder_create(C.byref(b), nrows, ncols, 0, -1))
+    try:
+        _push_leaves(H, b)
+        s = Stats()
+        _lib.check(L.hm_builder_layout_stats(b, part, nparts, C.byref(s)))
+    finally:
+        L.hm_builder_destroy(b)
+    return s.asdict()
+
+
+# --------------------------------------------------------------------------- free functions
+def blocksize(H, *a):
+    return H.blocksize(*a)
+
+
+def size(H, k=None):
+    return H.size(k)
+
+
+def _linear(a: np.ndarray, name: str) -> np.ndarray:
+    """Julia linear indexing = column-major order; must be a view so y is updated in place."""
+    if a.ndim == 1:
+        if a.strides[0] != a.itemsize and a.size > 1:
+            raise ValueError(f"{name} must be contiguous")
+        return a
+    if not a.flags.f_contiguous:
+        raise ValueError(f"{name} must be column-major (Fortran order), as Julia arrays are")
+    return a.reshape(-1, order="F")
+
+
+def mul_(y, H, x, istart: int = 1, jstart: int = 1, INCX: int = 1, INCY: int = 1):
+    """`mul!(y, H, x, istart, jstart, INCX, INCY)`: y[istart+(i-1)INCY] += Σ_j H[i,j] x[jstart+(j-1)INCX]
+    with 1-based linear indices (HierarchicalMatrix.jl:14-52, KernelMatrix.jl:14-45); returns y."""
+    if not isinstance(H, _HierarchicalBase):
+        raise TypeError("MethodError: H is not a hierarchical matrix")
+    if isinstance(H, KernelMatrix) and (INCX != 1 or INCY != 1):
+        raise TypeError("MethodError: mul!(u, ::KernelMatrix, v, istart, jstart) has no strided form")
+    if not isinstance(y, np.ndarray) or not isinstance(x, np.ndarray):
+        raise TypeError("y and x must be numpy arrays (y is updated in place)")
+    if not (y.dtype == x.dtype == H.T == np.float64):
+        raise TypeError("MethodError: y, H and x must all be Float64")
+    if INCX < 1 or INCY < 1 or istart < 1 or jstart < 1:
+        raise IndexError("BoundsError: offsets and strides are 1-based positive integers")
+    yl, xl = _linear(y, "y"), _linear(x, "x")
+    nr, nc = H.size()
+    if nr and istart - 1 + (nr - 1) * INCY >= yl.size:
+        raise IndexError("BoundsError: y is too short")
+    if nc and jstart - 1 + (nc - 1) * INCX >= xl.size:
+        raise IndexError("BoundsError: x is too short")
+    H.plan().matvec(xl, yl, INCX, INCY, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
+    return y

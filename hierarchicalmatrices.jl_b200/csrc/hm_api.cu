@@ -1,0 +1,871 @@
+// hm_api.cu -- C ABI (include/hmb200.h): builder, plan, mul!.
+//
+// No CPU fallback: every compute entry point needs a CUDA device and fails
+// with HM_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hmb200.h"
+#include "hm_kernels.cuh"
+#include "hm_layout.h"
+#include "hm_tree.h"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(hm_status st, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return (int32_t)st;
+}
+
+#define HM_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cudaGetLastError();                                                                    \
+            return fail(e_ == cudaErrorMemoryAllocation ? HM_ERR_NOMEM : HM_ERR_CUDA,              \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                          \
+    } while (0)
+
+// restore the caller's current device on scope exit (the host process may be
+// driving other devices through its own runtime, e.g. torch)
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        ok = err == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (ok && prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+#define HM_DEVICE(dev)                                                                             \
+    DeviceGuard guard_(dev);                                                                       \
+    if (!guard_.ok) {                                                                              \
+        cudaGetLastError();                                                                        \
+        return fail(HM_ERR_CUDA, "cannot select CUDA device %d: %s", (int)(dev),                   \
+                    cudaGetErrorString(guard_.err));                                               \
+    }
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void **)&p, count * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T> &v, cudaStream_t st)
+    {
+        cudaError_t e = alloc(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+};
+
+// ---------------------------------------------------------------------------
+// staging of raw leaf data onto the device (builder path)
+// ---------------------------------------------------------------------------
+class Uploader {
+  public:
+    static constexpr size_t WIN = (size_t)32 << 20;    // pinned window
+    static constexpr size_t CHUNK = (size_t)256 << 20; // device arena chunk
+
+    cudaError_t init()
+    {
+        cudaError_t e;
+        if ((e = cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        for (int i = 0; i < 2; i++) {
+            if ((e = cudaMallocHost((void **)&pin_[i], WIN)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+
+    ~Uploader()
+    {
+        for (int i = 0; i < 2; i++) {
+            if (pin_[i]) cudaFreeHost(pin_[i]);
+            if (ev_[i]) cudaEventDestroy(ev_[i]);
+        }
+        for (void *c : chunks_) cudaFree(c);
+        if (st_) cudaStreamDestroy(st_);
+    }
+
+    // copy a column-major rows x cols matrix (leading dimension ld) to a tight
+    // device copy; returns the device pointer in *out
+    cudaError_t put(const double *src, int64_t rows, int64_t cols, int64_t ld, const double **out)
+    {
+        size_t bytes = (size_t)rows * (size_t)cols * sizeof(double);
+        *out = nullptr;
+        if (bytes == 0) return cudaSuccess;
+        char *d = nullptr;
+        cudaError_t e = reserve(bytes, &d);
+        if (e != cudaSuccess) return e;
+        *out = reinterpret_cast<const double *>(d);
+        if (ld == rows) return append(d, reinterpret_cast<const char *>(src), bytes);
+        for (int64_t j = 0; j < cols; j++) {
+            e = append(d + (size_t)j * rows * sizeof(double), reinterpret_cast<const char *>(src + j * ld),
+                       (size_t)rows * sizeof(double));
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+
+    cudaError_t finish()
+    {
+        cudaError_t e = flush();
+        if (e != cudaSuccess) return e;
+        return cudaStreamSynchronize(st_);
+    }
+
+    size_t bytes_staged() const { return total_; }
+
+  private:
+    cudaError_t reserve(size_t bytes, char **out)
+    {
+        size_t need = (bytes + 15) & ~(size_t)15;
+        if (need > left_) {
+            size_t sz = std::max(need, CHUNK);
+            void *c = nullptr;
+            cudaError_t e = cudaMalloc(&c, sz);
+            if (e != cudaSuccess) return e;
+            chunks_.push_back(c);
+            cur_ = (char *)c;
+            left_ = sz;
+        }
+        *out = cur_;
+        cur_ += need;
+        left_ -= need;
+        total_ += need;
+        return cudaSuccess;
+    }
+
+    cudaError_t flush()
+    {
+        if (win_used_ == 0) {
+            win_dev_ = nullptr;
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMemcpyAsync(win_dev_, pin_[cur_buf_], win_used_, cudaMemcpyHostToDevice, st_);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaEventRecord(ev_[cur_buf_], st_)) != cudaSuccess) return e;
+        cur_buf_ ^= 1;
+        e = cudaEventSynchronize(ev_[cur_buf_]); // the other buffer's copy is done
+        win_used_ = 0;
+        win_dev_ = nullptr;
+        return e;
+    }
+
+    cudaError_t append(char *d, const char *src, size_t bytes)
+    {
+        while (bytes) {
+            if (win_dev_ && d > win_dev_ + win_used_ && (size_t)(d - (win_dev_ + win_used_)) < 64 &&
+                (size_t)(d - win_dev_) < WIN) {
+                size_t gap = (size_t)(d - (win_dev_ + win_used_));
+                memset(pin_[cur_buf_] + win_used_, 0, gap); // alignment padding between leaves
+                win_used_ += gap;
+            }
+            if (win_dev_ && (d != win_dev_ + win_used_ || win_used_ == WIN)) {
+                cudaError_t e = flush();
+                if (e != cudaSuccess) return e;
+            }
+            if (!win_dev_) {
+                win_dev_ = d;
+                win_used_ = 0;
+            }
+            size_t n = std::min(bytes, WIN - win_used_);
+            memcpy(pin_[cur_buf_] + win_used_, src, n);
+            win_used_ += n;
+            d += n;
+            src += n;
+            bytes -= n;
+        }
+        return cudaSuccess;
+    }
+
+    cudaStream_t st_ = nullptr;
+    char *pin_[2] = {nullptr, nullptr};
+    cudaEvent_t ev_[2] = {nullptr, nullptr};
+    int cur_buf_ = 0;
+    char *win_dev_ = nullptr;
+    size_t win_used_ = 0;
+    std::vector<void *> chunks_;
+    char *cur_ = nullptr;
+    size_t left_ = 0, total_ = 0;
+};
+
+void fill_stats(const HmLayout &L, hm_stats *s)
+{
+    memset(s, 0, sizeof *s);
+    s->nrows = L.nrows;
+    s->ncols = L.ncols;
+    s->n_dense = L.n_dense;
+    s->n_lowrank = L.n_lowrank;
+    s->n_bary2d = L.n_bary2d;
+    s->dense_words = L.dense_words;
+    s->lowrank_words = L.lowrank_words;
+    s->core_words = L.core_words_all;
+    s->algorithmic_bytes = 8 * (L.dense_words + L.lowrank_words) + 8 * L.ncols + 8 * L.nrows;
+    s->row_begin = L.row_begin;
+    s->row_end = L.row_end;
+    s->part_words = L.part_words;
+    s->v_stream_bytes = 8 * L.vstream_words;
+    s->u_stream_bytes = 8 * L.ustream_words;
+    s->stored_bytes = 8 * (L.vstream_words + L.ustream_words + L.core_words);
+    s->partial_bytes = 8 * L.partial_words;
+    s->n_stage1_items = (int64_t)L.items1.size();
+    s->n_stage2_blocks = (int64_t)L.cores.size();
+    s->n_stage3_items = (int64_t)L.items3.size();
+    s->n_stage3_rounds = (int64_t)L.round_begin.size() - 1;
+    s->part_algorithmic_bytes = 8 * L.part_words + 8 * L.ncols + 8 * (L.row_end - L.row_begin);
+    s->part_v_words = L.part_v_words;
+    s->part_core_words = L.part_core_words;
+    s->part_u_words = L.part_u_words;
+    s->part_dense_words = L.part_dense_words;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------
+struct hm_builder {
+    int64_t nrows = 0, ncols = 0;
+    int device = -1;
+    std::vector<HmLeaf> leaves;
+    Uploader *up = nullptr;
+    ~hm_builder() { delete up; }
+};
+
+struct hm_plan {
+    int device = 0;
+    HmLayout L; // host metadata (tables are kept for the test hooks)
+    int kernel_id = 0;
+    HmCheb cheb{};
+    // device arrays
+    DevBuf<double> vstream, ustream, core, svec, partial;
+    DevBuf<HmItem> items1, items3;
+    DevBuf<HmRun> runs;
+    DevBuf<HmCoreBlock> cores;
+    DevBuf<int32_t> plist;
+    // host-pointer path
+    cudaStream_t stream = nullptr;
+    DevBuf<double> dx, dy;
+    double *hx = nullptr, *hy = nullptr; // pinned, for strided arguments
+    int64_t nrhs_cap = 0;
+    DevBuf<double> dX, dY;
+    std::mutex mu;
+    // per-stage timing (bench bookkeeping)
+    std::vector<cudaEvent_t> tev;
+    int tcap = 0, tcount = 0;
+    // test hooks
+    std::unordered_multimap<int32_t, size_t> idx1, idx3;
+    bool indexed = false;
+    ~hm_plan()
+    {
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        if (hx) cudaFreeHost(hx);
+        if (hy) cudaFreeHost(hy);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+// Builds the device side of a plan from a finished layout whose leaves carry
+// their sources (device copies or kernel-evaluation parameters).
+int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
+{
+    HmLayout &L = P->L;
+    HM_CUDA(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    cudaStream_t st = P->stream;
+    HM_CUDA(P->vstream.alloc((size_t)L.vstream_words));
+    HM_CUDA(P->ustream.alloc((size_t)L.ustream_words));
+    HM_CUDA(P->core.alloc((size_t)L.core_words));
+    HM_CUDA(P->svec.alloc((size_t)std::max<int64_t>(L.s_words, 1)));
+    HM_CUDA(P->partial.alloc((size_t)std::max<int64_t>(L.partial_words, 1)));
+    if (L.vstream_words) HM_CUDA(cudaMemsetAsync(P->vstream.p, 0, (size_t)L.vstream_words * 8, st));
+    if (L.ustream_words) HM_CUDA(cudaMemsetAsync(P->ustream.p, 0, (size_t)L.ustream_words * 8, st));
+    if (L.core_words) HM_CUDA(cudaMemsetAsync(P->core.p, 0, (size_t)L.core_words * 8, st));
+    HM_CUDA(cudaMemsetAsync(P->partial.p, 0, P->partial.n * 8, st));
+    HM_CUDA(P->items1.upload(L.items1, st));
+    HM_CUDA(P->items3.upload(L.items3, st));
+    HM_CUDA(P->runs.upload(L.runs, st));
+    HM_CUDA(P->cores.upload(L.cores, st));
+    HM_CUDA(P->plist.upload(L.plist, st));
+    {
+        // temporary tables for the fill kernels
+        DevBuf<HmLeaf> dleaves;
+        DevBuf<HmFill> dfill1, dfill3;
+        DevBuf<int32_t> dcore_leaf;
+        HM_CUDA(dleaves.upload(L.leaves, st));
+        HM_CUDA(dfill1.upload(L.fill1, st));
+        HM_CUDA(dfill3.upload(L.fill3, st));
+        HM_CUDA(dcore_leaf.upload(L.core_leaf, st));
+        HM_CUDA(hm_launch_fill1(dfill1.p, (int64_t)L.fill1.size(), dleaves.p, P->vstream.p, dpy, P->cheb, st));
+        HM_CUDA(hm_launch_fill3(dfill3.p, (int64_t)L.fill3.size(), dleaves.p, P->ustream.p, dpx, dpy, P->cheb,
+                                P->kernel_id, st));
+        HM_CUDA(hm_launch_fillcore(P->cores.p, dcore_leaf.p, (int64_t)L.cores.size(), dleaves.p, P->core.p,
+                                   P->cheb, P->kernel_id, st));
+        HM_CUDA(cudaStreamSynchronize(st));
+    }
+    // the raw sources are gone after this point: drop the dangling pointers
+    for (HmLeaf &l : L.leaves) l.dU = l.dC = l.dV = nullptr;
+    return HM_OK;
+}
+
+int32_t check_block(const hm_builder *b, int64_t m, int64_t n, int64_t row0, int64_t col0)
+{
+    if (m < 0 || n < 0) return fail(HM_ERR_SHAPE, "negative block extent %lld x %lld", (long long)m, (long long)n);
+    if (row0 < 0 || col0 < 0 || row0 + m > b->nrows || col0 + n > b->ncols)
+        return fail(HM_ERR_RANGE, "block [%lld,%lld) x [%lld,%lld) outside the %lld x %lld operator",
+                    (long long)row0, (long long)(row0 + m), (long long)col0, (long long)(col0 + n),
+                    (long long)b->nrows, (long long)b->ncols);
+    return HM_OK;
+}
+
+int32_t stage(hm_builder *b, const double *src, int64_t rows, int64_t cols, int64_t ld, const char *what,
+              const double **out)
+{
+    *out = nullptr;
+    if (rows * cols == 0 || b->device < 0) return HM_OK;
+    if (!src) return fail(HM_ERR_NULL, "%s is NULL", what);
+    if (ld < rows) return fail(HM_ERR_SHAPE, "%s: leading dimension %lld < rows %lld", what, (long long)ld, (long long)rows);
+    HM_CUDA(b->up->put(src, rows, cols, ld, out));
+    return HM_OK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *hm_last_error(void) { return g_err.c_str(); }
+
+int32_t hm_version(void) { return 100; }
+
+int32_t hm_blockrank_f64(void) { return hm_blockrank_double(); }
+int32_t hm_blocksize_f64(void) { return hm_blocksize_double(); }
+
+int32_t hm_builder_create(hm_builder **out, int64_t nrows, int64_t ncols, int32_t dtype, int32_t device)
+{
+    if (!out) return fail(HM_ERR_NULL, "out is NULL");
+    *out = nullptr;
+    if (dtype != HM_F64) return fail(HM_ERR_UNSUPPORTED, "only Float64 (HM_F64) operators are supported");
+    if (nrows < 0 || ncols < 0) return fail(HM_ERR_SHAPE, "negative operator extent");
+    if (nrows >= ((int64_t)1 << 31) || ncols >= ((int64_t)1 << 31))
+        return fail(HM_ERR_UNSUPPORTED, "operator extent >= 2^31");
+    hm_builder *b = new (std::nothrow) hm_builder;
+    if (!b) return fail(HM_ERR_NOMEM, "out of host memory");
+    b->nrows = nrows;
+    b->ncols = ncols;
+    b->device = device;
+    if (device >= 0) {
+        DeviceGuard g(device);
+        if (!g.ok) {
+            delete b;
+            cudaGetLastError();
+            return fail(HM_ERR_CUDA, "cannot select CUDA device %d: %s", device, cudaGetErrorString(g.err));
+        }
+        b->up = new (std::nothrow) Uploader;
+        cudaError_t e = b->up ? b->up->init() : cudaErrorMemoryAllocation;
+        if (e != cudaSuccess) {
+            delete b;
+            cudaGetLastError();
+            return fail(HM_ERR_CUDA, "staging setup failed: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = b;
+    return HM_OK;
+}
+
+int32_t hm_builder_destroy(hm_builder *b)
+{
+    if (!b) return HM_OK;
+    if (b->device >= 0) {
+        DeviceGuard g(b->device);
+        delete b;
+    } else {
+        delete b;
+    }
+    return HM_OK;
+}
+
+int32_t hm_builder_add_dense(hm_builder *b, const double *A, int64_t m, int64_t n, int64_t lda, int64_t row0,
+                             int64_t col0)
+{
+    if (!b) return fail(HM_ERR_NULL, "builder is NULL");
+    if (int32_t st = check_block(b, m, n, row0, col0)) return st;
+    HmLeaf l{};
+    l.kind = HM_LEAF_DENSE;
+    l.source = b->device >= 0 ? HM_SRC_COPY : HM_SRC_NONE;
+    l.row0 = row0;
+    l.col0 = col0;
+    l.m = m;
+    l.n = n;
+    if (b->device >= 0) {
+        HM_DEVICE(b->device);
+        if (int32_t st = stage(b, A, m, n, lda, "A", &l.dU)) return st;
+    }
+    l.ldu = m;
+    b->leaves.push_back(l);
+    return HM_OK;
+}
+
+static int32_t add_factored(hm_builder *b, int32_t kind, const double *U, int64_t ldu, const double *C,
+                            int64_t ldc, const double *V, int64_t ldv, int64_t m, int64_t n, int64_t r,
+                            int64_t row0, int64_t col0)
+{
+    if (!b) return fail(HM_ERR_NULL, "builder is NULL");
+    if (int32_t st = check_block(b, m, n, row0, col0)) return st;
+    if (r < 0) return fail(HM_ERR_SHAPE, "negative rank");
+    if (r > 2048) return fail(HM_ERR_UNSUPPORTED, "rank %lld > 2048", (long long)r);
+    HmLeaf l{};
+    l.kind = kind;
+    l.source = b->device >= 0 ? HM_SRC_COPY : HM_SRC_NONE;
+    l.row0 = row0;
+    l.col0 = col0;
+    l.m = m;
+    l.n = n;
+    l.ru = l.rv = (int32_t)r;
+    if (b->device >= 0) {
+        HM_DEVICE(b->device);
+        if (int32_t st = stage(b, U, m, r, ldu, "U", &l.dU)) return st;
+        if (kind == HM_LEAF_LOWRANK) {
+            if (int32_t st = stage(b, C, r, 1, r, "S", &l.dC)) return st;
+        } else {
+            if (int32_t st = stage(b, C, r, r, ldc, "F", &l.dC)) return st;
+        }
+        if (int32_t st = stage(b, V, n, r, ldv, "V", &l.dV)) return st;
+    }
+    l.ldu = m;
+    l.ldc = r;
+    l.ldv = n;
+    b->leaves.push_back(l);
+    return HM_OK;
+}
+
+int32_t hm_builder_add_lowrank(hm_builder *b, const double *U, int64_t ldu, const double *S, const double *V,
+                               int64_t ldv, int64_t m, int64_t n, int64_t r, int64_t row0, int64_t col0)
+{
+    return add_factored(b, HM_LEAF_LOWRANK, U, ldu, S, r, V, ldv, m, n, r, row0, col0);
+}
+
+int32_t hm_builder_add_bary2d(hm_builder *b, const double *U, int64_t ldu, const double *F, int64_t ldf,
+                              const double *V, int64_t ldv, int64_t m, int64_t n, int64_t r, int64_t row0,
+                              int64_t col0)
+{
+    return add_factored(b, HM_LEAF_BARY2D, U, ldu, F, ldf, V, ldv, m, n, r, row0, col0);
+}
+
+int32_t hm_builder_layout_stats(hm_builder *b, int32_t part, int32_t nparts, hm_stats *out)
+{
+    if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
+    HmLayout L;
+    std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, HmLayoutParams(), L);
+    if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
+    fill_stats(L, out);
+    return HM_OK;
+}
+
+int32_t hm_plan_finalize_part(hm_builder *b, int32_t part, int32_t nparts, hm_plan **out)
+{
+    if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
+    *out = nullptr;
+    if (b->device < 0) return fail(HM_ERR_STATE, "structure-only builder (device = -1) cannot be finalized");
+    HM_DEVICE(b->device);
+    HM_CUDA(b->up->finish());
+    hm_plan *P = new (std::nothrow) hm_plan;
+    if (!P) return fail(HM_ERR_NOMEM, "out of host memory");
+    P->device = b->device;
+    std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, HmLayoutParams(), P->L);
+    if (!err.empty()) {
+        delete P;
+        return fail(HM_ERR_INVALID, "%s", err.c_str());
+    }
+    P->cheb.r = 0;
+    int32_t st = materialize(P, nullptr, nullptr);
+    if (st != HM_OK) {
+        delete P;
+        return st;
+    }
+    *out = P;
+    return HM_OK;
+}
+
+int32_t hm_plan_finalize(hm_builder *b, const int32_t *devices, int32_t ndev, hm_plan **out)
+{
+    if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
+    if (ndev != 1)
+        return fail(HM_ERR_UNSUPPORTED,
+                    "one plan drives one GPU; for multi-GPU run one process per GPU with hm_plan_finalize_part");
+    if (devices && devices[0] != b->device)
+        return fail(HM_ERR_INVALID, "devices[0] = %d but the builder staged its data on device %d", devices[0],
+                    b->device);
+    return hm_plan_finalize_part(b, 0, 1, out);
+}
+
+int32_t hm_plan_destroy(hm_plan *p)
+{
+    if (!p) return HM_OK;
+    DeviceGuard g(p->device);
+    delete p;
+    return HM_OK;
+}
+
+int32_t hm_plan_stats(const hm_plan *p, hm_stats *out)
+{
+    if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
+    fill_stats(p->L, out);
+    return HM_OK;
+}
+
+int32_t hm_plan_timing_begin(hm_plan *p, int32_t max_calls)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (max_calls < 0 || max_calls > 100000) return fail(HM_ERR_INVALID, "max_calls out of range");
+    HM_DEVICE(p->device);
+    while ((int)p->tev.size() < 4 * max_calls) {
+        cudaEvent_t e;
+        HM_CUDA(cudaEventCreate(&e));
+        p->tev.push_back(e);
+    }
+    p->tcap = max_calls;
+    p->tcount = 0;
+    return HM_OK;
+}
+
+int32_t hm_plan_timing_end(hm_plan *p, double *stage_ms3, int64_t *ncalls)
+{
+    if (!p || !stage_ms3 || !ncalls) return fail(HM_ERR_NULL, "NULL argument");
+    HM_DEVICE(p->device);
+    stage_ms3[0] = stage_ms3[1] = stage_ms3[2] = 0.0;
+    for (int c = 0; c < p->tcount; c++) {
+        cudaEvent_t *ev = &p->tev[(size_t)c * 4];
+        HM_CUDA(cudaEventSynchronize(ev[3]));
+        for (int s = 0; s < 3; s++) {
+            float ms = 0.f;
+            HM_CUDA(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+            stage_ms3[s] += ms;
+        }
+    }
+    *ncalls = p->tcount;
+    p->tcap = 0;
+    p->tcount = 0;
+    return HM_OK;
+}
+
+int32_t hm_plan_launches_per_matvec(const hm_plan *p)
+{
+    if (!p) return 0;
+    int n = 0;
+    if (!p->L.items1.empty()) n++;
+    if (!p->L.cores.empty()) n++;
+    for (size_t r = 0; r + 1 < p->L.round_begin.size(); r++)
+        if (p->L.round_begin[r + 1] > p->L.round_begin[r]) n++;
+    return n;
+}
+
+static int32_t kernel_tree_layout(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                                  double c, double d, int32_t part, int32_t nparts, HmLayout &L)
+{
+    if (!x || !y) return fail(HM_ERR_NULL, "point set is NULL");
+    if (nx < 0 || ny < 0) return fail(HM_ERR_SHAPE, "negative point count");
+    std::vector<HmLeaf> leaves;
+    int64_t nrows = 0, ncols = 0;
+    std::string err = hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
+    if (!err.empty()) return fail(HM_ERR_REFERENCE, "%s", err.c_str());
+    err = hm_build_layout(leaves, nrows, ncols, part, nparts, HmLayoutParams(), L);
+    if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
+    return HM_OK;
+}
+
+int32_t hm_kernel_tree_leaves(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                              double c, double d, hm_tree_leaf *out, int64_t cap, int64_t *count)
+{
+    if (!x || !y || !count) return fail(HM_ERR_NULL, "NULL argument");
+    if (nx < 0 || ny < 0) return fail(HM_ERR_SHAPE, "negative point count");
+    std::vector<HmLeaf> leaves;
+    int64_t nrows = 0, ncols = 0;
+    std::string err = hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
+    if (!err.empty()) return fail(HM_ERR_REFERENCE, "%s", err.c_str());
+    *count = (int64_t)leaves.size();
+    for (int64_t i = 0; out && i < cap && i < *count; i++) {
+        const HmLeaf &l = leaves[(size_t)i];
+        out[i] = hm_tree_leaf{l.kind, l.ru, l.row0, l.col0, l.m, l.n, l.xi0, l.yj0, l.a, l.b, l.c, l.d};
+    }
+    return HM_OK;
+}
+
+int32_t hm_assemble_kernel_stats(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                                 double c, double d, int32_t part, int32_t nparts, hm_stats *out)
+{
+    if (!out) return fail(HM_ERR_NULL, "out is NULL");
+    HmLayout L;
+    if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, L)) return st;
+    fill_stats(L, out);
+    return HM_OK;
+}
+
+int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                           double c, double d, int32_t kernel_id, int32_t device, int32_t part, int32_t nparts,
+                           hm_plan **out)
+{
+    if (!out) return fail(HM_ERR_NULL, "out is NULL");
+    *out = nullptr;
+    if (kernel_id < 0 || kernel_id > 3) return fail(HM_ERR_INVALID, "unknown kernel id %d", kernel_id);
+    if (hm_blockrank_double() != 20) return fail(HM_ERR_UNSUPPORTED, "BLOCKRANK(Float64) != 20");
+    HM_DEVICE(device);
+    hm_plan *P = new (std::nothrow) hm_plan;
+    if (!P) return fail(HM_ERR_NOMEM, "out of host memory");
+    P->device = device;
+    P->kernel_id = kernel_id;
+    if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, P->L)) {
+        delete P;
+        return st;
+    }
+    P->cheb.r = hm_blockrank_double();
+    hm_cheb_nodes_weights(P->cheb.r, P->cheb.node, P->cheb.lam);
+    DevBuf<double> dpx, dpy;
+    cudaError_t e = dpx.alloc((size_t)std::max<int64_t>(nx, 1));
+    if (e == cudaSuccess) e = dpy.alloc((size_t)std::max<int64_t>(ny, 1));
+    if (e == cudaSuccess && nx) e = cudaMemcpy(dpx.p, x, (size_t)nx * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ny) e = cudaMemcpy(dpy.p, y, (size_t)ny * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        delete P;
+        cudaGetLastError();
+        return fail(HM_ERR_CUDA, "point upload failed: %s", cudaGetErrorString(e));
+    }
+    int32_t st = materialize(P, dpx.p, dpy.p);
+    if (st != HM_OK) {
+        delete P;
+        return st;
+    }
+    *out = P;
+    return HM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// mul!
+// ---------------------------------------------------------------------------
+int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if ((!dx && p->L.ncols > 0) || (!dy && p->L.nrows > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+    HM_DEVICE(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const HmLayout &L = p->L;
+    cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
+    if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
+    HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p, st));
+    if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
+    HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
+                             p->svec.p, std::max(L.max_r, 1), st));
+    if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
+    for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
+        int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
+        HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
+                                 r == 0 ? (accumulate != 0) : 1, st));
+    }
+    if (ev) {
+        HM_CUDA(cudaEventRecord(ev[3], st));
+        p->tcount++;
+    }
+    return HM_OK;
+}
+
+int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy, int32_t accumulate)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    const HmLayout &L = p->L;
+    if ((!x && L.ncols > 0) || (!y && L.nrows > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+    if (incx == 0 || incy == 0) return fail(HM_ERR_INVALID, "zero stride");
+    std::lock_guard<std::mutex> lock(p->mu);
+    HM_DEVICE(p->device);
+    const int64_t nc = L.ncols, r0 = L.row_begin, nr = L.row_end - L.row_begin;
+    if (!p->dx.p) HM_CUDA(p->dx.alloc((size_t)std::max<int64_t>(nc, 1)));
+    if (!p->dy.p) HM_CUDA(p->dy.alloc((size_t)std::max<int64_t>(L.nrows, 1)));
+    cudaStream_t st = p->stream;
+    // x -> device
+    if (nc > 0) {
+        if (incx == 1) {
+            HM_CUDA(cudaMemcpyAsync(p->dx.p, x, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+        } else {
+            if (!p->hx) HM_CUDA(cudaMallocHost((void **)&p->hx, (size_t)nc * 8));
+            for (int64_t j = 0; j < nc; j++) p->hx[j] = x[j * incx];
+            HM_CUDA(cudaMemcpyAsync(p->dx.p, p->hx, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+        }
+    }
+    // y (owned rows) -> device when accumulating
+    if (nr > 0 && accumulate) {
+        if (incy == 1) {
+            HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, y + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, st));
+        } else {
+            if (!p->hy) HM_CUDA(cudaMallocHost((void **)&p->hy, (size_t)L.nrows * 8));
+            for (int64_t i = 0; i < nr; i++) p->hy[r0 + i] = y[(r0 + i) * incy];
+            HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, p->hy + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (int32_t rc = hm_matvec_device(p, p->dx.p, p->dy.p, accumulate, st)) return rc;
+    if (nr > 0) {
+        if (incy == 1) {
+            HM_CUDA(cudaMemcpyAsync(y + r0, p->dy.p + r0, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
+            HM_CUDA(cudaStreamSynchronize(st));
+        } else {
+            if (!p->hy) HM_CUDA(cudaMallocHost((void **)&p->hy, (size_t)L.nrows * 8));
+            HM_CUDA(cudaMemcpyAsync(p->hy + r0, p->dy.p + r0, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
+            HM_CUDA(cudaStreamSynchronize(st));
+            for (int64_t i = 0; i < nr; i++) y[(r0 + i) * incy] = p->hy[r0 + i];
+        }
+    } else {
+        HM_CUDA(cudaStreamSynchronize(st));
+    }
+    return HM_OK;
+}
+
+// Multi-RHS: column-by-column over the single-vector kernels for now (the
+// DMMA panel kernels replace this loop; see DESIGN.md "Next").
+int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t nrhs,
+                         int32_t accumulate, void *stream)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
+    if (nrhs > 0 && (ldx < std::max<int64_t>(p->L.ncols, 1) || ldy < std::max<int64_t>(p->L.nrows, 1)))
+        return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
+    for (int64_t c = 0; c < nrhs; c++)
+        if (int32_t rc = hm_matvec_device(p, dX + c * ldx, dY + c * ldy, accumulate, stream)) return rc;
+    return HM_OK;
+}
+
+int32_t hm_matmat(hm_plan *p, const double *X, int64_t ldx, double *Y, int64_t ldy, int64_t nrhs,
+                  int32_t accumulate)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
+    if (nrhs > 0 && (ldx < std::max<int64_t>(p->L.ncols, 1) || ldy < std::max<int64_t>(p->L.nrows, 1)))
+        return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
+    for (int64_t c = 0; c < nrhs; c++)
+        if (int32_t rc = hm_matvec(p, X + c * ldx, 1, Y + c * ldy, 1, accumulate)) return rc;
+    return HM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// test hooks
+// ---------------------------------------------------------------------------
+int32_t hm_plan_num_leaves(const hm_plan *p, int64_t *out)
+{
+    if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
+    *out = (int64_t)p->L.leaves.size();
+    return HM_OK;
+}
+
+int32_t hm_plan_leaf_info(const hm_plan *p, int64_t leaf, int32_t *kind, int64_t *row0, int64_t *col0,
+                          int64_t *m, int64_t *n, int64_t *r)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (leaf < 0 || leaf >= (int64_t)p->L.leaves.size()) return fail(HM_ERR_RANGE, "leaf index out of range");
+    const HmLeaf &l = p->L.leaves[(size_t)leaf];
+    if (kind) *kind = l.kind;
+    if (row0) *row0 = l.row0;
+    if (col0) *col0 = l.col0;
+    if (m) *m = l.m;
+    if (n) *n = l.n;
+    if (r) *r = l.ru;
+    return HM_OK;
+}
+
+int32_t hm_plan_read_leaf(hm_plan *p, int64_t leaf, int32_t which, double *out, int64_t cap)
+{
+    if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
+    if (leaf < 0 || leaf >= (int64_t)p->L.leaves.size()) return fail(HM_ERR_RANGE, "leaf index out of range");
+    std::lock_guard<std::mutex> lock(p->mu);
+    HM_DEVICE(p->device);
+    HmLayout &L = p->L;
+    if (!p->indexed) {
+        for (size_t i = 0; i < L.fill1.size(); i++) p->idx1.emplace(L.fill1[i].leaf, i);
+        for (size_t i = 0; i < L.fill3.size(); i++) p->idx3.emplace(L.fill3[i].leaf, i);
+        p->indexed = true;
+    }
+    const HmLeaf &l = L.leaves[(size_t)leaf];
+    const bool dense = l.kind == HM_LEAF_DENSE;
+    int64_t need = 0;
+    if (which == 0) need = dense ? -1 : l.m * l.ru;
+    else if (which == 1) need = dense ? -1 : (l.kind == HM_LEAF_BARY2D ? (int64_t)l.ru * l.rv : l.ru);
+    else if (which == 2) need = dense ? -1 : l.n * l.rv;
+    else if (which == 3) need = dense ? l.m * l.n : -1;
+    else return fail(HM_ERR_INVALID, "which must be 0..3");
+    if (need < 0) return fail(HM_ERR_INVALID, "leaf kind has no such factor");
+    if (cap < need) return fail(HM_ERR_SHAPE, "output capacity %lld < %lld", (long long)cap, (long long)need);
+    for (int64_t i = 0; i < need; i++) out[i] = 0.0; // rows outside this part stay 0
+    if (which == 1) {
+        for (size_t c = 0; c < L.cores.size(); c++)
+            if (L.core_leaf[c] == (int32_t)leaf)
+                HM_CUDA(cudaMemcpy(out, p->core.p + L.cores[c].core, (size_t)need * 8, cudaMemcpyDeviceToHost));
+        return HM_OK;
+    }
+    if (which == 0 || which == 3) {
+        auto range = p->idx3.equal_range((int32_t)leaf);
+        for (auto it = range.first; it != range.second; ++it) {
+            const HmFill &f = L.fill3[it->second];
+            // kn columns of F rows (ld Fp) -> out[(off + i) + (k0 + k) * m]
+            HM_CUDA(cudaMemcpy2D(out + f.off + (int64_t)f.k0 * l.m, (size_t)l.m * 8, p->ustream.p + f.dst,
+                                 (size_t)f.Fp * 8, (size_t)f.F * 8, (size_t)f.kn, cudaMemcpyDeviceToHost));
+        }
+        return HM_OK;
+    }
+    auto range = p->idx1.equal_range((int32_t)leaf);
+    std::vector<double> tmp;
+    for (auto it = range.first; it != range.second; ++it) {
+        const HmFill &f = L.fill1[it->second];
+        tmp.resize((size_t)f.S * f.kn);
+        HM_CUDA(cudaMemcpy2D(tmp.data(), (size_t)f.kn * 8, p->vstream.p + f.dst, (size_t)f.Fp * 8,
+                             (size_t)f.kn * 8, (size_t)f.S, cudaMemcpyDeviceToHost));
+        for (int s = 0; s < f.S; s++)
+            for (int k = 0; k < f.kn; k++) out[(f.off + s) + (int64_t)(f.k0 + k) * l.n] = tmp[(size_t)s * f.kn + k];
+    }
+    return HM_OK;
+}
+
+} // extern "C"

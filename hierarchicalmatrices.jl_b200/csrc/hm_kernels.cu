@@ -1,0 +1,408 @@
+// hm_kernels.cu -- hand-written sm_100a kernels of the H-matrix matvec.
+//
+// The reference walks the block tree and runs one scalar loop nest per leaf
+// (/root/reference/src/algebra.jl:37-48 dense, :110-131 LowRankMatrix, :243-277
+// BarycentricMatrix2D).  Here all leaves are applied by three flat passes over
+// packed streams (see hm_layout.cpp):
+//
+//   stage 1 / stage 3   hm_stream_kernel: out[f] = sum_s W[s][f] * z[s]
+//        one CTA per item, W is one contiguous slab read front to back with
+//        128-bit streaming loads; thread <-> fast index f, so the sum over s is
+//        a private register accumulation (no atomics, no shuffles); the few
+//        column groups of a CTA are combined in a fixed order through shared
+//        memory, so results are run-to-run deterministic.
+//   stage 2             hm_core_kernel: tiny r x r core apply per low-rank leaf.
+//
+// HBM-bound: 8 B of stream per FMA.  No tensor-core use on the single-vector path.
+#include "hm_kernels.cuh"
+
+namespace {
+
+__device__ __forceinline__ double2 ld_stream(const double2 *p)
+{
+    // read-once data: streaming (evict-first) so that x, s and the partial sums
+    // keep their place in the 126 MB L2
+    return __ldcs(p);
+}
+
+// ---------------------------------------------------------------------------
+// stage 1 / stage 3
+// ---------------------------------------------------------------------------
+template <bool GATHER>
+__global__ void __launch_bounds__(HM_THREADS, 4)
+hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
+                 const double *__restrict__ W, const double *__restrict__ x,
+                 const double *__restrict__ svec, double *__restrict__ out, int accumulate)
+{
+    constexpr int T = HM_THREADS;
+    __shared__ double zs[HM_SMAX];
+    __shared__ double2 red[T];
+    __shared__ int rpos[GATHER ? HM_MAXRUNS + 1 : 1];
+    __shared__ int rsrc[GATHER ? HM_MAXRUNS : 1];
+
+    const HmItem it = items[blockIdx.x];
+    const int t = threadIdx.x;
+    const int S = it.S, F = it.F, L = it.Fp >> 1;
+
+    // ---- stage z in shared memory ----
+    if (GATHER) {
+        for (int r = t; r < it.nrun; r += T) {
+            HmRun rr = runs[it.run0 + r];
+            rpos[r] = rr.pos;
+            rsrc[r] = rr.src;
+        }
+        if (t == 0) rpos[it.nrun] = S;
+        __syncthreads();
+        for (int e = t; e < S; e += T) {
+            int lo = 0, hi = it.nrun; // rpos[lo] <= e < rpos[hi]
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (rpos[mid] <= e)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            int src = rsrc[lo], off = e - rpos[lo];
+            zs[e] = src >= 0 ? x[src + off] : svec[(~src) + off];
+        }
+    } else {
+        for (int e = t; e < S; e += T) zs[e] = x[it.zoff + e];
+    }
+    __syncthreads();
+
+    const double2 *__restrict__ W2 = reinterpret_cast<const double2 *>(W + it.slab);
+
+    if (L <= T) {
+        // ncg column groups of L threads; thread t reads double2 number t, t+TA, ...
+        const int ncg = L > 0 ? T / L : 1;
+        const int TA = ncg * L;
+        double2 acc = make_double2(0.0, 0.0);
+        if (t < TA) {
+            const int cg = t / L;
+            const int nvec = S * L;
+            int i = t, si = cg;
+            for (; i + 7 * TA < nvec; i += 8 * TA, si += 8 * ncg) {
+                double2 w[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) w[u] = ld_stream(W2 + i + u * TA);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    double z = zs[si + u * ncg];
+                    acc.x = fma(w[u].x, z, acc.x);
+                    acc.y = fma(w[u].y, z, acc.y);
+                }
+            }
+            for (; i < nvec; i += TA, si += ncg) {
+                double2 w = ld_stream(W2 + i);
+                double z = zs[si];
+                acc.x = fma(w.x, z, acc.x);
+                acc.y = fma(w.y, z, acc.y);
+            }
+        }
+        if (ncg > 1) {
+            red[t] = acc;
+            __syncthreads();
+            if (t < L) {
+                double2 a = red[t];
+                for (int g = 1; g < ncg; g++) {
+                    double2 b = red[g * L + t];
+                    a.x += b.x;
+                    a.y += b.y;
+                }
+                acc = a;
+            }
+        }
+        if (t < L) {
+            int f = 2 * t;
+            double *o = out + it.out + f;
+            if (GATHER) {
+                if (f < F) o[0] = (accumulate ? o[0] : 0.0) + acc.x;
+                if (f + 1 < F) o[1] = (accumulate ? o[1] : 0.0) + acc.y;
+            } else {
+                if (f < F) o[0] = acc.x;
+                if (f + 1 < F) o[1] = acc.y;
+            }
+        }
+    } else {
+        // wide items: each thread owns whole columns of the slab
+        for (int f2 = t; f2 < L; f2 += T) {
+            double2 acc = make_double2(0.0, 0.0);
+            const double2 *p = W2 + f2;
+            int s = 0;
+            for (; s + 7 < S; s += 8) {
+                double2 w[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) w[u] = ld_stream(p + (size_t)(s + u) * L);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    double z = zs[s + u];
+                    acc.x = fma(w[u].x, z, acc.x);
+                    acc.y = fma(w[u].y, z, acc.y);
+                }
+            }
+            for (; s < S; s++) {
+                double2 w = ld_stream(p + (size_t)s * L);
+                double z = zs[s];
+                acc.x = fma(w.x, z, acc.x);
+                acc.y = fma(w.y, z, acc.y);
+            }
+            int f = 2 * f2;
+            double *o = out + it.out + f;
+            if (GATHER) {
+                if (f < F) o[0] = (accumulate ? o[0] : 0.0) + acc.x;
+                if (f + 1 < F) o[1] = (accumulate ? o[1] : 0.0) + acc.y;
+            } else {
+                if (f < F) o[0] = acc.x;
+                if (f + 1 < F) o[1] = acc.y;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stage 2: one warp per low-rank leaf
+//   t[k]  = sum over the leaf's stage-1 partial sums, in column order
+//   s     = Sigma .* t            (LowRankMatrix,       algebra.jl:120)
+//   s     = F * t  (l outer)      (BarycentricMatrix2D, algebra.jl:260-265)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
+               const int32_t *__restrict__ plist, const double *__restrict__ partial,
+               const double *__restrict__ core, double *__restrict__ svec, int max_r)
+{
+    extern __shared__ double tbuf_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (b >= nblocks) return;
+    double *tbuf = tbuf_all + (size_t)wib * max_r;
+    const HmCoreBlock cb = blocks[b];
+    const int32_t *pl = plist + cb.pl0;
+    for (int k = lane; k < cb.rv; k += 32) {
+        double t = 0.0;
+        int i = 0;
+        for (; i + 3 < cb.npl; i += 4) {
+            double p0 = partial[pl[i] + k], p1 = partial[pl[i + 1] + k];
+            double p2 = partial[pl[i + 2] + k], p3 = partial[pl[i + 3] + k];
+            t += p0;
+            t += p1;
+            t += p2;
+            t += p3;
+        }
+        for (; i < cb.npl; i++) t += partial[pl[i] + k];
+        tbuf[k] = t;
+    }
+    __syncwarp();
+    const double *c = core + cb.core;
+    if (cb.kind == HM_LEAF_LOWRANK) {
+        for (int k = lane; k < cb.ru; k += 32) svec[cb.soff + k] = tbuf[k] * c[k];
+    } else {
+        for (int k = lane; k < cb.ru; k += 32) {
+            double a = 0.0;
+            for (int l = 0; l < cb.rv; l++) a = fma(c[k + (size_t)l * cb.ru], tbuf[l], a);
+            svec[cb.soff + k] = a;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// plan construction: fill the streams
+// ---------------------------------------------------------------------------
+
+// examples/Kernel.jl:34-37
+__device__ __forceinline__ double kernel_eval(int id, double x, double y)
+{
+    double d = __dsub_rn(x, y);
+    switch (id) {
+    case 0: return __drcp_rn(d);
+    case 1: return __drcp_rn(__dmul_rn(d, d));
+    case 2: return __drcp_rn(__dmul_rn(__dmul_rn(d, d), d));
+    default: return log(fabs(d));
+    }
+}
+
+// Row of a barycentric factor, src/BarycentricMatrix.jl:256-287:
+//   w[k] = lam[k] * inv(p - node_k), node_k = mid + half*cheb_k (:159-167);
+//   row  = w / (w[0] + w[1] + ... sequentially).
+// Explicit _rn intrinsics: no FMA contraction, so the factors are bit-identical
+// to the two-rounding arithmetic of the reference.
+template <int R>
+__device__ __forceinline__ void bary_row(const HmCheb &cheb, double lo, double hi, double p,
+                                         double (&w)[R])
+{
+    const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi));
+    const double half = __dmul_rn(0.5, __dsub_rn(hi, lo));
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        double node = __dadd_rn(mid, __dmul_rn(half, cheb.node[k]));
+        w[k] = __dmul_rn(cheb.lam[k], __drcp_rn(__dsub_rn(p, node)));
+        sum = __dadd_rn(sum, w[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) w[k] = __ddiv_rn(w[k], sum);
+}
+
+template <int R>
+__global__ void __launch_bounds__(128)
+hm_fill3_kernel(const HmFill *__restrict__ fills, const HmLeaf *__restrict__ leaves,
+                double *__restrict__ W, const double *__restrict__ px,
+                const double *__restrict__ py, const HmCheb cheb, int kernel_id)
+{
+    const HmFill f = fills[blockIdx.x];
+    const HmLeaf *l = leaves + f.leaf;
+    const int t = threadIdx.x, T = blockDim.x;
+    double *dst = W + f.dst;
+    if (l->source == HM_SRC_COPY) {
+        const double *src = l->dU + f.off + (int64_t)f.k0 * l->ldu;
+        const int64_t ld = l->ldu;
+        for (int idx = t; idx < f.kn * f.F; idx += T) {
+            int k = idx / f.F, i = idx - k * f.F;
+            dst[(int64_t)k * f.Fp + i] = src[i + k * ld];
+        }
+    } else if (l->kind == HM_LEAF_DENSE) {
+        // T[f(x[i], y[j]) for i in ir, j in jr] -- src/KernelMatrix.jl:57-60
+        const double *xr = px + l->xi0 + f.off;
+        const double *yc = py + l->yj0 + f.k0;
+        for (int idx = t; idx < f.kn * f.F; idx += T) {
+            int k = idx / f.F, i = idx - k * f.F;
+            dst[(int64_t)k * f.Fp + i] = kernel_eval(kernel_id, xr[i], yc[k]);
+        }
+    } else {
+        const double *xr = px + l->xi0 + f.off;
+        const double a = l->a, b = l->b;
+        for (int i = t; i < f.F; i += T) {
+            double w[R];
+            bary_row<R>(cheb, a, b, xr[i], w);
+#pragma unroll
+            for (int k = 0; k < R; k++)
+                if (k >= f.k0 && k < f.k0 + f.kn) dst[(int64_t)(k - f.k0) * f.Fp + i] = w[k];
+        }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(128)
+hm_fill1_kernel(const HmFill *__restrict__ fills, const HmLeaf *__restrict__ leaves,
+                double *__restrict__ W, const double *__restrict__ py, const HmCheb cheb)
+{
+    const HmFill f = fills[blockIdx.x];
+    const HmLeaf *l = leaves + f.leaf;
+    const int t = threadIdx.x, T = blockDim.x;
+    double *dst = W + f.dst;
+    if (l->source == HM_SRC_COPY) {
+        const double *src = l->dV + f.off;
+        const int64_t ld = l->ldv;
+        for (int idx = t; idx < f.kn * f.S; idx += T) {
+            int k = idx / f.S, s = idx - k * f.S;
+            dst[(int64_t)s * f.Fp + k] = src[s + k * ld];
+        }
+    } else {
+        const double *yc = py + l->yj0 + f.off;
+        const double c = l->c, d = l->d;
+        for (int s = t; s < f.S; s += T) {
+            double w[R];
+            bary_row<R>(cheb, c, d, yc[s], w);
+#pragma unroll
+            for (int k = 0; k < R; k++) dst[(int64_t)s * f.Fp + k] = w[k];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+hm_fillcore_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__restrict__ core_leaf,
+                   const HmLeaf *__restrict__ leaves, double *__restrict__ core, const HmCheb cheb,
+                   int kernel_id)
+{
+    const HmCoreBlock cb = blocks[blockIdx.x];
+    const HmLeaf *l = leaves + core_leaf[blockIdx.x];
+    const int t = threadIdx.x, T = blockDim.x;
+    double *dst = core + cb.core;
+    if (l->source == HM_SRC_COPY) {
+        if (cb.kind == HM_LEAF_LOWRANK) {
+            for (int k = t; k < cb.ru; k += T) dst[k] = l->dC[k];
+        } else {
+            for (int idx = t; idx < cb.ru * cb.rv; idx += T) {
+                int n = idx / cb.ru, m = idx - n * cb.ru;
+                dst[idx] = l->dC[m + n * l->ldc];
+            }
+        }
+    } else {
+        // F[m,n] = f(x_m, y_n) at the mapped Chebyshev nodes -- BarycentricMatrix.jl:159-175
+        const double xm = __dmul_rn(0.5, __dadd_rn(l->a, l->b)), xh = __dmul_rn(0.5, __dsub_rn(l->b, l->a));
+        const double ym = __dmul_rn(0.5, __dadd_rn(l->c, l->d)), yh = __dmul_rn(0.5, __dsub_rn(l->d, l->c));
+        for (int idx = t; idx < cb.ru * cb.rv; idx += T) {
+            int n = idx / cb.ru, m = idx - n * cb.ru;
+            double xn = __dadd_rn(xm, __dmul_rn(xh, cheb.node[m]));
+            double yn = __dadd_rn(ym, __dmul_rn(yh, cheb.node[n]));
+            dst[idx] = kernel_eval(kernel_id, xn, yn);
+        }
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------
+cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *vstream,
+                             const double *x, double *partial, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    hm_stream_kernel<false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x, nullptr,
+                                                                     partial, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
+                             const double *partial, const double *core, double *svec, int max_r,
+                             cudaStream_t st)
+{
+    if (nblocks <= 0) return cudaSuccess;
+    int threads = 256;
+    size_t smem = (size_t)(threads / 32) * (size_t)max_r * sizeof(double);
+    while (smem > 48 * 1024 && threads > 32) {
+        threads >>= 1;
+        smem = (size_t)(threads / 32) * (size_t)max_r * sizeof(double);
+    }
+    if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
+    int wpb = threads / 32;
+    unsigned grid = (unsigned)((nblocks + wpb - 1) / wpb);
+    hm_core_kernel<<<grid, threads, smem, st>>>(blocks, nblocks, plist, partial, core, svec, max_r);
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *runs,
+                             const double *ustream, const double *x, const double *svec, double *y,
+                             int accumulate, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    hm_stream_kernel<true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec, y,
+                                                                    accumulate);
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_fill3(const HmFill *fills, int64_t nfills, const HmLeaf *leaves, double *ustream,
+                            const double *px, const double *py, const HmCheb &cheb, int kernel_id,
+                            cudaStream_t st)
+{
+    if (nfills <= 0) return cudaSuccess;
+    hm_fill3_kernel<20><<<(unsigned)nfills, 128, 0, st>>>(fills, leaves, ustream, px, py, cheb, kernel_id);
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_fill1(const HmFill *fills, int64_t nfills, const HmLeaf *leaves, double *vstream,
+                            const double *py, const HmCheb &cheb, cudaStream_t st)
+{
+    if (nfills <= 0) return cudaSuccess;
+    hm_fill1_kernel<20><<<(unsigned)nfills, 128, 0, st>>>(fills, leaves, vstream, py, cheb);
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_fillcore(const HmCoreBlock *blocks, const int32_t *core_leaf, int64_t nblocks,
+                               const HmLeaf *leaves, double *core, const HmCheb &cheb, int kernel_id,
+                               cudaStream_t st)
+{
+    if (nblocks <= 0) return cudaSuccess;
+    hm_fillcore_kernel<<<(unsigned)nblocks, 128, 0, st>>>(blocks, core_leaf, leaves, core, cheb, kernel_id);
+    return cudaGetLastError();
+}

@@ -1,0 +1,40 @@
+// hm_kernels.cuh -- launch wrappers of the sm_100a kernels (hm_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hm_types.h"
+
+#define HM_THREADS 256
+#define HM_SMAX 4096    // z staging capacity of a stream item (words)
+#define HM_MAXRUNS 256  // run-table capacity of a stage-3 item
+#define HM_RMAX_ASM 32  // max interpolation rank of on-device assembly
+
+// Chebyshev nodes / barycentric weights of the reference's BarycentricPoly2D
+// (src/BarycentricMatrix.jl:147-156), computed once on the host.
+struct HmCheb {
+    int r;
+    double node[HM_RMAX_ASM];
+    double lam[HM_RMAX_ASM];
+};
+
+// stage 1: partial[item.out + f] = sum_s V-slab[s][f] * x[item.zoff + s]
+cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *vstream,
+                             const double *x, double *partial, cudaStream_t st);
+// stage 2: s_b = F_b * (sum of partials) | Sigma_b .* (sum of partials)
+cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
+                             const double *partial, const double *core, double *svec, int max_r,
+                             cudaStream_t st);
+// stage 3: y[item.out + f] (+)= sum_s U-slab[s][f] * z[s],  z gathered from x and s
+cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *runs,
+                             const double *ustream, const double *x, const double *svec, double *y,
+                             int accumulate, cudaStream_t st);
+
+// plan construction
+cudaError_t hm_launch_fill3(const HmFill *fills, int64_t nfills, const HmLeaf *leaves, double *ustream,
+                            const double *px, const double *py, const HmCheb &cheb, int kernel_id,
+                            cudaStream_t st);
+cudaError_t hm_launch_fill1(const HmFill *fills, int64_t nfills, const HmLeaf *leaves, double *vstream,
+                            const double *py, const HmCheb &cheb, cudaStream_t st);
+cudaError_t hm_launch_fillcore(const HmCoreBlock *blocks, const int32_t *core_leaf, int64_t nblocks,
+                               const HmLeaf *leaves, double *core, const HmCheb &cheb, int kernel_id,
+                               cudaStream_t st);

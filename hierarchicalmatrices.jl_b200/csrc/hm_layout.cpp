@@ -1,0 +1,444 @@
+// hm_layout.cpp -- host planner.  See DESIGN.md "Data layout in HBM".
+//
+// The reference applies the operator by a recursive walk over `assigned`
+// (/root/reference/src/KernelMatrix.jl:17-45, src/HierarchicalMatrix.jl:24-52),
+// one leaf kernel per block (src/algebra.jl:37-48, 110-131, 243-277).  Here the
+// same leaves are regrouped so that every GPU thread block streams one
+// contiguous slab and every output element has exactly one writer:
+//
+//   stage 1  t_b = V_b' x          V-stream, grouped by column segment
+//   stage 2  s_b = F_b t_b | S_b.*t_b
+//   stage 3  y  += U_b s_b + A x   U-stream (+ dense tiles), grouped by row segment
+#include "hm_layout.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace {
+
+inline bool leaf_live(const HmLeaf &l)
+{
+    if (l.m <= 0 || l.n <= 0) return false;
+    if (l.kind != HM_LEAF_DENSE && (l.ru <= 0 || l.rv <= 0)) return false;
+    return true;
+}
+
+inline int64_t zlen(const HmLeaf &l) { return l.kind == HM_LEAF_DENSE ? l.n : l.ru; }
+
+inline int64_t core_words_of(const HmLeaf &l)
+{
+    if (l.kind == HM_LEAF_BARY2D) return (int64_t)l.ru * l.rv;
+    if (l.kind == HM_LEAF_LOWRANK) return l.ru;
+    return 0;
+}
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// Split the sorted boundary list into pieces of at most `cap` elements; pieces
+// never cross a boundary.  Returns piece starts plus a final sentinel.
+std::vector<int64_t> make_pieces(const std::vector<int64_t> &bounds, int64_t cap, bool even)
+{
+    std::vector<int64_t> starts;
+    for (size_t i = 0; i + 1 < bounds.size(); i++) {
+        int64_t s = bounds[i], e = bounds[i + 1], len = e - s;
+        if (len <= 0) continue;
+        int64_t np = (len + cap - 1) / cap;
+        int64_t sz = (len + np - 1) / np;
+        if (even && (sz & 1) && sz + 1 <= cap) sz += 1;
+        for (int64_t p = s; p < e; p += sz) starts.push_back(p);
+    }
+    starts.push_back(bounds.empty() ? 0 : bounds.back());
+    return starts;
+}
+
+// piece -> covering leaves (CSR), leaves in increasing index order.
+struct Cover {
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> idx;
+};
+
+template <class RangeFn>
+Cover cover_pieces(const std::vector<int64_t> &starts, size_t nleaves, RangeFn range)
+{
+    size_t np = starts.size() - 1;
+    Cover c;
+    c.ptr.assign(np + 1, 0);
+    for (int pass = 0; pass < 2; pass++) {
+        std::vector<int64_t> cur;
+        if (pass == 1) {
+            std::partial_sum(c.ptr.begin(), c.ptr.end(), c.ptr.begin());
+            c.idx.resize((size_t)c.ptr[np]);
+            cur.assign(c.ptr.begin(), c.ptr.end() - 1);
+        }
+        for (size_t li = 0; li < nleaves; li++) {
+            int64_t lo, hi;
+            if (!range(li, lo, hi) || hi <= lo) continue;
+            size_t p = (size_t)(std::upper_bound(starts.begin(), starts.end() - 1, lo) - starts.begin());
+            p = p ? p - 1 : 0;
+            for (; p < np && starts[p] < hi; p++) {
+                if (starts[p + 1] <= lo) continue;
+                if (pass == 0)
+                    c.ptr[p + 1]++;
+                else
+                    c.idx[(size_t)cur[p]++] = (int32_t)li;
+            }
+        }
+    }
+    return c;
+}
+
+} // namespace
+
+std::vector<int64_t> hm_partition_rows(const std::vector<HmLeaf> &leaves, int64_t nrows,
+                                       int nparts)
+{
+    std::vector<int64_t> cuts((size_t)nparts + 1, nrows);
+    cuts[0] = 0;
+    if (nparts <= 1 || nrows <= 0) return cuts;
+    // candidate cut points: block-row boundaries, refined every 128 rows
+    std::vector<int64_t> b{0, nrows};
+    for (const HmLeaf &l : leaves) {
+        if (!leaf_live(l)) continue;
+        b.push_back(std::min(std::max<int64_t>(l.row0, 0), nrows));
+        b.push_back(std::min(std::max<int64_t>(l.row0 + l.m, 0), nrows));
+    }
+    std::sort(b.begin(), b.end());
+    b.erase(std::unique(b.begin(), b.end()), b.end());
+    std::vector<int64_t> cand;
+    for (size_t i = 0; i + 1 < b.size(); i++)
+        for (int64_t p = b[i]; p < b[i + 1]; p += 128) cand.push_back(p);
+    cand.push_back(nrows);
+    // words per row on each candidate interval (difference array)
+    std::vector<double> diff(cand.size() + 1, 0.0);
+    for (const HmLeaf &l : leaves) {
+        if (!leaf_live(l)) continue;
+        double w = (double)zlen(l);
+        if (l.kind != HM_LEAF_DENSE) w += ((double)l.n * l.rv + (double)core_words_of(l)) / (double)l.m;
+        int64_t lo = std::max<int64_t>(l.row0, 0), hi = std::min(l.row0 + l.m, nrows);
+        if (hi <= lo) continue;
+        size_t ilo = (size_t)(std::lower_bound(cand.begin(), cand.end(), lo) - cand.begin());
+        size_t ihi = (size_t)(std::lower_bound(cand.begin(), cand.end(), hi) - cand.begin());
+        diff[ilo] += w;
+        diff[ihi] -= w;
+    }
+    std::vector<double> cum(cand.size(), 0.0);
+    double w = 0.0;
+    for (size_t i = 0; i + 1 < cand.size(); i++) {
+        w += diff[i];
+        cum[i + 1] = cum[i] + (w + 2.0) * (double)(cand[i + 1] - cand[i]); // +2: x and y words
+    }
+    double total = cum.back();
+    size_t last = 0;
+    for (int p = 1; p < nparts; p++) {
+        double target = total * (double)p / (double)nparts;
+        size_t i = (size_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+        if (i > 0 && i < cum.size() && target - cum[i - 1] < cum[i] - target) i -= 1;
+        i = std::min(std::max(i, last), cand.size() - 1);
+        cuts[(size_t)p] = cand[i];
+        last = i;
+    }
+    return cuts;
+}
+
+std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64_t ncols, int part,
+                            int nparts, const HmLayoutParams &prm, HmLayout &L)
+{
+    if (nparts < 1 || part < 0 || part >= nparts) return "part index out of range";
+    if (nrows < 0 || ncols < 0) return "negative matrix extent";
+    if (nrows >= (int64_t)1 << 31 || ncols >= (int64_t)1 << 31) return "matrix extent >= 2^31";
+    if (prm.cmax1 > prm.smax || prm.cmax0 > prm.smax) return "layout parameters: cmax > smax";
+    L = HmLayout();
+    L.nrows = nrows;
+    L.ncols = ncols;
+
+    // ---- accounting over the whole operator (SURVEY 8d formula) ----
+    for (const HmLeaf &l : all) {
+        if (l.kind == HM_LEAF_DENSE) {
+            L.n_dense++;
+            L.dense_words += std::max<int64_t>(l.m, 0) * std::max<int64_t>(l.n, 0);
+        } else {
+            (l.kind == HM_LEAF_BARY2D ? L.n_bary2d : L.n_lowrank)++;
+            int64_t cw = core_words_of(l);
+            L.lowrank_words += std::max<int64_t>(l.m, 0) * l.ru + std::max<int64_t>(l.n, 0) * l.rv + cw;
+            L.core_words_all += cw;
+        }
+    }
+
+    std::vector<int64_t> cuts = hm_partition_rows(all, nrows, nparts);
+    const int64_t rlo = cuts[(size_t)part], rhi = cuts[(size_t)part + 1];
+    L.row_begin = rlo;
+    L.row_end = rhi;
+
+    // ---- leaves of this part ----
+    for (size_t i = 0; i < all.size(); i++) {
+        const HmLeaf &l = all[i];
+        if (!leaf_live(l)) continue;
+        if (l.row0 + l.m <= rlo || l.row0 >= rhi) continue;
+        L.leaves.push_back(l);
+        L.leaf_global.push_back((int64_t)i);
+    }
+    const std::vector<HmLeaf> &lv = L.leaves;
+    const size_t nl = lv.size();
+    if (nl >= ((size_t)1 << 31)) return "too many leaves";
+
+    // ---- stage 2 tables ----
+    std::vector<int32_t> core_of(nl, -1);
+    for (size_t i = 0; i < nl; i++) {
+        const HmLeaf &l = lv[i];
+        int64_t rows = std::min(l.row0 + l.m, rhi) - std::max(l.row0, rlo);
+        if (l.kind == HM_LEAF_DENSE) {
+            L.part_words += rows * l.n;
+            L.part_dense_words += rows * l.n;
+            continue;
+        }
+        if (l.kind == HM_LEAF_LOWRANK && l.ru != l.rv) return "LowRankMatrix leaf with ru != rv";
+        HmCoreBlock cb{};
+        cb.kind = l.kind;
+        cb.ru = l.ru;
+        cb.rv = l.rv;
+        cb.core = L.core_words;
+        cb.soff = (int32_t)L.s_words;
+        core_of[i] = (int32_t)L.cores.size();
+        L.cores.push_back(cb);
+        L.core_leaf.push_back((int32_t)i);
+        L.core_words += align_up(core_words_of(l), 2);
+        L.s_words += l.ru;
+        L.max_r = std::max(L.max_r, std::max(l.ru, l.rv));
+        L.part_words += rows * l.ru + l.n * l.rv + core_words_of(l);
+        L.part_u_words += rows * l.ru;
+        L.part_v_words += l.n * l.rv;
+        L.part_core_words += core_words_of(l);
+        if (L.s_words >= ((int64_t)1 << 31) - 64) return "stage-2 vector too long";
+    }
+
+    // ---- stage 3: row segments ----
+    {
+        std::vector<int64_t> b{rlo, rhi};
+        for (const HmLeaf &l : lv) {
+            b.push_back(std::min(std::max(l.row0, rlo), rhi));
+            b.push_back(std::min(std::max(l.row0 + l.m, rlo), rhi));
+        }
+        std::sort(b.begin(), b.end());
+        b.erase(std::unique(b.begin(), b.end()), b.end());
+        std::vector<int64_t> starts = make_pieces(b, prm.rmax, true);
+        size_t np = starts.size() - 1;
+        Cover cov = cover_pieces(starts, nl, [&](size_t li, int64_t &lo, int64_t &hi) {
+            lo = std::max(lv[li].row0, rlo);
+            hi = std::min(lv[li].row0 + lv[li].m, rhi);
+            return true;
+        });
+
+        struct Tmp {
+            HmItem it;
+            int round;
+            int64_t words;
+        };
+        std::vector<Tmp> tmp;
+        tmp.reserve(np);
+        int64_t slab = 0;
+        int maxround = 0;
+        for (size_t p = 0; p < np; p++) {
+            int64_t ps = starts[p], pe = starts[p + 1];
+            int32_t F = (int32_t)(pe - ps), Fp = F + (F & 1);
+            int round = 0;
+            HmItem cur{};
+            auto open = [&]() {
+                cur = HmItem{};
+                cur.slab = slab;
+                cur.out = ps;
+                cur.F = F;
+                cur.Fp = Fp;
+                cur.S = 0;
+                cur.run0 = (int32_t)L.runs.size();
+                cur.nrun = 0;
+            };
+            auto close = [&]() {
+                int64_t words = (int64_t)cur.Fp * cur.S;
+                tmp.push_back(Tmp{cur, round, words});
+                slab = align_up(slab + words, 16);
+                maxround = std::max(maxround, round);
+            };
+            open();
+            for (int64_t e = cov.ptr[p]; e < cov.ptr[p + 1]; e++) {
+                int32_t li = cov.idx[(size_t)e];
+                const HmLeaf &l = lv[(size_t)li];
+                int64_t total = zlen(l), k = 0;
+                while (k < total) {
+                    int64_t room = prm.smax - cur.S;
+                    if (room <= 0 || cur.nrun >= prm.maxruns) {
+                        close();
+                        round++;
+                        open();
+                        continue;
+                    }
+                    int64_t take = std::min(total - k, room);
+                    HmRun r;
+                    r.src = l.kind == HM_LEAF_DENSE ? (int32_t)(l.col0 + k)
+                                                    : ~(int32_t)(L.cores[(size_t)core_of[(size_t)li]].soff + k);
+                    r.len = (int32_t)take;
+                    r.pos = cur.S;
+                    L.runs.push_back(r);
+                    HmFill f{};
+                    f.dst = cur.slab + (int64_t)cur.S * Fp;
+                    f.leaf = li;
+                    f.off = (int32_t)(ps - l.row0);
+                    f.k0 = (int32_t)k;
+                    f.kn = (int32_t)take;
+                    f.F = F;
+                    f.Fp = Fp;
+                    f.S = 0;
+                    L.fill3.push_back(f);
+                    cur.S += (int32_t)take;
+                    cur.nrun++;
+                    k += take;
+                }
+            }
+            close();
+        }
+        if (L.runs.size() >= ((size_t)1 << 31)) return "too many stage-3 runs";
+        L.ustream_words = slab;
+        std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp &a, const Tmp &b) {
+            if (a.round != b.round) return a.round < b.round;
+            return a.words > b.words;
+        });
+        L.items3.reserve(tmp.size());
+        L.round_begin.assign((size_t)maxround + 2, 0);
+        for (const Tmp &t : tmp) {
+            L.items3.push_back(t.it);
+            L.round_begin[(size_t)t.round + 1]++;
+        }
+        for (size_t r = 1; r < L.round_begin.size(); r++) L.round_begin[r] += L.round_begin[r - 1];
+    }
+
+    // ---- stage 1: column segments ----
+    {
+        std::vector<int32_t> npl(L.cores.size(), 0);
+        struct Pending {
+            int32_t core;
+            int32_t off;
+        };
+        std::vector<Pending> pend; // (core, partial offset) in column order per core
+        std::vector<std::pair<int64_t, HmItem>> tmp;
+        int64_t slab = 0, pout = 0;
+
+        // class 0: joint slabs over the small leaves
+        std::vector<int64_t> b;
+        for (const HmLeaf &l : lv)
+            if (l.kind != HM_LEAF_DENSE && l.n < prm.nbig) {
+                b.push_back(l.col0);
+                b.push_back(l.col0 + l.n);
+            }
+        std::sort(b.begin(), b.end());
+        b.erase(std::unique(b.begin(), b.end()), b.end());
+        if (b.size() >= 2) {
+            std::vector<int64_t> starts = make_pieces(b, prm.cmax0, false);
+            size_t np = starts.size() - 1;
+            Cover cov = cover_pieces(starts, nl, [&](size_t li, int64_t &lo, int64_t &hi) {
+                const HmLeaf &l = lv[li];
+                if (l.kind == HM_LEAF_DENSE || l.n >= prm.nbig) return false;
+                lo = l.col0;
+                hi = l.col0 + l.n;
+                return true;
+            });
+            for (size_t p = 0; p < np; p++) {
+                if (cov.ptr[p + 1] == cov.ptr[p]) continue;
+                int64_t ps = starts[p], pe = starts[p + 1];
+                int64_t F = 0;
+                for (int64_t e = cov.ptr[p]; e < cov.ptr[p + 1]; e++) F += lv[(size_t)cov.idx[(size_t)e]].rv;
+                if (F >= ((int64_t)1 << 24)) return "stage-1 item too wide";
+                HmItem it{};
+                it.slab = slab;
+                it.out = pout;
+                it.F = (int32_t)F;
+                it.Fp = (int32_t)(F + (F & 1));
+                it.S = (int32_t)(pe - ps);
+                it.zoff = (int32_t)ps;
+                int64_t fofs = 0;
+                for (int64_t e = cov.ptr[p]; e < cov.ptr[p + 1]; e++) {
+                    int32_t li = cov.idx[(size_t)e];
+                    const HmLeaf &l = lv[(size_t)li];
+                    HmFill f{};
+                    f.dst = slab + fofs;
+                    f.leaf = li;
+                    f.off = (int32_t)(ps - l.col0);
+                    f.k0 = 0;
+                    f.kn = l.rv;
+                    f.F = 0;
+                    f.Fp = it.Fp;
+                    f.S = it.S;
+                    L.fill1.push_back(f);
+                    int32_t c = core_of[(size_t)li];
+                    pend.push_back(Pending{c, (int32_t)(pout + fofs)});
+                    npl[(size_t)c]++;
+                    fofs += l.rv;
+                }
+                int64_t words = (int64_t)it.Fp * it.S;
+                tmp.emplace_back(words, it);
+                slab = align_up(slab + words, 16);
+                pout += it.Fp;
+            }
+        }
+        // class 1: one leaf per item
+        for (size_t li = 0; li < nl; li++) {
+            const HmLeaf &l = lv[li];
+            if (l.kind == HM_LEAF_DENSE || l.n < prm.nbig) continue;
+            int64_t np = (l.n + prm.cmax1 - 1) / prm.cmax1;
+            int64_t sz = (l.n + np - 1) / np;
+            for (int64_t c0 = 0; c0 < l.n; c0 += sz) {
+                int64_t c1 = std::min(c0 + sz, l.n);
+                HmItem it{};
+                it.slab = slab;
+                it.out = pout;
+                it.F = l.rv;
+                it.Fp = l.rv + (l.rv & 1);
+                it.S = (int32_t)(c1 - c0);
+                it.zoff = (int32_t)(l.col0 + c0);
+                HmFill f{};
+                f.dst = slab;
+                f.leaf = (int32_t)li;
+                f.off = (int32_t)c0;
+                f.k0 = 0;
+                f.kn = l.rv;
+                f.Fp = it.Fp;
+                f.S = it.S;
+                L.fill1.push_back(f);
+                int32_t c = core_of[li];
+                pend.push_back(Pending{c, (int32_t)pout});
+                npl[(size_t)c]++;
+                int64_t words = (int64_t)it.Fp * it.S;
+                tmp.emplace_back(words, it);
+                slab = align_up(slab + words, 16);
+                pout += it.Fp;
+            }
+        }
+        if (pout >= ((int64_t)1 << 31) - 64) return "stage-1 partial array too long";
+        L.vstream_words = slab;
+        L.partial_words = pout;
+        std::stable_sort(tmp.begin(), tmp.end(),
+                         [](const std::pair<int64_t, HmItem> &a, const std::pair<int64_t, HmItem> &b) {
+                             return a.first > b.first;
+                         });
+        L.items1.reserve(tmp.size());
+        for (auto &t : tmp) L.items1.push_back(t.second);
+        // partial lists, column order per core (class-0 pieces were emitted in
+        // increasing column order, class-1 pieces likewise; a leaf is in one class)
+        int32_t acc = 0;
+        for (size_t c = 0; c < L.cores.size(); c++) {
+            L.cores[c].pl0 = acc;
+            L.cores[c].npl = 0;
+            acc += npl[c];
+        }
+        L.plist.assign((size_t)acc, 0);
+        for (const Pending &pd : pend) {
+            HmCoreBlock &cb = L.cores[(size_t)pd.core];
+            L.plist[(size_t)(cb.pl0 + cb.npl++)] = pd.off;
+        }
+    }
+
+    for (const HmItem &it : L.items1)
+        if ((int64_t)it.Fp * it.S >= ((int64_t)1 << 31)) return "stage-1 item too large";
+    for (const HmItem &it : L.items3)
+        if ((int64_t)it.Fp * it.S >= ((int64_t)1 << 31)) return "stage-3 item too large";
+    return "";
+}

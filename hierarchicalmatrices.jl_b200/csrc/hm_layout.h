@@ -1,0 +1,57 @@
+// hm_layout.h -- host planner: flattens a leaf list into packed streams + work items.
+// Pure C++ (no CUDA), so it is testable on a machine without a GPU.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "hm_types.h"
+
+struct HmLayoutParams {
+    int rmax = 128;    // max rows of a stage-3 item (atomic row segments longer than this are split)
+    int cmax0 = 256;   // max columns of a joint stage-1 item (low-rank leaves with n < nbig)
+    int nbig = 1024;   // low-rank leaves with n >= nbig get their own stage-1 items
+    int cmax1 = 4096;  // max columns of such an item (must be <= smax)
+    int smax = 4096;   // max z length of an item (shared-memory staging capacity)
+    int maxruns = 256; // max runs of a stage-3 item
+};
+
+struct HmLayout {
+    int64_t nrows = 0, ncols = 0;
+    int64_t row_begin = 0, row_end = 0; // owned rows
+    // leaves of this part (those intersecting the owned rows), in walk order
+    std::vector<HmLeaf> leaves;
+    std::vector<int64_t> leaf_global; // index in the full leaf list
+    // stage 1
+    std::vector<HmItem> items1;
+    std::vector<HmFill> fill1;
+    int64_t vstream_words = 0;
+    int64_t partial_words = 0;
+    // stage 2
+    std::vector<HmCoreBlock> cores; // one per low-rank leaf of this part
+    std::vector<int32_t> core_leaf; // leaf index (into `leaves`) of each core block
+    std::vector<int32_t> plist;     // partial-sum offsets
+    int64_t core_words = 0;
+    int64_t s_words = 0;
+    int max_r = 0;
+    // stage 3 (items sorted by round, then by size descending)
+    std::vector<HmItem> items3;
+    std::vector<HmRun> runs;
+    std::vector<HmFill> fill3;
+    std::vector<int64_t> round_begin; // items3 index of each round start, plus end
+    int64_t ustream_words = 0;
+    // accounting
+    int64_t n_dense = 0, n_lowrank = 0, n_bary2d = 0; // whole operator
+    int64_t dense_words = 0, lowrank_words = 0, core_words_all = 0;
+    int64_t part_words = 0; // unpadded words this part stores
+    int64_t part_v_words = 0, part_core_words = 0, part_u_words = 0, part_dense_words = 0;
+};
+
+// Row cut points [0 = c_0 <= c_1 <= ... <= c_nparts = nrows], on block-row
+// boundaries, balancing the stored words per part.
+std::vector<int64_t> hm_partition_rows(const std::vector<HmLeaf> &leaves, int64_t nrows,
+                                       int nparts);
+
+// Returns "" on success, else an error message.
+std::string hm_build_layout(const std::vector<HmLeaf> &all_leaves, int64_t nrows, int64_t ncols,
+                            int part, int nparts, const HmLayoutParams &prm, HmLayout &out);

@@ -1,0 +1,82 @@
+// hm_types.h -- plain structs shared by the host planner and the CUDA kernels.
+//
+// Vocabulary:
+//   leaf     one dense / LowRankMatrix / BarycentricMatrix2D block of the tree
+//   stream   one contiguous packed array of Float64 words that a kernel reads
+//            front to back: the V-stream (stage 1) and the U-stream (stage 3,
+//            which also carries the dense tiles)
+//   item     the work of one CTA: a slab W[S][Fp] of a stream (fast index f,
+//            slow index s) applied as  out[f] = sum_s W[s][f] * z[s]
+//   run      a contiguous piece of an item's z vector gathered from x or from
+//            the stage-2 vector s
+#pragma once
+#include <cstdint>
+
+enum HmLeafKind : int32_t { HM_LEAF_LOWRANK = 2, HM_LEAF_DENSE = 3, HM_LEAF_BARY2D = 4 };
+
+enum HmLeafSource : int32_t {
+    HM_SRC_NONE = 0,  // structure only (planner dry run)
+    HM_SRC_COPY = 1,  // raw column-major copies staged on the device by the builder
+    HM_SRC_KERNEL = 2 // evaluated on the device from the point sets (hm_assemble_kernel)
+};
+
+struct HmLeaf {
+    int32_t kind;
+    int32_t source;
+    int64_t row0, col0, m, n;
+    int32_t ru, rv; // dense: 0; LowRankMatrix: r, r; BarycentricMatrix2D: r, r
+    // HM_SRC_COPY
+    const double *dU; // dense: A
+    const double *dC; // Sigma (r) or F (ru x rv)
+    const double *dV;
+    int64_t ldu, ldc, ldv;
+    // HM_SRC_KERNEL
+    int64_t xi0, yj0;  // first point index of the block's row / column range
+    double a, b, c, d; // interpolation box of the block
+};
+
+// One CTA's work.  48 bytes.
+struct HmItem {
+    int64_t slab; // word offset of W in its stream (multiple of 16)
+    int64_t out;  // stage 1: word offset into the partial-sum array; stage 3: first row of y
+    int32_t F;    // fast extent (stage 1: sum of ranks; stage 3: rows)
+    int32_t Fp;   // F rounded up to even = leading dimension of W
+    int32_t S;    // slow extent (stage 1: columns; stage 3: z length)
+    int32_t zoff; // stage 1: first column of x
+    int32_t run0; // stage 3: first run
+    int32_t nrun;
+    int32_t pad0, pad1;
+};
+
+struct HmRun {
+    int32_t src; // >= 0: index into x; < 0: index ~src into the stage-2 vector
+    int32_t len;
+    int32_t pos; // position of the run inside the item's z
+};
+
+// Stage 2: one low-rank leaf.
+struct HmCoreBlock {
+    int64_t core; // word offset of Sigma / F (tight, ru x rv column-major) in the core array
+    int32_t kind;
+    int32_t ru, rv;
+    int32_t soff; // offset of this block's ru outputs in the stage-2 vector
+    int32_t pl0;  // first entry in the partial list
+    int32_t npl;  // number of stage-1 partial sums to add (in column order)
+};
+
+// Slab filling (plan construction only): entry e of an item.
+struct HmFill {
+    int64_t dst;  // word offset in the stream of the entry's first element
+    int32_t leaf; // index into the (device) leaf table
+    int32_t off;  // stage 3: first row inside the leaf; stage 1: first column inside the leaf
+    int32_t k0;   // first factor column (dense: matrix column) of the entry
+    int32_t kn;   // number of factor columns
+    int32_t F;    // stage 3: rows of the item; stage 1: unused
+    int32_t Fp;   // leading dimension of the slab
+    int32_t S;    // stage 1: columns of the item
+    int32_t pad;
+};
+
+struct HmLaunchParams {
+    int threads = 256;
+};

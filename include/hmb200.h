@@ -1,0 +1,209 @@
+/*
+ * hmb200.h -- C ABI of the B200-native hierarchical-matrix matvec engine.
+ *
+ * This is the drop-in boundary for the `mul!` hot path of
+ * JuliaLinearAlgebra/HierarchicalMatrices.jl (citations: /root/reference/...).
+ * The reference has no FFI table for this path: it is Julia multiple dispatch
+ * (src/KernelMatrix.jl:14-45, src/HierarchicalMatrix.jl:14-52).  Its only FFI
+ * precedent is the (disabled) BLAS binding in src/blas.jl:6-14 -- column-major
+ * arrays, explicit leading dimensions, start offsets turned into pointer
+ * offsets, element strides, alpha = beta = 1 (accumulate).  The entry points
+ * below keep exactly those conventions; a Julia shim (`ccall`) that overrides
+ * the reference methods with them is in
+ * hierarchicalmatrices.jl_b200/julia/HierarchicalMatricesB200.jl and
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - all matrices column-major with explicit leading dimension, Float64;
+ *   - row/column offsets are 0-based, strides are in elements;
+ *   - every function returns an hm_status (0 = ok); hm_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - the library copies what it is given (device-resident snapshot) and never
+ *     keeps a host pointer;
+ *   - no CPU fallback exists: without a CUDA device every compute entry point
+ *     fails with HM_ERR_CUDA.
+ */
+#ifndef HMB200_H
+#define HMB200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define HM_API __attribute__((visibility("default")))
+#else
+#define HM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hm_builder hm_builder;
+typedef struct hm_plan hm_plan;
+
+typedef enum hm_status {
+    HM_OK = 0,
+    HM_ERR_INVALID = 1,     /* bad argument value */
+    HM_ERR_NULL = 2,        /* null pointer */
+    HM_ERR_SHAPE = 3,       /* negative extent, ld < rows, rank mismatch */
+    HM_ERR_RANGE = 4,       /* block does not fit inside nrows x ncols */
+    HM_ERR_STATE = 5,       /* call not valid in this object state */
+    HM_ERR_NOMEM = 6,       /* host or device allocation failed */
+    HM_ERR_CUDA = 7,        /* CUDA runtime error (or no device) */
+    HM_ERR_UNSUPPORTED = 8, /* valid request this build cannot serve */
+    HM_ERR_REFERENCE = 9    /* the reference itself would throw here (e.g. BoundsError) */
+} hm_status;
+
+enum { HM_F64 = 0 };
+
+/* kernel ids of examples/Kernel.jl:34-37 */
+enum { HM_KERNEL_CAUCHY = 0, HM_KERNEL_COULOMB = 1, HM_KERNEL_COULOMBPRIME = 2, HM_KERNEL_LOG = 3 };
+
+/* What the roofline is computed from.  "words" are Float64 words. */
+typedef struct hm_stats {
+    int64_t nrows, ncols;
+    int64_t n_dense, n_lowrank, n_bary2d;          /* leaves of the whole operator */
+    int64_t dense_words;                           /* sum m*n */
+    int64_t lowrank_words;                         /* sum (m+n)*r + (r*r | r) */
+    int64_t core_words;                            /* the (r*r | r) part of the line above */
+    int64_t algorithmic_bytes;                     /* 8*(dense+lowrank words) + 8*ncols + 8*nrows */
+    /* this plan (one row part) */
+    int64_t row_begin, row_end;                    /* owned rows [begin, end) */
+    int64_t part_words;                            /* unpadded words this part stores */
+    int64_t stored_bytes;                          /* device bytes of the packed streams (padded) */
+    int64_t v_stream_bytes, u_stream_bytes;        /* stage-1 / stage-3 stream sizes (padded) */
+    int64_t partial_bytes;                         /* stage-1 partial sums written per matvec */
+    int64_t n_stage1_items, n_stage2_blocks, n_stage3_items, n_stage3_rounds;
+    int64_t part_algorithmic_bytes;                /* 8*part_words + 8*ncols + 8*(row_end-row_begin) */
+    /* split of part_words by the stage that reads them */
+    int64_t part_v_words;                          /* stage 1: sum n*r */
+    int64_t part_core_words;                       /* stage 2: sum r*r | r */
+    int64_t part_u_words;                          /* stage 3: sum (owned rows)*r */
+    int64_t part_dense_words;                      /* stage 3: sum (owned rows)*n */
+} hm_stats;
+
+HM_API const char *hm_last_error(void);
+HM_API int32_t hm_version(void);
+
+/* BLOCKRANK(Float64) / BLOCKSIZE(Float64): src/HierarchicalMatrices.jl:5-7 */
+HM_API int32_t hm_blockrank_f64(void);
+HM_API int32_t hm_blocksize_f64(void);
+
+/* ------------------------------------------------------------------------
+ * Builder: the flattened block tree.  The host-side planner walks `assigned`
+ * (src/hierarchical.jl:49-52, codes :84-91) with the offset rule of
+ * src/KernelMatrix.jl:24-41 / src/HierarchicalMatrix.jl:30-48 and pushes each
+ * leaf here with its absolute 0-based (row0, col0).  Overlapping leaves are
+ * legal: contributions add, as in the reference walk.
+ *
+ * device >= 0: leaf data is staged onto that CUDA device as it is added.
+ * device = -1: structure-only builder (no data is read; pointers may be NULL);
+ *              only hm_builder_layout_stats() can be called on it.
+ * ------------------------------------------------------------------------ */
+HM_API int32_t hm_builder_create(hm_builder **out, int64_t nrows, int64_t ncols, int32_t dtype,
+                          int32_t device);
+HM_API int32_t hm_builder_destroy(hm_builder *b);
+
+/* Matrix leaf, code 3.  Replaces src/algebra.jl:37-48 (dgemv 'N' in src/blas.jl:6-14). */
+HM_API int32_t hm_builder_add_dense(hm_builder *b, const double *A, int64_t m, int64_t n, int64_t lda,
+                             int64_t row0, int64_t col0);
+/* LowRankMatrix leaf U*Diagonal(S)*V' (no conjugation), code 2 of HierarchicalMatrix.
+ * Replaces src/algebra.jl:110-131 (src/blas.jl:42-68). U m x r, V n x r. */
+HM_API int32_t hm_builder_add_lowrank(hm_builder *b, const double *U, int64_t ldu, const double *S,
+                               const double *V, int64_t ldv, int64_t m, int64_t n, int64_t r,
+                               int64_t row0, int64_t col0);
+/* BarycentricMatrix2D leaf U*F*V', code 2 of KernelMatrix.
+ * Replaces src/algebra.jl:243-277 (src/blas.jl:72-104). U m x r, F r x r, V n x r. */
+HM_API int32_t hm_builder_add_bary2d(hm_builder *b, const double *U, int64_t ldu, const double *F,
+                              int64_t ldf, const double *V, int64_t ldv, int64_t m, int64_t n,
+                              int64_t r, int64_t row0, int64_t col0);
+
+/* Planner only (no GPU needed): lay the operator out for row part `part` of
+ * `nparts` and report the sizes. */
+HM_API int32_t hm_builder_layout_stats(hm_builder *b, int32_t part, int32_t nparts, hm_stats *out);
+
+/* ------------------------------------------------------------------------
+ * Plan: immutable packed operator on one device.
+ * hm_plan_finalize      -- whole operator on devices[0] (ndev must be 1; one
+ *                          process drives one GPU, multi-GPU = one part per process)
+ * hm_plan_finalize_part -- block-row part `part` of `nparts` (rows balanced by
+ *                          stored bytes); y rows outside the part are not touched.
+ * The builder can be destroyed afterwards.
+ * ------------------------------------------------------------------------ */
+HM_API int32_t hm_plan_finalize(hm_builder *b, const int32_t *devices, int32_t ndev, hm_plan **out);
+HM_API int32_t hm_plan_finalize_part(hm_builder *b, int32_t part, int32_t nparts, hm_plan **out);
+HM_API int32_t hm_plan_destroy(hm_plan *p);
+HM_API int32_t hm_plan_stats(const hm_plan *p, hm_stats *out);
+
+/* KernelMatrix(f, x, y, a, b, c, d) assembled on the device
+ * (src/KernelMatrix.jl:47-116, src/BarycentricMatrix.jl:147-178, 236-307):
+ * the host builds only the tree of index ranges, the device fills U, V, F and
+ * the dense leaves straight into the packed streams.  x, y are host pointers,
+ * sorted descending as the reference requires. */
+HM_API int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t ny, double a,
+                           double b, double c, double d, int32_t kernel_id, int32_t device,
+                           int32_t part, int32_t nparts, hm_plan **out);
+/* One leaf of the assembled tree, as the planner sees it (device-free). */
+typedef struct hm_tree_leaf {
+    int32_t kind;          /* 3 = Matrix, 4 = BarycentricMatrix2D */
+    int32_t rank;
+    int64_t row0, col0, m, n; /* position in the operator (0-based) */
+    int64_t xi0, yj0;      /* first point index of the row / column range */
+    double a, b, c, d;     /* interpolation box (BarycentricMatrix.jl:147-167) */
+} hm_tree_leaf;
+/* Leaves of KernelMatrix(f, x, y, a, b, c, d) in the order and with the offsets of
+ * the reference's mul! walk (src/KernelMatrix.jl:17-45).  Writes at most `cap`
+ * records and always the total count. */
+HM_API int32_t hm_kernel_tree_leaves(const double *x, int64_t nx, const double *y, int64_t ny,
+                                     double a, double b, double c, double d, hm_tree_leaf *out,
+                                     int64_t cap, int64_t *count);
+/* Same tree, planner only (device-free): leaf counts and byte sizes. */
+HM_API int32_t hm_assemble_kernel_stats(const double *x, int64_t nx, const double *y, int64_t ny,
+                                 double a, double b, double c, double d, int32_t part,
+                                 int32_t nparts, hm_stats *out);
+
+/* ------------------------------------------------------------------------
+ * mul!: y[i*incy] (+)= sum_j H[i,j] x[j*incx]     (accumulate != 0: +=, the
+ * reference's mul!; accumulate == 0: =, the reference's `*`).
+ * Replaces LinearAlgebra.mul!(u, H, v) -> mul!(u, H, v, 1, 1[, INCX, INCY])
+ * (src/KernelMatrix.jl:14-45, src/HierarchicalMatrix.jl:14-52); the 1-based
+ * istart/jstart of the reference become pointer offsets at the call site, as in
+ * src/blas.jl:12.  Host pointers; copies are part of the call.
+ * ------------------------------------------------------------------------ */
+HM_API int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy,
+                  int32_t accumulate);
+/* Device pointers (contiguous), enqueued on `stream` (a cudaStream_t; NULL =
+ * default stream); returns without synchronising. */
+HM_API int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate,
+                         void *stream);
+
+/* Multi-right-hand-side form: Y[:, c] (+)= H X[:, c], c < nrhs; X ncols x nrhs
+ * (ldx), Y nrows x nrhs (ldy), column-major.  (The reference reaches this through
+ * the stride pair, test/runtests.jl:23-25.) */
+HM_API int32_t hm_matmat(hm_plan *p, const double *X, int64_t ldx, double *Y, int64_t ldy, int64_t nrhs,
+                  int32_t accumulate);
+HM_API int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, int64_t ldy,
+                         int64_t nrhs, int32_t accumulate, void *stream);
+
+/* Per-stage device timing (bench bookkeeping).  Between begin and end every
+ * hm_matvec_device call records CUDA events around its three stages on the
+ * launch stream; end synchronises and returns the summed milliseconds of
+ * stage 1, 2, 3 and the number of matvecs timed (at most max_calls). */
+HM_API int32_t hm_plan_timing_begin(hm_plan *p, int32_t max_calls);
+HM_API int32_t hm_plan_timing_end(hm_plan *p, double *stage_ms3, int64_t *ncalls);
+
+/* Number of kernel launches one hm_matvec_device enqueues (bench bookkeeping). */
+HM_API int32_t hm_plan_launches_per_matvec(const hm_plan *p);
+
+/* Test hooks: copy packed factors back to the host to compare the on-device
+ * assembly with the oracle's factors.  which: 0 = U (m x ru), 1 = core
+ * (F ru x rv | Sigma), 2 = V (n x rv), 3 = dense A (m x n); tight column-major. */
+HM_API int32_t hm_plan_num_leaves(const hm_plan *p, int64_t *out);
+HM_API int32_t hm_plan_leaf_info(const hm_plan *p, int64_t leaf, int32_t *kind, int64_t *row0,
+                          int64_t *col0, int64_t *m, int64_t *n, int64_t *r);
+HM_API int32_t hm_plan_read_leaf(hm_plan *p, int64_t leaf, int32_t which, double *out, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMB200_H */

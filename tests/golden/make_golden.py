@@ -1,0 +1,91 @@
+"""Generates the committed golden fixtures of tests/golden/ (run once, in the build
+container).  Everything here is computed with mpmath at 60 digits, independently of
+oracle/ and of the CUDA library:
+
+  cheb20.json        the 20 Chebyshev nodes and barycentric weights that
+                     BLOCKRANK(Float64) = 20 selects
+                     (/root/reference/src/BarycentricMatrix.jl:92-136): sin(pi q)
+                     of the Float64-rounded argument q, correctly rounded
+  points_*.json      sample entries of chebyshevpoints(Float64, N; kind) for large N
+  cauchy_dense_*.json  K*b for the example's setup (examples/Kernel.jl:61-78) with the
+                     kernel matrix applied densely at 60 digits -- the example's
+                     own yardstick for the hierarchical product
+
+The reference ships no golden vectors (test/runtests.jl draws from Julia's RNG), and
+Julia is not installed here, so these are the strongest reference-independent pins
+available.
+"""
+import json
+import os
+
+import mpmath as mp
+import numpy as np
+
+mp.mp.dps = 60
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sinpi_rounded(q: float) -> float:
+    return float(mp.sin(mp.pi * mp.mpf(q)))
+
+
+def chebpts(n, kind=1):
+    x = [0.0] * n
+    for k in range(1, n // 2 + 1):
+        q = (n - 2 * k + 1.0) / (2.0 * n) if kind == 1 else (n - 2 * k + 1.0) / (2.0 * (n - 1))
+        x[k - 1] = sinpi_rounded(q)
+    for k in range(1, n // 2 + 1):
+        x[n - k] = -x[k - 1]
+    return x
+
+
+def chebweights(n):
+    lam = [0.0] * n
+    for k in range(1, n // 2 + 2):
+        lam[k - 1] = sinpi_rounded((2.0 * k - 1.0) / (2.0 * n))
+    for k in range(1, n // 2 + 1):
+        lam[n - k] = lam[k - 1]
+    for k in range(2, n + 1, 2):
+        lam[k - 1] = -lam[k - 1]
+    return lam
+
+
+def hexlist(v):
+    return [float(a).hex() for a in v]
+
+
+def main():
+    json.dump({"n": 20, "nodes": hexlist(chebpts(20)), "weights": hexlist(chebweights(20))},
+              open(os.path.join(HERE, "cheb20.json"), "w"), indent=1)
+
+    samples = {}
+    for n in (4096, 1 << 20):
+        for kind in (1, 2):
+            idx = sorted(set([1, 2, 3, n // 7, n // 3, n // 2 - 1, n // 2]))
+            vals = []
+            for k in idx:
+                q = (n - 2 * k + 1.0) / (2.0 * n) if kind == 1 else (n - 2 * k + 1.0) / (2.0 * (n - 1))
+                vals.append(sinpi_rounded(q))
+            samples[f"{n}_{kind}"] = {"k": idx, "x": hexlist(vals)}
+    json.dump(samples, open(os.path.join(HERE, "points_samples.json"), "w"), indent=1)
+
+    # dense kernel product at 60 digits, N = 300 (ragged vs the 80-leaf size) and 1000
+    for n in (300, 1000):
+        x = chebpts(n, 1)
+        y = chebpts(n, 2)
+        b = np.random.default_rng(20261017 + n).standard_normal(n)
+        xm = [mp.mpf(v) for v in x]
+        ym = [mp.mpf(v) for v in y]
+        bm = [mp.mpf(float(v)) for v in b]
+        out = []
+        for i in range(n):
+            s = mp.mpf(0)
+            for j in range(n):
+                s += bm[j] / (xm[i] - ym[j])
+            out.append(float(s))
+        json.dump({"n": n, "seed": 20261017 + n, "b": hexlist(b), "Kb": hexlist(out)},
+                  open(os.path.join(HERE, f"cauchy_dense_{n}.json"), "w"))
+
+
+if __name__ == "__main__":
+    main()

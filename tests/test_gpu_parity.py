@@ -1,0 +1,335 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerance: 1e-12 relative ∞-norm in Float64 (BASELINE.json north_star; summation
+order differs from the reference).  The oracle is unpinned against Julia (none in
+this image) -- see oracle/hm_oracle.h; it is itself checked against the dense kernel
+product and the golden fixtures in tests/test_oracle.py.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import (TOL, oracle_tree_from_mirror, plan_from_oracle_tree, random_lowrank_tree, relinf)
+
+pytestmark = pytest.mark.gpu
+
+
+def _vec(n, seed=0):
+    return np.random.default_rng(seed).standard_normal(n)
+
+
+# ------------------------------------------------------------------ KernelMatrix through the builder
+@pytest.mark.parametrize("dist,N", [("cheb", 1000), ("cheb", 4096), ("unif", 4096), ("quad", 1000),
+                                    ("cheb", 300), ("unif", 77), ("cheb", 10000)])
+def test_kernelmatrix_builder_matches_oracle(hm, O, dist, N):
+    x, y, (a, b, c, d) = O.example_points(N, dist)
+    K = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    plan = plan_from_oracle_tree(hm, O, K)
+    v = _vec(N)
+    ref = K.matvec(v)
+    out = np.zeros(N)
+    plan.matvec(v, out, accumulate=False)
+    assert relinf(out, ref) <= TOL
+    # mul! accumulates: y += H x  (algebra.jl:43,126,272)
+    y0 = _vec(N, 1)
+    out2 = y0.copy()
+    plan.matvec(v, out2, accumulate=True)
+    assert relinf(out2, y0 + ref) <= TOL
+    st = plan.stats()
+    assert st["algorithmic_bytes"] == 8 * K.stored_words() + 16 * N
+
+
+def test_deterministic_run_to_run(hm, O):
+    x, y, (a, b, c, d) = O.example_points(4096, "cheb")
+    plan = plan_from_oracle_tree(hm, O, O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d))
+    v = _vec(4096)
+    outs = []
+    for _ in range(3):
+        o = np.zeros(4096)
+        plan.matvec(v, o, accumulate=False)
+        outs.append(o)
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+# ------------------------------------------------------------------ on-device assembly
+@pytest.mark.parametrize("kernel", [0, 1, 2, 3])
+@pytest.mark.parametrize("dist,N", [("cheb", 4096), ("unif", 1000), ("quad", 1000)])
+def test_device_assembly_matches_oracle(hm, O, kernel, dist, N):
+    x, y, (a, b, c, d) = O.example_points(N, dist)
+    Kref = O.kernelmatrix(kernel, x, y, a, b, c, d)
+    f = [hm.cauchykernel, hm.coulombkernel, hm.coulombprimekernel, hm.logkernel][kernel]
+    K = hm.KernelMatrix(f, x, y, a, b, c, d, device=0)
+    assert K.size() == Kref.shape
+    v = _vec(N)
+    ref = Kref.matvec(v)
+    out = K * v
+    assert relinf(out, ref) <= TOL
+    # factors: bit-identical to the oracle's for the rational kernels (IEEE div/mul/add,
+    # same operation order); log() differs by an ulp between libm and CUDA
+    plan = K.plan()
+    arr, n = Kref.leaves()
+    assert plan.num_leaves() == n
+    for i in list(range(0, n, max(1, n // 40))) + [n - 1]:
+        info = plan.leaf_info(i)
+        lf = arr[i]
+        assert (info["row0"], info["col0"], info["m"], info["n"]) == (lf.row0, lf.col0, lf.m, lf.n)
+        if lf.kind == O.DENSE:
+            A = np.ctypeslib.as_array(lf.A, shape=(lf.n, lf.m)).T
+            got = plan.read_leaf(i, 3)
+            if kernel == 3:
+                assert np.allclose(got, A, rtol=1e-15, atol=1e-15)
+            else:
+                assert np.array_equal(got, A)
+        else:
+            U = np.ctypeslib.as_array(lf.A, shape=(lf.r, lf.m)).T
+            V = np.ctypeslib.as_array(lf.V, shape=(lf.r, lf.n)).T
+            F = np.ctypeslib.as_array(lf.S, shape=(lf.r, lf.r)).T
+            assert np.array_equal(plan.read_leaf(i, 0), U)
+            assert np.array_equal(plan.read_leaf(i, 2), V)
+            if kernel == 3:
+                assert np.allclose(plan.read_leaf(i, 1), F, rtol=1e-15, atol=1e-15)
+            else:
+                assert np.array_equal(plan.read_leaf(i, 1), F)
+
+
+def test_device_assembly_against_dense_golden(hm):
+    """examples/Kernel.jl:78 with an actual assertion: K*b against the dense kernel
+    product evaluated at 60 digits (tests/golden/cauchy_dense_*.json)."""
+    import json
+    import os
+    for n in (300, 1000):
+        g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", f"cauchy_dense_{n}.json")))
+        b = np.array([float.fromhex(h) for h in g["b"]])
+        Kb = np.array([float.fromhex(h) for h in g["Kb"]])
+        x, y = hm.chebyshevpoints(n), hm.chebyshevpoints(n, 2)
+        K = hm.KernelMatrix(hm.cauchykernel, x, y, 1.0, -1.0, 1.0, -1.0, device=0)
+        out = K * b
+        assert np.linalg.norm(out - Kb) / np.linalg.norm(Kb) < 1e-13
+
+
+# ------------------------------------------------------------------ reference test cases (runtests.jl:15-33)
+def test_dense_offset_stride_cases(hm, O):
+    """The four dense offset/stride cases of test/runtests.jl:15-33, through mul_ with a
+    one-block HierarchicalMatrix (the transpose cases use the transposed matrix as the block)."""
+    rng = np.random.default_rng(0)
+    A = np.asfortranarray(rng.random((10, 5)))
+    x = rng.random(40)
+    eps = np.finfo(np.float64).eps
+
+    def one_block(M):
+        H = hm.HierarchicalMatrix(np.float64, 1, 1)
+        H[hm.Block(1), hm.Block(1)] = np.asfortranarray(M)
+        return H
+
+    H, Ht = one_block(A), one_block(A.T)
+    y = np.zeros(40)
+    hm.mul_(y, H, x, 1, 1)
+    assert np.linalg.norm(y[0:10] - A @ x[0:5]) <= 4 * eps * np.linalg.norm(A @ x[0:5])
+    assert not y[10:].any()
+
+    y[:] = 0
+    hm.mul_(y, H, x, 5, 5, 2, 2)
+    assert np.linalg.norm(y[4:23:2] - A @ x[4:13:2]) <= 4 * eps * np.linalg.norm(A @ x[4:13:2])
+    assert not y[5:23:2].any() and not y[:4].any() and not y[23:].any()
+
+    y[:] = 0
+    hm.mul_(y, Ht, x, 1, 5, 2, 1)
+    assert np.linalg.norm(y[0:5] - A.T @ x[4:23:2]) <= 4 * eps * np.linalg.norm(A.T @ x[4:23:2])
+
+    y[:] = 0
+    hm.mul_(y, Ht, x, 6, 3, 1, 3)
+    assert np.linalg.norm(y[5:18:3] - A.T @ x[2:12]) <= 4 * eps * np.linalg.norm(A.T @ x[2:12])
+
+    # integer data: exact, like the BigFloat cases of runtests.jl:35-52
+    Ai = np.asfortranarray(rng.integers(-8, 9, (10, 5)).astype(np.float64))
+    xi = rng.integers(-8, 9, 40).astype(np.float64)
+    yi = np.zeros(40)
+    hm.mul_(yi, one_block(Ai), xi, 5, 5, 2, 2)
+    assert np.array_equal(yi[4:23:2], Ai @ xi[4:13:2])
+
+
+# ------------------------------------------------------------------ HierarchicalMatrix (LowRankMatrix + Matrix)
+@pytest.mark.parametrize("n,seed", [(500, 1), (3000, 2), (129, 3)])
+def test_hierarchicalmatrix_lowrank_matches_oracle(hm, O, n, seed):
+    rng = np.random.default_rng(seed)
+    H = random_lowrank_tree(hm, rng, n)
+    T = oracle_tree_from_mirror(O, H)
+    assert H.size() == T.shape == (n, n)
+    v = rng.standard_normal(n)
+    ref = T.matvec(v)
+    out = H * v
+    assert relinf(out, ref) <= TOL
+    # strided mul!: k interleaved right-hand sides, column c via (c, c, k, k) -- runtests.jl:23-25
+    k = 3
+    X = np.asfortranarray(rng.standard_normal((k, n)))
+    Y = np.zeros((k, n), order="F")
+    Yref = np.zeros((k, n), order="F")
+    for c in range(1, k + 1):
+        hm.mul_(Y, H, X, c, c, k, k)
+        T.mul(Yref.reshape(-1, order="F"), X.reshape(-1, order="F"), c - 1, c - 1, k, k)
+    assert relinf(Y, Yref) <= TOL
+    # H * X
+    Xc = np.asfortranarray(rng.standard_normal((n, 4)))
+    Z = H * Xc
+    for c in range(4):
+        assert relinf(Z[:, c], T.matvec(np.ascontiguousarray(Xc[:, c]))) <= TOL
+
+
+def test_kernelmatrix_as_lowrankmatrix(hm, O):
+    """the same tree with every BarycentricMatrix2D rewritten as a
+    LowRankMatrix (U·Uf, Σ, V·Vf from svd(F)) exercises the U Σ V' path."""
+    N = 2000
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    K = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    arr, n = K.leaves()
+    L = hm.lib()
+    bld = C.c_void_p()
+    hm._lib.check(L.hm_builder_create(C.byref(bld), N, N, 0, 0))
+    T = O.Tree.create(1, 1)  # oracle side: apply leaf by leaf
+    ref = np.zeros(N)
+    v = _vec(N)
+    dp = C.POINTER(C.c_double)
+    for i in range(n):
+        lf = arr[i]
+        if lf.kind == O.DENSE:
+            hm._lib.check(L.hm_builder_add_dense(bld, lf.A, lf.m, lf.n, max(lf.m, 1), lf.row0, lf.col0))
+            A = np.ctypeslib.as_array(lf.A, shape=(lf.n, lf.m)).T
+            O.mul_dense(ref, A, v, lf.row0, lf.col0)
+        else:
+            U = np.ctypeslib.as_array(lf.A, shape=(lf.r, lf.m)).T
+            V = np.ctypeslib.as_array(lf.V, shape=(lf.r, lf.n)).T
+            F = np.ctypeslib.as_array(lf.S, shape=(lf.r, lf.r)).T
+            Uf, S, Vft = np.linalg.svd(F)
+            U2 = np.asfortranarray(U @ Uf)
+            V2 = np.asfortranarray(V @ Vft.T)
+            S = np.ascontiguousarray(S)
+            hm._lib.check(L.hm_builder_add_lowrank(bld, U2.ctypes.data_as(dp), max(lf.m, 1), S.ctypes.data_as(dp),
+                                                   V2.ctypes.data_as(dp), max(lf.n, 1), lf.m, lf.n, lf.r,
+                                                   lf.row0, lf.col0))
+            O.mul_lowrank(ref, U2, S, V2, v, lf.row0, lf.col0)
+    h = C.c_void_p()
+    hm._lib.check(L.hm_plan_finalize(bld, (C.c_int32 * 1)(0), 1, C.byref(h)))
+    L.hm_builder_destroy(bld)
+    plan = hm.Plan(h.value, 0)
+    out = np.zeros(N)
+    plan.matvec(v, out, accumulate=False)
+    assert relinf(out, ref) <= TOL
+    st = plan.stats()
+    assert st["n_lowrank"] == n - st["n_dense"] and st["n_bary2d"] == 0
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases(hm, O):
+    rng = np.random.default_rng(5)
+    # unassigned blocks are zero (hierarchical.jl:94,115); empty and ragged blocks
+    H = hm.HierarchicalMatrix(np.float64, 3, 3)
+    sizes_r, sizes_c = [5, 0, 131], [7, 3, 90]
+    for m in range(3):
+        for n in range(3):
+            if (m, n) in ((0, 1), (2, 0)):
+                continue  # left unassigned
+            if (m + n) % 2 == 0:
+                H[hm.Block(m + 1), hm.Block(n + 1)] = np.asfortranarray(rng.standard_normal((sizes_r[m], sizes_c[n])))
+            else:
+                r = 4
+                H[hm.Block(m + 1), hm.Block(n + 1)] = hm.LowRankMatrix(
+                    rng.standard_normal((sizes_r[m], r)), rng.standard_normal(r), rng.standard_normal((sizes_c[n], r)))
+    T = oracle_tree_from_mirror(O, H)
+    assert H.size() == T.shape
+    v = rng.standard_normal(H.size(2))
+    assert relinf(H * v, T.matvec(v)) <= TOL
+
+    # overlapping leaves add up (legal at the ABI, as in the reference walk)
+    L = hm.lib()
+    b = C.c_void_p()
+    hm._lib.check(L.hm_builder_create(C.byref(b), 300, 200, 0, 0))
+    dp = C.POINTER(C.c_double)
+    A1 = np.asfortranarray(rng.standard_normal((300, 200)))
+    A2 = np.asfortranarray(rng.standard_normal((150, 100)))
+    hm._lib.check(L.hm_builder_add_dense(b, A1.ctypes.data_as(dp), 300, 200, 300, 0, 0))
+    hm._lib.check(L.hm_builder_add_dense(b, A2.ctypes.data_as(dp), 150, 100, 150, 75, 33))
+    U = np.asfortranarray(rng.standard_normal((260, 9)))
+    V = np.asfortranarray(rng.standard_normal((199, 9)))
+    S = rng.standard_normal(9)
+    hm._lib.check(L.hm_builder_add_lowrank(b, U.ctypes.data_as(dp), 260, S.ctypes.data_as(dp), V.ctypes.data_as(dp),
+                                           199, 260, 199, 9, 40, 1))
+    h = C.c_void_p()
+    hm._lib.check(L.hm_plan_finalize(b, None, 1, C.byref(h)))
+    L.hm_builder_destroy(b)
+    plan = hm.Plan(h.value, 0)
+    v = rng.standard_normal(200)
+    ref = A1 @ v
+    ref[75:225] += A2 @ v[33:133]
+    ref[40:300] += U @ (S * (V.T @ v[1:200]))
+    out = np.zeros(300)
+    plan.matvec(v, out, accumulate=False)
+    assert relinf(out, ref) <= 1e-13
+
+    # empty operator and operator with no leaves
+    H0 = hm.HierarchicalMatrix(np.float64, 2, 2)
+    assert H0.size() == (0, 0)
+    assert (H0 * np.zeros(0)).shape == (0,)
+
+
+def test_large_single_blocks(hm, O):
+    """Blocks far larger than one work item: a 5000 x 4700 dense block (z longer than the
+    shared-memory staging -> several stage-3 rounds) and a tall low-rank block."""
+    rng = np.random.default_rng(7)
+    H = hm.HierarchicalMatrix(np.float64, 2, 1)
+    A = np.asfortranarray(rng.standard_normal((1500, 4700)))
+    H[hm.Block(1), hm.Block(1)] = A
+    r = 33
+    Lr = hm.LowRankMatrix(rng.standard_normal((9000, r)), rng.standard_normal(r), rng.standard_normal((4700, r)))
+    H[hm.Block(2), hm.Block(1)] = Lr
+    v = rng.standard_normal(4700)
+    ref = np.concatenate([A @ v, Lr.U @ (Lr.S * (Lr.V.T @ v))])
+    out = H * v
+    assert relinf(out, ref) <= TOL
+    assert H.plan().stats()["n_stage3_rounds"] >= 2
+
+
+# ------------------------------------------------------------------ row parts (multi-GPU layout on one device)
+@pytest.mark.parametrize("nparts", [2, 3, 8])
+def test_row_parts_tile_the_product(hm, O, nparts):
+    N = 4096
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    K = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    v = _vec(N)
+    ref = K.matvec(v)
+    out = np.full(N, np.nan)
+    covered = np.zeros(N, dtype=int)
+    for p in range(nparts):
+        plan = plan_from_oracle_tree(hm, O, K, part=p, nparts=nparts)
+        st = plan.stats()
+        plan.matvec(v, out, accumulate=False)  # writes only the owned rows
+        covered[st["row_begin"]:st["row_end"]] += 1
+    assert (covered == 1).all()
+    assert relinf(out, ref) <= TOL
+    # device-assembled parts
+    out2 = np.full(N, np.nan)
+    for p in range(nparts):
+        Kp = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=p, nparts=nparts)
+        Kp.plan().matvec(v, out2, accumulate=False)
+    assert relinf(out2, ref) <= TOL
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors(hm):
+    L = hm.lib()
+    b = C.c_void_p()
+    hm._lib.check(L.hm_builder_create(C.byref(b), 10, 10, 0, 0))
+    dp = C.POINTER(C.c_double)
+    A = np.zeros((4, 4), order="F")
+    assert L.hm_builder_add_dense(b, A.ctypes.data_as(dp), 4, 4, 4, 8, 0) == 4      # HM_ERR_RANGE
+    assert L.hm_builder_add_dense(b, A.ctypes.data_as(dp), 4, 4, 3, 0, 0) == 3      # HM_ERR_SHAPE (ld < m)
+    assert L.hm_builder_add_dense(b, None, 4, 4, 4, 0, 0) == 2                      # HM_ERR_NULL
+    assert L.hm_builder_add_dense(b, A.ctypes.data_as(dp), -1, 4, 4, 0, 0) == 3
+    assert b"NULL" in L.hm_last_error() or b"negative" in L.hm_last_error()
+    L.hm_builder_destroy(b)
+    H = hm.HierarchicalMatrix(np.float64, 1, 1)
+    H[hm.Block(1), hm.Block(1)] = np.zeros((3, 3), order="F")
+    with pytest.raises(IndexError):
+        hm.mul_(np.zeros(2), H, np.zeros(3))
+    with pytest.raises(TypeError):
+        hm.mul_(np.zeros(3, dtype=np.float32), H, np.zeros(3))

@@ -1,0 +1,228 @@
+"""CPU-side tests of the product: the C-ABI library loads and exports every symbol of
+include/hmb200.h, the host planner (tree of index ranges, stream layout, row partition)
+and the Python mirror of the reference API.  No compute calls (no GPU needed)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import stats_from_oracle_tree
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_abi_exports_every_declared_symbol(hm):
+    header = open(os.path.join(ROOT, "include", "hmb200.h")).read()
+    declared = set(re.findall(r"HM_API\s+[\w\s\*]+?\b(hm_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    assert declared == set(hm._lib.SIGNATURES), declared ^ set(hm._lib.SIGNATURES)
+    L = hm.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.hm_version() >= 100
+    assert L.hm_blockrank_f64() == 20 and L.hm_blocksize_f64() == 80
+
+
+def test_constants_mirror(hm):
+    # BLOCKRANK is even for every float type (runtests.jl:5-7); values of SURVEY §2
+    assert [hm.BLOCKRANK(t) for t in (np.float64, np.float32, np.float16)] == [20, 10, 4]
+    assert hm.BLOCKRANK(np.complex128) == 20
+    assert hm.BLOCKSIZE(np.float64) == 80
+    assert all(hm.BLOCKRANK(t) % 2 == 0 for t in (np.float16, np.float32, np.float64))
+
+
+def test_product_points_match_oracle(hm, O):
+    for n in (20, 1000, 4097):
+        for kind in (1, 2):
+            assert np.array_equal(hm.chebyshevpoints(n, kind), O.chebyshevpoints(n, kind))
+
+
+@pytest.mark.parametrize("dist,N", [("cheb", 4096), ("unif", 4096), ("quad", 1000), ("cheb", 300), ("unif", 50)])
+def test_kernel_tree_leaves_match_oracle(hm, O, dist, N):
+    """The product's own range-tree builder against the oracle's assembled tree: same
+    leaves, same walk order, same offsets (KernelMatrix.jl:47-116, :17-45)."""
+    x, y, (a, b, c, d) = O.example_points(N, dist)
+    K = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    arr, n = K.leaves()
+    dp = C.POINTER(C.c_double)
+    cnt = C.c_int64()
+    buf = (hm._lib.TreeLeaf * n)()
+    hm._lib.check(hm.lib().hm_kernel_tree_leaves(x.ctypes.data_as(dp), N, y.ctypes.data_as(dp), N, a, b, c, d,
+                                                 buf, n, C.byref(cnt)))
+    assert cnt.value == n
+    for i in range(n):
+        o, p = arr[i], buf[i]
+        assert p.kind == (3 if o.kind == O.DENSE else 4)
+        assert (p.row0, p.col0, p.m, p.n) == (o.row0, o.col0, o.m, o.n)
+        if o.kind != O.DENSE:
+            assert p.rank == 20
+            # the box of the block reproduces the oracle's factors
+            if i % 37 == 0:
+                U, F, V = O.bary2d_build(O.CAUCHY, p.a, p.b, p.c, p.d, x, p.xi0, p.xi0 + p.m, y, p.yj0, p.yj0 + p.n)
+                assert np.array_equal(U, np.ctypeslib.as_array(o.A, shape=(o.r, o.m)).T)
+                assert np.array_equal(F, np.ctypeslib.as_array(o.S, shape=(o.r, o.r)).T)
+                assert np.array_equal(V, np.ctypeslib.as_array(o.V, shape=(o.r, o.n)).T)
+
+
+def test_kernel_tree_reference_error(hm, O):
+    # all points in the upper half of the box: the reference recurses into the empty
+    # trailing range N+1:N, whose indsplit reads x[N+1] -> BoundsError
+    x = np.linspace(1.0, 0.5, 200)
+    dp = C.POINTER(C.c_double)
+    s = hm._lib.Stats()
+    rc = hm.lib().hm_assemble_kernel_stats(x.ctypes.data_as(dp), 200, x.ctypes.data_as(dp), 200, 1.0, -1.0, 1.0, -1.0,
+                                           0, 1, C.byref(s))
+    assert rc == 9  # HM_ERR_REFERENCE
+    assert b"BoundsError" in hm.lib().hm_last_error()
+    with pytest.raises(RuntimeError):
+        O.kernelmatrix(O.CAUCHY, x, x, 1.0, -1.0, 1.0, -1.0)
+    # ... while a box that fits the points is fine
+    rc = hm.lib().hm_assemble_kernel_stats(x.ctypes.data_as(dp), 200, x.ctypes.data_as(dp), 200, 1.0, 0.5, 1.0, 0.5,
+                                           0, 1, C.byref(s))
+    assert rc == 0 and s.nrows == 200
+
+
+def test_layout_stats_match_survey(hm, O):
+    """leaf counts and algorithmic bytes (the roofline numerator)."""
+    for dist, nd, nl in (("cheb", 274, 510), ("unif", 190, 342)):
+        x, y, (a, b, c, d) = O.example_points(4096, dist)
+        st = hm.KernelMatrix.layout_stats(x, y, a, b, c, d)
+        assert (st["n_dense"], st["n_bary2d"], st["n_lowrank"]) == (nd, nl, 0)
+        K = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+        assert st["algorithmic_bytes"] == 8 * K.stored_words() + 16 * 4096
+        assert st["dense_words"] + st["lowrank_words"] == K.stored_words()
+        assert st["core_words"] == 400 * nl
+        # builder path (leaves pushed one by one) lays out identically
+        st2 = stats_from_oracle_tree(hm, O, K)
+        for k in ("algorithmic_bytes", "stored_bytes", "n_stage1_items", "n_stage3_items", "partial_bytes"):
+            assert st[k] == st2[k], k
+        # padding overhead of the packed streams stays small
+        assert st["stored_bytes"] <= 1.02 * 8 * K.stored_words()
+        assert st["part_v_words"] + st["part_u_words"] + st["part_core_words"] + st["part_dense_words"] == K.stored_words()
+    assert st["algorithmic_bytes"] == 23237376  # uniform set, SURVEY 8(d)
+
+
+def test_layout_stats_2pow20(hm):
+    """62 794 / 125 460 leaves (Chebyshev), 49 150 / 98 214 and
+    14 021 327 616 B (uniform) at N = 2^20."""
+    n = 1 << 20
+    x, y = hm.chebyshevpoints(n), hm.chebyshevpoints(n, 2)
+    st = hm.KernelMatrix.layout_stats(x, y, 1.0, -1.0, 1.0, -1.0)
+    assert (st["n_dense"], st["n_bary2d"]) == (62794, 125460)
+    assert abs(st["algorithmic_bytes"] - 14078717200) <= 4096  # survey's figure, to its sinpi rounding
+    i = np.arange(1, n + 1, dtype=np.float64)
+    st = hm.KernelMatrix.layout_stats(1.0 - 2.0 * (i - 0.5) / n, 1.0 - 2.0 * (i - 0.25) / n, 1.0, -1.0, 1.0, -1.0)
+    assert (st["n_dense"], st["n_bary2d"]) == (49150, 98214)
+    assert st["algorithmic_bytes"] == 14021327616
+    assert st["stored_bytes"] < 1.01 * st["algorithmic_bytes"]
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 4, 8])
+def test_row_partition(hm, O, nparts):
+    x, y, (a, b, c, d) = O.example_points(20000, "cheb")
+    whole = hm.KernelMatrix.layout_stats(x, y, a, b, c, d)
+    parts = [hm.KernelMatrix.layout_stats(x, y, a, b, c, d, p, nparts) for p in range(nparts)]
+    assert parts[0]["row_begin"] == 0 and parts[-1]["row_end"] == 20000
+    for p, q in zip(parts, parts[1:]):
+        assert p["row_end"] == q["row_begin"]
+    words = [p["part_words"] for p in parts]
+    # balanced by stored words; V and F of blocks that straddle a cut are replicated
+    assert max(words) <= 1.15 * (sum(words) / nparts)
+    total = whole["dense_words"] + whole["lowrank_words"]
+    assert total <= sum(words) <= 1.25 * total
+    assert sum(p["part_u_words"] + p["part_dense_words"] for p in parts) == whole["part_u_words"] + whole["part_dense_words"]
+
+
+def test_builder_validation_and_structure_only_mode(hm):
+    L = hm.lib()
+    b = C.c_void_p()
+    assert L.hm_builder_create(C.byref(b), 10, 10, 1, -1) == 8      # dtype: only Float64
+    assert L.hm_builder_create(C.byref(b), -1, 10, 0, -1) == 3
+    hm._lib.check(L.hm_builder_create(C.byref(b), 100, 80, 0, -1))  # structure only, pointers unused
+    assert L.hm_builder_add_dense(b, None, 10, 10, 10, 95, 0) == 4  # HM_ERR_RANGE
+    assert b"outside" in L.hm_last_error()
+    assert L.hm_builder_add_dense(b, None, -1, 10, 10, 0, 0) == 3   # HM_ERR_SHAPE
+    assert L.hm_builder_add_lowrank(b, None, 1, None, None, 1, 5, 5, -2, 0, 0) == 3
+    hm._lib.check(L.hm_builder_add_dense(b, None, 60, 80, 60, 0, 0))
+    hm._lib.check(L.hm_builder_add_lowrank(b, None, 40, None, None, 80, 40, 80, 5, 60, 0))
+    hm._lib.check(L.hm_builder_add_bary2d(b, None, 40, None, 5, None, 30, 40, 30, 5, 60, 50))  # overlaps: legal
+    hm._lib.check(L.hm_builder_add_dense(b, None, 0, 7, 1, 3, 3))   # empty block
+    s = hm._lib.Stats()
+    hm._lib.check(L.hm_builder_layout_stats(b, 0, 1, C.byref(s)))
+    assert (s.n_dense, s.n_lowrank, s.n_bary2d) == (2, 1, 1)
+    assert s.dense_words == 60 * 80 and s.lowrank_words == (40 + 80) * 5 + 5 + (40 + 30) * 5 + 25
+    assert s.algorithmic_bytes == 8 * (s.dense_words + s.lowrank_words) + 8 * 180
+    assert L.hm_builder_layout_stats(b, 2, 2, C.byref(s)) == 1      # part out of range
+    h = C.c_void_p()
+    assert L.hm_plan_finalize(b, None, 1, C.byref(h)) == 5          # HM_ERR_STATE: nothing staged
+    assert L.hm_plan_finalize(b, None, 2, C.byref(h)) == 8          # one plan drives one GPU
+    L.hm_builder_destroy(b)
+
+
+def test_no_cpu_fallback(hm):
+    """Without a CUDA device every compute entry point fails loudly (no silent fallback)."""
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    L = hm.lib()
+    b = C.c_void_p()
+    assert L.hm_builder_create(C.byref(b), 10, 10, 0, 0) == 7       # HM_ERR_CUDA
+    x = hm.chebyshevpoints(300)
+    with pytest.raises(hm.HmError) as e:
+        hm.KernelMatrix(hm.cauchykernel, x, x + 1e-3, 1.0, -1.0, 1.0, -1.0, device=0)
+    assert e.value.status == 7
+    H = hm.HierarchicalMatrix(np.float64, 1, 1)
+    H[hm.Block(1), hm.Block(1)] = np.zeros((3, 3), order="F")
+    with pytest.raises(hm.HmError):
+        H * np.zeros(3)
+
+
+def test_python_mirror_container_semantics(hm):
+    """@hierarchical container behaviour (hierarchical.jl:31-172) of the host mirror."""
+    rng = np.random.default_rng(0)
+    H = hm.HierarchicalMatrix(np.float64, 2, 2)
+    assert H.blocksize() == (2, 2) and H.size() == (0, 0)
+    assert hasattr(H, "HierarchicalMatrixblocks") and hasattr(H, "LowRankMatrixblocks") and hasattr(H, "Matrixblocks")
+    A = np.asfortranarray(rng.standard_normal((4, 6)))
+    Lr = hm.LowRankMatrix(rng.standard_normal((4, 2)), rng.standard_normal(2), rng.standard_normal((3, 2)))
+    H[hm.Block(1), hm.Block(1)] = A
+    H[hm.Block(1), hm.Block(2)] = Lr
+    G = hm.HierarchicalMatrix(np.float64, 1, 1)
+    G[hm.Block(1), hm.Block(1)] = np.asfortranarray(rng.standard_normal((5, 3)))
+    H[hm.Block(2), hm.Block(2)] = G
+    assert H.assigned.tolist() == [[3, 2], [0, 1]]           # codes: 1 nested, 2 LowRank, 3 Matrix, 0 none
+    assert H.size() == (9, 9)                                 # rows: last block column; cols: first block row
+    assert H.blocksize(2, 1, 1) == 0 and H.blocksize(1, 2) == (4, 3) and hm.blocksize(H, 2, 2, 1) == 5
+    assert H[1, 1] == A[0, 0] and H[5, 2] == 0.0              # unassigned block reads as zero
+    assert abs(H[2, 8] - (Lr.U[1] * Lr.S) @ Lr.V[1]) < 1e-14
+    assert H[9, 9] == G.Matrixblocks[0, 0][4, 2]
+    # setindex! silently ignores values whose type matches no field (hierarchical.jl:155-169)
+    H[hm.Block(2), hm.Block(1)] = hm.BarycentricMatrix2D(np.zeros((5, 2)), np.zeros((2, 2)), np.zeros((6, 2)))
+    H[hm.Block(2), hm.Block(1)] = np.zeros((5, 6), dtype=np.float32)
+    assert H.assigned[1, 0] == 0
+    # leaves in walk order with the walk's offsets
+    lv = H.leaves()
+    assert [(k, r, c) for k, r, c, _ in lv] == [(3, 0, 0), (2, 0, 6), (3, 4, 6)]
+    st = H.stats()
+    assert st["n_dense"] == 2 and st["n_lowrank"] == 1 and st["nrows"] == 9
+    K = hm.KernelMatrix(np.float64, 1, 2)
+    assert hasattr(K, "KernelMatrixblocks") and hasattr(K, "BarycentricMatrix2Dblocks")
+    K[hm.Block(1), hm.Block(1)] = hm.BarycentricMatrix2D(np.zeros((5, 2)), np.zeros((2, 2)), np.zeros((6, 2)))
+    K[hm.Block(1), hm.Block(2)] = Lr                          # not a KernelMatrix leaf type
+    assert K.assigned.tolist() == [[2, 0]]
+    assert K.size() == (0, 6)  # rows come from the LAST block column, which is unassigned here
+    with pytest.raises(hm.HmError):
+        hm.hierarchical("Odd", dict)
+    # mul_ argument checking happens before any device work
+    with pytest.raises(TypeError):
+        hm.mul_(np.zeros(5), K, np.zeros(6), 1, 1, 2, 2)      # KernelMatrix has no strided mul!
+    with pytest.raises(IndexError):
+        hm.mul_(np.zeros(8), H, np.zeros(9))                  # y too short
+    with pytest.raises(ValueError):
+        hm.mul_(np.zeros((3, 9)), H, np.zeros((3, 9)))        # C-order 2-D: not Julia's linear indexing

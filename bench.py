@@ -328,6 +328,13 @@ def run_ours(args):
                "api": "hm_matvec (C ABI, host pointers)"}
 
     y_host = y_dev.cpu().numpy() if (rank == 0 and (gather or not dist_on)) else None
+    sampled = None
+    if y_host is not None:
+        # independent spot check (examples/Kernel.jl:78 on sampled rows): dense kernel rows in long double
+        rows = np.unique(np.random.default_rng(1).integers(0, n, 48))
+        xl, yl, vl = px.astype(np.longdouble), py.astype(np.longdouble), v.astype(np.longdouble)
+        dense = np.array([np.sum(vl / (xl[i] - yl)) for i in rows], dtype=np.float64)
+        sampled = float(np.max(np.abs(y_host[rows] - dense)) / np.max(np.abs(dense)))
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -357,6 +364,7 @@ def run_ours(args):
                        "stage3_gbs": b3 / (s3 / 1e3) / 1e9 if s3 > 0 else None},
             "e2e": e2e, "gpu_launches": plan.launches_per_matvec * args.steps, "clocks": clocks,
             "leaves": {"dense": st["n_dense"], "bary2d": st["n_bary2d"]},
+            "check_sampled_dense_rows_relerr": sampled,
         }
         if world == 1 and not args.no_cpu_baseline:
             del K, plan

@@ -1,0 +1,204 @@
+# HierarchicalMatricesB200.jl -- the reference-side binding of libhmb200.so.
+#
+# `using HierarchicalMatrices, HierarchicalMatricesB200` adds more specific methods of
+# the reference's `mul!` / `*` for Float64 `KernelMatrix` and `HierarchicalMatrix`
+# operators (reference: src/KernelMatrix.jl:5-45, src/HierarchicalMatrix.jl:5-52) and
+# forwards them through `ccall` to the C ABI of include/hmb200.h.  The Julia side only
+# walks `assigned` and pushes leaves (the planner front end); packing, partitioning and
+# all arithmetic happen in the library.
+#
+# NOTE: Julia is not installed in the build image, so this file has not been executed
+# there; the identical ABI calls are exercised from Python (api.py, tests/).
+module HierarchicalMatricesB200
+
+using LinearAlgebra
+using HierarchicalMatrices
+import HierarchicalMatrices: KernelMatrix, HierarchicalMatrix, LowRankMatrix, BarycentricMatrix2D,
+                             blocksize
+
+const libhm = get(ENV, "HMB200_LIB", joinpath(@__DIR__, "..", "lib", "libhmb200.so"))
+
+struct HmError <: Exception
+    status::Int32
+    msg::String
+end
+Base.showerror(io::IO, e::HmError) = print(io, "libhmb200 status ", e.status, ": ", e.msg)
+
+function check(st::Int32)
+    st == 0 && return nothing
+    msg = unsafe_string(ccall((:hm_last_error, libhm), Cstring, ()))
+    st == 9 && throw(BoundsError())          # HM_ERR_REFERENCE: what the reference throws
+    st == 3 && throw(DimensionMismatch(msg)) # HM_ERR_SHAPE
+    throw(HmError(st, msg))
+end
+
+# ---------------------------------------------------------------------------
+# plan handle, freed by the GC
+# ---------------------------------------------------------------------------
+mutable struct Plan
+    ptr::Ptr{Cvoid}
+    function Plan(ptr::Ptr{Cvoid})
+        p = new(ptr)
+        finalizer(p) do q
+            q.ptr == C_NULL || ccall((:hm_plan_destroy, libhm), Int32, (Ptr{Cvoid},), q.ptr)
+            q.ptr = C_NULL
+        end
+        p
+    end
+end
+
+device() = parse(Int32, get(ENV, "HMB200_DEVICE", "0"))
+
+# ---------------------------------------------------------------------------
+# planner front end: the reference's own walk (KernelMatrix.jl:24-41), run once
+# ---------------------------------------------------------------------------
+function push_leaves!(b::Ptr{Cvoid}, H, i0::Int, j0::Int)
+    M, N = blocksize(H)
+    p = 0
+    for m = 1:M
+        q = 0
+        for n = 1:N
+            Hmn = H.assigned[m, n]
+            if Hmn == 1
+                push_leaves!(b, getfield(H, 1)[m, n], i0 + p, j0 + q)
+            elseif Hmn == 2
+                push_leaf!(b, getfield(H, 2)[m, n], i0 + p, j0 + q)
+            elseif Hmn == 3
+                push_leaf!(b, getfield(H, 3)[m, n], i0 + p, j0 + q)
+            end
+            q += blocksize(H, 1, n, 2)
+        end
+        p += blocksize(H, m, N, 1)
+    end
+end
+
+function push_leaf!(b, A::Matrix{Float64}, i0, j0)
+    m, n = size(A)
+    GC.@preserve A check(ccall((:hm_builder_add_dense, libhm), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Int64, Int64),
+        b, A, m, n, max(stride(A, 2), 1), i0, j0))
+end
+
+function push_leaf!(b, L::LowRankMatrix{Float64}, i0, j0)
+    U, S, V = L.U, L.Σ.diag, L.V
+    m, n, r = size(U, 1), size(V, 1), length(S)
+    GC.@preserve U S V check(ccall((:hm_builder_add_lowrank, libhm), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int64, Int64, Int64, Int64),
+        b, U, max(stride(U, 2), 1), S, V, max(stride(V, 2), 1), m, n, r, i0, j0))
+end
+
+function push_leaf!(b, B::BarycentricMatrix2D{Float64}, i0, j0)
+    U, F, V = B.U, B.B.F, B.V
+    m, n, r = size(U, 1), size(V, 1), size(F, 1)
+    GC.@preserve U F V check(ccall((:hm_builder_add_bary2d, libhm), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Int64, Int64, Int64),
+        b, U, max(stride(U, 2), 1), F, max(stride(F, 2), 1), V, max(stride(V, 2), 1), m, n, r, i0, j0))
+end
+
+"""
+    plan(H) -> Plan
+
+Flatten `H` and pack it on the GPU.  The plan is a snapshot keyed on the identity of
+`H`: after `H[Block(m), Block(n)] = A`, `scale!`, `add_col!`, ... call `invalidate!(H)`.
+"""
+const PLANS = IdDict{Any,Plan}()
+
+function plan(H::Union{KernelMatrix{Float64},HierarchicalMatrix{Float64}})
+    get!(PLANS, H) do
+        nr, nc = size(H)
+        b = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:hm_builder_create, libhm), Int32, (Ref{Ptr{Cvoid}}, Int64, Int64, Int32, Int32),
+                    b, nr, nc, 0, device()))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        try
+            push_leaves!(b[], H, 0, 0)
+            dev = Int32[device()]
+            check(ccall((:hm_plan_finalize, libhm), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+                        b[], dev, 1, out))
+        finally
+            ccall((:hm_builder_destroy, libhm), Int32, (Ptr{Cvoid},), b[])
+        end
+        Plan(out[])
+    end
+end
+
+invalidate!(H) = (delete!(PLANS, H); H)
+
+"""
+    assemble(f, x, y, a, b, c, d) -> Plan
+
+`KernelMatrix(f, x, y, a, b, c, d)` (KernelMatrix.jl:47) assembled on the GPU; `f` is one
+of the kernels of examples/Kernel.jl (`:cauchy`, `:coulomb`, `:coulombprime`, `:log`).
+"""
+function assemble(f::Symbol, x::Vector{Float64}, y::Vector{Float64}, a, b, c, d)
+    id = Dict(:cauchy => 0, :coulomb => 1, :coulombprime => 2, :log => 3)[f]
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve x y check(ccall((:hm_assemble_kernel, libhm), Int32,
+        (Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Float64, Float64, Float64, Int32, Int32, Int32, Int32,
+         Ref{Ptr{Cvoid}}),
+        x, length(x), y, length(y), a, b, c, d, id, device(), 0, 1, out))
+    Plan(out[])
+end
+
+# ---------------------------------------------------------------------------
+# mul!: y[istart + (i-1)INCY] += sum_j H[i,j] x[jstart + (j-1)INCX]
+# (1-based offsets become pointer offsets, as in src/blas.jl:12)
+# ---------------------------------------------------------------------------
+function matvec!(y::StridedArray{Float64}, P::Plan, x::StridedArray{Float64}, istart::Int, jstart::Int,
+                 INCX::Int, INCY::Int, accumulate::Bool)
+    GC.@preserve x y check(ccall((:hm_matvec, libhm), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int32),
+        P.ptr, pointer(x, jstart), INCX, pointer(y, istart), INCY, accumulate ? 1 : 0))
+    y
+end
+
+function checkbounds_mul(y, H, x, istart, jstart, INCX, INCY)
+    nr, nc = size(H)
+    (nr == 0 || istart + (nr - 1) * INCY <= length(y)) || throw(BoundsError(y, istart + (nr - 1) * INCY))
+    (nc == 0 || jstart + (nc - 1) * INCX <= length(x)) || throw(BoundsError(x, jstart + (nc - 1) * INCX))
+end
+
+# KernelMatrix: src/KernelMatrix.jl:14,17 (vectors only, unit stride)
+function HierarchicalMatrices.mul!(u::Vector{Float64}, H::KernelMatrix{Float64}, v::StridedVector{Float64},
+                                   istart::Int, jstart::Int)
+    checkbounds_mul(u, H, v, istart, jstart, 1, 1)
+    matvec!(u, plan(H), v, istart, jstart, 1, 1, true)
+end
+LinearAlgebra.mul!(u::Vector{Float64}, H::KernelMatrix{Float64}, v::StridedVector{Float64}) =
+    HierarchicalMatrices.mul!(u, H, v, 1, 1)
+
+# HierarchicalMatrix: src/HierarchicalMatrix.jl:14,19,24 (linear indexing, strides)
+function HierarchicalMatrices.mul!(y::StridedVecOrMat{Float64}, H::HierarchicalMatrix{Float64},
+                                   x::StridedVecOrMat{Float64}, istart::Int, jstart::Int, INCX::Int, INCY::Int)
+    checkbounds_mul(y, H, x, istart, jstart, INCX, INCY)
+    matvec!(y, plan(H), x, istart, jstart, INCX, INCY, true)
+end
+HierarchicalMatrices.mul!(y::StridedVecOrMat{Float64}, H::HierarchicalMatrix{Float64},
+                          x::StridedVecOrMat{Float64}, istart::Int, jstart::Int) =
+    HierarchicalMatrices.mul!(y, H, x, istart, jstart, 1, 1)
+LinearAlgebra.mul!(y::StridedVector{Float64}, H::HierarchicalMatrix{Float64}, x::StridedVector{Float64}) =
+    HierarchicalMatrices.mul!(y, H, x, 1, 1, 1, 1)
+
+# Plans built by `assemble` act as operators themselves
+Base.:*(P::Plan, v::Vector{Float64}) = begin
+    st = stats(P)
+    matvec!(zeros(st.nrows), P, v, 1, 1, 1, 1, false)
+end
+
+struct Stats
+    nrows::Int64; ncols::Int64; n_dense::Int64; n_lowrank::Int64; n_bary2d::Int64
+    dense_words::Int64; lowrank_words::Int64; core_words::Int64; algorithmic_bytes::Int64
+    row_begin::Int64; row_end::Int64; part_words::Int64; stored_bytes::Int64
+    v_stream_bytes::Int64; u_stream_bytes::Int64; partial_bytes::Int64
+    n_stage1_items::Int64; n_stage2_blocks::Int64; n_stage3_items::Int64; n_stage3_rounds::Int64
+    part_algorithmic_bytes::Int64; part_v_words::Int64; part_core_words::Int64; part_u_words::Int64
+    part_dense_words::Int64
+end
+
+function stats(P::Plan)
+    s = Ref{Stats}()
+    check(ccall((:hm_plan_stats, libhm), Int32, (Ptr{Cvoid}, Ref{Stats}), P.ptr, s))
+    s[]
+end
+
+end # module

@@ -55,7 +55,7 @@ def workload_name(n, dist):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -78,31 +78,39 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def stop(self, t_begin=None):
+        """Samples taken after wall-clock time t_begin (the timed region); if the region was
+        too short to catch three, all samples since start (warm-up + timed, same load)."""
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        recs = []
         for ln in self.lines:
             f = [a.strip() for a in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                recs.append((ts, float(f[1]), float(f[2]), [nm for nm, val in zip(names, f[5:9])
+                                                            if val.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        timed = [r for r in recs if t_begin is not None and r[0] >= t_begin]
+        window = "timed region"
+        if len(timed) < 3:
+            timed, window = recs, "warm-up + timed region (timed region shorter than 3 samples)"
+        sm = [r[1] for r in timed]
+        reasons = sorted({nm for r in timed for nm in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(r[2] for r in timed) if timed else None,
+                "samples": len(sm), "window": window, "reasons": reasons}
 
 
 def measured_peak():
@@ -305,14 +313,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    run(max(args.warmup, 3))
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    run(max(args.warmup, 3))
+    barrier()
     plan.timing_begin(args.steps)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_wall0 = time.time()
     e0.record(stream)
     run(args.steps)
     e1.record(stream)
@@ -320,7 +329,7 @@ def run_ours(args):
     y_dev = y_bufs[(args.steps - 1) % nbuf]
     ms = e0.elapsed_time(e1)
     stage_ms, ncalls = plan.timing_end()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist_on:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -165,6 +165,44 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
 //   s     = Sigma .* t            (LowRankMatrix,       algebra.jl:120)
 //   s     = F * t  (l outer)      (BarycentricMatrix2D, algebra.jl:260-265)
 // ---------------------------------------------------------------------------
+// Fast path for the rank the assembler produces (BLOCKRANK(Float64) = 20, F 20 x 20):
+// lane k < R first issues its R loads of row k of F (independent, all in flight), then
+// walks the partial-sum list while they land.
+template <int R>
+__device__ __forceinline__ void core_apply_fixed(const HmCoreBlock &cb, const int32_t *__restrict__ pl,
+                                                 const double *__restrict__ partial,
+                                                 const double *__restrict__ c, double *__restrict__ svec,
+                                                 int lane)
+{
+    double f[R];
+    const bool act = lane < R;
+    if (act) {
+#pragma unroll
+        for (int l = 0; l < R; l++) f[l] = __ldcs(c + lane + l * R);
+    }
+    double t = 0.0;
+    if (act) {
+        int i = 0;
+        for (; i + 3 < cb.npl; i += 4) {
+            int o0 = pl[i], o1 = pl[i + 1], o2 = pl[i + 2], o3 = pl[i + 3];
+            double p0 = partial[o0 + lane], p1 = partial[o1 + lane];
+            double p2 = partial[o2 + lane], p3 = partial[o3 + lane];
+            t += p0;
+            t += p1;
+            t += p2;
+            t += p3;
+        }
+        for (; i < cb.npl; i++) t += partial[pl[i] + lane];
+    }
+    double a = 0.0;
+#pragma unroll
+    for (int l = 0; l < R; l++) {
+        double tl = __shfl_sync(0xffffffffu, t, l);
+        a = fma(f[l], tl, a);
+    }
+    if (act) svec[cb.soff + lane] = a;
+}
+
 __global__ void __launch_bounds__(256)
 hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
                const int32_t *__restrict__ plist, const double *__restrict__ partial,
@@ -174,9 +212,14 @@ hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (b >= nblocks) return;
-    double *tbuf = tbuf_all + (size_t)wib * max_r;
     const HmCoreBlock cb = blocks[b];
     const int32_t *pl = plist + cb.pl0;
+    const double *c = core + cb.core;
+    if (cb.kind == HM_LEAF_BARY2D && cb.ru == 20 && cb.rv == 20) {
+        core_apply_fixed<20>(cb, pl, partial, c, svec, lane);
+        return;
+    }
+    double *tbuf = tbuf_all + (size_t)wib * max_r;
     for (int k = lane; k < cb.rv; k += 32) {
         double t = 0.0;
         int i = 0;
@@ -192,7 +235,6 @@ hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
         tbuf[k] = t;
     }
     __syncwarp();
-    const double *c = core + cb.core;
     if (cb.kind == HM_LEAF_LOWRANK) {
         for (int k = lane; k < cb.ru; k += 32) svec[cb.soff + k] = tbuf[k] * c[k];
     } else {

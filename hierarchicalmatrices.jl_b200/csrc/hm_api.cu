@@ -294,6 +294,9 @@ struct hm_plan {
     double *hx = nullptr, *hy = nullptr; // pinned, for strided arguments
     int64_t nrhs_cap = 0;
     DevBuf<double> dX, dY;
+    // panel workspace of the multi-RHS path (row pitch ws_cs)
+    int ws_cs = 0;
+    DevBuf<double> wXt, wPp, wSp, wYt;
     std::mutex mu;
     // per-stage timing (bench bookkeeping)
     std::vector<cudaEvent_t> tev;
@@ -765,17 +768,45 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
     return HM_OK;
 }
 
-// Multi-RHS: column-by-column over the single-vector kernels for now (the
-// DMMA panel kernels replace this loop; see DESIGN.md "Next").
+// Multi-RHS: Y[:, c] (+)= H X[:, c].  Columns are processed in panels of up to 64 with the
+// FP64 tensor-core kernels of hm_panel.cu; a single column takes the matvec path.
 int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t nrhs,
                          int32_t accumulate, void *stream)
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
     if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
-    if (nrhs > 0 && (ldx < std::max<int64_t>(p->L.ncols, 1) || ldy < std::max<int64_t>(p->L.nrows, 1)))
+    if (nrhs == 0) return HM_OK;
+    const HmLayout &L = p->L;
+    if (ldx < std::max<int64_t>(L.ncols, 1) || ldy < std::max<int64_t>(L.nrows, 1))
         return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
-    for (int64_t c = 0; c < nrhs; c++)
-        if (int32_t rc = hm_matvec_device(p, dX + c * ldx, dY + c * ldy, accumulate, stream)) return rc;
+    if ((!dX && L.ncols > 0) || (!dY && L.nrows > 0)) return fail(HM_ERR_NULL, "panel pointer is NULL");
+    if (nrhs == 1) return hm_matvec_device(p, dX, dY, accumulate, stream);
+    HM_DEVICE(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int64_t c0 = 0; c0 < nrhs; c0 += 64) {
+        const int nc = (int)std::min<int64_t>(64, nrhs - c0);
+        const int CS = hm_panel_width(nc);
+        if (CS > p->ws_cs) {
+            HM_CUDA(cudaStreamSynchronize(st));
+            HM_CUDA(p->wXt.alloc((size_t)std::max<int64_t>(L.ncols, 1) * CS));
+            HM_CUDA(p->wPp.alloc((size_t)std::max<int64_t>(L.partial_words, 1) * CS));
+            HM_CUDA(p->wSp.alloc((size_t)std::max<int64_t>(L.s_words, 1) * CS));
+            HM_CUDA(p->wYt.alloc((size_t)std::max<int64_t>(L.nrows, 1) * CS));
+            p->ws_cs = CS;
+        }
+        HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st));
+        HM_CUDA(hm_launch_panel_stage1(CS, p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->wXt.p,
+                                       p->wPp.p, st));
+        HM_CUDA(hm_launch_panel_stage2(CS, p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->wPp.p, p->core.p,
+                                       p->wSp.p, std::max(L.max_r, 1), st));
+        for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
+            int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
+            HM_CUDA(hm_launch_panel_stage3(CS, p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->wXt.p,
+                                           p->wSp.p, p->wYt.p, r == 0 ? 0 : 1, st));
+        }
+        HM_CUDA(hm_launch_panel_out(p->wYt.p, CS, L.row_begin, L.row_end, nc, dY + c0 * ldy, ldy,
+                                    accumulate != 0, st));
+    }
     return HM_OK;
 }
 
@@ -784,10 +815,32 @@ int32_t hm_matmat(hm_plan *p, const double *X, int64_t ldx, double *Y, int64_t l
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
     if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
-    if (nrhs > 0 && (ldx < std::max<int64_t>(p->L.ncols, 1) || ldy < std::max<int64_t>(p->L.nrows, 1)))
+    if (nrhs == 0) return HM_OK;
+    const HmLayout &L = p->L;
+    if (ldx < std::max<int64_t>(L.ncols, 1) || ldy < std::max<int64_t>(L.nrows, 1))
         return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
-    for (int64_t c = 0; c < nrhs; c++)
-        if (int32_t rc = hm_matvec(p, X + c * ldx, 1, Y + c * ldy, 1, accumulate)) return rc;
+    if ((!X && L.ncols > 0) || (!Y && L.nrows > 0)) return fail(HM_ERR_NULL, "panel pointer is NULL");
+    std::lock_guard<std::mutex> lock(p->mu);
+    HM_DEVICE(p->device);
+    cudaStream_t st = p->stream;
+    const int64_t nc = std::max<int64_t>(L.ncols, 1), nr = std::max<int64_t>(L.nrows, 1);
+    if (nrhs > p->nrhs_cap) {
+        HM_CUDA(p->dX.alloc((size_t)nc * nrhs));
+        HM_CUDA(p->dY.alloc((size_t)nr * nrhs));
+        p->nrhs_cap = nrhs;
+    }
+    const int64_t r0 = L.row_begin, rows = L.row_end - L.row_begin;
+    if (L.ncols > 0)
+        HM_CUDA(cudaMemcpy2DAsync(p->dX.p, (size_t)nc * 8, X, (size_t)ldx * 8, (size_t)L.ncols * 8, (size_t)nrhs,
+                                  cudaMemcpyHostToDevice, st));
+    if (accumulate && rows > 0)
+        HM_CUDA(cudaMemcpy2DAsync(p->dY.p + r0, (size_t)nr * 8, Y + r0, (size_t)ldy * 8, (size_t)rows * 8,
+                                  (size_t)nrhs, cudaMemcpyHostToDevice, st));
+    if (int32_t rc = hm_matmat_device(p, p->dX.p, nc, p->dY.p, nr, nrhs, accumulate, st)) return rc;
+    if (rows > 0)
+        HM_CUDA(cudaMemcpy2DAsync(Y + r0, (size_t)ldy * 8, p->dY.p + r0, (size_t)nr * 8, (size_t)rows * 8,
+                                  (size_t)nrhs, cudaMemcpyDeviceToHost, st));
+    HM_CUDA(cudaStreamSynchronize(st));
     return HM_OK;
 }
 

@@ -38,3 +38,17 @@ cudaError_t hm_launch_fill1(const HmFill *fills, int64_t nfills, const HmLeaf *l
 cudaError_t hm_launch_fillcore(const HmCoreBlock *blocks, const int32_t *core_leaf, int64_t nblocks,
                                const HmLeaf *leaves, double *core, const HmCheb &cheb, int kernel_id,
                                cudaStream_t st);
+
+// many right-hand sides (hm_panel.cu): panels are row-major with pitch CS = hm_panel_width(nrhs)
+int hm_panel_width(int nrhs);
+cudaError_t hm_launch_panel_in(const double *X, int64_t ldx, int64_t n, int nrhs, int CS, double *Xt,
+                               cudaStream_t st);
+cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1, int nrhs, double *Y,
+                                int64_t ldy, int accumulate, cudaStream_t st);
+cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, const double *vstream,
+                                   const double *Xt, double *Pp, cudaStream_t st);
+cudaError_t hm_launch_panel_stage2(int CS, const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
+                                   const double *Pp, const double *core, double *Sp, int max_r, cudaStream_t st);
+cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, const HmRun *runs,
+                                   const double *ustream, const double *Xt, const double *Sp, double *Yt,
+                                   int accumulate, cudaStream_t st);

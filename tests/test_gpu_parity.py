@@ -333,3 +333,67 @@ def test_errors(hm):
         hm.mul_(np.zeros(2), H, np.zeros(3))
     with pytest.raises(TypeError):
         hm.mul_(np.zeros(3, dtype=np.float32), H, np.zeros(3))
+
+
+# ------------------------------------------------------------------ many right-hand sides (DMMA panel kernels)
+@pytest.mark.parametrize("nrhs", [2, 16, 17, 33, 64, 65, 130])
+def test_matmat_kernelmatrix(hm, O, nrhs):
+    N = 3000
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0)
+    rng = np.random.default_rng(nrhs)
+    X = np.asfortranarray(rng.standard_normal((N, nrhs)))
+    Y = K * X
+    assert Y.shape == (N, nrhs)
+    for c_ in sorted({0, 1, nrhs // 2, nrhs - 1}):
+        assert relinf(Y[:, c_], Kref.matvec(np.ascontiguousarray(X[:, c_]))) <= TOL
+    # accumulate form with leading dimensions larger than the extents
+    Xb = np.zeros((N + 5, nrhs), order="F")
+    Xb[:N] = X
+    Y0 = np.asfortranarray(rng.standard_normal((N + 3, nrhs)))
+    Yb = Y0.copy(order="F")
+    dp = C.POINTER(C.c_double)
+    hm._lib.check(hm.lib().hm_matmat(K.plan().handle, Xb.ctypes.data_as(dp), N + 5, Yb.ctypes.data_as(dp), N + 3,
+                                     nrhs, 1))
+    assert relinf(Yb[:N], Y0[:N] + Y) <= TOL
+    assert np.array_equal(Yb[N:], Y0[N:])
+    # the panel path agrees with the single-vector path to rounding
+    y1 = K * np.ascontiguousarray(X[:, 0])
+    assert relinf(Y[:, 0], y1) <= 1e-13
+
+
+def test_matmat_lowrank_wide_and_multiround(hm, O):
+    rng = np.random.default_rng(11)
+    # generic tree: ragged LowRankMatrix/dense blocks
+    H = random_lowrank_tree(hm, rng, 1500)
+    T = oracle_tree_from_mirror(O, H)
+    X = np.asfortranarray(rng.standard_normal((1500, 24)))
+    Y = H * X
+    for c_ in (0, 7, 23):
+        assert relinf(Y[:, c_], T.matvec(np.ascontiguousarray(X[:, c_]))) <= TOL
+    # one block far larger than a work item: z longer than the staging (several stage-3
+    # rounds), a fast dimension wider than one pass (rank 150 -> stage-1 F = 150 > 128)
+    H2 = hm.HierarchicalMatrix(np.float64, 2, 1)
+    A = np.asfortranarray(rng.standard_normal((700, 4700)))
+    H2[hm.Block(1), hm.Block(1)] = A
+    r = 150
+    Lr = hm.LowRankMatrix(rng.standard_normal((2500, r)), rng.standard_normal(r), rng.standard_normal((4700, r)))
+    H2[hm.Block(2), hm.Block(1)] = Lr
+    X2 = np.asfortranarray(rng.standard_normal((4700, 20)))
+    ref = np.vstack([A @ X2, Lr.U @ (Lr.S[:, None] * (Lr.V.T @ X2))])
+    Y2 = H2 * X2
+    assert relinf(Y2, ref) <= TOL
+
+
+def test_matmat_row_parts(hm, O):
+    N = 4096
+    x, y, (a, b, c, d) = O.example_points(N, "unif")
+    Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    X = np.asfortranarray(np.random.default_rng(3).standard_normal((N, 16)))
+    Y = np.full((N, 16), np.nan, order="F")
+    for p in range(3):
+        Kp = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=p, nparts=3)
+        Kp.plan().matmat(X, Y, accumulate=False)
+    for c_ in (0, 15):
+        assert relinf(Y[:, c_], Kref.matvec(np.ascontiguousarray(X[:, c_]))) <= TOL

@@ -781,6 +781,12 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
         return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
     if ((!dX && L.ncols > 0) || (!dY && L.nrows > 0)) return fail(HM_ERR_NULL, "panel pointer is NULL");
     if (nrhs == 1) return hm_matvec_device(p, dX, dY, accumulate, stream);
+    if ((size_t)L.max_r * 64 * sizeof(double) > 160 * 1024) {
+        // ranks beyond the panel kernels' shared-memory staging: column by column
+        for (int64_t c = 0; c < nrhs; c++)
+            if (int32_t rc = hm_matvec_device(p, dX + c * ldx, dY + c * ldy, accumulate, stream)) return rc;
+        return HM_OK;
+    }
     HM_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     for (int64_t c0 = 0; c0 < nrhs; c0 += 64) {

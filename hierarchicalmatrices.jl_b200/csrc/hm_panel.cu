@@ -217,13 +217,11 @@ hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__re
     constexpr int CS = NB * 8;
     extern __shared__ double sm[];
     double *Tsm = sm;                         // [rv][CS]
-    double *Fsm = sm + (size_t)max_r * CS;    // ru x rv (bary) or r (low rank)
+    const double *__restrict__ Fg = core + cb.core; // ru x rv (bary) or r (low rank); L1-resident
     const HmCoreBlock cb = blocks[blockIdx.x];
     const int t = threadIdx.x, T = blockDim.x;
     const int32_t *pl = plist + cb.pl0;
     const int nT = cb.rv * CS;
-    const int ncore = cb.kind == HM_LEAF_BARY2D ? cb.ru * cb.rv : cb.ru;
-    for (int i = t; i < ncore; i += T) Fsm[i] = core[cb.core + i];
     for (int e = t; e < nT; e += T) {
         double a = 0.0;
         int i = 0;
@@ -242,12 +240,12 @@ hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__re
     double *o = Sp + (size_t)cb.soff * CS;
     const int nS = cb.ru * CS;
     if (cb.kind == HM_LEAF_LOWRANK) {
-        for (int e = t; e < nS; e += T) o[e] = Tsm[e] * Fsm[e / CS];
+        for (int e = t; e < nS; e += T) o[e] = Tsm[e] * __ldg(Fg + e / CS);
     } else {
         for (int e = t; e < nS; e += T) {
             int k = e / CS, c = e - k * CS;
             double a = 0.0;
-            for (int l = 0; l < cb.rv; l++) a = fma(Fsm[k + l * cb.ru], Tsm[l * CS + c], a);
+            for (int l = 0; l < cb.rv; l++) a = fma(__ldg(Fg + k + (size_t)l * cb.ru), Tsm[l * CS + c], a);
             o[e] = a;
         }
     }
@@ -323,8 +321,8 @@ cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const 
                               const double *core, double *Sp, int max_r, cudaStream_t st)
 {
     if (nblocks <= 0) return cudaSuccess;
-    const size_t smem = ((size_t)max_r * NB * 8 + (size_t)max_r * max_r) * sizeof(double);
-    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    const size_t smem = (size_t)max_r * NB * 8 * sizeof(double);
+    if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(hm_core_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -217,8 +217,9 @@ hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__re
     constexpr int CS = NB * 8;
     extern __shared__ double sm[];
     double *Tsm = sm;                         // [rv][CS]
-    const double *__restrict__ Fg = core + cb.core; // ru x rv (bary) or r (low rank); L1-resident
     const HmCoreBlock cb = blocks[blockIdx.x];
+    const double *__restrict__ Fg = core + cb.core; // ru x rv (bary) or r (low rank); L1-resident
+    (void)max_r;
     const int t = threadIdx.x, T = blockDim.x;
     const int32_t *pl = plist + cb.pl0;
     const int nT = cb.rv * CS;

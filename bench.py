@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--dist", default="cheb", choices=["cheb", "unif"],
                     help="cheb = examples/Kernel.jl:61-62 point sets; unif = uniform interlaced")
     ap.add_argument("--no-gather", action="store_true", help="skip the all-gather of y (N > 1)")
+    ap.add_argument("--nrhs", type=int, default=1,
+                    help="> 1: time the multi-right-hand-side product (BASELINE configs[2]/[4]) instead")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -226,6 +228,89 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# --------------------------------------------------------------------------- multi-RHS mode (single GPU)
+def run_matmat(args, hm, torch, plan, st, px, py, dev, t_asm):
+    """Y = K X with X of `nrhs` columns (BASELINE configs[2]: N = 2^20, 64 right-hand sides; FP64
+    tensor-core panel kernels).  A step is one product; value = columns per second."""
+    n, nrhs = args.n, args.nrhs
+    rng = np.random.default_rng(0)
+    X = torch.from_numpy(rng.standard_normal((nrhs, n))).to(dev)   # column-major n x nrhs
+    Y = torch.zeros((nrhs, n), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def run(k):
+        for _ in range(k):
+            plan.matmat_device(X.data_ptr(), n, Y.data_ptr(), n, nrhs, accumulate=False, stream=stream.cuda_stream)
+
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    run(max(args.warmup, 3))
+    torch.cuda.synchronize()
+    plan.timing_begin(args.steps * ((nrhs + 63) // 64))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    run(args.steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    stage_ms, ncalls = plan.timing_end()
+    clocks = sampler.stop(t_wall0)
+    # measured FP64 GEMM peak on this box (cuBLAS DGEMM 8192^3), the FP64-pipe denominator
+    A = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    B = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        torch.matmul(A, B)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        torch.matmul(A, B)
+        a1.record()
+        torch.cuda.synchronize()
+        best = min(best, a0.elapsed_time(a1))
+    dgemm_tflops = 2 * 8192 ** 3 / (best / 1e3) / 1e12
+    del A, B
+    words = st["dense_words"] + st["lowrank_words"]
+    flops = 2.0 * words * nrhs
+    cs = 16 if nrhs <= 16 else 32 if nrhs <= 32 else 64
+    bytes_alg = 8 * words + 16 * n * nrhs
+    peak, peak_src = measured_peak()
+    # spot check of a few entries against dense kernel rows in long double
+    Yh = Y.cpu().numpy()
+    Xh = X.cpu().numpy()
+    rows = np.unique(rng.integers(0, n, 12))
+    cols = [0, nrhs - 1]
+    xl, yl = px.astype(np.longdouble), py.astype(np.longdouble)
+    err = 0.0
+    for c in cols:
+        dense = np.array([np.sum(Xh[c].astype(np.longdouble) / (xl[i] - yl)) for i in rows], dtype=np.float64)
+        err = max(err, float(np.max(np.abs(Yh[c, rows] - dense)) / np.max(np.abs(dense))))
+    tf = flops / (ms / 1e3) / 1e12
+    gbs = bytes_alg / (ms / 1e3) / 1e9
+    line = {
+        "metric": "H-matmat columns/s", "value": nrhs / (ms / 1e3), "unit": "columns/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n, args.dist).replace("single-vector mul!", f"{nrhs} right-hand sides"),
+                   "n": n, "dist": args.dist, "nrhs": nrhs, "panel_width": cs, "assembly_s": round(t_asm, 3),
+                   "l2": "inputs larger than L2"},
+        "tflops": tf, "effective_gbs": gbs,
+        "roofline": {"bound": "tensor" if tf / dgemm_tflops > gbs / peak else "hbm",
+                     "kernel": "hm_panel_kernel (DMMA m8n8k4, stage 1 + stage 3)",
+                     "achieved_tflops": tf, "peak_tflops": dgemm_tflops,
+                     "peak_tflops_source": "cuBLAS DGEMM 8192^3 measured in this run (best of 5)",
+                     "frac_fp64": tf / dgemm_tflops, "achieved_gbs": gbs, "peak_gbs": peak, "peak_gbs_source": peak_src,
+                     "frac_hbm": gbs / peak, "traffic": None,
+                     "ms_per_launch": {"stage1+in": stage_ms[0] / max(ncalls, 1), "stage2": stage_ms[1] / max(ncalls, 1),
+                                       "stage3+out": stage_ms[2] / max(ncalls, 1)}},
+        "gpu_launches": args.steps * ((nrhs + 63) // 64) * (plan.launches_per_matvec + 2), "clocks": clocks,
+        "check_sampled_dense_entries_relerr": err,
+    }
+    print(json.dumps(line), flush=True)
+
+
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -254,6 +339,9 @@ def run_ours(args):
     plan = K.plan()
     st = plan.stats()
     r0, r1 = st["row_begin"], st["row_end"]
+
+    if args.nrhs > 1:
+        return run_matmat(args, hm, torch, plan, st, px, py, dev, t_asm)
 
     v = np.random.default_rng(0).standard_normal(n)
     gather = dist_on and not args.no_gather

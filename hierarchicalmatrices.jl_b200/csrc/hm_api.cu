@@ -800,11 +800,15 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
             HM_CUDA(p->wYt.alloc((size_t)std::max<int64_t>(L.nrows, 1) * CS));
             p->ws_cs = CS;
         }
+        cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
+        if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
         HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st));
         HM_CUDA(hm_launch_panel_stage1(CS, p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->wXt.p,
                                        p->wPp.p, st));
+        if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
         HM_CUDA(hm_launch_panel_stage2(CS, p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->wPp.p, p->core.p,
                                        p->wSp.p, std::max(L.max_r, 1), st));
+        if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
         for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
             int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
             HM_CUDA(hm_launch_panel_stage3(CS, p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->wXt.p,
@@ -812,6 +816,10 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
         }
         HM_CUDA(hm_launch_panel_out(p->wYt.p, CS, L.row_begin, L.row_end, nc, dY + c0 * ldy, ldy,
                                     accumulate != 0, st));
+        if (ev) {
+            HM_CUDA(cudaEventRecord(ev[3], st));
+            p->tcount++;
+        }
     }
     return HM_OK;
 }

@@ -17,20 +17,7 @@
 
 namespace {
 
-constexpr int PT = 256;  // threads per CTA
-constexpr int NST = 3;   // cp.async pipeline stages
-constexpr int MT = 128;  // rows of the fast dimension per pass
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
+constexpr int PT = 256; // threads per CTA
 
 // D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
@@ -41,17 +28,24 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 }
 
 // ---------------------------------------------------------------------------
-// stage 1 / stage 3 on a panel
+// stage 1 / stage 3 on a panel.
+//
+// The fast dimension is cut into tiles of 16 rows (two 8-row MMA blocks); a warp owns
+// a tile and streams its 128-byte row pieces of the slab straight from HBM into A
+// fragments (lane (g, t) reads W[s0 + t][f0 + g]: four 64-byte pieces per load
+// instruction, every sector fully used), U k-steps in flight.  B fragments (the z rows)
+// come through L1: all warps of the CTA read the same rows.  No shared-memory staging
+// and no barriers in the main loop.  Items with fewer than 8 tiles split the slow
+// dimension over warp groups, combined in a fixed order through shared memory.
 // ---------------------------------------------------------------------------
-template <bool GATHER, int NB>
+template <bool GATHER, int NB, int U>
 __global__ void __launch_bounds__(PT, 2)
 hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                 const double *__restrict__ W, const double *__restrict__ Xt,
-                const double *__restrict__ Sp, double *__restrict__ out, int accumulate,
-                int budget_words)
+                const double *__restrict__ Sp, double *__restrict__ out, int accumulate)
 {
-    constexpr int CS = NB * 8, ZP = CS + 8;
-    extern __shared__ __align__(16) double dsm[];
+    constexpr int CS = NB * 8, CP = CS + 8;
+    extern __shared__ __align__(16) double csm[]; // [<= 8 tiles][16][CP] split-K combine buffer
     __shared__ int zrow[GATHER ? HM_SMAX : 1];
     __shared__ int rpos[GATHER ? HM_MAXRUNS + 1 : 1];
     __shared__ int rsrc[GATHER ? HM_MAXRUNS : 1];
@@ -86,21 +80,25 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
     }
 
     const double *__restrict__ Wg = W + it.slab;
+    const int nfb = (Fp + 7) >> 3;  // 8-row blocks
+    const int nft = (nfb + 1) >> 1; // 16-row tiles
+    if (nft == 0) return;
+    const int kgroups = nft >= 8 ? 1 : 8 / nft;
+    const int ntw = nft >= 8 ? 8 : nft; // warps per k-group
+    const int kg = warp / ntw;
+    const bool active = kg < kgroups;
+    int s_lo = 0, s_hi = S;
+    if (kgroups > 1) {
+        int sg = (((S + kgroups - 1) / kgroups) + 3) & ~3;
+        s_lo = min(S, kg * sg);
+        s_hi = min(S, s_lo + sg);
+    }
 
-    for (int f0 = 0; f0 < Fp; f0 += MT) {
-        const int mt = min(MT, Fp - f0);         // even
-        const int WP = ((mt + 15) & ~15) + 8;    // smem pitch: = 8 (mod 16) -> conflict-free fragments
-        int KC = (budget_words / NST / (WP + ZP)) & ~3;
-        KC = max(4, min(32, KC));
-        const int stage_words = KC * (WP + ZP);
-        const int nfb = (mt + 7) >> 3;           // 8-row blocks
-        const int fwarps = (nfb + 1) >> 1;       // a warp owns up to two of them
-        const int kgroups = 8 / fwarps;          // split-K groups
-        const int fw = warp % fwarps, kg = warp / fwarps;
-        const bool active = kg < kgroups;
-        const int fb0 = fw * 2;
-        const bool two = fb0 + 1 < nfb;
-        const int nchunks = (S + KC - 1) / KC;
+    for (int ft = warp % ntw; ft < nft && active; ft += ntw) {
+        const bool two = ft * 2 + 1 < nfb;
+        const int col0 = ft * 16 + gid;
+        const bool c0ok = col0 < Fp, c1ok = two && (col0 + 8 < Fp);
+        const double *__restrict__ ap = Wg + col0;
 
         double acc[2][NB][2];
 #pragma unroll
@@ -108,91 +106,86 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
 #pragma unroll
             for (int n = 0; n < NB; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
 
-        auto issue = [&](int ch) {
-            double *Wsm = dsm + (size_t)(ch % NST) * stage_words;
-            double *Zsm = Wsm + KC * WP;
-            const int s0 = ch * KC, rows = min(KC, S - s0);
-            const int hw = mt >> 1;
-            for (int idx = t; idx < rows * hw; idx += PT) {
-                int r = idx / hw, p = idx - r * hw;
-                cp_async16(Wsm + r * WP + 2 * p, Wg + (size_t)(s0 + r) * Fp + f0 + 2 * p);
-            }
-            constexpr int hz = CS / 2;
-            for (int idx = t; idx < rows * hz; idx += PT) {
-                int r = idx / hz, p = idx - r * hz;
-                const double *src;
-                if (GATHER) {
-                    int zr = zrow[s0 + r];
-                    src = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
-                } else {
-                    src = Xt + (size_t)(it.zoff + s0 + r) * CS;
+        for (int k0 = s_lo; k0 < s_hi; k0 += 4 * U) {
+            double a0[U], a1[U], b[U][NB];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int row = k0 + 4 * u + tig;
+                const bool v = row < s_hi;
+                a0[u] = (v && c0ok) ? __ldcs(ap + (size_t)row * Fp) : 0.0;
+                a1[u] = (v && c1ok) ? __ldcs(ap + (size_t)row * Fp + 8) : 0.0;
+                const double *zp = Xt;
+                if (v) {
+                    if (GATHER) {
+                        int zr = zrow[row];
+                        zp = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
+                    } else {
+                        zp = Xt + (size_t)(it.zoff + row) * CS;
+                    }
                 }
-                cp_async16(Zsm + r * ZP + 2 * p, src + 2 * p);
+#pragma unroll
+                for (int n = 0; n < NB; n++) b[u][n] = v ? __ldg(zp + n * 8 + gid) : 0.0;
             }
-            if (rows < KC) { // zero the tail of the last chunk (0 * stale NaN would poison the sums)
-                for (int idx = t; idx < (KC - rows) * WP; idx += PT) Wsm[rows * WP + idx] = 0.0;
-                for (int idx = t; idx < (KC - rows) * ZP; idx += PT) Zsm[rows * ZP + idx] = 0.0;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int n = 0; n < NB; n++) {
+                    dmma884(acc[0][n][0], acc[0][n][1], a0[u], b[u][n]);
+                    if (two) dmma884(acc[1][n][0], acc[1][n][1], a1[u], b[u][n]);
+                }
             }
-        };
-
-        for (int ch = 0; ch < NST - 1; ch++) {
-            if (ch < nchunks) issue(ch);
-            cp_async_commit();
         }
-        for (int ch = 0; ch < nchunks; ch++) {
-            if (ch + NST - 1 < nchunks) issue(ch + NST - 1);
-            cp_async_commit();
-            cp_async_wait<NST - 1>();
-            __syncthreads();
-            if (active) {
-                const double *Wsm = dsm + (size_t)(ch % NST) * stage_words;
-                const double *Zsm = Wsm + KC * WP;
-                const double *ap = Wsm + tig * WP + fb0 * 8 + gid;
-                const double *bp = Zsm + tig * ZP + gid;
-#pragma unroll 2
-                for (int ks = kg; ks < (KC >> 2); ks += kgroups) {
-                    const double a0 = ap[ks * 4 * WP];
-                    const double a1 = two ? ap[ks * 4 * WP + 8] : 0.0;
+
+        if (kgroups == 1) {
+            // sole owner of the tile: write the C fragments straight out
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const int f = ft * 16 + a * 8 + gid;
+                if (f < F && (a == 0 || two)) {
+                    double2 *g = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + tig;
 #pragma unroll
                     for (int n = 0; n < NB; n++) {
-                        const double b = bp[ks * 4 * ZP + n * 8];
-                        dmma884(acc[0][n][0], acc[0][n][1], a0, b);
-                        if (two) dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+                        double2 v = make_double2(acc[a][n][0], acc[a][n][1]);
+                        if (GATHER && accumulate) {
+                            double2 o = g[n * 4];
+                            v.x += o.x;
+                            v.y += o.y;
+                        }
+                        g[n * 4] = v;
                     }
                 }
             }
-            __syncthreads();
-        }
-        cp_async_wait<0>();
-
-        // combine the split-K groups in a fixed order through shared memory, then write
-        double *Csm = dsm;
-        for (int g = 0; g < kgroups; g++) {
-            if (active && kg == g) {
+        } else {
+            // keep for the combine below (nft < 8: exactly one tile per warp)
+            for (int g = 0; g < kgroups; g++) {
+                if (kg == g) {
 #pragma unroll
-                for (int a = 0; a < 2; a++) {
-                    if (a == 1 && !two) break;
-                    double *row = Csm + ((fb0 + a) * 8 + gid) * ZP + 2 * tig;
+                    for (int a = 0; a < 2; a++) {
+                        double *row = csm + ((size_t)ft * 16 + a * 8 + gid) * CP + 2 * tig;
 #pragma unroll
-                    for (int n = 0; n < NB; n++) {
-                        if (g == 0) {
-                            row[n * 8] = acc[a][n][0];
-                            row[n * 8 + 1] = acc[a][n][1];
-                        } else {
-                            row[n * 8] += acc[a][n][0];
-                            row[n * 8 + 1] += acc[a][n][1];
+                        for (int n = 0; n < NB; n++) {
+                            if (g == 0) {
+                                row[n * 8] = acc[a][n][0];
+                                row[n * 8 + 1] = acc[a][n][1];
+                            } else {
+                                row[n * 8] += acc[a][n][0];
+                                row[n * 8 + 1] += acc[a][n][1];
+                            }
                         }
                     }
                 }
+                // all 8 warps pass here the same number of times (see below)
+                asm volatile("bar.sync 1, %0;\n" ::"r"(kgroups * ntw * 32) : "memory");
             }
-            __syncthreads();
         }
-        const int rows_out = min(mt, F - f0);
+    }
+    if (kgroups > 1) {
+        __syncthreads();
         constexpr int hz = CS / 2;
-        for (int idx = t; idx < rows_out * hz; idx += PT) {
+        for (int idx = t; idx < F * hz; idx += PT) {
             int r = idx / hz, p = idx - r * hz;
-            double2 v = *reinterpret_cast<const double2 *>(Csm + r * ZP + 2 * p);
-            double2 *g = reinterpret_cast<double2 *>(out + (size_t)(it.out + f0 + r) * CS) + p;
+            double2 v = *reinterpret_cast<const double2 *>(csm + (size_t)r * CP + 2 * p);
+            double2 *g = reinterpret_cast<double2 *>(out + (size_t)(it.out + r) * CS) + p;
             if (GATHER && accumulate) {
                 double2 o = *g;
                 v.x += o.x;
@@ -200,7 +193,6 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
             }
             *g = v;
         }
-        __syncthreads();
     }
 }
 
@@ -298,22 +290,20 @@ __global__ void hm_panel_out_kernel(const double *__restrict__ Yt, int CS, int64
     }
 }
 
-template <bool GATHER, int NB>
+template <bool GATHER, int NB, int U>
 cudaError_t launch_panel(const HmItem *items, int64_t nitems, const HmRun *runs, const double *W,
                          const double *Xt, const double *Sp, double *out, int accumulate, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
-    const int budget_words = 84 * 1024 / 8;
-    const size_t smem = (size_t)budget_words * sizeof(double);
+    const size_t smem = (size_t)8 * 16 * (NB * 8 + 8) * sizeof(double); // split-K combine buffer
     static bool configured = false; // per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(hm_panel_kernel<GATHER, NB>,
+    if (!configured && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(hm_panel_kernel<GATHER, NB, U>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    hm_panel_kernel<GATHER, NB><<<(unsigned)nitems, PT, smem, st>>>(items, runs, W, Xt, Sp, out, accumulate,
-                                                                    budget_words);
+    hm_panel_kernel<GATHER, NB, U><<<(unsigned)nitems, PT, smem, st>>>(items, runs, W, Xt, Sp, out, accumulate);
     return cudaGetLastError();
 }
 
@@ -361,9 +351,9 @@ cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, 
                                    const double *Xt, double *Pp, cudaStream_t st)
 {
     switch (CS) {
-    case 16: return launch_panel<false, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
-    case 32: return launch_panel<false, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
-    case 64: return launch_panel<false, 8>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+    case 16: return launch_panel<false, 2, 8>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+    case 32: return launch_panel<false, 4, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+    case 64: return launch_panel<false, 8, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -384,9 +374,9 @@ cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, 
                                    int accumulate, cudaStream_t st)
 {
     switch (CS) {
-    case 16: return launch_panel<true, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
-    case 32: return launch_panel<true, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
-    case 64: return launch_panel<true, 8>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+    case 16: return launch_panel<true, 2, 8>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+    case 32: return launch_panel<true, 4, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+    case 64: return launch_panel<true, 8, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
     default: return cudaErrorInvalidValue;
     }
 }

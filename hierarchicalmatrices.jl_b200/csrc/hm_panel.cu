@@ -297,7 +297,7 @@ cudaError_t launch_panel(const HmItem *items, int64_t nitems, const HmRun *runs,
     if (nitems <= 0) return cudaSuccess;
     const size_t smem = (size_t)8 * 16 * (NB * 8 + 8) * sizeof(double); // split-K combine buffer
     static bool configured = false; // per instantiation
-    if (!configured && smem > 48 * 1024) {
+    if (!configured) { // static + dynamic shared memory can exceed 48 KB
         cudaError_t e = cudaFuncSetAttribute(hm_panel_kernel<GATHER, NB, U>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -17,22 +17,7 @@
 
 namespace {
 
-constexpr int PT = 256;   // threads per CTA
-constexpr int RD = 8;     // depth of the per-warp A ring (k-steps in flight)
-constexpr int RP = 24;    // ring row pitch in doubles: = 8 (mod 16) -> conflict-free fragment reads
-constexpr int RSLOT = 4 * RP; // one k-step: 4 slab rows x 16 columns
-
-// 16-byte async copy global -> shared; bytes = 0 zero-fills the destination
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, int bytes)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait()
-{
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
+constexpr int PT = 256; // threads per CTA
 
 // D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
@@ -45,24 +30,22 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // ---------------------------------------------------------------------------
 // stage 1 / stage 3 on a panel.
 //
-// The fast dimension is cut into tiles of 16 rows (two 8-row MMA blocks); a warp owns a
-// tile and streams its 128-byte row pieces of the slab from HBM through a private
-// cp.async ring (RD k-steps = 4 KB in flight per warp, no block-wide barrier in the main
-// loop).  B fragments (the z rows, shared by all warps of the CTA) come through L1 with
-// 128-bit loads: lane (g, t) reads columns 16j+2g, 16j+2g+1 of row t and uses them as the
-// B values of MMA column blocks 2j and 2j+1, i.e. the 64 panel columns are permuted
-// inside each group of 16 so that one load feeds two MMAs and a lane ends up holding four
-// consecutive output columns.  Items with fewer than 8 tiles split the slow dimension
-// over warp groups, combined in a fixed order through shared memory.
+// The fast dimension is cut into tiles of 16 rows (two 8-row MMA blocks); a warp owns
+// a tile and streams its 128-byte row pieces of the slab straight from HBM into A
+// fragments (lane (g, t) reads W[s0 + t][f0 + g]: four 64-byte pieces per load
+// instruction, every sector fully used), U k-steps in flight.  B fragments (the z rows)
+// come through L1: all warps of the CTA read the same rows.  No shared-memory staging
+// and no barriers in the main loop.  Items with fewer than 8 tiles split the slow
+// dimension over warp groups, combined in a fixed order through shared memory.
 // ---------------------------------------------------------------------------
-template <bool GATHER, int NB>
+template <bool GATHER, int NB, int U>
 __global__ void __launch_bounds__(PT, 2)
 hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                 const double *__restrict__ W, const double *__restrict__ Xt,
                 const double *__restrict__ Sp, double *__restrict__ out, int accumulate)
 {
-    constexpr int CS = NB * 8, CP = CS + 8, NP = NB / 2;
-    extern __shared__ __align__(16) double dsm[]; // A rings [8 warps][RD][RSLOT]; later the combine buffer
+    constexpr int CS = NB * 8, CP = CS + 8;
+    extern __shared__ __align__(16) double csm[]; // [<= 8 tiles][16][CP] split-K combine buffer
     __shared__ int zrow[GATHER ? HM_SMAX : 1];
     __shared__ int rpos[GATHER ? HM_MAXRUNS + 1 : 1];
     __shared__ int rsrc[GATHER ? HM_MAXRUNS : 1];
@@ -110,24 +93,12 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         s_lo = min(S, kg * sg);
         s_hi = min(S, s_lo + sg);
     }
-    const int nk = (s_hi - s_lo + 3) >> 2; // k-steps of this warp
-    double *ring = dsm + (size_t)warp * RD * RSLOT;
-    // this lane's 16-byte piece of a k-step: slab row (lane / 8), columns 2*(lane % 8), +1 of the tile
-    const int prow = lane >> 3, pcol = (lane & 7) * 2;
-
-    auto z_row = [&](int row) -> const double * {
-        if (GATHER) {
-            int zr = zrow[row];
-            return zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
-        }
-        return Xt + (size_t)(it.zoff + row) * CS;
-    };
 
     for (int ft = warp % ntw; ft < nft && active; ft += ntw) {
         const bool two = ft * 2 + 1 < nfb;
-        const int fcol = ft * 16 + pcol;
-        const bool colok = fcol < Fp;
-        const double *__restrict__ wsrc = Wg + fcol;
+        const int col0 = ft * 16 + gid;
+        const bool c0ok = col0 < Fp, c1ok = two && (col0 + 8 < Fp);
+        const double *__restrict__ ap = Wg + col0;
 
         double acc[2][NB][2];
 #pragma unroll
@@ -135,116 +106,85 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
 #pragma unroll
             for (int n = 0; n < NB; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
 
-        auto issue = [&](int ks) {
-            const int row = s_lo + 4 * ks + prow;
-            const bool ok = colok && row < s_hi;
-            cp_async16(ring + (ks % RD) * RSLOT + prow * RP + pcol, ok ? wsrc + (size_t)row * Fp : Wg, ok ? 16 : 0);
-        };
-        auto load_b = [&](int ks, double2 (&b)[NP]) {
-            const int row = s_lo + 4 * ks + tig;
-            if (row < s_hi) {
-                const double2 *zp = reinterpret_cast<const double2 *>(z_row(row)) + gid;
+        for (int k0 = s_lo; k0 < s_hi; k0 += 4 * U) {
+            double a0[U], a1[U], b[U][NB];
 #pragma unroll
-                for (int j = 0; j < NP; j++) b[j] = __ldg(zp + 8 * j);
-            } else {
+            for (int u = 0; u < U; u++) {
+                const int row = k0 + 4 * u + tig;
+                const bool v = row < s_hi;
+                a0[u] = (v && c0ok) ? __ldcs(ap + (size_t)row * Fp) : 0.0;
+                a1[u] = (v && c1ok) ? __ldcs(ap + (size_t)row * Fp + 8) : 0.0;
+                const double *zp = Xt;
+                if (v) {
+                    if (GATHER) {
+                        int zr = zrow[row];
+                        zp = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
+                    } else {
+                        zp = Xt + (size_t)(it.zoff + row) * CS;
+                    }
+                }
 #pragma unroll
-                for (int j = 0; j < NP; j++) b[j] = make_double2(0.0, 0.0);
+                for (int n = 0; n < NB; n++) b[u][n] = v ? __ldg(zp + n * 8 + gid) : 0.0;
             }
-        };
-
-        __syncwarp();
-        for (int ks = 0; ks < RD - 1; ks++) {
-            if (ks < nk) issue(ks);
-            cp_async_commit();
-        }
-        double2 bcur[NP], bnext[NP];
-        if (nk > 0) load_b(0, bcur);
-        for (int ks = 0; ks < nk; ks++) {
-            __syncwarp(); // every lane is done reading the slot that is refilled next
-            if (ks + RD - 1 < nk) issue(ks + RD - 1);
-            cp_async_commit();
-            if (ks + 1 < nk) load_b(ks + 1, bnext);
-            cp_async_wait<RD - 1>();
-            __syncwarp(); // the other lanes' pieces of this k-step have landed too
-            const double *ap = ring + (ks % RD) * RSLOT + tig * RP + gid;
-            const double a0 = ap[0];
-            const double a1 = ap[8];
 #pragma unroll
-            for (int j = 0; j < NP; j++) {
-                dmma884(acc[0][2 * j][0], acc[0][2 * j][1], a0, bcur[j].x);
-                dmma884(acc[0][2 * j + 1][0], acc[0][2 * j + 1][1], a0, bcur[j].y);
-                if (two) {
-                    dmma884(acc[1][2 * j][0], acc[1][2 * j][1], a1, bcur[j].x);
-                    dmma884(acc[1][2 * j + 1][0], acc[1][2 * j + 1][1], a1, bcur[j].y);
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int n = 0; n < NB; n++) {
+                    dmma884(acc[0][n][0], acc[0][n][1], a0[u], b[u][n]);
+                    if (two) dmma884(acc[1][n][0], acc[1][n][1], a1[u], b[u][n]);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < NP; j++) bcur[j] = bnext[j];
         }
-        cp_async_wait<0>();
 
-        // C fragment of MMA column block 2j (2j+1) holds out columns 16j + 4t + {0,2} ({1,3})
         if (kgroups == 1) {
+            // sole owner of the tile: write the C fragments straight out
 #pragma unroll
             for (int a = 0; a < 2; a++) {
                 const int f = ft * 16 + a * 8 + gid;
                 if (f < F && (a == 0 || two)) {
-                    double2 *g = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + 2 * tig;
+                    double2 *g = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + tig;
 #pragma unroll
-                    for (int j = 0; j < NP; j++) {
-                        double2 v0 = make_double2(acc[a][2 * j][0], acc[a][2 * j + 1][0]);
-                        double2 v1 = make_double2(acc[a][2 * j][1], acc[a][2 * j + 1][1]);
+                    for (int n = 0; n < NB; n++) {
+                        double2 v = make_double2(acc[a][n][0], acc[a][n][1]);
                         if (GATHER && accumulate) {
-                            double2 o0 = g[8 * j], o1 = g[8 * j + 1];
-                            v0.x += o0.x;
-                            v0.y += o0.y;
-                            v1.x += o1.x;
-                            v1.y += o1.y;
+                            double2 o = g[n * 4];
+                            v.x += o.x;
+                            v.y += o.y;
                         }
-                        g[8 * j] = v0;
-                        g[8 * j + 1] = v1;
+                        g[n * 4] = v;
                     }
                 }
             }
         } else {
-            // nft < 8: every active warp owns exactly one tile and runs this body once.
-            // The combine buffer [tile rows][CP] aliases the A rings: wait until all
-            // active warps have drained theirs, then add the k-groups in a fixed order.
-            const int nact = kgroups * ntw * 32;
-            asm volatile("bar.sync 1, %0;\n" ::"r"(nact) : "memory");
+            // keep for the combine below (nft < 8: exactly one tile per warp)
             for (int g = 0; g < kgroups; g++) {
                 if (kg == g) {
 #pragma unroll
                     for (int a = 0; a < 2; a++) {
-                        double *row = dsm + ((size_t)ft * 16 + a * 8 + gid) * CP + 4 * tig;
+                        double *row = csm + ((size_t)ft * 16 + a * 8 + gid) * CP + 2 * tig;
 #pragma unroll
-                        for (int j = 0; j < NP; j++) {
-                            double *q = row + 16 * j;
+                        for (int n = 0; n < NB; n++) {
                             if (g == 0) {
-                                q[0] = acc[a][2 * j][0];
-                                q[1] = acc[a][2 * j + 1][0];
-                                q[2] = acc[a][2 * j][1];
-                                q[3] = acc[a][2 * j + 1][1];
+                                row[n * 8] = acc[a][n][0];
+                                row[n * 8 + 1] = acc[a][n][1];
                             } else {
-                                q[0] += acc[a][2 * j][0];
-                                q[1] += acc[a][2 * j + 1][0];
-                                q[2] += acc[a][2 * j][1];
-                                q[3] += acc[a][2 * j + 1][1];
+                                row[n * 8] += acc[a][n][0];
+                                row[n * 8 + 1] += acc[a][n][1];
                             }
                         }
                     }
                 }
-                asm volatile("bar.sync 1, %0;\n" ::"r"(nact) : "memory");
+                // all 8 warps pass here the same number of times (see below)
+                asm volatile("bar.sync 1, %0;\n" ::"r"(kgroups * ntw * 32) : "memory");
             }
         }
     }
-
     if (kgroups > 1) {
         __syncthreads();
         constexpr int hz = CS / 2;
         for (int idx = t; idx < F * hz; idx += PT) {
             int r = idx / hz, p = idx - r * hz;
-            double2 v = *reinterpret_cast<const double2 *>(dsm + (size_t)r * CP + 2 * p);
+            double2 v = *reinterpret_cast<const double2 *>(csm + (size_t)r * CP + 2 * p);
             double2 *g = reinterpret_cast<double2 *>(out + (size_t)(it.out + r) * CS) + p;
             if (GATHER && accumulate) {
                 double2 o = *g;
@@ -350,22 +290,20 @@ __global__ void hm_panel_out_kernel(const double *__restrict__ Yt, int CS, int64
     }
 }
 
-template <bool GATHER, int NB>
+template <bool GATHER, int NB, int U>
 cudaError_t launch_panel(const HmItem *items, int64_t nitems, const HmRun *runs, const double *W,
                          const double *Xt, const double *Sp, double *out, int accumulate, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
-    const size_t rings = (size_t)8 * RD * RSLOT * sizeof(double);             // 48 KB
-    const size_t comb = (size_t)7 * 16 * (NB * 8 + 8) * sizeof(double);       // split-K combine buffer
-    const size_t smem = rings > comb ? rings : comb;
-    static bool configured = false; // per instantiation; static + dynamic smem exceeds 48 KB
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(hm_panel_kernel<GATHER, NB>,
+    const size_t smem = (size_t)8 * 16 * (NB * 8 + 8) * sizeof(double); // split-K combine buffer
+    static bool configured = false; // per instantiation
+    if (!configured) { // static + dynamic shared memory can exceed 48 KB
+        cudaError_t e = cudaFuncSetAttribute(hm_panel_kernel<GATHER, NB, U>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    hm_panel_kernel<GATHER, NB><<<(unsigned)nitems, PT, smem, st>>>(items, runs, W, Xt, Sp, out, accumulate);
+    hm_panel_kernel<GATHER, NB, U><<<(unsigned)nitems, PT, smem, st>>>(items, runs, W, Xt, Sp, out, accumulate);
     return cudaGetLastError();
 }
 
@@ -413,9 +351,9 @@ cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, 
                                    const double *Xt, double *Pp, cudaStream_t st)
 {
     switch (CS) {
-    case 16: return launch_panel<false, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
-    case 32: return launch_panel<false, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
-    case 64: return launch_panel<false, 8>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+    case 16: return launch_panel<false, 2, 8>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+    case 32: return launch_panel<false, 4, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+    case 64: return launch_panel<false, 8, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -436,9 +374,9 @@ cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, 
                                    int accumulate, cudaStream_t st)
 {
     switch (CS) {
-    case 16: return launch_panel<true, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
-    case 32: return launch_panel<true, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
-    case 64: return launch_panel<true, 8>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+    case 16: return launch_panel<true, 2, 8>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+    case 32: return launch_panel<true, 4, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+    case 64: return launch_panel<true, 8, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -456,7 +456,7 @@ def run_ours(args):
     sampled = None
     if y_host is not None:
         # independent spot check (examples/Kernel.jl:78 on sampled rows): dense kernel rows in long double
-        rows = np.unique(np.random.default_rng(1).integers(0, n, 48))
+        rows = np.unique(np.random.default_rng(1).integers(0, n, 48 if n <= (1 << 21) else 12))
         xl, yl, vl = px.astype(np.longdouble), py.astype(np.longdouble), v.astype(np.longdouble)
         dense = np.array([np.sum(vl / (xl[i] - yl)) for i in rows], dtype=np.float64)
         sampled = float(np.max(np.abs(y_host[rows] - dense)) / np.max(np.abs(dense)))

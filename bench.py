@@ -32,7 +32,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1 << 20, help="points per side (default 2^20)")
+    ap.add_argument("--npoints", "--size", dest="n", type=int, default=1 << 20,
+                    help="points per side (default 2^20)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="N > 1: launch every step from Python instead of one CUDA graph of the whole loop")
     ap.add_argument("--dist", default="cheb", choices=["cheb", "unif"],
                     help="cheb = examples/Kernel.jl:61-62 point sets; unif = uniform interlaced")
     ap.add_argument("--no-gather", action="store_true", help="skip the all-gather of y (N > 1)")
@@ -362,7 +365,7 @@ def run_ours(args):
         y_ready = [torch.cuda.Event() for _ in range(nbuf)]
         y_done = [torch.cuda.Event() for _ in range(nbuf)]
 
-    def bcast(k):
+    def bcast(k, main):
         b = k % nbuf
         with torch.cuda.stream(cs):
             cs.wait_event(xy_free[b])          # the matvec that last read x_bufs[b] is done
@@ -370,31 +373,32 @@ def run_ours(args):
             x_ready[b].record(cs)
 
     def run(nsteps):
+        main = torch.cuda.current_stream()
         if not dist_on:
             for _ in range(nsteps):
                 plan.matvec_device(x_bufs[0].data_ptr(), y_bufs[0].data_ptr(), accumulate=False,
-                                   stream=stream.cuda_stream)
+                                   stream=main.cuda_stream)
             return
         for b in range(nbuf):
-            xy_free[b].record(stream)
-            y_done[b].record(stream)
-        bcast(0)
+            xy_free[b].record(main)
+            y_done[b].record(main)
+        bcast(0, main)
         for k in range(nsteps):
             b = k % nbuf
-            stream.wait_event(x_ready[b])
-            stream.wait_event(y_done[b])       # the all-gather that last read y_bufs[b] is done
+            main.wait_event(x_ready[b])
+            main.wait_event(y_done[b])         # the all-gather that last read y_bufs[b] is done
             plan.matvec_device(x_bufs[b].data_ptr(), y_bufs[b].data_ptr(), accumulate=False,
-                               stream=stream.cuda_stream)
-            xy_free[b].record(stream)
-            y_ready[b].record(stream)
+                               stream=main.cuda_stream)
+            xy_free[b].record(main)
+            y_ready[b].record(main)
             if k + 1 < nsteps:
-                bcast(k + 1)
+                bcast(k + 1, main)
             with torch.cuda.stream(cs):
                 if gather:
                     cs.wait_event(y_ready[b])
                     dist.all_gather(y_views[b], y_views[b][rank])  # uneven slices, in place
                 y_done[b].record(cs)
-        stream.wait_stream(cs)
+        main.wait_stream(cs)
 
     def barrier():
         if dist_on:
@@ -406,14 +410,34 @@ def run_ours(args):
         sampler.start()
     run(max(args.warmup, 3))
     barrier()
-    plan.timing_begin(args.steps)
+    use_graph = dist_on and not args.no_graph
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t_wall0 = time.time()
-    e0.record(stream)
-    run(args.steps)
-    e1.record(stream)
-    barrier()
+    if use_graph:
+        # the whole K-step pipeline (our kernels + the NCCL collectives, two streams) as ONE
+        # CUDA graph: at 0.3 ms of GPU work per step the Python/NCCL launch path is the bottleneck
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run(args.steps)
+        barrier()
+        graph.replay()                          # untimed replay (graph upload, NCCL warm-up)
+        barrier()
+        t_wall0 = time.time()
+        e0.record(stream)
+        graph.replay()
+        e1.record(stream)
+        barrier()
+        # per-stage kernel times for the roofline: the same steps launched eagerly
+        plan.timing_begin(args.steps)
+        run(args.steps)
+        barrier()
+    else:
+        plan.timing_begin(args.steps)
+        barrier()
+        t_wall0 = time.time()
+        e0.record(stream)
+        run(args.steps)
+        e1.record(stream)
+        barrier()
     y_dev = y_bufs[(args.steps - 1) % nbuf]
     ms = e0.elapsed_time(e1)
     stage_ms, ncalls = plan.timing_end()
@@ -472,7 +496,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(n, args.dist), "n": n, "dist": args.dist,
                        "partition": f"block-row x{world}" if world > 1 else "single GPU",
-                       "collectives": ("NCCL broadcast(x) + all-gather(y) per step, pipelined on a second stream" if gather else
+                       "collectives": (("NCCL broadcast(x) + all-gather(y) per step, pipelined on a second stream"
+                                        + (", whole loop replayed as one CUDA graph" if use_graph else "")) if gather else
                                        "NCCL broadcast(x) per step" if dist_on else "none"),
                        "l2": "inputs larger than L2 (%.1f GB streamed per step per GPU)" % (st["stored_bytes"] / 1e9),
                        "assembly_s": round(t_asm, 3)},

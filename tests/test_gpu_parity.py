@@ -397,3 +397,22 @@ def test_matmat_row_parts(hm, O):
         Kp.plan().matmat(X, Y, accumulate=False)
     for c_ in (0, 15):
         assert relinf(Y[:, c_], Kref.matvec(np.ascontiguousarray(X[:, c_]))) <= TOL
+
+
+def test_pinned_output_zero_copy(hm, O):
+    """hm_matvec writes a pinned (page-locked) y directly from stage 3; result and
+    accumulate semantics are those of the staged path."""
+    import torch
+    N = 4096
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0)
+    plan = K.plan()
+    v = _vec(N)
+    ref = np.zeros(N)
+    plan.matvec(v, ref, accumulate=False)
+    yp = torch.zeros(N, dtype=torch.float64).pin_memory().numpy()
+    xp = torch.from_numpy(v.copy()).pin_memory().numpy()
+    plan.matvec(xp, yp, accumulate=False)
+    assert np.array_equal(yp, ref)
+    plan.matvec(xp, yp, accumulate=True)
+    assert relinf(yp, 2 * ref) <= 1e-15

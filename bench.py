@@ -358,7 +358,9 @@ def run_ours(args):
     if dist_on:
         cuts = [None] * world
         dist.all_gather_object(cuts, (r0, r1))
-        y_views = [[yb[a:b] for a, b in cuts] for yb in y_bufs]
+        maxrows = max(b - a for a, b in cuts)
+        pad = torch.zeros(maxrows, dtype=torch.float64, device=dev)
+        gathered = torch.zeros(world * maxrows, dtype=torch.float64, device=dev)
         cs = torch.cuda.Stream(device=dev)
         x_ready = [torch.cuda.Event() for _ in range(nbuf)]
         xy_free = [torch.cuda.Event() for _ in range(nbuf)]
@@ -396,7 +398,12 @@ def run_ours(args):
             with torch.cuda.stream(cs):
                 if gather:
                     cs.wait_event(y_ready[b])
-                    dist.all_gather(y_views[b], y_views[b][rank])  # uneven slices, in place
+                    # row parts are balanced by bytes, not rows: gather padded slices
+                    pad[: r1 - r0].copy_(y_bufs[b][r0:r1])
+                    dist.all_gather_into_tensor(gathered, pad)
+                    for q, (qa, qb) in enumerate(cuts):
+                        if q != rank:
+                            y_bufs[b][qa:qb].copy_(gathered[q * maxrows: q * maxrows + (qb - qa)])
                 y_done[b].record(cs)
         main.wait_stream(cs)
 

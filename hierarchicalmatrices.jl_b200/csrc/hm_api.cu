@@ -741,23 +741,6 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
             HM_CUDA(cudaMemcpyAsync(p->dx.p, p->hx, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
         }
     }
-    // When the caller's y is pinned (page-locked, device-mapped) host memory with unit
-    // stride, stage 3 writes it directly over PCIe while it runs (zero-copy) instead of a
-    // device buffer followed by a D2H copy.
-    double *ymapped = nullptr;
-    if (nr > 0 && incy == 1) {
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, y) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-            attr.devicePointer != nullptr)
-            ymapped = static_cast<double *>(attr.devicePointer);
-        else
-            cudaGetLastError();
-    }
-    if (ymapped) {
-        if (int32_t rc = hm_matvec_device(p, p->dx.p, ymapped, accumulate, st)) return rc;
-        HM_CUDA(cudaStreamSynchronize(st));
-        return HM_OK;
-    }
     // y (owned rows) -> device when accumulating
     if (nr > 0 && accumulate) {
         if (incy == 1) {

@@ -399,9 +399,8 @@ def test_matmat_row_parts(hm, O):
         assert relinf(Y[:, c_], Kref.matvec(np.ascontiguousarray(X[:, c_]))) <= TOL
 
 
-def test_pinned_output_zero_copy(hm, O):
-    """hm_matvec writes a pinned (page-locked) y directly from stage 3; result and
-    accumulate semantics are those of the staged path."""
+def test_pinned_host_buffers(hm, O):
+    """hm_matvec with pinned (page-locked) host vectors, as bench.py's e2e leg uses them."""
     import torch
     N = 4096
     x, y, (a, b, c, d) = O.example_points(N, "cheb")

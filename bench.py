@@ -531,8 +531,16 @@ def run_ours(args):
             line["parity_relinf_vs_oracle"] = parity
         print(json.dumps(line), flush=True)
     if dist_on:
+        # Tearing NCCL down while a captured graph still references its streams can hang:
+        # release the graph, make sure every rank is done, then leave without the
+        # communicator destructor.
+        if use_graph:
+            graph.reset()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -287,7 +287,8 @@ struct hm_plan {
     DevBuf<HmItem> items1, items3;
     DevBuf<HmRun> runs;
     DevBuf<HmCoreBlock> cores;
-    DevBuf<int32_t> plist;
+    DevBuf<int32_t> plist, bigcores; // bigcores: leaves with more than HM_CORE_BIG partial sums
+    int64_t nbig = 0;
     // host-pointer path
     cudaStream_t stream = nullptr;
     DevBuf<double> dx, dy;
@@ -336,6 +337,13 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
     HM_CUDA(P->runs.upload(L.runs, st));
     HM_CUDA(P->cores.upload(L.cores, st));
     HM_CUDA(P->plist.upload(L.plist, st));
+    {
+        std::vector<int32_t> big;
+        for (size_t c = 0; c < L.cores.size(); c++)
+            if (L.cores[c].npl > HM_CORE_BIG) big.push_back((int32_t)c);
+        P->nbig = (int64_t)big.size();
+        HM_CUDA(P->bigcores.upload(big, st));
+    }
     {
         // temporary tables for the fill kernels
         DevBuf<HmLeaf> dleaves;
@@ -606,6 +614,7 @@ int32_t hm_plan_launches_per_matvec(const hm_plan *p)
     int n = 0;
     if (!p->L.items1.empty()) n++;
     if (!p->L.cores.empty()) n++;
+    if (p->nbig > 0) n++;
     for (size_t r = 0; r + 1 < p->L.round_begin.size(); r++)
         if (p->L.round_begin[r + 1] > p->L.round_begin[r]) n++;
     return n;
@@ -706,6 +715,8 @@ int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accum
     if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
     HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
                              p->svec.p, std::max(L.max_r, 1), st));
+    HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
+                                 p->svec.p, std::max(L.max_r, 1), st));
     if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
     for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
         int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];

@@ -213,6 +213,7 @@ hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (b >= nblocks) return;
     const HmCoreBlock cb = blocks[b];
+    if (cb.npl > HM_CORE_BIG) return; // long partial lists: hm_core_big_kernel
     const int32_t *pl = plist + cb.pl0;
     const double *c = core + cb.core;
     if (cb.kind == HM_LEAF_BARY2D && cb.ru == 20 && cb.rv == 20) {
@@ -239,6 +240,52 @@ hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
         for (int k = lane; k < cb.ru; k += 32) svec[cb.soff + k] = tbuf[k] * c[k];
     } else {
         for (int k = lane; k < cb.ru; k += 32) {
+            double a = 0.0;
+            for (int l = 0; l < cb.rv; l++) a = fma(c[k + (size_t)l * cb.ru], tbuf[l], a);
+            svec[cb.soff + k] = a;
+        }
+    }
+}
+
+// Leaves with more than HM_CORE_BIG stage-1 partial sums (n >= 32 * 4096 columns): one
+// CTA per leaf; warp w adds partials w, w+8, ... and the eight warp sums are combined in
+// warp order, so the result does not depend on timing.
+__global__ void __launch_bounds__(256)
+hm_core_big_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__restrict__ big,
+                   const int32_t *__restrict__ plist, const double *__restrict__ partial,
+                   const double *__restrict__ core, double *__restrict__ svec, int max_r)
+{
+    extern __shared__ double sm[]; // [8][max_r] warp sums, then [max_r] t
+    const HmCoreBlock cb = blocks[big[blockIdx.x]];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int32_t *pl = plist + cb.pl0;
+    for (int k = lane; k < cb.rv; k += 32) {
+        double t = 0.0;
+        int i = w;
+        for (; i + 24 < cb.npl; i += 32) {
+            double p0 = partial[pl[i] + k], p1 = partial[pl[i + 8] + k];
+            double p2 = partial[pl[i + 16] + k], p3 = partial[pl[i + 24] + k];
+            t += p0;
+            t += p1;
+            t += p2;
+            t += p3;
+        }
+        for (; i < cb.npl; i += 8) t += partial[pl[i] + k];
+        sm[w * max_r + k] = t;
+    }
+    __syncthreads();
+    double *tbuf = sm + 8 * max_r;
+    for (int k = threadIdx.x; k < cb.rv; k += blockDim.x) {
+        double t = 0.0;
+        for (int g = 0; g < 8; g++) t += sm[g * max_r + k];
+        tbuf[k] = t;
+    }
+    __syncthreads();
+    const double *c = core + cb.core;
+    if (cb.kind == HM_LEAF_LOWRANK) {
+        for (int k = threadIdx.x; k < cb.ru; k += blockDim.x) svec[cb.soff + k] = tbuf[k] * c[k];
+    } else {
+        for (int k = threadIdx.x; k < cb.ru; k += blockDim.x) {
             double a = 0.0;
             for (int l = 0; l < cb.rv; l++) a = fma(c[k + (size_t)l * cb.ru], tbuf[l], a);
             svec[cb.soff + k] = a;
@@ -392,6 +439,26 @@ cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *
     if (nitems <= 0) return cudaSuccess;
     hm_stream_kernel<false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x, nullptr,
                                                                      partial, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_stage2_big(const HmCoreBlock *blocks, const int32_t *big, int64_t nbig,
+                                 const int32_t *plist, const double *partial, const double *core,
+                                 double *svec, int max_r, cudaStream_t st)
+{
+    if (nbig <= 0) return cudaSuccess;
+    size_t smem = (size_t)9 * max_r * sizeof(double);
+    if (smem > 48 * 1024) {
+        static size_t configured = 0;
+        if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(hm_core_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+    }
+    hm_core_big_kernel<<<(unsigned)nbig, 256, smem, st>>>(blocks, big, plist, partial, core, svec, max_r);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,7 @@
 #define HM_SMAX 4096    // z staging capacity of a stream item (words)
 #define HM_MAXRUNS 256  // run-table capacity of a stage-3 item
 #define HM_RMAX_ASM 32  // max interpolation rank of on-device assembly
+#define HM_CORE_BIG 32  // stage 2: leaves with more partial sums than this get a whole CTA
 
 // Chebyshev nodes / barycentric weights of the reference's BarycentricPoly2D
 // (src/BarycentricMatrix.jl:147-156), computed once on the host.
@@ -24,6 +25,9 @@ cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *
 cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
                              const double *partial, const double *core, double *svec, int max_r,
                              cudaStream_t st);
+cudaError_t hm_launch_stage2_big(const HmCoreBlock *blocks, const int32_t *big, int64_t nbig,
+                                 const int32_t *plist, const double *partial, const double *core,
+                                 double *svec, int max_r, cudaStream_t st);
 // stage 3: y[item.out + f] (+)= sum_s U-slab[s][f] * z[s],  z gathered from x and s
 cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *runs,
                              const double *ustream, const double *x, const double *svec, double *y,

@@ -13,6 +13,8 @@
 //   Xt[j][c]  transposed copy of the user's X       Pp[p][c]  stage-1 partial sums
 //   Sp[k][c]  stage-2 results                        Yt[i][c]  stage-3 results
 // so that the z rows an item needs are contiguous CS*8-byte pieces (cp.async friendly).
+#include <cstdlib>
+
 #include "hm_kernels.cuh"
 
 namespace {
@@ -197,6 +199,270 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
 }
 
 // ---------------------------------------------------------------------------
+// stage 1 / stage 3 on a panel, warp-specialised bulk-copy pipeline (the default).
+//
+// Warp 8 is the producer: per chunk of KC slab rows it issues one cp.async.bulk (TMA 1-D,
+// SASS UBLKCP) per W row piece and per z row into padded shared-memory rows and lets an
+// mbarrier count the bytes.  Warps 0-7 consume: fragments by LDS (row pitches = 8 mod 16
+// doubles, conflict-free), FP64 MMAs, one mbarrier arrive per warp to hand the stage
+// back.  TS stages keep both operands >= TS-1 chunks ahead of the math, so neither HBM nor
+// L2 latency is exposed, and there is no block-wide barrier in the main loop.
+// ---------------------------------------------------------------------------
+constexpr int TS = 3;             // pipeline stages
+constexpr int TSTAGE = 2304;      // doubles per stage (18 KB): KC rows of W (pitch WP) + of z (pitch ZP)
+constexpr int TMT = 128;          // fast-dimension rows per pass
+constexpr int TCROWS = 64;        // rows of the split-K combine buffer (split-K only when mt <= 64)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// geometry of one pass over rows [f0, f0 + mt) of the fast dimension
+struct PassGeom {
+    int mt, WP, KC, nchunks;
+};
+template <int ZP> __device__ __forceinline__ PassGeom pass_geom(int Fp, int f0, int S)
+{
+    PassGeom g;
+    g.mt = min(TMT, Fp - f0);
+    g.WP = ((g.mt + 15) & ~15) + 8; // = 8 (mod 16): conflict-free fragment reads
+    g.KC = min(32, (TSTAGE / (g.WP + ZP)) & ~3);
+    g.nchunks = (S + g.KC - 1) / g.KC;
+    return g;
+}
+
+template <bool GATHER, int NB>
+__global__ void __launch_bounds__(288, 2)
+hm_panel_tma_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
+                    const double *__restrict__ W, const double *__restrict__ Xt,
+                    const double *__restrict__ Sp, double *__restrict__ out, int accumulate)
+{
+    constexpr int CS = NB * 8, ZP = CS + 8;
+    extern __shared__ __align__(128) double dsm[]; // [TS][TSTAGE] stages, then [TCROWS][ZP] combine buffer
+    __shared__ __align__(8) uint64_t full[TS], empty[TS];
+    __shared__ int rpos[GATHER ? HM_MAXRUNS + 1 : 1];
+    __shared__ int rsrc[GATHER ? HM_MAXRUNS : 1];
+
+    const HmItem it = items[blockIdx.x];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int S = it.S, F = it.F, Fp = it.Fp;
+
+    if (t == 0) {
+        for (int i = 0; i < TS; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (GATHER) {
+        for (int r = t; r < it.nrun; r += blockDim.x) {
+            HmRun rr = runs[it.run0 + r];
+            rpos[r] = rr.pos;
+            rsrc[r] = rr.src;
+        }
+        if (t == 0) rpos[it.nrun] = S;
+    }
+    __syncthreads();
+
+    const double *__restrict__ Wg = W + it.slab;
+    const int npass = (Fp + TMT - 1) / TMT;
+
+    if (warp == 8) {
+        // ------------------------------ producer ------------------------------
+        int q = 0; // running chunk counter across passes -> stage index and mbarrier phase
+        for (int pass = 0; pass < npass; pass++) {
+            const int f0 = pass * TMT;
+            const PassGeom g = pass_geom<ZP>(Fp, f0, S);
+            for (int ch = 0; ch < g.nchunks; ch++, q++) {
+                const int st = q % TS;
+                if (q >= TS) mbar_wait(&empty[st], ((q / TS) - 1) & 1);
+                double *Wsm = dsm + (size_t)st * TSTAGE;
+                double *Zsm = Wsm + g.KC * g.WP;
+                const int s0 = ch * g.KC, rows = min(g.KC, S - s0);
+                if (lane == 0) mbar_arrive_expect_tx(&full[st], (unsigned)(rows * (g.mt + CS) * 8));
+                __syncwarp();
+                if (lane < rows) {
+                    const int row = s0 + lane;
+                    bulk_g2s(Wsm + lane * g.WP, Wg + (size_t)row * Fp + f0, (unsigned)(g.mt * 8), &full[st]);
+                    const double *zp;
+                    if (GATHER) {
+                        int lo = 0, hi = it.nrun; // rpos[lo] <= row < rpos[hi]
+                        while (hi - lo > 1) {
+                            int mid = (lo + hi) >> 1;
+                            if (rpos[mid] <= row)
+                                lo = mid;
+                            else
+                                hi = mid;
+                        }
+                        const int src = rsrc[lo], off = row - rpos[lo];
+                        zp = src >= 0 ? Xt + (size_t)(src + off) * CS : Sp + (size_t)((~src) + off) * CS;
+                    } else {
+                        zp = Xt + (size_t)(it.zoff + row) * CS;
+                    }
+                    bulk_g2s(Zsm + lane * ZP, zp, (unsigned)(CS * 8), &full[st]);
+                }
+            }
+        }
+        return;
+    }
+
+    // -------------------------------- consumers --------------------------------
+    int q = 0;
+    for (int pass = 0; pass < npass; pass++) {
+        const int f0 = pass * TMT;
+        const PassGeom g = pass_geom<ZP>(Fp, f0, S);
+        const int nfb = (g.mt + 7) >> 3;
+        const int fwarps = (nfb + 1) >> 1;
+        const int kgroups = 8 / fwarps; // > 1 only when mt <= 64
+        const int fw = warp % fwarps, kg = warp / fwarps;
+        const bool active = kg < kgroups;
+        const int fb0 = fw * 2;
+        const bool two = fb0 + 1 < nfb;
+
+        double acc[2][NB][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int n = 0; n < NB; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
+
+        for (int ch = 0; ch < g.nchunks; ch++, q++) {
+            const int st = q % TS;
+            mbar_wait(&full[st], (q / TS) & 1);
+            if (active) {
+                const double *Wsm = dsm + (size_t)st * TSTAGE;
+                const double *Zsm = Wsm + g.KC * g.WP;
+                const int rows = min(g.KC, S - ch * g.KC);
+                const double *ap = Wsm + tig * g.WP + fb0 * 8 + gid;
+                const double *bp = Zsm + tig * ZP + gid;
+                for (int ks = kg; ks * 4 < rows; ks += kgroups) {
+                    const bool v = ks * 4 + tig < rows; // rows past the end of the slab hold stale data
+                    const double a0 = v ? ap[ks * 4 * g.WP] : 0.0;
+                    const double a1 = (v && two) ? ap[ks * 4 * g.WP + 8] : 0.0;
+#pragma unroll
+                    for (int n = 0; n < NB; n++) {
+                        const double b = v ? bp[ks * 4 * ZP + n * 8] : 0.0;
+                        dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+                        if (two) dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+
+        if (kgroups == 1) {
+            // sole owner of its rows: C fragments straight to global memory
+            if (active) {
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const int f = f0 + (fb0 + a) * 8 + gid;
+                    if (f < F && (a == 0 || two)) {
+                        double2 *gp = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + tig;
+#pragma unroll
+                        for (int n = 0; n < NB; n++) {
+                            double2 v = make_double2(acc[a][n][0], acc[a][n][1]);
+                            if (GATHER && accumulate) {
+                                double2 o = gp[n * 4];
+                                v.x += o.x;
+                                v.y += o.y;
+                            }
+                            gp[n * 4] = v;
+                        }
+                    }
+                }
+            }
+        } else {
+            // combine the split-K groups in a fixed order (consumer-only named barrier).  The
+            // buffer lives behind the pipeline stages: the producer may already be filling
+            // stages for the next pass.
+            double *Csm = dsm + (size_t)TS * TSTAGE;
+            for (int gq = 0; gq < kgroups; gq++) {
+                if (active && kg == gq) {
+#pragma unroll
+                    for (int a = 0; a < 2; a++) {
+                        if (a == 1 && !two) break;
+                        double *row = Csm + ((fb0 + a) * 8 + gid) * ZP + 2 * tig;
+#pragma unroll
+                        for (int n = 0; n < NB; n++) {
+                            if (gq == 0) {
+                                row[n * 8] = acc[a][n][0];
+                                row[n * 8 + 1] = acc[a][n][1];
+                            } else {
+                                row[n * 8] += acc[a][n][0];
+                                row[n * 8 + 1] += acc[a][n][1];
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            }
+            const int rows_out = min(g.mt, F - f0);
+            constexpr int hz = CS / 2;
+            for (int idx = t; idx < rows_out * hz; idx += 256) {
+                int r = idx / hz, p = idx - r * hz;
+                double2 v = *reinterpret_cast<const double2 *>(Csm + r * ZP + 2 * p);
+                double2 *gp = reinterpret_cast<double2 *>(out + (size_t)(it.out + f0 + r) * CS) + p;
+                if (GATHER && accumulate) {
+                    double2 o = *gp;
+                    v.x += o.x;
+                    v.y += o.y;
+                }
+                *gp = v;
+            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        }
+    }
+}
+
+template <bool GATHER, int NB>
+cudaError_t launch_panel_tma(const HmItem *items, int64_t nitems, const HmRun *runs, const double *W,
+                             const double *Xt, const double *Sp, double *out, int accumulate, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    constexpr int CS = NB * 8, ZP = CS + 8;
+    const size_t smem = ((size_t)TS * TSTAGE + (size_t)TCROWS * ZP) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(hm_panel_tma_kernel<GATHER, NB>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    hm_panel_tma_kernel<GATHER, NB><<<(unsigned)nitems, 288, smem, st>>>(items, runs, W, Xt, Sp, out, accumulate);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // stage 2 on a panel: one CTA per low-rank leaf
 //   T[k][c] = sum of the leaf's partial panels (column order); S = F T | Sigma .* T
 // ---------------------------------------------------------------------------
@@ -347,9 +613,25 @@ cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1
     return cudaGetLastError();
 }
 
+static bool use_stream_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HMB200_PANEL");
+        v = (e && e[0] == 's') ? 1 : 0; // HMB200_PANEL=stream: register-streaming kernels (no smem staging)
+    }
+    return v == 1;
+}
+
 cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, const double *vstream,
                                    const double *Xt, double *Pp, cudaStream_t st)
 {
+    if (!use_stream_variant()) switch (CS) {
+        case 16: return launch_panel_tma<false, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+        case 32: return launch_panel_tma<false, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+        case 64: return launch_panel_tma<false, 8>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+        default: return cudaErrorInvalidValue;
+        }
     switch (CS) {
     case 16: return launch_panel<false, 2, 8>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
     case 32: return launch_panel<false, 4, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
@@ -373,6 +655,12 @@ cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, 
                                    const double *ustream, const double *Xt, const double *Sp, double *Yt,
                                    int accumulate, cudaStream_t st)
 {
+    if (!use_stream_variant()) switch (CS) {
+        case 16: return launch_panel_tma<true, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+        case 32: return launch_panel_tma<true, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+        case 64: return launch_panel_tma<true, 8>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+        default: return cudaErrorInvalidValue;
+        }
     switch (CS) {
     case 16: return launch_panel<true, 2, 8>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
     case 32: return launch_panel<true, 4, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);

@@ -208,10 +208,9 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
 // back.  TS stages keep both operands >= TS-1 chunks ahead of the math, so neither HBM nor
 // L2 latency is exposed, and there is no block-wide barrier in the main loop.
 // ---------------------------------------------------------------------------
-constexpr int TS = 3;             // pipeline stages
+constexpr int TS = 5;             // pipeline stages
 constexpr int TSTAGE = 2304;      // doubles per stage (18 KB): KC rows of W (pitch WP) + of z (pitch ZP)
 constexpr int TMT = 128;          // fast-dimension rows per pass
-constexpr int TCROWS = 64;        // rows of the split-K combine buffer (split-K only when mt <= 64)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -267,7 +266,7 @@ hm_panel_tma_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ 
                     const double *__restrict__ Sp, double *__restrict__ out, int accumulate)
 {
     constexpr int CS = NB * 8, ZP = CS + 8;
-    extern __shared__ __align__(128) double dsm[]; // [TS][TSTAGE] stages, then [TCROWS][ZP] combine buffer
+    extern __shared__ __align__(128) double dsm[]; // [TS][TSTAGE] pipeline stages
     __shared__ __align__(8) uint64_t full[TS], empty[TS];
     __shared__ int rpos[GATHER ? HM_MAXRUNS + 1 : 1];
     __shared__ int rsrc[GATHER ? HM_MAXRUNS : 1];
@@ -337,16 +336,21 @@ hm_panel_tma_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ 
     }
 
     // -------------------------------- consumers --------------------------------
+    // 8 warps as fwarps (16-row tiles of the pass) x cwarps (groups of panel columns):
+    // every warp owns its outputs, so there is no split-K and no combine step.
     int q = 0;
     for (int pass = 0; pass < npass; pass++) {
         const int f0 = pass * TMT;
         const PassGeom g = pass_geom<ZP>(Fp, f0, S);
         const int nfb = (g.mt + 7) >> 3;
-        const int fwarps = (nfb + 1) >> 1;
-        const int kgroups = 8 / fwarps; // > 1 only when mt <= 64
-        const int fw = warp % fwarps, kg = warp / fwarps;
-        const bool active = kg < kgroups;
+        const int ntile = (nfb + 1) >> 1;                                  // 1..8 tiles of 16 rows
+        const int fwarps = ntile > 4 ? 8 : ntile > 2 ? 4 : ntile > 1 ? 2 : 1;
+        const int cwarps = 8 / fwarps;                                     // 1, 2, 4, 8
+        const int nbw = (NB + cwarps - 1) / cwarps;                        // MMA column blocks per warp
+        const int fw = warp % fwarps, cw = warp / fwarps;
+        const int n0 = cw * nbw;                                           // first column block of this warp
         const int fb0 = fw * 2;
+        const bool active = fb0 < nfb && n0 < NB;
         const bool two = fb0 + 1 < nfb;
 
         double acc[2][NB][2];
@@ -363,16 +367,18 @@ hm_panel_tma_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ 
                 const double *Zsm = Wsm + g.KC * g.WP;
                 const int rows = min(g.KC, S - ch * g.KC);
                 const double *ap = Wsm + tig * g.WP + fb0 * 8 + gid;
-                const double *bp = Zsm + tig * ZP + gid;
-                for (int ks = kg; ks * 4 < rows; ks += kgroups) {
+                const double *bp = Zsm + tig * ZP + n0 * 8 + gid;
+                for (int ks = 0; ks * 4 < rows; ks++) {
                     const bool v = ks * 4 + tig < rows; // rows past the end of the slab hold stale data
                     const double a0 = v ? ap[ks * 4 * g.WP] : 0.0;
                     const double a1 = (v && two) ? ap[ks * 4 * g.WP + 8] : 0.0;
 #pragma unroll
                     for (int n = 0; n < NB; n++) {
-                        const double b = v ? bp[ks * 4 * ZP + n * 8] : 0.0;
-                        dmma884(acc[0][n][0], acc[0][n][1], a0, b);
-                        if (two) dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+                        if (n < nbw && n0 + n < NB) {
+                            const double b = v ? bp[ks * 4 * ZP + n * 8] : 0.0;
+                            dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+                            if (two) dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+                        }
                     }
                 }
             }
@@ -380,16 +386,15 @@ hm_panel_tma_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ 
             if (lane == 0) mbar_arrive(&empty[st]);
         }
 
-        if (kgroups == 1) {
-            // sole owner of its rows: C fragments straight to global memory
-            if (active) {
+        if (active) {
 #pragma unroll
-                for (int a = 0; a < 2; a++) {
-                    const int f = f0 + (fb0 + a) * 8 + gid;
-                    if (f < F && (a == 0 || two)) {
-                        double2 *gp = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + tig;
+            for (int a = 0; a < 2; a++) {
+                const int f = f0 + (fb0 + a) * 8 + gid;
+                if (f < F && (a == 0 || two)) {
+                    double2 *gp = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + n0 * 4 + tig;
 #pragma unroll
-                        for (int n = 0; n < NB; n++) {
+                    for (int n = 0; n < NB; n++) {
+                        if (n < nbw && n0 + n < NB) {
                             double2 v = make_double2(acc[a][n][0], acc[a][n][1]);
                             if (GATHER && accumulate) {
                                 double2 o = gp[n * 4];
@@ -401,45 +406,6 @@ hm_panel_tma_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ 
                     }
                 }
             }
-        } else {
-            // combine the split-K groups in a fixed order (consumer-only named barrier).  The
-            // buffer lives behind the pipeline stages: the producer may already be filling
-            // stages for the next pass.
-            double *Csm = dsm + (size_t)TS * TSTAGE;
-            for (int gq = 0; gq < kgroups; gq++) {
-                if (active && kg == gq) {
-#pragma unroll
-                    for (int a = 0; a < 2; a++) {
-                        if (a == 1 && !two) break;
-                        double *row = Csm + ((fb0 + a) * 8 + gid) * ZP + 2 * tig;
-#pragma unroll
-                        for (int n = 0; n < NB; n++) {
-                            if (gq == 0) {
-                                row[n * 8] = acc[a][n][0];
-                                row[n * 8 + 1] = acc[a][n][1];
-                            } else {
-                                row[n * 8] += acc[a][n][0];
-                                row[n * 8 + 1] += acc[a][n][1];
-                            }
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
-            }
-            const int rows_out = min(g.mt, F - f0);
-            constexpr int hz = CS / 2;
-            for (int idx = t; idx < rows_out * hz; idx += 256) {
-                int r = idx / hz, p = idx - r * hz;
-                double2 v = *reinterpret_cast<const double2 *>(Csm + r * ZP + 2 * p);
-                double2 *gp = reinterpret_cast<double2 *>(out + (size_t)(it.out + f0 + r) * CS) + p;
-                if (GATHER && accumulate) {
-                    double2 o = *gp;
-                    v.x += o.x;
-                    v.y += o.y;
-                }
-                *gp = v;
-            }
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");
         }
     }
 }
@@ -449,8 +415,7 @@ cudaError_t launch_panel_tma(const HmItem *items, int64_t nitems, const HmRun *r
                              const double *Xt, const double *Sp, double *out, int accumulate, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
-    constexpr int CS = NB * 8, ZP = CS + 8;
-    const size_t smem = ((size_t)TS * TSTAGE + (size_t)TCROWS * ZP) * sizeof(double);
+    const size_t smem = (size_t)TS * TSTAGE * sizeof(double);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(hm_panel_tma_kernel<GATHER, NB>,

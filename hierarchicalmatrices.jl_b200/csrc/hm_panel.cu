@@ -199,7 +199,7 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
 }
 
 // ---------------------------------------------------------------------------
-// stage 1 / stage 3 on a panel, warp-specialised bulk-copy pipeline (the default).
+// stage 1 / stage 3 on a panel, warp-specialised bulk-copy pipeline (HMB200_PANEL=tma).
 //
 // Warp 8 is the producer: per chunk of KC slab rows it issues one cp.async.bulk (TMA 1-D,
 // SASS UBLKCP) per W row piece and per z row into padded shared-memory rows and lets an
@@ -578,12 +578,17 @@ cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1
     return cudaGetLastError();
 }
 
+// Two implementations of the panel kernels are kept:
+//   stream (default)  hm_panel_kernel: A fragments straight from HBM into registers, B through L1
+//   tma               hm_panel_tma_kernel: warp-specialised cp.async.bulk + mbarrier pipeline
+// Measured on one B200 at N = 2^20 (ms per product, 16 / 64 right-hand sides): stream 5.2 / 15.0,
+// tma 11.4 / 16.6.  HMB200_PANEL=tma selects the second one.
 static bool use_stream_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("HMB200_PANEL");
-        v = (e && e[0] == 's') ? 1 : 0; // HMB200_PANEL=stream: register-streaming kernels (no smem staging)
+        v = (e && e[0] == 't') ? 0 : 1;
     }
     return v == 1;
 }

@@ -76,6 +76,7 @@ SIGNATURES = {
     "hm_matvec_device": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "hm_matmat": (_i32, [_vp, _dp, _i64, _dp, _i64, _i64, _i32]),
     "hm_matmat_device": (_i32, [_vp, _vp, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "hm_plan_scale": (_i32, [_vp, _dp, _i64, _i32]),
     "hm_plan_timing_begin": (_i32, [_vp, _i32]),
     "hm_plan_timing_end": (_i32, [_vp, _dp, C.POINTER(_i64)]),
     "hm_plan_launches_per_matvec": (_i32, [_vp]),

@@ -36,7 +36,7 @@ __all__ = [
     "BLOCKRANK", "BLOCKSIZE", "Block", "LowRankMatrix", "BarycentricMatrix2D", "Matrix",
     "hierarchical", "HierarchicalMatrix", "KernelMatrix", "blocksize", "size", "mul_",
     "cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel", "Plan", "flatten",
-    "chebyshevpoints", "HmError",
+    "chebyshevpoints", "HmError", "rmul_", "lmul_", "scale_",
 ]
 
 Matrix = np.ndarray  # the dense leaf type of the reference
@@ -225,6 +225,12 @@ class Plan:
 
     def matmat_device(self, dX: int, ldx: int, dY: int, ldy: int, nrhs: int, accumulate=False, stream: int = 0):
         _lib.check(_lib.lib().hm_matmat_device(self._h, dX, ldx, dY, ldy, nrhs, 1 if accumulate else 0, stream))
+
+    # H <- H*Diagonal(b) (side 0) or Diagonal(b)*H (side 1), on the device, no re-planning
+    def scale(self, b: np.ndarray, side: int, off: int = 0):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        pb = C.cast(b.ctypes.data + off * 8, _dp)
+        _lib.check(_lib.lib().hm_plan_scale(self._h, pb, 1, side))
 
     def timing_begin(self, max_calls: int):
         _lib.check(_lib.lib().hm_plan_timing_begin(self._h, max_calls))
@@ -606,6 +612,64 @@ def blocksize(H, *a):
 
 def size(H, k=None):
     return H.size(k)
+
+
+def _scale_host(H, b, off, side):
+    """The reference's scale! walks on the host mirror's own blocks (kept consistent with the
+    device plan): HierarchicalMatrix.jl:54-108, leaf rules algebra.jl:280-315."""
+    p = 0
+    outer, inner = (range(H.N), range(H.M)) if side == 0 else (range(H.M), range(H.N))
+    for o in outer:
+        for i in inner:
+            m, n = (i, o) if side == 0 else (o, i)
+            A = H._block(m, n)
+            if A is None:
+                continue
+            if isinstance(A, _HierarchicalBase):
+                _scale_host(A, b, off + p, side)
+            elif isinstance(A, np.ndarray):
+                if side == 0:
+                    A *= b[off + p: off + p + A.shape[1]][None, :]
+                else:
+                    A *= b[off + p: off + p + A.shape[0]][:, None]
+            elif side == 0:
+                A.V *= b[off + p: off + p + A.V.shape[0]][:, None]
+            else:
+                A.U *= b[off + p: off + p + A.U.shape[0]][:, None]
+        p += H.blocksize(1, o + 1, 2) if side == 0 else H.blocksize(o + 1, H.N, 1)
+
+
+def scale_(a, b, start: int = 1):
+    """`scale!(H, b, jstart)`: H <- H*Diagonal(b[jstart:...]) or `scale!(b, H, istart)`:
+    H <- Diagonal(b[istart:...])*H (HierarchicalMatrix.jl:54-108), 1-based start.  The packed
+    operator on the GPU is updated in place by streaming kernels (no re-planning)."""
+    if isinstance(a, _HierarchicalBase):
+        H, vec, side = a, np.asarray(b, dtype=np.float64), 0
+    elif isinstance(b, _HierarchicalBase):
+        H, vec, side = b, np.asarray(a, dtype=np.float64), 1
+    else:
+        raise TypeError("MethodError: scale!(H, b, jstart) or scale!(b, H, istart)")
+    n = H.size(2 if side == 0 else 1)
+    if start < 1 or start - 1 + n > vec.size:
+        raise IndexError("BoundsError: b is too short")
+    assembled = getattr(H, "_assembled", None)
+    if assembled is not None:
+        assembled.scale(vec, side, start - 1)
+        return H
+    _scale_host(H, vec, start - 1, side)
+    if H._plan is not None:
+        H._plan[1].scale(vec, side, start - 1)
+    return H
+
+
+def rmul_(H, b):
+    """`rmul!(H, Diagonal(b))` -- HierarchicalMatrix.jl:15."""
+    return scale_(H, b, 1)
+
+
+def lmul_(b, H):
+    """`lmul!(Diagonal(b), H)` -- HierarchicalMatrix.jl:16."""
+    return scale_(b, H, 1)
 
 
 def _linear(a: np.ndarray, name: str) -> np.ndarray:

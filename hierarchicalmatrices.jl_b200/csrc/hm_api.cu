@@ -573,6 +573,32 @@ int32_t hm_plan_stats(const hm_plan *p, hm_stats *out)
     return HM_OK;
 }
 
+int32_t hm_plan_scale(hm_plan *p, const double *b, int64_t incb, int32_t side)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (side != 0 && side != 1) return fail(HM_ERR_INVALID, "side must be 0 (columns) or 1 (rows)");
+    if (incb == 0) return fail(HM_ERR_INVALID, "zero stride");
+    const HmLayout &L = p->L;
+    const int64_t n = side == 0 ? L.ncols : L.nrows;
+    if (n == 0) return HM_OK;
+    if (!b) return fail(HM_ERR_NULL, "b is NULL");
+    std::lock_guard<std::mutex> lock(p->mu);
+    HM_DEVICE(p->device);
+    std::vector<double> hb((size_t)n);
+    for (int64_t i = 0; i < n; i++) hb[(size_t)i] = b[i * incb];
+    DevBuf<double> db;
+    HM_CUDA(db.alloc((size_t)n));
+    cudaStream_t st = p->stream;
+    HM_CUDA(cudaMemcpyAsync(db.p, hb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (side == 1)
+        HM_CUDA(hm_launch_scale_rows(p->items3.p, (int64_t)L.items3.size(), p->ustream.p, db.p, st));
+    else
+        HM_CUDA(hm_launch_scale_cols(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->items3.p,
+                                     (int64_t)L.items3.size(), p->runs.p, p->ustream.p, db.p, st));
+    HM_CUDA(cudaStreamSynchronize(st));
+    return HM_OK;
+}
+
 int32_t hm_plan_timing_begin(hm_plan *p, int32_t max_calls)
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");

@@ -428,7 +428,68 @@ hm_fillcore_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
     }
 }
 
+// ---------------------------------------------------------------------------
+// operator updates on the packed streams: H <- H*Diagonal(b) and
+// H <- Diagonal(b)*H without re-planning.  Reference: rmul!/lmul! ->
+// scale! (/root/reference/src/HierarchicalMatrix.jl:15-16, 54-108) and its leaf methods
+// (src/algebra.jl:280-315): dense A[i,j] *= b_j | b_i, low rank V[j,:] *= b_j | U[i,:] *= b_i.
+// ---------------------------------------------------------------------------
+// every element of a stage-3 slab by its row: W[s][f] *= b[row0 + f]
+__global__ void __launch_bounds__(256)
+hm_scale_rows_kernel(const HmItem *__restrict__ items, double *__restrict__ W, const double *__restrict__ b)
+{
+    const HmItem it = items[blockIdx.x];
+    double *w = W + it.slab;
+    const int n = it.Fp * it.S;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        int f = idx % it.Fp;
+        if (f < it.F) w[idx] *= b[it.out + f];
+    }
+}
+
+// every element of a stage-1 slab by its column of the operator: W[s][f] *= b[col0 + s]
+__global__ void __launch_bounds__(256)
+hm_scale_cols_v_kernel(const HmItem *__restrict__ items, double *__restrict__ W, const double *__restrict__ b)
+{
+    const HmItem it = items[blockIdx.x];
+    double *w = W + it.slab;
+    const int n = it.Fp * it.S;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) w[idx] *= b[it.zoff + idx / it.Fp];
+}
+
+// the dense-tile columns of a stage-3 slab (runs gathered from x): W[s][f] *= b[col(s)]
+__global__ void __launch_bounds__(256)
+hm_scale_cols_dense_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
+                           double *__restrict__ W, const double *__restrict__ b)
+{
+    const HmItem it = items[blockIdx.x];
+    double *w = W + it.slab;
+    for (int r = 0; r < it.nrun; r++) {
+        const HmRun rr = runs[it.run0 + r];
+        if (rr.src < 0) continue; // low-rank columns: their V rows carry the scaling
+        const int n = rr.len * it.Fp;
+        double *wr = w + (size_t)rr.pos * it.Fp;
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) wr[idx] *= b[rr.src + idx / it.Fp];
+    }
+}
+
 } // namespace
+
+cudaError_t hm_launch_scale_rows(const HmItem *items3, int64_t n3, double *ustream, const double *b, cudaStream_t st)
+{
+    if (n3 <= 0) return cudaSuccess;
+    hm_scale_rows_kernel<<<(unsigned)n3, 256, 0, st>>>(items3, ustream, b);
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_scale_cols(const HmItem *items1, int64_t n1, double *vstream, const HmItem *items3,
+                                 int64_t n3, const HmRun *runs, double *ustream, const double *b,
+                                 cudaStream_t st)
+{
+    if (n1 > 0) hm_scale_cols_v_kernel<<<(unsigned)n1, 256, 0, st>>>(items1, vstream, b);
+    if (n3 > 0) hm_scale_cols_dense_kernel<<<(unsigned)n3, 256, 0, st>>>(items3, runs, ustream, b);
+    return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------------------
 // launch wrappers

@@ -33,6 +33,13 @@ cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *r
                              const double *ustream, const double *x, const double *svec, double *y,
                              int accumulate, cudaStream_t st);
 
+// operator updates in place: H <- Diagonal(b) H (rows) and H <- H Diagonal(b) (columns)
+cudaError_t hm_launch_scale_rows(const HmItem *items3, int64_t n3, double *ustream, const double *b,
+                                 cudaStream_t st);
+cudaError_t hm_launch_scale_cols(const HmItem *items1, int64_t n1, double *vstream, const HmItem *items3,
+                                 int64_t n3, const HmRun *runs, double *ustream, const double *b,
+                                 cudaStream_t st);
+
 // plan construction
 cudaError_t hm_launch_fill3(const HmFill *fills, int64_t nfills, const HmLeaf *leaves, double *ustream,
                             const double *px, const double *py, const HmCheb &cheb, int kernel_id,

@@ -185,6 +185,19 @@ HM_API int32_t hm_matmat(hm_plan *p, const double *X, int64_t ldx, double *Y, in
 HM_API int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, int64_t ldy,
                          int64_t nrhs, int32_t accumulate, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Operator updates on the device, no re-planning.
+ * side = 0: H <- H * Diagonal(b), b has ncols entries   (rmul!(H, b::Diagonal) ->
+ *           scale!(H, b.diag, 1), src/HierarchicalMatrix.jl:15, 54-80)
+ * side = 1: H <- Diagonal(b) * H, b has nrows entries   (lmul!(b::Diagonal, H) ->
+ *           scale!(b.diag, H, 1), src/HierarchicalMatrix.jl:16, 82-108)
+ * Leaf rule of src/algebra.jl:280-315: dense A[i,j] *= b; LowRankMatrix V[j,:] *= b_j
+ * resp. U[i,:] *= b_i (BarycentricMatrix2D likewise; the reference defines no scale!
+ * for it).  b is a host pointer with element stride incb; the 1-based jstart/istart of
+ * the reference is a pointer offset at the call site.
+ * ------------------------------------------------------------------------ */
+HM_API int32_t hm_plan_scale(hm_plan *p, const double *b, int64_t incb, int32_t side);
+
 /* Per-stage device timing (bench bookkeeping).  Between begin and end every
  * hm_matvec_device call records CUDA events around its three stages on the
  * launch stream; end synchronises and returns the summed milliseconds of

@@ -492,6 +492,56 @@ void hmo_mul(double *y, const hmo_node *h, const double *x, int64_t i0, int64_t 
 }
 
 /* ------------------------------------------------------------------ */
+/* scale!: H*Diagonal(b) and Diagonal(b)*H, in place  */
+/* ------------------------------------------------------------------ */
+
+/* scale!(H, b, jstart) -- HierarchicalMatrix.jl:54-80: n outer, m inner, the column
+ * offset q advances by blocksize(H,1,n,2); leaves by algebra.jl:280-297: dense
+ * C[i,j] = A[i,j]*b[j], LowRankMatrix: V[j,k] = b[j]*V[j,k].  BarycentricMatrix2D has
+ * no scale! in the reference; it is treated like LowRankMatrix (V rows).  j0 0-based. */
+void hmo_scale_cols(hmo_node *h, const double *b, int64_t j0)
+{
+    int64_t q = 0;
+    for (int n = 0; n < h->N; n++) {
+        for (int m = 0; m < h->M; m++) {
+            hmo_block *k = blk(h, m, n);
+            if (k->kind == HMO_NODE) {
+                hmo_scale_cols(k->child, b, j0 + q);
+            } else if (k->kind == HMO_DENSE) {
+                for (int64_t j = 0; j < k->n; j++)
+                    for (int64_t i = 0; i < k->m; i++) k->U[i + j * k->m] = k->U[i + j * k->m] * b[j0 + q + j];
+            } else if (k->kind != HMO_NONE) {
+                for (int64_t c = 0; c < k->r; c++)
+                    for (int64_t j = 0; j < k->n; j++) k->V[j + c * k->n] = k->V[j + c * k->n] * b[j0 + q + j];
+            }
+        }
+        q += hmo_blocksize(h, 0, n, 2);
+    }
+}
+
+/* scale!(b, H, istart) -- HierarchicalMatrix.jl:82-108 with algebra.jl:299-315:
+ * dense C[i,j] = A[i,j]*b[i], LowRankMatrix: U[i,k] = U[i,k]*b[i].  i0 0-based. */
+void hmo_scale_rows(const double *b, hmo_node *h, int64_t i0)
+{
+    int64_t p = 0;
+    for (int m = 0; m < h->M; m++) {
+        for (int n = 0; n < h->N; n++) {
+            hmo_block *k = blk(h, m, n);
+            if (k->kind == HMO_NODE) {
+                hmo_scale_rows(b, k->child, i0 + p);
+            } else if (k->kind == HMO_DENSE) {
+                for (int64_t j = 0; j < k->n; j++)
+                    for (int64_t i = 0; i < k->m; i++) k->U[i + j * k->m] = k->U[i + j * k->m] * b[i0 + p + i];
+            } else if (k->kind != HMO_NONE) {
+                for (int64_t c = 0; c < k->r; c++)
+                    for (int64_t i = 0; i < k->m; i++) k->U[i + c * k->m] = k->U[i + c * k->m] * b[i0 + p + i];
+            }
+        }
+        p += hmo_blocksize(h, m, h->N - 1, 1);
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* leaf enumeration (same order and the same offset rule as the walk)  */
 /* ------------------------------------------------------------------ */
 

@@ -94,6 +94,10 @@ void hmo_mul(double *y, const hmo_node *h, const double *x, int64_t i0, int64_t 
 void hmo_mul_omp(double *y, const hmo_node *h, const double *x, int64_t i0, int64_t j0,
                  int nthreads);
 
+/* ---- scale!: HierarchicalMatrix.jl:54-108, algebra.jl:280-315 (in place) ---- */
+void hmo_scale_cols(hmo_node *h, const double *b, int64_t j0); /* H <- H*Diagonal(b[j0:]) */
+void hmo_scale_rows(const double *b, hmo_node *h, int64_t i0); /* H <- Diagonal(b[i0:])*H */
+
 /* ---- assembly: KernelMatrix.jl:47-116, BarycentricMatrix.jl:147-178, 236-297 ----
  * x, y descending; (a,b), (c,d) as in the example.  Returns NULL where the
  * reference would throw. */

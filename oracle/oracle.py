@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
         "hmo_getindex": (C.c_double, [vp, _i64, _i64]),
         "hmo_mul": (None, [_dp, vp, _dp, _i64, _i64, _i64, _i64]),
         "hmo_mul_omp": (None, [_dp, vp, _dp, _i64, _i64, C.c_int]),
+        "hmo_scale_cols": (None, [vp, _dp, _i64]),
+        "hmo_scale_rows": (None, [_dp, vp, _i64]),
         "hmo_kernelmatrix": (vp, [C.c_int, _dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double]),
         "hmo_bary2d_build": (None, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _dp, _i64, _i64, _dp, _i64, _i64, _dp, _dp, _dp]),
         "hmo_count_leaves": (_i64, [vp]),
@@ -254,6 +256,17 @@ class Tree:
     def mul_omp(self, y, x, nthreads, i0=0, j0=0):
         lib().hmo_mul_omp(_p(y), self.h, _p(x), i0, j0, nthreads)
         return y
+
+    # rmul!(H, Diagonal(b)) / lmul!(Diagonal(b), H) -- HierarchicalMatrix.jl:15-16
+    def scale_cols(self, b, j0=0):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        lib().hmo_scale_cols(self.h, _p(b), j0)
+        return self
+
+    def scale_rows(self, b, i0=0):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        lib().hmo_scale_rows(_p(b), self.h, i0)
+        return self
 
     # H * x
     def matvec(self, x):

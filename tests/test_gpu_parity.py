@@ -433,3 +433,47 @@ def test_pinned_host_buffers(hm, O):
     assert np.array_equal(yp, ref)
     plan.matvec(xp, yp, accumulate=True)
     assert relinf(yp, 2 * ref) <= 1e-15
+
+
+# ------------------------------------------------------------------ rmul!/lmul!/scale! on the packed operator
+def test_scale_updates_the_device_operator(hm, O):
+    rng = np.random.default_rng(21)
+    n = 1800
+    H = random_lowrank_tree(hm, rng, n)
+    T = oracle_tree_from_mirror(O, H)
+    v = rng.standard_normal(n)
+    bc, br = rng.standard_normal(n + 3), rng.standard_normal(n + 2)
+    _ = H * v                                   # plan exists before the update: updated in place, not rebuilt
+    plan_before = H.plan()
+    hm.scale_(H, bc, 4)                         # scale!(H, b, jstart = 4): columns
+    T.scale_cols(bc, 3)
+    assert H.plan() is plan_before
+    assert relinf(H * v, T.matvec(v)) <= TOL
+    hm.scale_(br, H, 3)                         # scale!(b, H, istart = 3): rows
+    T.scale_rows(br, 2)
+    assert relinf(H * v, T.matvec(v)) <= TOL
+    H.invalidate()                              # the host mirror was kept consistent: a fresh plan agrees
+    assert relinf(H * v, T.matvec(v)) <= TOL
+    # rmul!/lmul! on a device-assembled KernelMatrix (Diagonally scaled Cauchy operator)
+    N = 3000
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0)
+    dcol, drow = rng.standard_normal(N), rng.standard_normal(N)
+    hm.rmul_(K, dcol)
+    hm.lmul_(drow, K)
+    Kref.scale_cols(dcol).scale_rows(drow)
+    w = rng.standard_normal(N)
+    assert relinf(K * w, Kref.matvec(w)) <= TOL
+    X = np.asfortranarray(rng.standard_normal((N, 16)))
+    Y = K * X
+    assert relinf(Y[:, 5], Kref.matvec(np.ascontiguousarray(X[:, 5]))) <= TOL
+    # large single blocks: several stage-3 rounds, own stage-1 items
+    H2 = hm.HierarchicalMatrix(np.float64, 1, 1)
+    A = np.asfortranarray(rng.standard_normal((300, 4500)))
+    H2[hm.Block(1), hm.Block(1)] = A.copy(order="F")
+    v2 = rng.standard_normal(4500)
+    _ = H2 * v2
+    b2 = rng.standard_normal(4500)
+    hm.rmul_(H2, b2)
+    assert relinf(H2 * v2, A @ (b2 * v2)) <= TOL

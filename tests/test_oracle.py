@@ -205,3 +205,23 @@ def test_tree_shape_matches_survey(O):
     U, F, V = O.bary2d_build(O.CAUCHY, 1.0, 0.5, -0.5, -1.0, x, 0, 50, y, 3000, 3100)
     assert np.allclose(U.sum(axis=1), 1.0, atol=1e-13) and np.allclose(V.sum(axis=1), 1.0, atol=1e-13)
     assert np.allclose(U @ F @ V.T, 1.0 / (x[:50, None] - y[None, 3000:3100]), rtol=1e-13)
+
+
+def test_scale_walks(O):
+    """scale!(H, b, jstart) / scale!(b, H, istart) (HierarchicalMatrix.jl:54-108, leaf rules
+    algebra.jl:280-315): H*Diagonal(b) and Diagonal(b)*H."""
+    rng = np.random.default_rng(8)
+    T = O.Tree.create(2, 2)
+    A11, A22 = rng.standard_normal((4, 6)), rng.standard_normal((5, 3))
+    U, S, V = rng.standard_normal((4, 2)), rng.standard_normal(2), rng.standard_normal((3, 2))
+    T.set_dense(0, 0, A11)
+    T.set_lowrank(0, 1, U, S, V)
+    T.set_dense(1, 1, A22)
+    D = np.zeros((9, 9))
+    D[:4, :6], D[:4, 6:], D[4:, 6:] = A11, (U * S) @ V.T, A22
+    bc, br = rng.standard_normal(12), rng.standard_normal(11)
+    T.scale_cols(bc, 2)
+    T.scale_rows(br, 1)
+    Dn = br[1:10, None] * D * bc[None, 2:11]
+    G = np.array([[T.getindex(i, j) for j in range(9)] for i in range(9)])
+    assert np.allclose(G, Dn, rtol=1e-14, atol=1e-14)

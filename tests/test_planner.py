@@ -226,3 +226,26 @@ def test_python_mirror_container_semantics(hm):
         hm.mul_(np.zeros(8), H, np.zeros(9))                  # y too short
     with pytest.raises(ValueError):
         hm.mul_(np.zeros((3, 9)), H, np.zeros((3, 9)))        # C-order 2-D: not Julia's linear indexing
+
+
+def test_python_mirror_scale_host_side(hm, O):
+    """scale_ / rmul_ / lmul_ keep the host mirror's blocks consistent with the reference's
+    scale! walks (no plan -> no device work)."""
+    from helpers import oracle_tree_from_mirror, random_lowrank_tree
+    rng = np.random.default_rng(9)
+    H = random_lowrank_tree(hm, rng, 400)
+    T = oracle_tree_from_mirror(O, H)
+    bc, br = rng.standard_normal(405), rng.standard_normal(401)
+    hm.scale_(H, bc, 3)
+    hm.scale_(br, H, 2)
+    T.scale_cols(bc, 2)
+    T.scale_rows(br, 1)
+    T2 = oracle_tree_from_mirror(O, H)
+    v = rng.standard_normal(400)
+    assert np.allclose(T2.matvec(v), T.matvec(v), rtol=1e-13, atol=1e-13)
+    hm.rmul_(H, bc[:400])
+    hm.lmul_(br[:400], H)
+    with pytest.raises(IndexError):
+        hm.scale_(H, bc[:100], 1)
+    with pytest.raises(TypeError):
+        hm.scale_(bc, br)

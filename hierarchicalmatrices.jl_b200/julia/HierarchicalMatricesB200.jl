@@ -179,6 +179,27 @@ HierarchicalMatrices.mul!(y::StridedVecOrMat{Float64}, H::HierarchicalMatrix{Flo
 LinearAlgebra.mul!(y::StridedVector{Float64}, H::HierarchicalMatrix{Float64}, x::StridedVector{Float64}) =
     HierarchicalMatrices.mul!(y, H, x, 1, 1, 1, 1)
 
+# rmul!(H, Diagonal(b)) / lmul!(Diagonal(b), H): src/HierarchicalMatrix.jl:15-16, 54-108.
+# The reference methods update the Julia blocks; afterwards the cached device plan (if any)
+# is updated in place by the library's streaming kernels instead of being rebuilt.
+function scale_plan!(H, b::Vector{Float64}, side::Integer)
+    haskey(PLANS, H) || return H
+    GC.@preserve b check(ccall((:hm_plan_scale, libhm), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32),
+                               PLANS[H].ptr, b, 1, side))
+    H
+end
+function LinearAlgebra.rmul!(H::HierarchicalMatrix{Float64}, b::Diagonal{Float64,Vector{Float64}})
+    HierarchicalMatrices.scale!(H, b.diag, 1)
+    scale_plan!(H, b.diag, 0)
+end
+function LinearAlgebra.lmul!(b::Diagonal{Float64,Vector{Float64}}, H::HierarchicalMatrix{Float64})
+    HierarchicalMatrices.scale!(b.diag, H, 1)
+    scale_plan!(H, b.diag, 1)
+end
+scale!(P::Plan, b::Vector{Float64}, side::Integer) =
+    (GC.@preserve b check(ccall((:hm_plan_scale, libhm), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32),
+                                P.ptr, b, 1, side)); P)
+
 # Plans built by `assemble` act as operators themselves
 Base.:*(P::Plan, v::Vector{Float64}) = begin
     st = stats(P)

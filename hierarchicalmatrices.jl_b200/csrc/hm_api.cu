@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -289,6 +290,10 @@ struct hm_plan {
     DevBuf<HmCoreBlock> cores;
     DevBuf<int32_t> plist, bigcores; // bigcores: leaves with more than HM_CORE_BIG partial sums
     int64_t nbig = 0;
+    // stage 2 fused into the tail of stage 1 (default; HMB200_FUSE_STAGE2=0 keeps the separate kernels)
+    DevBuf<int32_t> s1ent;
+    DevBuf<int> counters;
+    bool fuse = true;
     // host-pointer path
     cudaStream_t stream = nullptr;
     DevBuf<double> dx, dy;
@@ -337,6 +342,13 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
     HM_CUDA(P->runs.upload(L.runs, st));
     HM_CUDA(P->cores.upload(L.cores, st));
     HM_CUDA(P->plist.upload(L.plist, st));
+    HM_CUDA(P->s1ent.upload(L.s1ent, st));
+    HM_CUDA(P->counters.alloc(std::max<size_t>(L.cores.size(), 1)));
+    HM_CUDA(cudaMemsetAsync(P->counters.p, 0, P->counters.n * sizeof(int), st));
+    {
+        const char *e = getenv("HMB200_FUSE_STAGE2");
+        P->fuse = !(e && e[0] == '0') && (size_t)L.max_r * 8 <= HM_SMAX;
+    }
     {
         std::vector<int32_t> big;
         for (size_t c = 0; c < L.cores.size(); c++)
@@ -639,8 +651,8 @@ int32_t hm_plan_launches_per_matvec(const hm_plan *p)
     if (!p) return 0;
     int n = 0;
     if (!p->L.items1.empty()) n++;
-    if (!p->L.cores.empty()) n++;
-    if (p->nbig > 0) n++;
+    if (!p->fuse && !p->L.cores.empty()) n++;
+    if (!p->fuse && p->nbig > 0) n++;
     for (size_t r = 0; r + 1 < p->L.round_begin.size(); r++)
         if (p->L.round_begin[r + 1] > p->L.round_begin[r]) n++;
     return n;
@@ -737,12 +749,25 @@ int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accum
     const HmLayout &L = p->L;
     cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
     if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
-    HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p, st));
+    HmFuse fz;
+    if (p->fuse) {
+        fz.s1ent = p->s1ent.p;
+        fz.counters = p->counters.p;
+        fz.blocks = p->cores.p;
+        fz.plist = p->plist.p;
+        fz.core = p->core.p;
+        fz.svec = p->svec.p;
+        fz.max_r = std::max(L.max_r, 1);
+    }
+    HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p,
+                             p->fuse ? &fz : nullptr, st));
     if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
-    HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
-                             p->svec.p, std::max(L.max_r, 1), st));
-    HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
+    if (!p->fuse) {
+        HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
                                  p->svec.p, std::max(L.max_r, 1), st));
+        HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
+                                     p->svec.p, std::max(L.max_r, 1), st));
+    }
     if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
     for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
         int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];

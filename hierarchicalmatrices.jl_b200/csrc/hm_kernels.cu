@@ -26,13 +26,158 @@ __device__ __forceinline__ double2 ld_stream(const double2 *p)
 }
 
 // ---------------------------------------------------------------------------
+// stage 2: the core apply of one low-rank leaf
+//   t[k]  = sum over the leaf's stage-1 partial sums, in column order
+//   s     = Sigma .* t            (LowRankMatrix,       algebra.jl:120)
+//   s     = F * t  (l outer)      (BarycentricMatrix2D, algebra.jl:260-265)
+// Written as device functions because they run in two places: fused into the tail of
+// stage 1 (the CTA that delivers a leaf's last partial sum applies its core at once) and
+// in the stand-alone kernels (HMB200_FUSE_STAGE2=0).  Partial sums are read with ld.cg:
+// other SMs wrote them.
+// ---------------------------------------------------------------------------
+
+// one warp, at most HM_CORE_BIG partial sums; tbuf: max_r doubles of shared memory
+__device__ __noinline__ void core_apply_warp(const HmCoreBlock &cb, const int32_t *__restrict__ plist,
+                                                const double *partial, const double *__restrict__ core,
+                                                double *__restrict__ svec, double *tbuf, int lane)
+{
+    const int32_t *pl = plist + cb.pl0;
+    const double *c = core + cb.core;
+    if (cb.kind == HM_LEAF_BARY2D && cb.ru == 20 && cb.rv == 20) {
+        // the rank the assembler produces (BLOCKRANK(Float64) = 20): lane k first issues its 20
+        // loads of row k of F (independent, all in flight), then walks the partial list
+        constexpr int R = 20;
+        double f[R];
+        const bool act = lane < R;
+        if (act) {
+#pragma unroll
+            for (int l = 0; l < R; l++) f[l] = __ldcs(c + lane + l * R);
+        }
+        double t = 0.0;
+        if (act) {
+            int i = 0;
+            for (; i + 3 < cb.npl; i += 4) {
+                int o0 = pl[i], o1 = pl[i + 1], o2 = pl[i + 2], o3 = pl[i + 3];
+                double p0 = __ldcg(partial + o0 + lane), p1 = __ldcg(partial + o1 + lane);
+                double p2 = __ldcg(partial + o2 + lane), p3 = __ldcg(partial + o3 + lane);
+                t += p0;
+                t += p1;
+                t += p2;
+                t += p3;
+            }
+            for (; i < cb.npl; i++) t += __ldcg(partial + pl[i] + lane);
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int l = 0; l < R; l++) {
+            double tl = __shfl_sync(0xffffffffu, t, l);
+            a = fma(f[l], tl, a);
+        }
+        if (act) svec[cb.soff + lane] = a;
+        return;
+    }
+    for (int k = lane; k < cb.rv; k += 32) {
+        double t = 0.0;
+        int i = 0;
+        for (; i + 3 < cb.npl; i += 4) {
+            double p0 = __ldcg(partial + pl[i] + k), p1 = __ldcg(partial + pl[i + 1] + k);
+            double p2 = __ldcg(partial + pl[i + 2] + k), p3 = __ldcg(partial + pl[i + 3] + k);
+            t += p0;
+            t += p1;
+            t += p2;
+            t += p3;
+        }
+        for (; i < cb.npl; i++) t += __ldcg(partial + pl[i] + k);
+        tbuf[k] = t;
+    }
+    __syncwarp();
+    if (cb.kind == HM_LEAF_LOWRANK) {
+        for (int k = lane; k < cb.ru; k += 32) svec[cb.soff + k] = tbuf[k] * c[k];
+    } else {
+        for (int k = lane; k < cb.ru; k += 32) {
+            double a = 0.0;
+            for (int l = 0; l < cb.rv; l++) a = fma(c[k + (size_t)l * cb.ru], tbuf[l], a);
+            svec[cb.soff + k] = a;
+        }
+    }
+    __syncwarp();
+}
+
+// a whole CTA of 256 threads for a leaf with a long partial list: warp w adds partials
+// w, w+8, ..., the eight warp sums are combined in warp order.  sm: 9*max_r doubles.
+// Must be called by all threads of the CTA.
+__device__ __noinline__ void core_apply_cta(const HmCoreBlock &cb, const int32_t *__restrict__ plist,
+                                               const double *partial, const double *__restrict__ core,
+                                               double *__restrict__ svec, double *sm, int max_r, int tid)
+{
+    const int lane = tid & 31, w = tid >> 5;
+    const int32_t *pl = plist + cb.pl0;
+    for (int k = lane; k < cb.rv; k += 32) {
+        double t = 0.0;
+        int i = w;
+        for (; i + 24 < cb.npl; i += 32) {
+            double p0 = __ldcg(partial + pl[i] + k), p1 = __ldcg(partial + pl[i + 8] + k);
+            double p2 = __ldcg(partial + pl[i + 16] + k), p3 = __ldcg(partial + pl[i + 24] + k);
+            t += p0;
+            t += p1;
+            t += p2;
+            t += p3;
+        }
+        for (; i < cb.npl; i += 8) t += __ldcg(partial + pl[i] + k);
+        sm[w * max_r + k] = t;
+    }
+    __syncthreads();
+    double *tbuf = sm + 8 * max_r;
+    for (int k = tid; k < cb.rv; k += 256) {
+        double t = 0.0;
+        for (int g = 0; g < 8; g++) t += sm[g * max_r + k];
+        tbuf[k] = t;
+    }
+    __syncthreads();
+    const double *c = core + cb.core;
+    if (cb.kind == HM_LEAF_LOWRANK) {
+        for (int k = tid; k < cb.ru; k += 256) svec[cb.soff + k] = tbuf[k] * c[k];
+    } else {
+        for (int k = tid; k < cb.ru; k += 256) {
+            double a = 0.0;
+            for (int l = 0; l < cb.rv; l++) a = fma(c[k + (size_t)l * cb.ru], tbuf[l], a);
+            svec[cb.soff + k] = a;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
+               const int32_t *__restrict__ plist, const double *__restrict__ partial,
+               const double *__restrict__ core, double *__restrict__ svec, int max_r)
+{
+    extern __shared__ double tbuf_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (b >= nblocks) return;
+    const HmCoreBlock cb = blocks[b];
+    if (cb.npl > HM_CORE_BIG) return; // long partial lists: hm_core_big_kernel
+    core_apply_warp(cb, plist, partial, core, svec, tbuf_all + (size_t)wib * max_r, lane);
+}
+
+__global__ void __launch_bounds__(256)
+hm_core_big_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__restrict__ big,
+                   const int32_t *__restrict__ plist, const double *__restrict__ partial,
+                   const double *__restrict__ core, double *__restrict__ svec, int max_r)
+{
+    extern __shared__ double sm[]; // [8][max_r] warp sums, then [max_r] t
+    core_apply_cta(blocks[big[blockIdx.x]], plist, partial, core, svec, sm, max_r, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------
 // stage 1 / stage 3
 // ---------------------------------------------------------------------------
-template <bool GATHER>
+template <bool GATHER, bool FUSE>
 __global__ void __launch_bounds__(HM_THREADS, 4)
 hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                  const double *__restrict__ W, const double *__restrict__ x,
-                 const double *__restrict__ svec, double *__restrict__ out, int accumulate)
+                 const double *__restrict__ svec, double *out, int accumulate, HmFuse fz)
 {
     constexpr int T = HM_THREADS;
     __shared__ double zs[HM_SMAX];
@@ -157,138 +302,42 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
             }
         }
     }
-}
 
-// ---------------------------------------------------------------------------
-// stage 2: one warp per low-rank leaf
-//   t[k]  = sum over the leaf's stage-1 partial sums, in column order
-//   s     = Sigma .* t            (LowRankMatrix,       algebra.jl:120)
-//   s     = F * t  (l outer)      (BarycentricMatrix2D, algebra.jl:260-265)
-// ---------------------------------------------------------------------------
-// Fast path for the rank the assembler produces (BLOCKRANK(Float64) = 20, F 20 x 20):
-// lane k < R first issues its R loads of row k of F (independent, all in flight), then
-// walks the partial-sum list while they land.
-template <int R>
-__device__ __forceinline__ void core_apply_fixed(const HmCoreBlock &cb, const int32_t *__restrict__ pl,
-                                                 const double *__restrict__ partial,
-                                                 const double *__restrict__ c, double *__restrict__ svec,
-                                                 int lane)
-{
-    double f[R];
-    const bool act = lane < R;
-    if (act) {
-#pragma unroll
-        for (int l = 0; l < R; l++) f[l] = __ldcs(c + lane + l * R);
-    }
-    double t = 0.0;
-    if (act) {
-        int i = 0;
-        for (; i + 3 < cb.npl; i += 4) {
-            int o0 = pl[i], o1 = pl[i + 1], o2 = pl[i + 2], o3 = pl[i + 3];
-            double p0 = partial[o0 + lane], p1 = partial[o1 + lane];
-            double p2 = partial[o2 + lane], p3 = partial[o3 + lane];
-            t += p0;
-            t += p1;
-            t += p2;
-            t += p3;
-        }
-        for (; i < cb.npl; i++) t += partial[pl[i] + lane];
-    }
-    double a = 0.0;
-#pragma unroll
-    for (int l = 0; l < R; l++) {
-        double tl = __shfl_sync(0xffffffffu, t, l);
-        a = fma(f[l], tl, a);
-    }
-    if (act) svec[cb.soff + lane] = a;
-}
-
-__global__ void __launch_bounds__(256)
-hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
-               const int32_t *__restrict__ plist, const double *__restrict__ partial,
-               const double *__restrict__ core, double *__restrict__ svec, int max_r)
-{
-    extern __shared__ double tbuf_all[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (b >= nblocks) return;
-    const HmCoreBlock cb = blocks[b];
-    if (cb.npl > HM_CORE_BIG) return; // long partial lists: hm_core_big_kernel
-    const int32_t *pl = plist + cb.pl0;
-    const double *c = core + cb.core;
-    if (cb.kind == HM_LEAF_BARY2D && cb.ru == 20 && cb.rv == 20) {
-        core_apply_fixed<20>(cb, pl, partial, c, svec, lane);
-        return;
-    }
-    double *tbuf = tbuf_all + (size_t)wib * max_r;
-    for (int k = lane; k < cb.rv; k += 32) {
-        double t = 0.0;
-        int i = 0;
-        for (; i + 3 < cb.npl; i += 4) {
-            double p0 = partial[pl[i] + k], p1 = partial[pl[i + 1] + k];
-            double p2 = partial[pl[i + 2] + k], p3 = partial[pl[i + 3] + k];
-            t += p0;
-            t += p1;
-            t += p2;
-            t += p3;
-        }
-        for (; i < cb.npl; i++) t += partial[pl[i] + k];
-        tbuf[k] = t;
-    }
-    __syncwarp();
-    if (cb.kind == HM_LEAF_LOWRANK) {
-        for (int k = lane; k < cb.ru; k += 32) svec[cb.soff + k] = tbuf[k] * c[k];
-    } else {
-        for (int k = lane; k < cb.ru; k += 32) {
-            double a = 0.0;
-            for (int l = 0; l < cb.rv; l++) a = fma(c[k + (size_t)l * cb.ru], tbuf[l], a);
-            svec[cb.soff + k] = a;
-        }
-    }
-}
-
-// Leaves with more than HM_CORE_BIG stage-1 partial sums (n >= 32 * 4096 columns): one
-// CTA per leaf; warp w adds partials w, w+8, ... and the eight warp sums are combined in
-// warp order, so the result does not depend on timing.
-__global__ void __launch_bounds__(256)
-hm_core_big_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__restrict__ big,
-                   const int32_t *__restrict__ plist, const double *__restrict__ partial,
-                   const double *__restrict__ core, double *__restrict__ svec, int max_r)
-{
-    extern __shared__ double sm[]; // [8][max_r] warp sums, then [max_r] t
-    const HmCoreBlock cb = blocks[big[blockIdx.x]];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int32_t *pl = plist + cb.pl0;
-    for (int k = lane; k < cb.rv; k += 32) {
-        double t = 0.0;
-        int i = w;
-        for (; i + 24 < cb.npl; i += 32) {
-            double p0 = partial[pl[i] + k], p1 = partial[pl[i + 8] + k];
-            double p2 = partial[pl[i + 16] + k], p3 = partial[pl[i + 24] + k];
-            t += p0;
-            t += p1;
-            t += p2;
-            t += p3;
-        }
-        for (; i < cb.npl; i += 8) t += partial[pl[i] + k];
-        sm[w * max_r + k] = t;
-    }
-    __syncthreads();
-    double *tbuf = sm + 8 * max_r;
-    for (int k = threadIdx.x; k < cb.rv; k += blockDim.x) {
-        double t = 0.0;
-        for (int g = 0; g < 8; g++) t += sm[g * max_r + k];
-        tbuf[k] = t;
-    }
-    __syncthreads();
-    const double *c = core + cb.core;
-    if (cb.kind == HM_LEAF_LOWRANK) {
-        for (int k = threadIdx.x; k < cb.ru; k += blockDim.x) svec[cb.soff + k] = tbuf[k] * c[k];
-    } else {
-        for (int k = threadIdx.x; k < cb.ru; k += blockDim.x) {
-            double a = 0.0;
-            for (int l = 0; l < cb.rv; l++) a = fma(c[k + (size_t)l * cb.ru], tbuf[l], a);
-            svec[cb.soff + k] = a;
+    if (FUSE) {
+        // Stage 2 fused into the tail of stage 1: count this item's arrival on every leaf it
+        // contributes to; whoever delivers a leaf's last partial sum applies its core.
+        __shared__ int nlast, nbig;
+        __shared__ int lastlist[HM_MAXRUNS], biglist[8];
+        __threadfence(); // this thread's partial sums are visible device-wide before the count
+        __syncthreads();
+        for (int e0 = 0; e0 < it.nrun; e0 += HM_MAXRUNS) {
+            if (t == 0) nlast = nbig = 0;
+            __syncthreads();
+            for (int e = e0 + t; e < min(it.nrun, e0 + HM_MAXRUNS); e += T) {
+                const int c = fz.s1ent[it.run0 + e];
+                const int npl = fz.blocks[c].npl;
+                if (atomicAdd(fz.counters + c, 1) == npl - 1) {
+                    fz.counters[c] = 0; // re-armed for the next matvec
+                    if (npl > HM_CORE_BIG && fz.max_r * 9 <= HM_SMAX) {
+                        int k = atomicAdd(&nbig, 1);
+                        if (k < 8) biglist[k] = c; else lastlist[atomicAdd(&nlast, 1)] = c;
+                    } else {
+                        lastlist[atomicAdd(&nlast, 1)] = c;
+                    }
+                }
+            }
+            __syncthreads();
+            if (nlast > 0 || nbig > 0) {
+                __threadfence();
+                const int lane = t & 31, wib = t >> 5;
+                for (int i = wib; i < nlast; i += T / 32)
+                    core_apply_warp(fz.blocks[lastlist[i]], fz.plist, out, fz.core, fz.svec,
+                                    zs + (size_t)wib * fz.max_r, lane);
+                __syncthreads();
+                for (int i = 0; i < min(nbig, 8); i++)
+                    core_apply_cta(fz.blocks[biglist[i]], fz.plist, out, fz.core, fz.svec, zs, fz.max_r, t);
+            }
+            __syncthreads();
         }
     }
 }
@@ -495,11 +544,15 @@ cudaError_t hm_launch_scale_cols(const HmItem *items1, int64_t n1, double *vstre
 // launch wrappers
 // ---------------------------------------------------------------------------
 cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *vstream,
-                             const double *x, double *partial, cudaStream_t st)
+                             const double *x, double *partial, const HmFuse *fuse, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
-    hm_stream_kernel<false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x, nullptr,
-                                                                     partial, 0);
+    if (fuse && fuse->counters && (size_t)fuse->max_r * 8 <= HM_SMAX)
+        hm_stream_kernel<false, true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x, nullptr,
+                                                                               partial, 0, *fuse);
+    else
+        hm_stream_kernel<false, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x,
+                                                                                nullptr, partial, 0, HmFuse{});
     return cudaGetLastError();
 }
 
@@ -546,8 +599,8 @@ cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *r
                              int accumulate, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
-    hm_stream_kernel<true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec, y,
-                                                                    accumulate);
+    hm_stream_kernel<true, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec, y,
+                                                                           accumulate, HmFuse{});
     return cudaGetLastError();
 }
 

@@ -18,9 +18,21 @@ struct HmCheb {
     double lam[HM_RMAX_ASM];
 };
 
+// Stage 2 fused into the tail of stage 1 (see hm_kernels.cu): per-leaf arrival counters and
+// what the core apply needs.  counters == nullptr: not fused.
+struct HmFuse {
+    const int32_t *s1ent = nullptr; // core index of every (stage-1 item, leaf) entry; item.run0/nrun index it
+    int *counters = nullptr;        // one per low-rank leaf, zero between matvecs
+    const HmCoreBlock *blocks = nullptr;
+    const int32_t *plist = nullptr;
+    const double *core = nullptr;
+    double *svec = nullptr;
+    int max_r = 0;
+};
+
 // stage 1: partial[item.out + f] = sum_s V-slab[s][f] * x[item.zoff + s]
 cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *vstream,
-                             const double *x, double *partial, cudaStream_t st);
+                             const double *x, double *partial, const HmFuse *fuse, cudaStream_t st);
 // stage 2: s_b = F_b * (sum of partials) | Sigma_b .* (sum of partials)
 cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
                              const double *partial, const double *core, double *svec, int max_r,

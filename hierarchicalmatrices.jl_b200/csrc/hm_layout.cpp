@@ -354,6 +354,8 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
                 it.Fp = (int32_t)(F + (F & 1));
                 it.S = (int32_t)(pe - ps);
                 it.zoff = (int32_t)ps;
+                it.run0 = (int32_t)L.s1ent.size();
+                it.nrun = (int32_t)(cov.ptr[p + 1] - cov.ptr[p]);
                 int64_t fofs = 0;
                 for (int64_t e = cov.ptr[p]; e < cov.ptr[p + 1]; e++) {
                     int32_t li = cov.idx[(size_t)e];
@@ -370,6 +372,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
                     L.fill1.push_back(f);
                     int32_t c = core_of[(size_t)li];
                     pend.push_back(Pending{c, (int32_t)(pout + fofs)});
+                    L.s1ent.push_back(c);
                     npl[(size_t)c]++;
                     fofs += l.rv;
                 }
@@ -405,6 +408,9 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
                 L.fill1.push_back(f);
                 int32_t c = core_of[li];
                 pend.push_back(Pending{c, (int32_t)pout});
+                it.run0 = (int32_t)L.s1ent.size();
+                it.nrun = 1;
+                L.s1ent.push_back(c);
                 npl[(size_t)c]++;
                 int64_t words = (int64_t)it.Fp * it.S;
                 tmp.emplace_back(words, it);

@@ -25,6 +25,7 @@ struct HmLayout {
     // stage 1
     std::vector<HmItem> items1;
     std::vector<HmFill> fill1;
+    std::vector<int32_t> s1ent; // core index of every (stage-1 item, leaf) entry (items1[i].run0/nrun)
     int64_t vstream_words = 0;
     int64_t partial_words = 0;
     // stage 2

@@ -290,10 +290,12 @@ struct hm_plan {
     DevBuf<HmCoreBlock> cores;
     DevBuf<int32_t> plist, bigcores; // bigcores: leaves with more than HM_CORE_BIG partial sums
     int64_t nbig = 0;
-    // stage 2 fused into the tail of stage 1 (default; HMB200_FUSE_STAGE2=0 keeps the separate kernels)
+    // Optional: stage 2 fused into the tail of stage 1 (HMB200_FUSE_STAGE2=1).  Measured slower
+    // on one B200 at N = 2^20 (2.233 vs 2.121 ms per matvec: the fence + arrival atomics at the
+    // end of every stage-1 CTA cost more than the 0.1 ms stand-alone kernel), so it is off by default.
     DevBuf<int32_t> s1ent;
     DevBuf<int> counters;
-    bool fuse = true;
+    bool fuse = false;
     // host-pointer path
     cudaStream_t stream = nullptr;
     DevBuf<double> dx, dy;
@@ -347,7 +349,7 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
     HM_CUDA(cudaMemsetAsync(P->counters.p, 0, P->counters.n * sizeof(int), st));
     {
         const char *e = getenv("HMB200_FUSE_STAGE2");
-        P->fuse = !(e && e[0] == '0') && (size_t)L.max_r * 8 <= HM_SMAX;
+        P->fuse = (e && e[0] == '1') && (size_t)L.max_r * 8 <= HM_SMAX;
     }
     {
         std::vector<int32_t> big;

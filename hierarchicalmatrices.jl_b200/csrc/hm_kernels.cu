@@ -32,7 +32,7 @@ __device__ __forceinline__ double2 ld_stream(const double2 *p)
 //   s     = F * t  (l outer)      (BarycentricMatrix2D, algebra.jl:260-265)
 // Written as device functions because they run in two places: fused into the tail of
 // stage 1 (the CTA that delivers a leaf's last partial sum applies its core at once) and
-// in the stand-alone kernels (HMB200_FUSE_STAGE2=0).  Partial sums are read with ld.cg:
+// in the stand-alone kernels (the default; the fused form is HMB200_FUSE_STAGE2=1).  Partial sums are read with ld.cg:
 // other SMs wrote them.
 // ---------------------------------------------------------------------------
 

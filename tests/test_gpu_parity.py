@@ -477,3 +477,24 @@ def test_scale_updates_the_device_operator(hm, O):
     b2 = rng.standard_normal(4500)
     hm.rmul_(H2, b2)
     assert relinf(H2 * v2, A @ (b2 * v2)) <= TOL
+
+
+def test_fused_stage2_option(hm, O):
+    """HMB200_FUSE_STAGE2=1 (core apply in the tail of stage 1) gives the same result."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import hmb200_loader; hm = hmb200_loader.load();"
+        "x, y = hm.chebyshevpoints(5000), hm.chebyshevpoints(5000, 2);"
+        "K = hm.KernelMatrix(hm.cauchykernel, x, y, 1.0, -1.0, 1.0, -1.0, device=0);"
+        "v = np.random.default_rng(0).standard_normal(5000); u = K * v; u2 = K * v;"
+        "assert np.array_equal(u, u2); np.save(sys.argv[1], u)"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        path = f"/tmp/hm_fuse_{flag}.npy"
+        env = dict(os.environ, HMB200_FUSE_STAGE2=flag)
+        subprocess.check_call([sys.executable, "-c", code, path], env=env)
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1])  # same arithmetic, same order

@@ -8,7 +8,7 @@
 #define HM_SMAX 4096    // z staging capacity of a stream item (words)
 #define HM_MAXRUNS 256  // run-table capacity of a stage-3 item
 #define HM_RMAX_ASM 32  // max interpolation rank of on-device assembly
-#define HM_CORE_BIG 32  // stage 2: leaves with more partial sums than this get a whole CTA
+#define HM_CORE_BIG 128 // stage 2: leaves with more partial sums than this get a whole CTA
 
 // Chebyshev nodes / barycentric weights of the reference's BarycentricPoly2D
 // (src/BarycentricMatrix.jl:147-156), computed once on the host.

@@ -293,17 +293,17 @@ def test_large_single_blocks(hm, O):
     out = H * v
     assert relinf(out, ref) <= TOL
     assert H.plan().stats()["n_stage3_rounds"] >= 2
-    # a leaf with more stage-1 partial sums than one warp handles (n > 32 * 4096 columns)
+    # a leaf with more stage-1 partial sums than one warp handles (n > 128 * 4096 columns)
     H3 = hm.HierarchicalMatrix(np.float64, 1, 2)
-    L3 = hm.LowRankMatrix(rng.standard_normal((300, 6)), rng.standard_normal(6), rng.standard_normal((140001, 6)))
+    L3 = hm.LowRankMatrix(rng.standard_normal((300, 6)), rng.standard_normal(6), rng.standard_normal((540001, 6)))
     B3 = hm.BarycentricMatrix2D(rng.standard_normal((300, 20)), rng.standard_normal((20, 20)),
-                                rng.standard_normal((150000, 20)))
+                                rng.standard_normal((530000, 20)))
     H3[hm.Block(1), hm.Block(1)] = L3
     K3 = hm.KernelMatrix(np.float64, 1, 1)
     K3[hm.Block(1), hm.Block(1)] = B3
-    v3 = rng.standard_normal(140001)
+    v3 = rng.standard_normal(540001)
     assert relinf(H3.__class__.__mul__(_one_col(hm, L3), v3), L3.U @ (L3.S * (L3.V.T @ v3))) <= TOL
-    v4 = rng.standard_normal(150000)
+    v4 = rng.standard_normal(530000)
     assert relinf(K3 * v4, B3.U @ (B3.F @ (B3.V.T @ v4))) <= TOL
 
 

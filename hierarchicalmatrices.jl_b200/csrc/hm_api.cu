@@ -235,6 +235,25 @@ class Uploader {
     size_t left_ = 0, total_ = 0;
 };
 
+// Layout parameters; HMB200_RMAX / HMB200_CMAX0 / HMB200_CMAX1 / HMB200_NBIG override the
+// defaults (tuning experiments: finer items shorten the tail of each launch when a GPU
+// owns only a small part of the operator).
+HmLayoutParams layout_params()
+{
+    HmLayoutParams prm;
+    auto geti = [](const char *name, int def, int lo, int hi) {
+        const char *e = getenv(name);
+        if (!e) return def;
+        int v = atoi(e);
+        return (v < lo || v > hi) ? def : v;
+    };
+    prm.rmax = geti("HMB200_RMAX", prm.rmax, 8, 512);
+    prm.cmax0 = geti("HMB200_CMAX0", prm.cmax0, 8, HM_SMAX);
+    prm.cmax1 = geti("HMB200_CMAX1", prm.cmax1, 64, HM_SMAX);
+    prm.nbig = geti("HMB200_NBIG", prm.nbig, 64, 1 << 30);
+    return prm;
+}
+
 void fill_stats(const HmLayout &L, hm_stats *s)
 {
     memset(s, 0, sizeof *s);
@@ -529,7 +548,7 @@ int32_t hm_builder_layout_stats(hm_builder *b, int32_t part, int32_t nparts, hm_
 {
     if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
     HmLayout L;
-    std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, HmLayoutParams(), L);
+    std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, layout_params(), L);
     if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
     fill_stats(L, out);
     return HM_OK;
@@ -545,7 +564,7 @@ int32_t hm_plan_finalize_part(hm_builder *b, int32_t part, int32_t nparts, hm_pl
     hm_plan *P = new (std::nothrow) hm_plan;
     if (!P) return fail(HM_ERR_NOMEM, "out of host memory");
     P->device = b->device;
-    std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, HmLayoutParams(), P->L);
+    std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, layout_params(), P->L);
     if (!err.empty()) {
         delete P;
         return fail(HM_ERR_INVALID, "%s", err.c_str());
@@ -669,7 +688,7 @@ static int32_t kernel_tree_layout(const double *x, int64_t nx, const double *y, 
     int64_t nrows = 0, ncols = 0;
     std::string err = hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
     if (!err.empty()) return fail(HM_ERR_REFERENCE, "%s", err.c_str());
-    err = hm_build_layout(leaves, nrows, ncols, part, nparts, HmLayoutParams(), L);
+    err = hm_build_layout(leaves, nrows, ncols, part, nparts, layout_params(), L);
     if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
     return HM_OK;
 }

@@ -21,6 +21,9 @@ namespace {
 
 constexpr int PT = 256; // threads per CTA
 
+constexpr int PD = 2; // L2 prefetch distance of the streaming panel kernel, in load batches
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
+
 // D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -114,6 +117,21 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
             for (int u = 0; u < U; u++) {
                 const int row = k0 + 4 * u + tig;
                 const bool v = row < s_hi;
+                // software prefetch into L2, PD load batches ahead: the demand loads below then
+                // see L2 latency instead of HBM latency (no registers held)
+                const int prow = row + 4 * U * PD;
+                if (prow < s_hi) {
+                    if (c0ok) prefetch_l2(ap + (size_t)prow * Fp);
+                    if (c1ok) prefetch_l2(ap + (size_t)prow * Fp + 8);
+                    const double *pz;
+                    if (GATHER) {
+                        int zr = zrow[prow];
+                        pz = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
+                    } else {
+                        pz = Xt + (size_t)(it.zoff + prow) * CS;
+                    }
+                    if (gid * 8 < CS) prefetch_l2(pz + gid * 8);
+                }
                 a0[u] = (v && c0ok) ? __ldcs(ap + (size_t)row * Fp) : 0.0;
                 a1[u] = (v && c1ok) ? __ldcs(ap + (size_t)row * Fp + 8) : 0.0;
                 const double *zp = Xt;

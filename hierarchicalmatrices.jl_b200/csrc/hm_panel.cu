@@ -21,7 +21,7 @@ namespace {
 
 constexpr int PT = 256; // threads per CTA
 
-constexpr int PD = 2; // L2 prefetch distance of the streaming panel kernel, in load batches
+constexpr int PD = 2; // L2 prefetch distance (load batches) of the streaming panel kernel at 64 columns
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
 
 // D(8x8) += A(8x4, row) * B(4x8, col), FP64 tensor core
@@ -120,7 +120,7 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
                 // software prefetch into L2, PD load batches ahead: the demand loads below then
                 // see L2 latency instead of HBM latency (no registers held)
                 const int prow = row + 4 * U * PD;
-                if (prow < s_hi) {
+                if (NB == 8 && prow < s_hi) { // measured: helps the MMA-bound 64-column case only
                     if (c0ok) prefetch_l2(ap + (size_t)prow * Fp);
                     if (c1ok) prefetch_l2(ap + (size_t)prow * Fp + 8);
                     const double *pz;

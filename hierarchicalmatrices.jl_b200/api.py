@@ -36,7 +36,7 @@ __all__ = [
     "BLOCKRANK", "BLOCKSIZE", "Block", "LowRankMatrix", "BarycentricMatrix2D", "Matrix",
     "hierarchical", "HierarchicalMatrix", "KernelMatrix", "blocksize", "size", "mul_",
     "cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel", "Plan", "flatten",
-    "chebyshevpoints", "HmError", "rmul_", "lmul_", "scale_",
+    "chebyshevpoints", "HmError", "rmul_", "lmul_", "scale_", "adjoint", "Adjoint",
 ]
 
 Matrix = np.ndarray  # the dense leaf type of the reference
@@ -209,6 +209,16 @@ class Plan:
         px = C.cast(x.ctypes.data + xoff * isz, _dp)
         py = C.cast(y.ctypes.data + yoff * isz, _dp)
         _lib.check(_lib.lib().hm_matvec(self._h, px, incx, py, incy, 1 if accumulate else 0))
+        return y
+
+    # y[j*incy] (+)= (H' x)[j]
+    def rmatvec(self, x: np.ndarray, y: np.ndarray, incx=1, incy=1, accumulate=True, xoff=0, yoff=0):
+        for a, nm in ((x, "x"), (y, "y")):
+            if a.dtype != np.float64:
+                raise TypeError(f"{nm} must be Float64")
+        px = C.cast(x.ctypes.data + xoff * 8, _dp)
+        py = C.cast(y.ctypes.data + yoff * 8, _dp)
+        _lib.check(_lib.lib().hm_matvec_adjoint(self._h, px, incx, py, incy, 1 if accumulate else 0))
         return y
 
     def matmat(self, X: np.ndarray, Y: np.ndarray, accumulate=True):
@@ -672,6 +682,38 @@ def lmul_(b, H):
     return scale_(b, H, 1)
 
 
+class Adjoint:
+    """`adjoint(H)` / `H'` of a hierarchical matrix (real case: the transpose).  The reference
+    wraps only its leaves this way (algebra.jl:50-82, 133-159); here the whole operator
+    applies through the same packed streams, reduced over the fast index."""
+
+    def __init__(self, parent):
+        self.parent = parent
+
+    def size(self, k=None):
+        p, q = self.parent.size()
+        return (q, p) if k is None else (q, p)[k - 1]
+
+    shape = property(lambda self: self.size())
+
+    def __mul__(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if x.ndim != 1:
+            raise TypeError("adjoint(H) * x is defined for vectors")
+        if x.size != self.parent.size(1):
+            raise ValueError("DimensionMismatch")
+        y = np.zeros(self.parent.size(2))
+        return self.parent.plan().rmatvec(x, y, accumulate=False)
+
+    __matmul__ = __mul__
+
+
+def adjoint(H):
+    if not isinstance(H, _HierarchicalBase):
+        raise TypeError("MethodError: adjoint of a hierarchical matrix")
+    return Adjoint(H)
+
+
 def _linear(a: np.ndarray, name: str) -> np.ndarray:
     """Julia linear indexing = column-major order; must be a view so y is updated in place."""
     if a.ndim == 1:
@@ -686,6 +728,20 @@ def _linear(a: np.ndarray, name: str) -> np.ndarray:
 def mul_(y, H, x, istart: int = 1, jstart: int = 1, INCX: int = 1, INCY: int = 1):
     """`mul!(y, H, x, istart, jstart, INCX, INCY)`: y[istart+(i-1)INCY] += Σ_j H[i,j] x[jstart+(j-1)INCX]
     with 1-based linear indices (HierarchicalMatrix.jl:14-52, KernelMatrix.jl:14-45); returns y."""
+    if isinstance(H, Adjoint):  # mul!(y, H', x, ...): y += H' x with the same offset/stride rules
+        Hp = H.parent
+        if not (y.dtype == x.dtype == Hp.T == np.float64):
+            raise TypeError("MethodError: y, H and x must all be Float64")
+        if INCX < 1 or INCY < 1 or istart < 1 or jstart < 1:
+            raise IndexError("BoundsError: offsets and strides are 1-based positive integers")
+        yl, xl = _linear(y, "y"), _linear(x, "x")
+        nr, nc = Hp.size()
+        if nc and istart - 1 + (nc - 1) * INCY >= yl.size:
+            raise IndexError("BoundsError: y is too short")
+        if nr and jstart - 1 + (nr - 1) * INCX >= xl.size:
+            raise IndexError("BoundsError: x is too short")
+        Hp.plan().rmatvec(xl, yl, INCX, INCY, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
+        return y
     if not isinstance(H, _HierarchicalBase):
         raise TypeError("MethodError: H is not a hierarchical matrix")
     if isinstance(H, KernelMatrix) and (INCX != 1 or INCY != 1):

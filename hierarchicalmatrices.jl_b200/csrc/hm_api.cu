@@ -309,6 +309,12 @@ struct hm_plan {
     DevBuf<HmCoreBlock> cores;
     DevBuf<int32_t> plist, bigcores; // bigcores: leaves with more than HM_CORE_BIG partial sums
     int64_t nbig = 0;
+    // adjoint apply (allocated on first use)
+    DevBuf<double> pq;
+    DevBuf<int32_t> qlist, core_q0, core_qn;
+    DevBuf<HmColSeg> colsegs;
+    DevBuf<int64_t> colbases;
+    bool adj_ready = false;
     // Optional: stage 2 fused into the tail of stage 1 (HMB200_FUSE_STAGE2=1).  Measured slower
     // on one B200 at N = 2^20 (2.233 vs 2.121 ms per matvec: the fence + arrival atomics at the
     // end of every stage-1 CTA cost more than the 0.1 ms stand-alone kernel), so it is off by default.
@@ -848,6 +854,78 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
     } else {
         HM_CUDA(cudaStreamSynchronize(st));
     }
+    return HM_OK;
+}
+
+// Adjoint apply y (+)= H' x.
+int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    const HmLayout &L = p->L;
+    if ((!dx && L.nrows > 0) || (!dy && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+    if (L.adj_max_f > HM_SMAX) return fail(HM_ERR_UNSUPPORTED, "adjoint: a column segment is covered by too many ranks");
+    HM_DEVICE(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->adj_ready) {
+        HM_CUDA(cudaStreamSynchronize(st));
+        HM_CUDA(p->pq.alloc((size_t)std::max<int64_t>(L.pq_words, 1)));
+        HM_CUDA(p->qlist.upload(L.qlist, st));
+        HM_CUDA(p->core_q0.upload(L.core_q0, st));
+        HM_CUDA(p->core_qn.upload(L.core_qn, st));
+        HM_CUDA(p->colsegs.upload(L.colsegs, st));
+        HM_CUDA(p->colbases.upload(L.colbases, st));
+        if (!p->s1ent.p) HM_CUDA(p->s1ent.upload(L.s1ent, st));
+        HM_CUDA(cudaStreamSynchronize(st));
+        p->adj_ready = true;
+    }
+    HmAdjoint A;
+    A.items3 = p->items3.p;
+    A.items1 = p->items1.p;
+    A.n3 = (int64_t)L.items3.size();
+    A.n1 = (int64_t)L.items1.size();
+    A.ncores = (int64_t)L.cores.size();
+    A.nsegs = (int64_t)L.colsegs.size();
+    A.ustream = p->ustream.p;
+    A.vstream = p->vstream.p;
+    A.core = p->core.p;
+    A.blocks = p->cores.p;
+    A.q0 = p->core_q0.p;
+    A.qn = p->core_qn.p;
+    A.qlist = p->qlist.p;
+    A.s1ent = p->s1ent.p;
+    A.segs = p->colsegs.p;
+    A.bases = p->colbases.p;
+    A.PQ = p->pq.p;
+    A.svec = p->svec.p;
+    A.max_r = std::max(L.max_r, 1);
+    HM_CUDA(hm_launch_adjoint(A, dx, dy, accumulate != 0, st));
+    return HM_OK;
+}
+
+int32_t hm_matvec_adjoint(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy, int32_t accumulate)
+{
+    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    const HmLayout &L = p->L;
+    if ((!x && L.nrows > 0) || (!y && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+    if (incx == 0 || incy == 0) return fail(HM_ERR_INVALID, "zero stride");
+    std::lock_guard<std::mutex> lock(p->mu);
+    HM_DEVICE(p->device);
+    const int64_t nr = L.nrows, nc = L.ncols;
+    // the forward path's staging buffers are reused with the roles of x and y swapped
+    if (!p->dx.p) HM_CUDA(p->dx.alloc((size_t)std::max<int64_t>(nc, 1)));
+    if (!p->dy.p) HM_CUDA(p->dy.alloc((size_t)std::max<int64_t>(nr, 1)));
+    cudaStream_t st = p->stream;
+    std::vector<double> hx((size_t)nr), hy((size_t)nc);
+    for (int64_t i = 0; i < nr; i++) hx[(size_t)i] = x[i * incx];
+    if (nr > 0) HM_CUDA(cudaMemcpyAsync(p->dy.p, hx.data(), (size_t)nr * 8, cudaMemcpyHostToDevice, st));
+    if (accumulate && nc > 0) {
+        for (int64_t j = 0; j < nc; j++) hy[(size_t)j] = y[j * incy];
+        HM_CUDA(cudaMemcpyAsync(p->dx.p, hy.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (int32_t rc = hm_matvec_adjoint_device(p, p->dy.p, p->dx.p, accumulate, st)) return rc;
+    if (nc > 0) HM_CUDA(cudaMemcpyAsync(hy.data(), p->dx.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+    HM_CUDA(cudaStreamSynchronize(st));
+    for (int64_t j = 0; j < nc; j++) y[j * incy] = hy[(size_t)j];
     return HM_OK;
 }
 

@@ -522,7 +522,175 @@ hm_scale_cols_dense_kernel(const HmItem *__restrict__ items, const HmRun *__rest
     }
 }
 
+// ---------------------------------------------------------------------------
+// adjoint apply y = H' x.  No hierarchical adjoint exists in the
+// reference; the leaf rules are those of its Transpose/Adjoint leaves
+// (/root/reference/src/algebra.jl:52-82 dense, :138-159 LowRankMatrix): y_j += sum_i A[i,j] x_i,
+// temp = Sigma .* (U' x), y += V temp; BarycentricMatrix2D likewise with F'.
+// The packed streams are read exactly as in the forward product, but reduced over the
+// fast index: a group of lanes owns one slab row and combines with shuffles.
+// ---------------------------------------------------------------------------
+// MODE 0 (stage A'): items of the U-stream, z = x[rows of the item]
+// MODE 1 (stage C'): items of the V-stream, z gathered from the adjoint stage-2 vector
+template <int MODE>
+__global__ void __launch_bounds__(HM_THREADS, 4)
+hm_rowdot_kernel(const HmItem *__restrict__ items, const double *__restrict__ W,
+                 const double *__restrict__ zsrc, const int32_t *__restrict__ s1ent,
+                 const HmCoreBlock *__restrict__ blocks, double *__restrict__ PQ)
+{
+    constexpr int T = HM_THREADS;
+    __shared__ double zs[HM_SMAX + 2];
+    const HmItem it = items[blockIdx.x];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int S = it.S, F = it.F, L = it.Fp >> 1;
+    if (MODE == 0) {
+        for (int f = t; f < it.Fp; f += T) zs[f] = f < F ? zsrc[it.out + f] : 0.0;
+    } else {
+        // z[f], f = (leaf, k) in the order of the item's leaf list
+        if (warp == 0) {
+            int fofs = 0;
+            for (int e = 0; e < it.nrun; e++) {
+                const HmCoreBlock cb = blocks[s1ent[it.run0 + e]];
+                for (int k = lane; k < cb.rv; k += 32) zs[fofs + k] = zsrc[cb.soff + k];
+                fofs += cb.rv;
+            }
+            if (lane == 0 && fofs < it.Fp) zs[fofs] = 0.0;
+        }
+    }
+    __syncthreads();
+    const double2 *__restrict__ W2 = reinterpret_cast<const double2 *>(W + it.slab);
+    double *__restrict__ o = PQ + it.aux;
+    if (L <= 32) {
+        int LR = 1; // lanes per row: next power of two >= L
+        while (LR < L) LR <<= 1;
+        const int rpw = 32 / LR, g = lane / LR, lg = lane - g * LR;
+        const bool act = lg < L;
+        const double z0 = act ? zs[2 * lg] : 0.0, z1 = act ? zs[2 * lg + 1] : 0.0;
+        const int stride = 8 * rpw;
+        int s = warp * rpw + g;
+        // loop bounds are warp-uniform (s - g is the warp's first row): every lane joins the shuffles
+        for (; (s - g) + 3 * stride + rpw - 1 < S; s += 4 * stride) {
+            double2 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) w[u] = act ? __ldcs(W2 + (size_t)(s + u * stride) * L + lg) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                double a = fma(w[u].x, z0, w[u].y * z1);
+                for (int d = LR >> 1; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+                if (lg == 0) o[s + u * stride] = a;
+            }
+        }
+        // remaining rows: keep every lane in the shuffles
+        for (; s - g < S; s += stride) {
+            const bool rv = s < S;
+            double2 w = (act && rv) ? __ldcs(W2 + (size_t)s * L + lg) : make_double2(0.0, 0.0);
+            double a = fma(w.x, z0, w.y * z1);
+            for (int d = LR >> 1; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+            if (lg == 0 && rv) o[s] = a;
+        }
+    } else {
+        for (int s = warp; s < S; s += T / 32) {
+            double a = 0.0;
+            const double2 *row = W2 + (size_t)s * L;
+            for (int i = lane; i < L; i += 32) {
+                double2 w = __ldcs(row + i);
+                a = fma(w.x, zs[2 * i], a);
+                a = fma(w.y, zs[2 * i + 1], a);
+            }
+            for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+            if (lane == 0) o[s] = a;
+        }
+    }
+}
+
+// stage B': t'[k] = sum of the leaf's q pieces (row order); s' = F' t' | Sigma .* t'
+__global__ void __launch_bounds__(256)
+hm_core_adj_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks, const int32_t *__restrict__ q0,
+                   const int32_t *__restrict__ qn, const int32_t *__restrict__ qlist,
+                   const double *__restrict__ PQ, const double *__restrict__ core, double *__restrict__ svec,
+                   int max_r)
+{
+    extern __shared__ double tbuf_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (b >= nblocks) return;
+    double *tbuf = tbuf_all + (size_t)wib * max_r;
+    const HmCoreBlock cb = blocks[b];
+    const int32_t *ql = qlist + q0[b];
+    const int n = qn[b];
+    for (int k = lane; k < cb.ru; k += 32) {
+        double t = 0.0;
+        int i = 0;
+        for (; i + 3 < n; i += 4) {
+            double p0 = PQ[ql[i] + k], p1 = PQ[ql[i + 1] + k], p2 = PQ[ql[i + 2] + k], p3 = PQ[ql[i + 3] + k];
+            t += p0;
+            t += p1;
+            t += p2;
+            t += p3;
+        }
+        for (; i < n; i++) t += PQ[ql[i] + k];
+        tbuf[k] = t;
+    }
+    __syncwarp();
+    const double *c = core + cb.core;
+    if (cb.kind == HM_LEAF_LOWRANK) {
+        for (int k = lane; k < cb.rv; k += 32) svec[cb.soff + k] = tbuf[k] * c[k];
+    } else {
+        for (int l = lane; l < cb.rv; l += 32) {
+            double a = 0.0;
+            const double *col = c + (size_t)l * cb.ru; // F[:, l]
+            for (int k = 0; k < cb.ru; k++) a = fma(col[k], tbuf[k], a);
+            svec[cb.soff + l] = a;
+        }
+    }
+}
+
+// stage D': y[j] = (accumulate ? y[j] : 0) + sum_i PQ[base_i + j], one writer per column
+__global__ void __launch_bounds__(256)
+hm_colsum_kernel(const HmColSeg *__restrict__ segs, const int64_t *__restrict__ bases,
+                 const double *__restrict__ PQ, double *__restrict__ y, int accumulate)
+{
+    const HmColSeg sg = segs[blockIdx.x];
+    const int j = sg.c0 + threadIdx.x;
+    if (j >= sg.c1) return;
+    double a = 0.0;
+    const int64_t *b = bases + sg.b0;
+    int i = 0;
+    for (; i + 3 < sg.nb; i += 4) {
+        double p0 = PQ[b[i] + j], p1 = PQ[b[i + 1] + j], p2 = PQ[b[i + 2] + j], p3 = PQ[b[i + 3] + j];
+        a += p0;
+        a += p1;
+        a += p2;
+        a += p3;
+    }
+    for (; i < sg.nb; i++) a += PQ[b[i] + j];
+    y[j] = (accumulate ? y[j] : 0.0) + a;
+}
+
 } // namespace
+
+cudaError_t hm_launch_adjoint(const HmAdjoint &A, const double *x, double *y, int accumulate, cudaStream_t st)
+{
+    if (A.n3 > 0)
+        hm_rowdot_kernel<0><<<(unsigned)A.n3, HM_THREADS, 0, st>>>(A.items3, A.ustream, x, nullptr, nullptr, A.PQ);
+    if (A.ncores > 0) {
+        int threads = 256;
+        size_t smem = (size_t)(threads / 32) * (size_t)A.max_r * sizeof(double);
+        while (smem > 48 * 1024 && threads > 32) {
+            threads >>= 1;
+            smem = (size_t)(threads / 32) * (size_t)A.max_r * sizeof(double);
+        }
+        if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
+        int wpb = threads / 32;
+        hm_core_adj_kernel<<<(unsigned)((A.ncores + wpb - 1) / wpb), threads, smem, st>>>(
+            A.blocks, A.ncores, A.q0, A.qn, A.qlist, A.PQ, A.core, A.svec, A.max_r);
+    }
+    if (A.n1 > 0)
+        hm_rowdot_kernel<1><<<(unsigned)A.n1, HM_THREADS, 0, st>>>(A.items1, A.vstream, A.svec, A.s1ent, A.blocks,
+                                                                    A.PQ);
+    if (A.nsegs > 0) hm_colsum_kernel<<<(unsigned)A.nsegs, 256, 0, st>>>(A.segs, A.bases, A.PQ, y, accumulate);
+    return cudaGetLastError();
+}
 
 cudaError_t hm_launch_scale_rows(const HmItem *items3, int64_t n3, double *ustream, const double *b, cudaStream_t st)
 {

@@ -45,6 +45,20 @@ cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *r
                              const double *ustream, const double *x, const double *svec, double *y,
                              int accumulate, cudaStream_t st);
 
+// adjoint apply y (+)= H' x: four launches over the same streams (hm_kernels.cu)
+struct HmAdjoint {
+    const HmItem *items3 = nullptr, *items1 = nullptr;
+    int64_t n3 = 0, n1 = 0, ncores = 0, nsegs = 0;
+    const double *ustream = nullptr, *vstream = nullptr, *core = nullptr;
+    const HmCoreBlock *blocks = nullptr;
+    const int32_t *q0 = nullptr, *qn = nullptr, *qlist = nullptr, *s1ent = nullptr;
+    const HmColSeg *segs = nullptr;
+    const int64_t *bases = nullptr;
+    double *PQ = nullptr, *svec = nullptr;
+    int max_r = 1;
+};
+cudaError_t hm_launch_adjoint(const HmAdjoint &A, const double *x, double *y, int accumulate, cudaStream_t st);
+
 // operator updates in place: H <- Diagonal(b) H (rows) and H <- H Diagonal(b) (columns)
 cudaError_t hm_launch_scale_rows(const HmItem *items3, int64_t n3, double *ustream, const double *b,
                                  cudaStream_t st);

@@ -212,6 +212,17 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         if (L.s_words >= ((int64_t)1 << 31) - 64) return "stage-2 vector too long";
     }
 
+    // collectors for the adjoint apply
+    struct AdjCol {
+        int64_t c0, c1, base; // y[j] += PQ[base + j] for c0 <= j < c1
+    };
+    struct AdjQ {
+        int32_t core, k0;
+        int64_t off; // PQ offset of the piece's first column (columns k0.. of the leaf)
+    };
+    std::vector<AdjCol> adj_cols;
+    std::vector<AdjQ> adj_q;
+
     // ---- stage 3: row segments ----
     {
         std::vector<int64_t> b{rlo, rhi};
@@ -238,6 +249,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         tmp.reserve(np);
         int64_t slab = 0;
         int maxround = 0;
+        int64_t qwords = 0;
         for (size_t p = 0; p < np; p++) {
             int64_t ps = starts[p], pe = starts[p + 1];
             int32_t F = (int32_t)(pe - ps), Fp = F + (F & 1);
@@ -255,6 +267,8 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
             };
             auto close = [&]() {
                 int64_t words = (int64_t)cur.Fp * cur.S;
+                cur.aux = qwords; // adjoint: this item's S row-dot results
+                qwords += cur.S;
                 tmp.push_back(Tmp{cur, round, words});
                 slab = align_up(slab + words, 16);
                 maxround = std::max(maxround, round);
@@ -266,7 +280,9 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
                 int64_t total = zlen(l), k = 0;
                 while (k < total) {
                     int64_t room = prm.smax - cur.S;
-                    if (room <= 0 || cur.nrun >= prm.maxruns) {
+                    // a low-rank leaf's columns stay together (the adjoint sums them as one piece)
+                    const bool lr_whole = l.kind != HM_LEAF_DENSE && room < total && total <= prm.smax;
+                    if (room <= 0 || cur.nrun >= prm.maxruns || (lr_whole && cur.S > 0)) {
                         close();
                         round++;
                         open();
@@ -289,6 +305,10 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
                     f.Fp = Fp;
                     f.S = 0;
                     L.fill3.push_back(f);
+                    if (l.kind == HM_LEAF_DENSE)
+                        adj_cols.push_back(AdjCol{l.col0 + k, l.col0 + k + take, qwords + cur.S - (l.col0 + k)});
+                    else
+                        adj_q.push_back(AdjQ{core_of[(size_t)li], (int32_t)k, qwords + cur.S});
                     cur.S += (int32_t)take;
                     cur.nrun++;
                     k += take;
@@ -298,6 +318,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         }
         if (L.runs.size() >= ((size_t)1 << 31)) return "too many stage-3 runs";
         L.ustream_words = slab;
+        L.pq_words = qwords;
         std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp &a, const Tmp &b) {
             if (a.round != b.round) return a.round < b.round;
             return a.words > b.words;
@@ -354,6 +375,10 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
                 it.Fp = (int32_t)(F + (F & 1));
                 it.S = (int32_t)(pe - ps);
                 it.zoff = (int32_t)ps;
+                it.aux = L.pq_words;
+                adj_cols.push_back(AdjCol{ps, pe, L.pq_words - ps});
+                L.pq_words += pe - ps;
+                L.adj_max_f = std::max<int>(L.adj_max_f, (int)(F + (F & 1)));
                 it.run0 = (int32_t)L.s1ent.size();
                 it.nrun = (int32_t)(cov.ptr[p + 1] - cov.ptr[p]);
                 int64_t fofs = 0;
@@ -388,6 +413,10 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
             if (l.kind == HM_LEAF_DENSE || l.n < prm.nbig) continue;
             int64_t np = (l.n + prm.cmax1 - 1) / prm.cmax1;
             int64_t sz = (l.n + np - 1) / np;
+            const int64_t rleaf = L.pq_words; // the leaf's n row-dot results are contiguous
+            adj_cols.push_back(AdjCol{l.col0, l.col0 + l.n, rleaf - l.col0});
+            L.pq_words += l.n;
+            L.adj_max_f = std::max<int>(L.adj_max_f, l.rv + (l.rv & 1));
             for (int64_t c0 = 0; c0 < l.n; c0 += sz) {
                 int64_t c1 = std::min(c0 + sz, l.n);
                 HmItem it{};
@@ -397,6 +426,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
                 it.Fp = l.rv + (l.rv & 1);
                 it.S = (int32_t)(c1 - c0);
                 it.zoff = (int32_t)(l.col0 + c0);
+                it.aux = rleaf + c0;
                 HmFill f{};
                 f.dst = slab;
                 f.leaf = (int32_t)li;
@@ -440,6 +470,53 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
             HmCoreBlock &cb = L.cores[(size_t)pd.core];
             L.plist[(size_t)(cb.pl0 + cb.npl++)] = pd.off;
         }
+    }
+
+    // ---- adjoint tables ----
+    {
+        if (L.pq_words >= ((int64_t)1 << 31) - 64) return "adjoint work buffer too long";
+        L.core_q0.assign(L.cores.size(), 0);
+        L.core_qn.assign(L.cores.size(), 0);
+        for (const AdjQ &q : adj_q) {
+            if (q.k0 != 0) return "internal: split low-rank entry";
+            L.core_qn[(size_t)q.core]++;
+        }
+        int32_t acc = 0;
+        for (size_t c = 0; c < L.cores.size(); c++) {
+            L.core_q0[c] = acc;
+            acc += L.core_qn[c];
+            L.core_qn[c] = 0;
+        }
+        L.qlist.assign((size_t)acc, 0);
+        for (const AdjQ &q : adj_q) // emitted in increasing row order per leaf
+            L.qlist[(size_t)(L.core_q0[(size_t)q.core] + L.core_qn[(size_t)q.core]++)] = (int32_t)q.off;
+        // final gather: column intervals on which the set of contributors is constant
+        std::vector<int64_t> b{0, ncols};
+        for (const AdjCol &a : adj_cols) {
+            b.push_back(a.c0);
+            b.push_back(a.c1);
+        }
+        std::sort(b.begin(), b.end());
+        b.erase(std::unique(b.begin(), b.end()), b.end());
+        std::vector<int64_t> starts = make_pieces(b, 256, false);
+        size_t np = starts.size() - 1;
+        Cover cov = cover_pieces(starts, adj_cols.size(), [&](size_t i, int64_t &lo, int64_t &hi) {
+            lo = adj_cols[i].c0;
+            hi = adj_cols[i].c1;
+            return true;
+        });
+        L.colsegs.reserve(np);
+        L.colbases.reserve(cov.idx.size());
+        for (size_t p = 0; p < np; p++) {
+            HmColSeg cs;
+            cs.c0 = (int32_t)starts[p];
+            cs.c1 = (int32_t)starts[p + 1];
+            cs.b0 = (int32_t)L.colbases.size();
+            cs.nb = (int32_t)(cov.ptr[p + 1] - cov.ptr[p]);
+            for (int64_t e = cov.ptr[p]; e < cov.ptr[p + 1]; e++) L.colbases.push_back(adj_cols[(size_t)cov.idx[(size_t)e]].base);
+            L.colsegs.push_back(cs);
+        }
+        if (L.colbases.size() >= ((size_t)1 << 31)) return "too many adjoint gather entries";
     }
 
     for (const HmItem &it : L.items1)

@@ -41,6 +41,17 @@ struct HmLayout {
     std::vector<HmFill> fill3;
     std::vector<int64_t> round_begin; // items3 index of each round start, plus end
     int64_t ustream_words = 0;
+    // adjoint apply y = H' x: the same two streams, reduced over the fast index
+    //   A'  q = (row dots of every U-stream slab row with x)      -> PQ[item3.aux + s]
+    //   B'  t'_b = sum of the leaf's q pieces; s'_b = F_b' t'_b | Sigma_b .* t'_b
+    //   C'  r = (row dots of every V-stream slab row with s')     -> PQ[item1.aux + s]
+    //   D'  y[j] = sum of the q (dense tiles) and r entries that belong to column j
+    int64_t pq_words = 0;
+    std::vector<int32_t> qlist;            // per core: PQ offsets of its q pieces, in row order
+    std::vector<int32_t> core_q0, core_qn; // parallel to `cores`
+    std::vector<HmColSeg> colsegs;
+    std::vector<int64_t> colbases;
+    int adj_max_f = 0; // widest stage-1 item (the z staging of stage C')
     // accounting
     int64_t n_dense = 0, n_lowrank = 0, n_bary2d = 0; // whole operator
     int64_t dense_words = 0, lowrank_words = 0, core_words_all = 0;

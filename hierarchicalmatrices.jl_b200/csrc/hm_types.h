@@ -43,9 +43,15 @@ struct HmItem {
     int32_t Fp;   // F rounded up to even = leading dimension of W
     int32_t S;    // slow extent (stage 1: columns; stage 3: z length)
     int32_t zoff; // stage 1: first column of x
-    int32_t run0; // stage 3: first run
+    int32_t run0; // stage 3: first run (stage 1: first entry of the leaf list s1ent)
     int32_t nrun;
-    int32_t pad0, pad1;
+    int64_t aux;  // adjoint apply: word offset of this item's S row-dot results in the buffer PQ
+};
+
+// Adjoint apply, final gather: y[j] = sum_i PQ[base_i + j] for j in [c0, c1)
+struct HmColSeg {
+    int32_t c0, c1;
+    int32_t b0, nb; // bases [b0, b0 + nb) in the base list
 };
 
 struct HmRun {

@@ -177,6 +177,16 @@ HM_API int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, i
 HM_API int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate,
                          void *stream);
 
+/* Adjoint apply: y[j*incy] (+)= sum_i H[i,j] x[i*incx], x with nrows
+ * entries, y with ncols.  The reference has no adjoint of its hierarchical types; the
+ * leaf rules are those of its Transpose/Adjoint leaf methods (src/algebra.jl:52-82,
+ * 138-159).  For a row part the result is the contribution of the owned rows (sum the
+ * parts to get H'x). */
+HM_API int32_t hm_matvec_adjoint(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy,
+                                 int32_t accumulate);
+HM_API int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate,
+                                        void *stream);
+
 /* Multi-right-hand-side form: Y[:, c] (+)= H X[:, c], c < nrhs; X ncols x nrhs
  * (ldx), Y nrows x nrhs (ldy), column-major.  (The reference reaches this through
  * the stride pair, test/runtests.jl:23-25.) */

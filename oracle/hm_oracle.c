@@ -492,6 +492,53 @@ void hmo_mul(double *y, const hmo_node *h, const double *x, int64_t i0, int64_t 
 }
 
 /* ------------------------------------------------------------------ */
+/* adjoint apply y += H' x                           */
+/* ------------------------------------------------------------------ */
+
+/* The reference defines no adjoint of its hierarchical types.  This walks the tree like
+ * mul! (offsets as in KernelMatrix.jl:24-41) and applies to each leaf the reference's own
+ * transposed leaf rule: dense -- algebra.jl:52-65 (y_i += sum_j A[j,i] x_j, inner sum
+ * first); LowRankMatrix -- algebra.jl:138-159 (temp = Sigma .* (U' x); y += V temp);
+ * BarycentricMatrix2D by analogy (temp1 = U' x; temp2 = F' temp1; y += V temp2).
+ * x has size(H,1) entries starting at x[i0], y size(H,2) starting at y[j0]. */
+void hmo_mul_adjoint(double *y, const hmo_node *h, const double *x, int64_t i0, int64_t j0)
+{
+    int64_t p = 0;
+    for (int m = 0; m < h->M; m++) {
+        int64_t q = 0;
+        for (int n = 0; n < h->N; n++) {
+            const hmo_block *b = blk(h, m, n);
+            if (b->kind == HMO_NODE) {
+                hmo_mul_adjoint(y, b->child, x, i0 + p, j0 + q);
+            } else if (b->kind == HMO_DENSE) {
+                hmo_mul_dense_t(y, b->U, b->m, b->n, b->m, x, j0 + q, i0 + p, 1, 1);
+            } else if (b->kind != HMO_NONE) {
+                double t1[64], t2[64];
+                int64_t r = b->r;
+                for (int64_t k = 0; k < r; k++) {
+                    double t = 0.0;
+                    for (int64_t i = 0; i < b->m; i++) t += b->U[i + k * b->m] * x[i0 + p + i];
+                    t1[k] = t;
+                }
+                if (b->kind == HMO_LOWRANK) {
+                    for (int64_t k = 0; k < r; k++) t2[k] = t1[k] * b->S[k];
+                } else {
+                    for (int64_t l = 0; l < r; l++) {
+                        double t = 0.0;
+                        for (int64_t k = 0; k < r; k++) t += b->S[k + l * r] * t1[k];
+                        t2[l] = t;
+                    }
+                }
+                for (int64_t k = 0; k < r; k++)
+                    for (int64_t j = 0; j < b->n; j++) y[j0 + q + j] += b->V[j + k * b->n] * t2[k];
+            }
+            q += hmo_blocksize(h, 0, n, 2);
+        }
+        p += hmo_blocksize(h, m, h->N - 1, 1);
+    }
+}
+
+/* ------------------------------------------------------------------ */
 /* scale!: H*Diagonal(b) and Diagonal(b)*H, in place  */
 /* ------------------------------------------------------------------ */
 

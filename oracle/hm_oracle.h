@@ -94,6 +94,10 @@ void hmo_mul(double *y, const hmo_node *h, const double *x, int64_t i0, int64_t 
 void hmo_mul_omp(double *y, const hmo_node *h, const double *x, int64_t i0, int64_t j0,
                  int nthreads);
 
+/* ---- adjoint apply y += H' x with the reference's transposed leaf rules
+ * (algebra.jl:52-65, 138-159); ranks up to 64 ---- */
+void hmo_mul_adjoint(double *y, const hmo_node *h, const double *x, int64_t i0, int64_t j0);
+
 /* ---- scale!: HierarchicalMatrix.jl:54-108, algebra.jl:280-315 (in place) ---- */
 void hmo_scale_cols(hmo_node *h, const double *b, int64_t j0); /* H <- H*Diagonal(b[j0:]) */
 void hmo_scale_rows(const double *b, hmo_node *h, int64_t i0); /* H <- Diagonal(b[i0:])*H */

@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
         "hmo_getindex": (C.c_double, [vp, _i64, _i64]),
         "hmo_mul": (None, [_dp, vp, _dp, _i64, _i64, _i64, _i64]),
         "hmo_mul_omp": (None, [_dp, vp, _dp, _i64, _i64, C.c_int]),
+        "hmo_mul_adjoint": (None, [_dp, vp, _dp, _i64, _i64]),
         "hmo_scale_cols": (None, [vp, _dp, _i64]),
         "hmo_scale_rows": (None, [_dp, vp, _i64]),
         "hmo_kernelmatrix": (vp, [C.c_int, _dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double]),
@@ -267,6 +268,12 @@ class Tree:
         b = np.ascontiguousarray(b, dtype=np.float64)
         lib().hmo_scale_rows(_p(b), self.h, i0)
         return self
+
+    # H' * x
+    def rmatvec(self, x):
+        y = np.zeros(self.shape[1])
+        lib().hmo_mul_adjoint(_p(y), self.h, _p(np.ascontiguousarray(x, dtype=np.float64)), 0, 0)
+        return y
 
     # H * x
     def matvec(self, x):

@@ -89,3 +89,19 @@ def test_fullsize_panel_matches_vector_path(K):
     Y = K * X
     for c in (0, 9, 15):
         assert relinf(Y[:, c], K * np.ascontiguousarray(X[:, c])) <= TOL
+
+
+def test_fullsize_adjoint(K):
+    rng = np.random.default_rng(5)
+    v, w = rng.standard_normal(N), rng.standard_normal(N)
+    import hmb200_loader
+    hm = hmb200_loader.load()
+    Ktw = hm.adjoint(K) * w
+    Kv = K * v
+    assert abs(w @ Kv - Ktw @ v) <= 1e-11 * np.linalg.norm(w) * np.linalg.norm(Kv)
+    e = np.zeros(N)
+    e[N // 5] = 1.0                                                     # a row of K: 1/(x_i - y_j)
+    x, y = hm.chebyshevpoints(N), hm.chebyshevpoints(N, 2)
+    row = hm.adjoint(K) * e
+    exact = 1.0 / (x[N // 5] - y)
+    assert np.max(np.abs(row - exact) / np.abs(exact)) < 1e-11

@@ -498,3 +498,80 @@ def test_fused_stage2_option(hm, O):
         subprocess.check_call([sys.executable, "-c", code, path], env=env)
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1])  # same arithmetic, same order
+
+
+# ------------------------------------------------------------------ adjoint apply H'x
+@pytest.mark.parametrize("dist,N", [("cheb", 4096), ("unif", 1000), ("quad", 3000), ("cheb", 77)])
+def test_adjoint_kernelmatrix(hm, O, dist, N):
+    x, y, (a, b, c, d) = O.example_points(N, dist)
+    Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0)
+    w = _vec(N, 5)
+    ref = Kref.rmatvec(w)
+    out = hm.adjoint(K) * w
+    assert relinf(out, ref) <= TOL
+    # <w, K v> == <K' w, v>
+    v = _vec(N, 6)
+    assert abs(w @ (K * v) - out @ v) <= 1e-11 * np.linalg.norm(w) * np.linalg.norm(K * v)
+    # mul!(y, K', x): accumulates
+    y0 = _vec(N, 7)
+    y1 = y0.copy()
+    hm.mul_(y1, hm.adjoint(K), w)
+    assert relinf(y1, y0 + ref) <= TOL
+    assert np.array_equal(hm.adjoint(K) * w, out)  # deterministic
+
+
+def test_adjoint_generic_trees(hm, O):
+    rng = np.random.default_rng(31)
+    H = random_lowrank_tree(hm, rng, 2100)
+    T = oracle_tree_from_mirror(O, H)
+    w = rng.standard_normal(2100)
+    assert relinf(hm.adjoint(H) * w, T.rmatvec(w)) <= TOL
+    # offsets and strides on both vectors
+    k = 3
+    X = np.asfortranarray(rng.standard_normal((k, 2100)))
+    Y = np.zeros((k, 2100), order="F")
+    hm.mul_(Y, hm.adjoint(H), X, 2, 3, k, k)
+    assert relinf(Y[1], T.rmatvec(np.ascontiguousarray(X[2]))) <= TOL
+    assert not Y[0].any() and not Y[2].any()
+    # rectangular, unassigned and empty blocks
+    G = hm.HierarchicalMatrix(np.float64, 3, 3)
+    sr, sc = [5, 0, 131], [7, 3, 90]
+    for m in range(3):
+        for n in range(3):
+            if (m, n) in ((0, 1), (2, 0)):
+                continue
+            if (m + n) % 2 == 0:
+                G[hm.Block(m + 1), hm.Block(n + 1)] = np.asfortranarray(rng.standard_normal((sr[m], sc[n])))
+            else:
+                G[hm.Block(m + 1), hm.Block(n + 1)] = hm.LowRankMatrix(
+                    rng.standard_normal((sr[m], 4)), rng.standard_normal(4), rng.standard_normal((sc[n], 4)))
+    TG = oracle_tree_from_mirror(O, G)
+    wg = rng.standard_normal(G.size(1))
+    assert relinf(hm.adjoint(G) * wg, TG.rmatvec(wg)) <= TOL
+    # blocks far larger than one work item: wide dense block (several rounds), rank-150 leaf
+    H2 = hm.HierarchicalMatrix(np.float64, 2, 1)
+    A = np.asfortranarray(rng.standard_normal((700, 4700)))
+    H2[hm.Block(1), hm.Block(1)] = A
+    Lr = hm.LowRankMatrix(rng.standard_normal((2500, 150)), rng.standard_normal(150), rng.standard_normal((4700, 150)))
+    H2[hm.Block(2), hm.Block(1)] = Lr
+    w2 = rng.standard_normal(3200)
+    ref = A.T @ w2[:700] + Lr.V @ (Lr.S * (Lr.U.T @ w2[700:]))
+    assert relinf(hm.adjoint(H2) * w2, ref) <= TOL
+    # after rmul!/lmul! the adjoint sees the scaled operator
+    bc = rng.standard_normal(2100)
+    hm.rmul_(H, bc)
+    T.scale_cols(bc)
+    assert relinf(hm.adjoint(H) * w, T.rmatvec(w)) <= TOL
+
+
+def test_adjoint_row_parts_sum(hm, O):
+    N = 4096
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    w = _vec(N, 8)
+    acc = np.zeros(N)
+    for p in range(3):
+        Kp = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=p, nparts=3)
+        acc += hm.adjoint(Kp) * w        # contribution of the part's rows
+    assert relinf(acc, Kref.rmatvec(w)) <= TOL

@@ -225,3 +225,15 @@ def test_scale_walks(O):
     Dn = br[1:10, None] * D * bc[None, 2:11]
     G = np.array([[T.getindex(i, j) for j in range(9)] for i in range(9)])
     assert np.allclose(G, Dn, rtol=1e-14, atol=1e-14)
+
+
+def test_adjoint_walk(O):
+    """y += H'x with the reference's transposed leaf rules (algebra.jl:52-65, 138-159)."""
+    rng = np.random.default_rng(12)
+    for dist, N in (("cheb", 900), ("quad", 500)):
+        x, y, (a, b, c, d) = O.example_points(N, dist)
+        K = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+        w, v = rng.standard_normal(N), rng.standard_normal(N)
+        D = 1.0 / (x[:, None] - y[None, :])
+        assert np.linalg.norm(K.rmatvec(w) - D.T @ w) / np.linalg.norm(D.T @ w) < 1e-13
+        assert abs(w @ K.matvec(v) - K.rmatvec(w) @ v) <= 1e-12 * np.linalg.norm(w) * np.linalg.norm(K.matvec(v))

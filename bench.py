@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--no-gather", action="store_true", help="skip the all-gather of y (N > 1)")
     ap.add_argument("--nrhs", type=int, default=1,
                     help="> 1: time the multi-right-hand-side product (BASELINE configs[2]/[4]) instead")
+    ap.add_argument("--adjoint", action="store_true",
+                    help="single GPU: time the adjoint apply y = K'x (SURVEY 8f f2) instead of K x")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -345,6 +347,32 @@ def run_ours(args):
 
     if args.nrhs > 1:
         return run_matmat(args, hm, torch, plan, st, px, py, dev, t_asm)
+    if args.adjoint:
+        xa = torch.from_numpy(np.random.default_rng(0).standard_normal(n)).to(dev)
+        ya = torch.zeros(n, dtype=torch.float64, device=dev)
+        sm = torch.cuda.current_stream()
+        for _ in range(max(args.warmup, 3)):
+            plan.rmatvec_device(xa.data_ptr(), ya.data_ptr(), False, sm.cuda_stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(sm)
+        for _ in range(args.steps):
+            plan.rmatvec_device(xa.data_ptr(), ya.data_ptr(), False, sm.cuda_stream)
+        e1.record(sm)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        rows = np.unique(np.random.default_rng(1).integers(0, n, 24))
+        xl, yl, vl = px.astype(np.longdouble), py.astype(np.longdouble), xa.cpu().numpy().astype(np.longdouble)
+        dense = np.array([np.sum(vl / (xl - yl[j])) for j in rows], dtype=np.float64)
+        err = float(np.max(np.abs(ya.cpu().numpy()[rows] - dense)) / np.max(np.abs(dense)))
+        peak, _ = measured_peak()
+        print(json.dumps({"metric": "H-matvec adjoint matvecs/s", "value": 1e3 / ms, "unit": "matvecs/s", "n_gpus": 1,
+                          "steps": args.steps, "ms_per_step": ms, "dtype": "f64",
+                          "config": {"workload": workload_name(n, args.dist).replace("mul!", "adjoint mul!"), "n": n},
+                          "effective_gbs": st["algorithmic_bytes"] / ms / 1e6,
+                          "frac_of_measured_hbm": st["algorithmic_bytes"] / ms / 1e6 / peak,
+                          "check_sampled_dense_columns_relerr": err}), flush=True)
+        return
 
     v = np.random.default_rng(0).standard_normal(n)
     gather = dist_on and not args.no_gather

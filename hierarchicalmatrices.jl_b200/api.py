@@ -233,6 +233,9 @@ class Plan:
     def matvec_device(self, dx: int, dy: int, accumulate=False, stream: int = 0):
         _lib.check(_lib.lib().hm_matvec_device(self._h, dx, dy, 1 if accumulate else 0, stream))
 
+    def rmatvec_device(self, dx: int, dy: int, accumulate=False, stream: int = 0):
+        _lib.check(_lib.lib().hm_matvec_adjoint_device(self._h, dx, dy, 1 if accumulate else 0, stream))
+
     def matmat_device(self, dX: int, ldx: int, dY: int, ldy: int, nrhs: int, accumulate=False, stream: int = 0):
         _lib.check(_lib.lib().hm_matmat_device(self._h, dX, ldx, dY, ldy, nrhs, 1 if accumulate else 0, stream))
 

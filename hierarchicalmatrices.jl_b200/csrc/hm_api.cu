@@ -311,7 +311,8 @@ struct hm_plan {
     int64_t nbig = 0;
     // adjoint apply (allocated on first use)
     DevBuf<double> pq;
-    DevBuf<int32_t> qlist, core_q0, core_qn;
+    DevBuf<int32_t> qlist, core_q0, core_qn, adjbig;
+    int nadjbig = 0;
     DevBuf<HmColSeg> colsegs;
     DevBuf<int64_t> colbases;
     bool adj_ready = false;
@@ -874,6 +875,13 @@ int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32
         HM_CUDA(p->core_qn.upload(L.core_qn, st));
         HM_CUDA(p->colsegs.upload(L.colsegs, st));
         HM_CUDA(p->colbases.upload(L.colbases, st));
+        {
+            std::vector<int32_t> big;
+            for (size_t c = 0; c < L.cores.size(); c++)
+                if (L.core_qn[c] > HM_CORE_BIG) big.push_back((int32_t)c);
+            p->nadjbig = (int)big.size();
+            HM_CUDA(p->adjbig.upload(big, st));
+        }
         if (!p->s1ent.p) HM_CUDA(p->s1ent.upload(L.s1ent, st));
         HM_CUDA(cudaStreamSynchronize(st));
         p->adj_ready = true;
@@ -893,6 +901,8 @@ int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32
     A.qn = p->core_qn.p;
     A.qlist = p->qlist.p;
     A.s1ent = p->s1ent.p;
+    A.big = p->adjbig.p;
+    A.nbig = p->nadjbig;
     A.segs = p->colsegs.p;
     A.bases = p->colbases.p;
     A.PQ = p->pq.p;

@@ -14,6 +14,8 @@
 //   stage 2             hm_core_kernel: tiny r x r core apply per low-rank leaf.
 //
 // HBM-bound: 8 B of stream per FMA.  No tensor-core use on the single-vector path.
+#include <algorithm>
+
 #include "hm_kernels.cuh"
 
 namespace {
@@ -530,10 +532,78 @@ hm_scale_cols_dense_kernel(const HmItem *__restrict__ items, const HmRun *__rest
 // The packed streams are read exactly as in the forward product, but reduced over the
 // fast index: a group of lanes owns one slab row and combines with shuffles.
 // ---------------------------------------------------------------------------
+// Eight row sums held per lane (a[r] = this lane's share of row r) are reduced across a
+// group of LR lanes by folding: each step halves the number of live values instead of
+// running one butterfly per row (9 shuffles per 8 rows at LR = 32 instead of 40).  The
+// order of the additions is fixed.  Returns the row (0..7) whose total ends up in a[0];
+// `owner` tells whether this lane holds a complete total.
+template <int LR>
+__device__ __forceinline__ int fold8(double (&a)[8], int lg, bool &owner)
+{
+    static_assert(LR == 8 || LR == 16 || LR == 32, "group width");
+    constexpr int B0 = LR / 2, B1 = LR / 4, B2 = LR / 8;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const bool up = lg & B0;
+        double send = up ? a[i] : a[i + 4];
+        double keep = up ? a[i + 4] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, B0);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const bool up = lg & B1;
+        double send = up ? a[i] : a[i + 2];
+        double keep = up ? a[i + 2] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, B1);
+    }
+    {
+        const bool up = lg & B2;
+        double send = up ? a[0] : a[1];
+        double keep = up ? a[1] : a[0];
+        a[0] = keep + __shfl_xor_sync(0xffffffffu, send, B2);
+    }
+#pragma unroll
+    for (int d = B2 / 2; d > 0; d >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], d);
+    owner = (lg & (B2 - 1)) == 0;
+    return ((lg & B0) ? 4 : 0) + ((lg & B1) ? 2 : 0) + ((lg & B2) ? 1 : 0);
+}
+
+// rows of L <= 2*LR double2 words, groups of LR lanes, 8 rows per group and step
+template <int LR>
+__device__ __forceinline__ void rowdot_groups(const double2 *__restrict__ W2, const double *zs, double *__restrict__ o,
+                                              int S, int L, int t)
+{
+    constexpr int G = HM_THREADS / LR; // groups per CTA
+    const int gi = t / LR, lg = t - gi * LR;
+    const bool act0 = lg < L, act1 = lg + LR < L;
+    const double z0 = act0 ? zs[2 * lg] : 0.0, z1 = act0 ? zs[2 * lg + 1] : 0.0;
+    const double z2 = act1 ? zs[2 * (lg + LR)] : 0.0, z3 = act1 ? zs[2 * (lg + LR) + 1] : 0.0;
+    for (int base = 0; base < S; base += G * 8) { // uniform over the CTA: every lane joins the shuffles
+        const int row0 = base + gi * 8;
+        double a[8];
+        double2 w[8], w2[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const bool v = row0 + r < S;
+            w[r] = (v && act0) ? __ldcs(W2 + (size_t)(row0 + r) * L + lg) : make_double2(0.0, 0.0);
+            w2[r] = (v && act1) ? __ldcs(W2 + (size_t)(row0 + r) * L + lg + LR) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            double q = fma(w[r].x, z0, w[r].y * z1);
+            q = fma(w2[r].x, z2, q);
+            a[r] = fma(w2[r].y, z3, q);
+        }
+        bool owner;
+        const int r = fold8<LR>(a, lg, owner);
+        if (owner && row0 + r < S) o[row0 + r] = a[0];
+    }
+}
+
 // MODE 0 (stage A'): items of the U-stream, z = x[rows of the item]
 // MODE 1 (stage C'): items of the V-stream, z gathered from the adjoint stage-2 vector
 template <int MODE>
-__global__ void __launch_bounds__(HM_THREADS, 4)
+__global__ void __launch_bounds__(HM_THREADS, 3)
 hm_rowdot_kernel(const HmItem *__restrict__ items, const double *__restrict__ W,
                  const double *__restrict__ zsrc, const int32_t *__restrict__ s1ent,
                  const HmCoreBlock *__restrict__ blocks, double *__restrict__ PQ)
@@ -560,34 +630,12 @@ hm_rowdot_kernel(const HmItem *__restrict__ items, const double *__restrict__ W,
     __syncthreads();
     const double2 *__restrict__ W2 = reinterpret_cast<const double2 *>(W + it.slab);
     double *__restrict__ o = PQ + it.aux;
-    if (L <= 32) {
-        int LR = 1; // lanes per row: next power of two >= L
-        while (LR < L) LR <<= 1;
-        const int rpw = 32 / LR, g = lane / LR, lg = lane - g * LR;
-        const bool act = lg < L;
-        const double z0 = act ? zs[2 * lg] : 0.0, z1 = act ? zs[2 * lg + 1] : 0.0;
-        const int stride = 8 * rpw;
-        int s = warp * rpw + g;
-        // loop bounds are warp-uniform (s - g is the warp's first row): every lane joins the shuffles
-        for (; (s - g) + 3 * stride + rpw - 1 < S; s += 4 * stride) {
-            double2 w[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) w[u] = act ? __ldcs(W2 + (size_t)(s + u * stride) * L + lg) : make_double2(0.0, 0.0);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                double a = fma(w[u].x, z0, w[u].y * z1);
-                for (int d = LR >> 1; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-                if (lg == 0) o[s + u * stride] = a;
-            }
-        }
-        // remaining rows: keep every lane in the shuffles
-        for (; s - g < S; s += stride) {
-            const bool rv = s < S;
-            double2 w = (act && rv) ? __ldcs(W2 + (size_t)s * L + lg) : make_double2(0.0, 0.0);
-            double a = fma(w.x, z0, w.y * z1);
-            for (int d = LR >> 1; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-            if (lg == 0 && rv) o[s] = a;
-        }
+    if (L <= 8) {
+        rowdot_groups<8>(W2, zs, o, S, L, t);
+    } else if (L <= 16) {
+        rowdot_groups<16>(W2, zs, o, S, L, t);
+    } else if (L <= 64) {
+        rowdot_groups<32>(W2, zs, o, S, L, t);
     } else {
         for (int s = warp; s < S; s += T / 32) {
             double a = 0.0;
@@ -603,19 +651,79 @@ hm_rowdot_kernel(const HmItem *__restrict__ items, const double *__restrict__ W,
     }
 }
 
-// stage B': t'[k] = sum of the leaf's q pieces (row order); s' = F' t' | Sigma .* t'
+// stage B': t'[k] = sum of the leaf's q pieces (row order); s' = F' t' | Sigma .* t'.
+// CTAs [0, nbig) take one leaf with a long piece list each (a leaf of m rows has m/64
+// pieces: thousands for the top levels) and split the list over 12 thread groups, combined
+// in group order; the remaining CTAs take one leaf per warp.
 __global__ void __launch_bounds__(256)
 hm_core_adj_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks, const int32_t *__restrict__ q0,
                    const int32_t *__restrict__ qn, const int32_t *__restrict__ qlist,
                    const double *__restrict__ PQ, const double *__restrict__ core, double *__restrict__ svec,
-                   int max_r)
+                   int max_r, const int32_t *__restrict__ big, int nbig)
 {
-    extern __shared__ double tbuf_all[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (b >= nblocks) return;
-    double *tbuf = tbuf_all + (size_t)wib * max_r;
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    if ((int)blockIdx.x < nbig) {
+        const HmCoreBlock cb = blocks[big[blockIdx.x]];
+        const int32_t *ql = qlist + q0[big[blockIdx.x]];
+        const int n = qn[big[blockIdx.x]];
+        const int ngrp = max(1, 256 / max(cb.ru, 1));
+        const int g = tid / max(cb.ru, 1), k = tid - g * cb.ru;
+        double *part = sm; // [ngrp][ru] group sums, then t' at part + ngrp*ru
+        if (cb.ru <= 256) {
+            if (g < ngrp) {
+                double t = 0.0;
+                int i = g;
+                for (; i + 3 * ngrp < n; i += 4 * ngrp) {
+                    double p0 = PQ[ql[i] + k], p1 = PQ[ql[i + ngrp] + k];
+                    double p2 = PQ[ql[i + 2 * ngrp] + k], p3 = PQ[ql[i + 3 * ngrp] + k];
+                    t += p0;
+                    t += p1;
+                    t += p2;
+                    t += p3;
+                }
+                for (; i < n; i += ngrp) t += PQ[ql[i] + k];
+                part[g * cb.ru + k] = t;
+            }
+            __syncthreads();
+            double *tb = part + ngrp * cb.ru;
+            for (int kk = tid; kk < cb.ru; kk += 256) {
+                double t = 0.0;
+                for (int gg = 0; gg < ngrp; gg++) t += part[gg * cb.ru + kk];
+                tb[kk] = t;
+            }
+            __syncthreads();
+            const double *c = core + cb.core;
+            if (cb.kind == HM_LEAF_LOWRANK) {
+                for (int kk = tid; kk < cb.rv; kk += 256) svec[cb.soff + kk] = tb[kk] * c[kk];
+            } else {
+                for (int l = tid; l < cb.rv; l += 256) {
+                    double a = 0.0;
+                    const double *col = c + (size_t)l * cb.ru;
+                    for (int kk = 0; kk < cb.ru; kk++) a = fma(col[kk], tb[kk], a);
+                    svec[cb.soff + l] = a;
+                }
+            }
+            return;
+        }
+        // ranks beyond 256: fall through to the serial warp path on warp 0
+        if (wib != 0) return;
+    }
+    int64_t b;
+    if ((int)blockIdx.x < nbig) {
+        b = big[blockIdx.x];
+    } else {
+        b = (int64_t)(blockIdx.x - nbig) * (blockDim.x >> 5) + wib;
+        if (b >= nblocks) return;
+        if (qn[b] > HM_CORE_BIG) return; // handled by a "big" CTA
+    }
+    double *tbuf = sm + (size_t)wib * (max_r + 32 * 32);
+    double *Fs = tbuf + max_r; // F staged in shared memory when it fits (ru, rv <= 32)
     const HmCoreBlock cb = blocks[b];
+    const double *c = core + cb.core;
+    const bool staged = cb.kind == HM_LEAF_BARY2D && cb.ru <= 32 && cb.rv <= 32;
+    if (staged)
+        for (int i = lane; i < cb.ru * cb.rv; i += 32) Fs[i] = __ldcs(c + i); // coalesced
     const int32_t *ql = qlist + q0[b];
     const int n = qn[b];
     for (int k = lane; k < cb.ru; k += 32) {
@@ -632,13 +740,12 @@ hm_core_adj_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks, cons
         tbuf[k] = t;
     }
     __syncwarp();
-    const double *c = core + cb.core;
     if (cb.kind == HM_LEAF_LOWRANK) {
         for (int k = lane; k < cb.rv; k += 32) svec[cb.soff + k] = tbuf[k] * c[k];
     } else {
         for (int l = lane; l < cb.rv; l += 32) {
             double a = 0.0;
-            const double *col = c + (size_t)l * cb.ru; // F[:, l]
+            const double *col = staged ? Fs + l * cb.ru : c + (size_t)l * cb.ru; // F[:, l]
             for (int k = 0; k < cb.ru; k++) a = fma(col[k], tbuf[k], a);
             svec[cb.soff + l] = a;
         }
@@ -674,16 +781,19 @@ cudaError_t hm_launch_adjoint(const HmAdjoint &A, const double *x, double *y, in
     if (A.n3 > 0)
         hm_rowdot_kernel<0><<<(unsigned)A.n3, HM_THREADS, 0, st>>>(A.items3, A.ustream, x, nullptr, nullptr, A.PQ);
     if (A.ncores > 0) {
-        int threads = 256;
-        size_t smem = (size_t)(threads / 32) * (size_t)A.max_r * sizeof(double);
-        while (smem > 48 * 1024 && threads > 32) {
-            threads >>= 1;
-            smem = (size_t)(threads / 32) * (size_t)A.max_r * sizeof(double);
+        // per warp: t' (max_r) + staged F (32 x 32); big CTAs: 13 * max_r at most
+        size_t smem = (size_t)8 * ((size_t)A.max_r + 32 * 32) * sizeof(double);
+        smem = std::max(smem, (size_t)(256 + A.max_r) * 2 * sizeof(double));
+        if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(hm_core_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
         }
-        if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
-        int wpb = threads / 32;
-        hm_core_adj_kernel<<<(unsigned)((A.ncores + wpb - 1) / wpb), threads, smem, st>>>(
-            A.blocks, A.ncores, A.q0, A.qn, A.qlist, A.PQ, A.core, A.svec, A.max_r);
+        unsigned grid = (unsigned)(A.nbig + (A.ncores + 7) / 8);
+        hm_core_adj_kernel<<<grid, 256, smem, st>>>(A.blocks, A.ncores, A.q0, A.qn, A.qlist, A.PQ, A.core, A.svec,
+                                                   A.max_r, A.big, A.nbig);
     }
     if (A.n1 > 0)
         hm_rowdot_kernel<1><<<(unsigned)A.n1, HM_THREADS, 0, st>>>(A.items1, A.vstream, A.svec, A.s1ent, A.blocks,

@@ -52,6 +52,8 @@ struct HmAdjoint {
     const double *ustream = nullptr, *vstream = nullptr, *core = nullptr;
     const HmCoreBlock *blocks = nullptr;
     const int32_t *q0 = nullptr, *qn = nullptr, *qlist = nullptr, *s1ent = nullptr;
+    const int32_t *big = nullptr; // leaves with more than HM_CORE_BIG q pieces
+    int nbig = 0;
     const HmColSeg *segs = nullptr;
     const int64_t *bases = nullptr;
     double *PQ = nullptr, *svec = nullptr;

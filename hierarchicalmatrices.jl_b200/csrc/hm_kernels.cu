@@ -568,31 +568,38 @@ __device__ __forceinline__ int fold8(double (&a)[8], int lg, bool &owner)
     return ((lg & B0) ? 4 : 0) + ((lg & B1) ? 2 : 0) + ((lg & B2) ? 1 : 0);
 }
 
-// rows of L <= 2*LR double2 words, groups of LR lanes, 8 rows per group and step
+// groups of LR lanes, 8 rows per group and step; rows longer than 2*LR double2 words are
+// walked in chunks of 2*LR (two loads per row and lane in flight), folded once at the end
 template <int LR>
 __device__ __forceinline__ void rowdot_groups(const double2 *__restrict__ W2, const double *zs, double *__restrict__ o,
                                               int S, int L, int t)
 {
     constexpr int G = HM_THREADS / LR; // groups per CTA
     const int gi = t / LR, lg = t - gi * LR;
-    const bool act0 = lg < L, act1 = lg + LR < L;
-    const double z0 = act0 ? zs[2 * lg] : 0.0, z1 = act0 ? zs[2 * lg + 1] : 0.0;
-    const double z2 = act1 ? zs[2 * (lg + LR)] : 0.0, z3 = act1 ? zs[2 * (lg + LR) + 1] : 0.0;
     for (int base = 0; base < S; base += G * 8) { // uniform over the CTA: every lane joins the shuffles
         const int row0 = base + gi * 8;
         double a[8];
-        double2 w[8], w2[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const bool v = row0 + r < S;
-            w[r] = (v && act0) ? __ldcs(W2 + (size_t)(row0 + r) * L + lg) : make_double2(0.0, 0.0);
-            w2[r] = (v && act1) ? __ldcs(W2 + (size_t)(row0 + r) * L + lg + LR) : make_double2(0.0, 0.0);
-        }
+        for (int r = 0; r < 8; r++) a[r] = 0.0;
+        for (int c0 = 0; c0 < L; c0 += 2 * LR) {
+            const int i0 = c0 + lg, i1 = c0 + lg + LR;
+            const bool act0 = i0 < L, act1 = i1 < L;
+            const double z0 = act0 ? zs[2 * i0] : 0.0, z1 = act0 ? zs[2 * i0 + 1] : 0.0;
+            const double z2 = act1 ? zs[2 * i1] : 0.0, z3 = act1 ? zs[2 * i1 + 1] : 0.0;
+            double2 w[8], w2[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            double q = fma(w[r].x, z0, w[r].y * z1);
-            q = fma(w2[r].x, z2, q);
-            a[r] = fma(w2[r].y, z3, q);
+            for (int r = 0; r < 8; r++) {
+                const bool v = row0 + r < S;
+                w[r] = (v && act0) ? __ldcs(W2 + (size_t)(row0 + r) * L + i0) : make_double2(0.0, 0.0);
+                w2[r] = (v && act1) ? __ldcs(W2 + (size_t)(row0 + r) * L + i1) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                double q = fma(w[r].x, z0, a[r]);
+                q = fma(w[r].y, z1, q);
+                q = fma(w2[r].x, z2, q);
+                a[r] = fma(w2[r].y, z3, q);
+            }
         }
         bool owner;
         const int r = fold8<LR>(a, lg, owner);
@@ -634,20 +641,8 @@ hm_rowdot_kernel(const HmItem *__restrict__ items, const double *__restrict__ W,
         rowdot_groups<8>(W2, zs, o, S, L, t);
     } else if (L <= 16) {
         rowdot_groups<16>(W2, zs, o, S, L, t);
-    } else if (L <= 64) {
-        rowdot_groups<32>(W2, zs, o, S, L, t);
     } else {
-        for (int s = warp; s < S; s += T / 32) {
-            double a = 0.0;
-            const double2 *row = W2 + (size_t)s * L;
-            for (int i = lane; i < L; i += 32) {
-                double2 w = __ldcs(row + i);
-                a = fma(w.x, zs[2 * i], a);
-                a = fma(w.y, zs[2 * i + 1], a);
-            }
-            for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
-            if (lane == 0) o[s] = a;
-        }
+        rowdot_groups<32>(W2, zs, o, S, L, t);
     }
 }
 

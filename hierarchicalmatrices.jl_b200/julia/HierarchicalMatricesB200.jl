@@ -200,6 +200,18 @@ scale!(P::Plan, b::Vector{Float64}, side::Integer) =
     (GC.@preserve b check(ccall((:hm_plan_scale, libhm), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32),
                                 P.ptr, b, 1, side)); P)
 
+# Adjoint apply (no hierarchical adjoint exists in the reference; leaf rules of
+# src/algebra.jl:52-82, 138-159): y += H' x through the same packed operator.
+function adjoint_mul!(y::StridedVector{Float64}, H::Union{KernelMatrix{Float64},HierarchicalMatrix{Float64}},
+                      x::StridedVector{Float64}; accumulate::Bool = true)
+    nr, nc = size(H)
+    (length(x) >= nr && length(y) >= nc) || throw(DimensionMismatch("adjoint_mul!"))
+    GC.@preserve x y check(ccall((:hm_matvec_adjoint, libhm), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int32),
+        plan(H).ptr, x, stride(x, 1), y, stride(y, 1), accumulate ? 1 : 0))
+    y
+end
+
 # Plans built by `assemble` act as operators themselves
 Base.:*(P::Plan, v::Vector{Float64}) = begin
     st = stats(P)

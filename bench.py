@@ -321,7 +321,18 @@ def run_ours(args):
     import torch
     import hmb200_loader
     hm = hmb200_loader.load()
-    hm.lib()  # fails loudly if the CUDA library is missing
+    if not os.path.exists(hm._lib.LIB_PATH):
+        # a fresh checkout carries no binaries: compile the CUDA library (nvcc, sm_100a) once;
+        # under torchrun only local rank 0 builds, the others wait for the file
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            hm.build()
+        else:
+            for _ in range(600):
+                if os.path.exists(hm._lib.LIB_PATH):
+                    break
+                time.sleep(0.5)
+            time.sleep(1.0)
+    hm.lib()  # fails loudly if the CUDA library is missing: there is no CPU fallback
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -333,6 +344,7 @@ def run_ours(args):
     dist_on = world > 1
     if dist_on:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n

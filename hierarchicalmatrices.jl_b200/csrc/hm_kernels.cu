@@ -780,11 +780,9 @@ cudaError_t hm_launch_adjoint(const HmAdjoint &A, const double *x, double *y, in
         size_t smem = (size_t)8 * ((size_t)A.max_r + 32 * 32) * sizeof(double);
         smem = std::max(smem, (size_t)(256 + A.max_r) * 2 * sizeof(double));
         if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
+        if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(hm_core_adj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            configured = smem;
         }
         unsigned grid = (unsigned)(A.nbig + (A.ncores + 7) / 8);
         hm_core_adj_kernel<<<grid, 256, smem, st>>>(A.blocks, A.ncores, A.q0, A.qn, A.qlist, A.PQ, A.core, A.svec,
@@ -836,13 +834,11 @@ cudaError_t hm_launch_stage2_big(const HmCoreBlock *blocks, const int32_t *big, 
     if (nbig <= 0) return cudaSuccess;
     size_t smem = (size_t)9 * max_r * sizeof(double);
     if (smem > 48 * 1024) {
-        static size_t configured = 0;
         if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-        if (smem > configured) {
+        {
             cudaError_t e = cudaFuncSetAttribute(hm_core_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem);
             if (e != cudaSuccess) return e;
-            configured = smem;
         }
     }
     hm_core_big_kernel<<<(unsigned)nbig, 256, smem, st>>>(blocks, big, plist, partial, core, svec, max_r);

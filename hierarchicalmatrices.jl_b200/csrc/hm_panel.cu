@@ -434,12 +434,10 @@ cudaError_t launch_panel_tma(const HmItem *items, int64_t nitems, const HmRun *r
 {
     if (nitems <= 0) return cudaSuccess;
     const size_t smem = (size_t)TS * TSTAGE * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    { // the attribute is per device: set it on every call (cheap) rather than once per process
         cudaError_t e = cudaFuncSetAttribute(hm_panel_tma_kernel<GATHER, NB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     hm_panel_tma_kernel<GATHER, NB><<<(unsigned)nitems, 288, smem, st>>>(items, runs, W, Xt, Sp, out, accumulate);
     return cudaGetLastError();
@@ -545,12 +543,10 @@ cudaError_t launch_panel(const HmItem *items, int64_t nitems, const HmRun *runs,
 {
     if (nitems <= 0) return cudaSuccess;
     const size_t smem = (size_t)8 * 16 * (NB * 8 + 8) * sizeof(double); // split-K combine buffer
-    static bool configured = false; // per instantiation
-    if (!configured) { // static + dynamic shared memory can exceed 48 KB
+    { // the attribute is per device: set it on every call (cheap) rather than once per process
         cudaError_t e = cudaFuncSetAttribute(hm_panel_kernel<GATHER, NB, U>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     hm_panel_kernel<GATHER, NB, U><<<(unsigned)nitems, PT, smem, st>>>(items, runs, W, Xt, Sp, out, accumulate);
     return cudaGetLastError();
@@ -563,12 +559,10 @@ cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const 
     if (nblocks <= 0) return cudaSuccess;
     const size_t smem = (size_t)max_r * NB * 8 * sizeof(double);
     if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(hm_core_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     hm_core_panel_kernel<NB><<<(unsigned)nblocks, 256, smem, st>>>(blocks, plist, Pp, core, Sp, max_r);
     return cudaGetLastError();

@@ -575,3 +575,28 @@ def test_adjoint_row_parts_sum(hm, O):
         Kp = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=p, nparts=3)
         acc += hm.adjoint(Kp) * w        # contribution of the part's rows
     assert relinf(acc, Kref.rmatvec(w)) <= TOL
+
+
+def test_panel_kernel_variants_agree(hm, O):
+    """The two implementations of the multi-RHS kernels (register-streaming default,
+    HMB200_PANEL=tma bulk-copy/mbarrier pipeline) compute the same products."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import hmb200_loader; hm = hmb200_loader.load();"
+        "x, y = hm.chebyshevpoints(6000), hm.chebyshevpoints(6000, 2);"
+        "K = hm.KernelMatrix(hm.cauchykernel, x, y, 1.0, -1.0, 1.0, -1.0, device=0);"
+        "X = np.asfortranarray(np.random.default_rng(0).standard_normal((6000, 40)));"
+        "np.save(sys.argv[1], K * X)"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("stream", "tma"):
+        path = f"/tmp/hm_panel_{flag}.npy"
+        subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, HMB200_PANEL=flag))
+        outs.append(np.load(path))
+    assert relinf(outs[0], outs[1]) <= 1e-13
+    x, y, (a, b, c, d) = O.example_points(6000, "cheb")
+    Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    X = np.asfortranarray(np.random.default_rng(0).standard_normal((6000, 40)))
+    assert relinf(outs[1][:, 39], Kref.matvec(np.ascontiguousarray(X[:, 39]))) <= TOL

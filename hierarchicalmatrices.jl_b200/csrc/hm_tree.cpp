@@ -53,6 +53,12 @@ struct Builder {
     int bs, r;
     std::vector<Node> nodes;
     bool failed = false;
+    bool too_deep = false;
+    int depth = 0;
+    // Bisection halves the box every level; once it has collapsed to a point (about 1100
+    // levels from [-1, 1]) a cluster of >= BLOCKSIZE coincident points can never be split
+    // and the reference recurses until StackOverflowError.
+    static constexpr int MAX_DEPTH = 1200;
 
     static int64_t len(int64_t lo, int64_t hi) { return hi > lo ? hi - lo : 0; }
 
@@ -110,10 +116,19 @@ struct Builder {
               double c, double d)
     {
         int64_t im, jm;
+        if (depth > MAX_DEPTH) {
+            failed = too_deep = true;
+            return -1;
+        }
         if (!split(x, nx, i0, i1, a, b, im) || !split(y, ny, j0, j1, c, d, jm)) {
             failed = true;
             return -1;
         }
+        struct DepthScope {
+            int &d;
+            explicit DepthScope(int &dd) : d(dd) { ++d; }
+            ~DepthScope() { --d; }
+        } scope(depth);
         const double xm = 0.5 * (a + b), ym = 0.5 * (c + d);
         const bool small = len(i0, im) < bs && len(im, i1) < bs && len(j0, jm) < bs && len(jm, j1) < bs;
         Node nd;
@@ -211,6 +226,8 @@ std::string hm_kernel_tree(const double *x, int64_t nx, const double *y, int64_t
     bld.bs = hm_blocksize_double();
     bld.r = hm_blockrank_double();
     int root = bld.build(0, 0, nx, 0, ny, a, b, c, d);
+    if (bld.too_deep)
+        return "KernelMatrix: a cluster of coincident points cannot be bisected (StackOverflowError in the reference)";
     if (root < 0 || bld.failed) return "KernelMatrix: index split ran past the end of the point set (BoundsError in the reference)";
     nrows = bld.nodes[(size_t)root].rows;
     ncols = bld.nodes[(size_t)root].cols;

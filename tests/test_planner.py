@@ -83,6 +83,12 @@ def test_kernel_tree_reference_error(hm, O):
     assert b"BoundsError" in hm.lib().hm_last_error()
     with pytest.raises(RuntimeError):
         O.kernelmatrix(O.CAUCHY, x, x, 1.0, -1.0, 1.0, -1.0)
+    # a cluster of >= BLOCKSIZE coincident points can never be bisected: the reference recurses
+    # until StackOverflowError; the planner reports it instead of overflowing its own stack
+    xc = np.concatenate([np.linspace(1.0, 0.31, 50), np.full(200, 0.3), np.linspace(0.29, -1.0, 50)])
+    rc = hm.lib().hm_assemble_kernel_stats(xc.ctypes.data_as(dp), 300, xc.ctypes.data_as(dp), 300, 1.0, -1.0, 1.0, -1.0,
+                                           0, 1, C.byref(s))
+    assert rc == 9 and (b"StackOverflow" in hm.lib().hm_last_error() or b"BoundsError" in hm.lib().hm_last_error())
     # ... while a box that fits the points is fine
     rc = hm.lib().hm_assemble_kernel_stats(x.ctypes.data_as(dp), 200, x.ctypes.data_as(dp), 200, 1.0, 0.5, 1.0, 0.5,
                                            0, 1, C.byref(s))

@@ -444,6 +444,198 @@ cudaError_t launch_panel_tma(const HmItem *items, int64_t nitems, const HmRun *r
 }
 
 // ---------------------------------------------------------------------------
+// stage 1 / stage 3 on a panel as a tiled GEMM (HMB200_PANEL=mm; default at 64 columns).
+//
+// One CTA of 4 warps per item and pass of 64 slab rows: C[64 x CS] += W'[64 x S] Z[S x CS].
+// Both operands are staged through a 4-deep cp.async pipeline of 16-row chunks (padded
+// pitches, conflict-free fragment reads); a warp owns a 32-row x (CS/2 or CS/4)-column
+// tile, i.e. up to 16 independent MMA accumulators, so the tensor pipe stays busy across
+// the fragment loads; no split-K, C fragments go straight to global memory.
+// ---------------------------------------------------------------------------
+#ifndef HM_PANEL_DEFAULT_64
+#define HM_PANEL_DEFAULT_64 0 // implementation used at 64 columns unless HMB200_PANEL says otherwise
+#endif
+constexpr int MM_T = 128;   // threads
+constexpr int MM_ST = 3;    // stages
+constexpr int MM_KC = 16;   // slab rows per stage
+constexpr int MM_MT = 64;   // fast-dimension rows per pass
+constexpr int MM_WP = MM_MT + 8;
+
+__device__ __forceinline__ void cp_async16_plain(void *smem_dst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <bool GATHER, int NB>
+__global__ void __launch_bounds__(MM_T, 3)
+hm_panel_mm_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
+                   const double *__restrict__ W, const double *__restrict__ Xt,
+                   const double *__restrict__ Sp, double *__restrict__ out, int accumulate)
+{
+    constexpr int CS = NB * 8, ZP = CS + 8;
+    constexpr int STAGE = MM_KC * (MM_WP + ZP);
+    constexpr int NBW = NB >= 4 ? NB / 2 : NB; // column blocks per warp in the 2 x 2 warp grid
+    extern __shared__ __align__(16) double dsm[];
+    __shared__ int zrow[GATHER ? HM_SMAX : 1];
+    __shared__ int rpos[GATHER ? HM_MAXRUNS + 1 : 1];
+    __shared__ int rsrc[GATHER ? HM_MAXRUNS : 1];
+
+    const HmItem it = items[blockIdx.x];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int S = it.S, F = it.F, Fp = it.Fp;
+
+    if (GATHER) {
+        for (int r = t; r < it.nrun; r += MM_T) {
+            HmRun rr = runs[it.run0 + r];
+            rpos[r] = rr.pos;
+            rsrc[r] = rr.src;
+        }
+        if (t == 0) rpos[it.nrun] = S;
+        __syncthreads();
+        for (int e = t; e < S; e += MM_T) {
+            int lo = 0, hi = it.nrun;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (rpos[mid] <= e)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            int src = rsrc[lo], off = e - rpos[lo];
+            zrow[e] = src >= 0 ? src + off : ~((~src) + off);
+        }
+        __syncthreads();
+    }
+
+    const double *__restrict__ Wg = W + it.slab;
+    const int nchunks = (S + MM_KC - 1) / MM_KC;
+
+    for (int f0 = 0; f0 < Fp; f0 += MM_MT) {
+        const int mt = min(MM_MT, Fp - f0); // even
+        const int nfb = (mt + 7) >> 3;      // 8-row blocks in this pass (<= 8)
+        // warp grid: rows beyond 32 exist -> 2 (rows) x 2 (columns); else 1 x 4
+        const bool tall = nfb > 4;
+        const int wr = tall ? (warp >> 1) : 0;                 // row half
+        const int wc = tall ? (warp & 1) : warp;               // column group
+        const int nbw = tall ? NBW : max(1, NB / 4);           // column blocks of this warp
+        const int n0 = wc * nbw;
+        const int fb0 = wr * 4;
+        const int na = min(4, nfb - fb0);                      // row blocks of this warp (<= 0: idle)
+        const bool active = na > 0 && n0 < NB;
+
+        double acc[4][NBW][2];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int n = 0; n < NBW; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
+
+        auto issue = [&](int ch) {
+            double *Wsm = dsm + (size_t)(ch % MM_ST) * STAGE;
+            double *Zsm = Wsm + MM_KC * MM_WP;
+            const int s0 = ch * MM_KC, rows = min(MM_KC, S - s0);
+            const int hw = mt >> 1;
+            for (int idx = t; idx < rows * hw; idx += MM_T) {
+                int r = idx / hw, p = idx - r * hw;
+                cp_async16_plain(Wsm + r * MM_WP + 2 * p, Wg + (size_t)(s0 + r) * Fp + f0 + 2 * p);
+            }
+            constexpr int hz = CS / 2;
+            for (int idx = t; idx < rows * hz; idx += MM_T) {
+                int r = idx / hz, p = idx - r * hz;
+                const double *src;
+                if (GATHER) {
+                    int zr = zrow[s0 + r];
+                    src = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
+                } else {
+                    src = Xt + (size_t)(it.zoff + s0 + r) * CS;
+                }
+                cp_async16_plain(Zsm + r * ZP + 2 * p, src + 2 * p);
+            }
+            if (rows < MM_KC) { // zero the tail rows of the last chunk: 0 * stale NaN would poison the sums
+                for (int idx = t; idx < (MM_KC - rows) * MM_WP; idx += MM_T) Wsm[rows * MM_WP + idx] = 0.0;
+                for (int idx = t; idx < (MM_KC - rows) * ZP; idx += MM_T) Zsm[rows * ZP + idx] = 0.0;
+            }
+        };
+
+        __syncthreads(); // the previous pass is done with the stages
+        for (int ch = 0; ch < MM_ST - 1; ch++) {
+            if (ch < nchunks) issue(ch);
+            cp_async_commit_group();
+        }
+        for (int ch = 0; ch < nchunks; ch++) {
+            cp_async_wait_group<MM_ST - 2>(); // chunk ch has landed (this thread's pieces)
+            __syncthreads();                  // ... everyone's; and stage (ch-1) % ST is free again
+            if (ch + MM_ST - 1 < nchunks) issue(ch + MM_ST - 1);
+            cp_async_commit_group();
+            if (active) {
+                const double *Wsm = dsm + (size_t)(ch % MM_ST) * STAGE;
+                const double *Zsm = Wsm + MM_KC * MM_WP;
+                const double *ap = Wsm + tig * MM_WP + fb0 * 8 + gid;
+                const double *bp = Zsm + tig * ZP + n0 * 8 + gid;
+#pragma unroll
+                for (int ks = 0; ks < MM_KC / 4; ks++) {
+                    double a[4], b[NBW];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) a[i] = i < na ? ap[ks * 4 * MM_WP + i * 8] : 0.0;
+#pragma unroll
+                    for (int n = 0; n < NBW; n++) b[n] = n < nbw ? bp[ks * 4 * ZP + n * 8] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (i < na) {
+#pragma unroll
+                            for (int n = 0; n < NBW; n++)
+                                if (n < nbw) dmma884(acc[i][n][0], acc[i][n][1], a[i], b[n]);
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_wait_group<0>();
+
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int f = f0 + (fb0 + i) * 8 + gid;
+                if (i < na && f < F) {
+                    double2 *gp = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + n0 * 4 + tig;
+#pragma unroll
+                    for (int n = 0; n < NBW; n++) {
+                        if (n < nbw) {
+                            double2 v = make_double2(acc[i][n][0], acc[i][n][1]);
+                            if (GATHER && accumulate) {
+                                double2 o = gp[n * 4];
+                                v.x += o.x;
+                                v.y += o.y;
+                            }
+                            gp[n * 4] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool GATHER, int NB>
+cudaError_t launch_panel_mm(const HmItem *items, int64_t nitems, const HmRun *runs, const double *W,
+                            const double *Xt, const double *Sp, double *out, int accumulate, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    const size_t smem = (size_t)MM_ST * MM_KC * (MM_WP + NB * 8 + 8) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(hm_panel_mm_kernel<GATHER, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    hm_panel_mm_kernel<GATHER, NB><<<(unsigned)nitems, MM_T, smem, st>>>(items, runs, W, Xt, Sp, out, accumulate);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // stage 2 on a panel: one CTA per low-rank leaf
 //   T[k][c] = sum of the leaf's partial panels (column order); S = F T | Sigma .* T
 // ---------------------------------------------------------------------------
@@ -595,23 +787,31 @@ cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1
 //   tma               hm_panel_tma_kernel: warp-specialised cp.async.bulk + mbarrier pipeline
 // Measured on one B200 at N = 2^20 (ms per product, 16 / 64 right-hand sides): stream 5.2 / 15.0,
 // tma 11.4 / 16.6.  HMB200_PANEL=tma selects the second one.
-static bool use_stream_variant()
+static int panel_variant(int CS)
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("HMB200_PANEL");
-        v = (e && e[0] == 't') ? 0 : 1;
+        v = !e ? 3 : e[0] == 't' ? 1 : e[0] == 'm' ? 2 : e[0] == 's' ? 0 : 3;
     }
-    return v == 1;
+    if (v == 3) return CS == 64 ? HM_PANEL_DEFAULT_64 : 0; // default: per panel width
+    return v;
 }
 
 cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, const double *vstream,
                                    const double *Xt, double *Pp, cudaStream_t st)
 {
-    if (!use_stream_variant()) switch (CS) {
+    const int variant = panel_variant(CS);
+    if (variant == 1) switch (CS) {
         case 16: return launch_panel_tma<false, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
         case 32: return launch_panel_tma<false, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
         case 64: return launch_panel_tma<false, 8>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+        default: return cudaErrorInvalidValue;
+        }
+    if (variant == 2) switch (CS) {
+        case 16: return launch_panel_mm<false, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+        case 32: return launch_panel_mm<false, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
+        case 64: return launch_panel_mm<false, 8>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
         default: return cudaErrorInvalidValue;
         }
     switch (CS) {
@@ -637,10 +837,17 @@ cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, 
                                    const double *ustream, const double *Xt, const double *Sp, double *Yt,
                                    int accumulate, cudaStream_t st)
 {
-    if (!use_stream_variant()) switch (CS) {
+    const int variant = panel_variant(CS);
+    if (variant == 1) switch (CS) {
         case 16: return launch_panel_tma<true, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
         case 32: return launch_panel_tma<true, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
         case 64: return launch_panel_tma<true, 8>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+        default: return cudaErrorInvalidValue;
+        }
+    if (variant == 2) switch (CS) {
+        case 16: return launch_panel_mm<true, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+        case 32: return launch_panel_mm<true, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
+        case 64: return launch_panel_mm<true, 8>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
         default: return cudaErrorInvalidValue;
         }
     switch (CS) {

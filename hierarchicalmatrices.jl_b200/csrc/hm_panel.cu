@@ -536,26 +536,45 @@ hm_panel_mm_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ r
 #pragma unroll
             for (int n = 0; n < NBW; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
 
+        // Each thread copies the same pieces of every chunk: up to 4 sixteen-byte pieces of W
+        // (row wr, column pair wp of the pass) and CS/64 * 4 of Z.  Their offsets are computed
+        // once per pass; per chunk only the base moves (keeps the copy code off the
+        // instruction budget: it used to cost 4x the instructions of the math).
+        const int hw = mt >> 1;
+        int w_s[4], w_r[4];
+        long long w_g[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int idx = t + j * MM_T;
+            const int r = idx / hw, pp = idx - r * hw;
+            w_r[j] = r < MM_KC ? r : MM_KC; // MM_KC: no such piece
+            w_s[j] = r * MM_WP + 2 * pp;
+            w_g[j] = (long long)r * Fp + f0 + 2 * pp;
+        }
+        constexpr int hz = CS / 2;                    // 16-byte pieces per z row
+        constexpr int ZPT = (MM_KC * hz + MM_T - 1) / MM_T; // z pieces per thread
         auto issue = [&](int ch) {
             double *Wsm = dsm + (size_t)(ch % MM_ST) * STAGE;
             double *Zsm = Wsm + MM_KC * MM_WP;
             const int s0 = ch * MM_KC, rows = min(MM_KC, S - s0);
-            const int hw = mt >> 1;
-            for (int idx = t; idx < rows * hw; idx += MM_T) {
-                int r = idx / hw, p = idx - r * hw;
-                cp_async16_plain(Wsm + r * MM_WP + 2 * p, Wg + (size_t)(s0 + r) * Fp + f0 + 2 * p);
-            }
-            constexpr int hz = CS / 2;
-            for (int idx = t; idx < rows * hz; idx += MM_T) {
-                int r = idx / hz, p = idx - r * hz;
-                const double *src;
-                if (GATHER) {
-                    int zr = zrow[s0 + r];
-                    src = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
-                } else {
-                    src = Xt + (size_t)(it.zoff + s0 + r) * CS;
+            const double *wsrc = Wg + (size_t)s0 * Fp;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (w_r[j] < rows) cp_async16_plain(Wsm + w_s[j], wsrc + w_g[j]);
+#pragma unroll
+            for (int j = 0; j < ZPT; j++) {
+                const int idx = t + j * MM_T;
+                const int r = idx / hz, pp = idx % hz; // hz is a compile-time power of two
+                if (r < rows) {
+                    const double *src;
+                    if (GATHER) {
+                        const int zr = zrow[s0 + r];
+                        src = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
+                    } else {
+                        src = Xt + (size_t)(it.zoff + s0 + r) * CS;
+                    }
+                    cp_async16_plain(Zsm + r * ZP + 2 * pp, src + 2 * pp);
                 }
-                cp_async16_plain(Zsm + r * ZP + 2 * p, src + 2 * p);
             }
             if (rows < MM_KC) { // zero the tail rows of the last chunk: 0 * stale NaN would poison the sums
                 for (int idx = t; idx < (MM_KC - rows) * MM_WP; idx += MM_T) Wsm[rows * MM_WP + idx] = 0.0;
@@ -578,19 +597,34 @@ hm_panel_mm_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ r
                 const double *Zsm = Wsm + MM_KC * MM_WP;
                 const double *ap = Wsm + tig * MM_WP + fb0 * 8 + gid;
                 const double *bp = Zsm + tig * ZP + n0 * 8 + gid;
+                if (na == 4 && nbw == NBW) { // full tile: no masking in the inner loop
 #pragma unroll
-                for (int ks = 0; ks < MM_KC / 4; ks++) {
-                    double a[4], b[NBW];
+                    for (int ks = 0; ks < MM_KC / 4; ks++) {
+                        double a[4], b[NBW];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) a[i] = i < na ? ap[ks * 4 * MM_WP + i * 8] : 0.0;
+                        for (int i = 0; i < 4; i++) a[i] = ap[ks * 4 * MM_WP + i * 8];
 #pragma unroll
-                    for (int n = 0; n < NBW; n++) b[n] = n < nbw ? bp[ks * 4 * ZP + n * 8] : 0.0;
+                        for (int n = 0; n < NBW; n++) b[n] = bp[ks * 4 * ZP + n * 8];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        if (i < na) {
+                        for (int i = 0; i < 4; i++)
 #pragma unroll
-                            for (int n = 0; n < NBW; n++)
-                                if (n < nbw) dmma884(acc[i][n][0], acc[i][n][1], a[i], b[n]);
+                            for (int n = 0; n < NBW; n++) dmma884(acc[i][n][0], acc[i][n][1], a[i], b[n]);
+                    }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < MM_KC / 4; ks++) {
+                        double a[4], b[NBW];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) a[i] = i < na ? ap[ks * 4 * MM_WP + i * 8] : 0.0;
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) b[n] = n < nbw ? bp[ks * 4 * ZP + n * 8] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            if (i < na) {
+#pragma unroll
+                                for (int n = 0; n < NBW; n++)
+                                    if (n < nbw) dmma884(acc[i][n][0], acc[i][n][1], a[i], b[n]);
+                            }
                         }
                     }
                 }

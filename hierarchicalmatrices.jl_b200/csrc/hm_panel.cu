@@ -452,9 +452,6 @@ cudaError_t launch_panel_tma(const HmItem *items, int64_t nitems, const HmRun *r
 // tile, i.e. up to 16 independent MMA accumulators, so the tensor pipe stays busy across
 // the fragment loads; no split-K, C fragments go straight to global memory.
 // ---------------------------------------------------------------------------
-#ifndef HM_PANEL_DEFAULT_64
-#define HM_PANEL_DEFAULT_64 0 // implementation used at 64 columns unless HMB200_PANEL says otherwise
-#endif
 constexpr int MM_T = 128;   // threads
 constexpr int MM_ST = 3;    // stages
 constexpr int MM_KC = 16;   // slab rows per stage
@@ -674,7 +671,7 @@ cudaError_t launch_panel_mm(const HmItem *items, int64_t nitems, const HmRun *ru
 //   T[k][c] = sum of the leaf's partial panels (column order); S = F T | Sigma .* T
 // ---------------------------------------------------------------------------
 template <int NB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(64)
 hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__restrict__ plist,
                      const double *__restrict__ Pp, const double *__restrict__ core,
                      double *__restrict__ Sp, int max_r)
@@ -790,7 +787,8 @@ cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const 
                                              (int)smem);
         if (e != cudaSuccess) return e;
     }
-    hm_core_panel_kernel<NB><<<(unsigned)nblocks, 256, smem, st>>>(blocks, plist, Pp, core, Sp, max_r);
+    // small CTAs: the kernel is latency-bound, more leaves in flight per SM
+    hm_core_panel_kernel<NB><<<(unsigned)nblocks, 64, smem, st>>>(blocks, plist, Pp, core, Sp, max_r);
     return cudaGetLastError();
 }
 
@@ -821,21 +819,29 @@ cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1
 //   tma               hm_panel_tma_kernel: warp-specialised cp.async.bulk + mbarrier pipeline
 // Measured on one B200 at N = 2^20 (ms per product, 16 / 64 right-hand sides): stream 5.2 / 15.0,
 // tma 11.4 / 16.6.  HMB200_PANEL=tma selects the second one.
-static int panel_variant(int CS)
+// Which implementation runs: HMB200_PANEL = stream | tma | mm forces one for both stages;
+// by default stage 1 (short slow dimension: 64-column slabs, rank-20 leaves) takes the
+// register-streaming kernel and stage 3 (slow dimension ~1000-2000) the tiled GEMM --
+// measured per stage at N = 2^20, ms for 16 / 64 columns:
+//              stage 1        stage 3
+//   stream   1.98 / 6.05    2.48 / 6.17
+//   mm       2.64 / 6.39    2.10 / 5.19
+//   tma      5.70 / 7.79    5.00 / 6.85
+static int panel_variant(int stage)
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("HMB200_PANEL");
         v = !e ? 3 : e[0] == 't' ? 1 : e[0] == 'm' ? 2 : e[0] == 's' ? 0 : 3;
     }
-    if (v == 3) return CS == 64 ? HM_PANEL_DEFAULT_64 : 0; // default: per panel width
+    if (v == 3) return stage == 3 ? 2 : 0;
     return v;
 }
 
 cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, const double *vstream,
                                    const double *Xt, double *Pp, cudaStream_t st)
 {
-    const int variant = panel_variant(CS);
+    const int variant = panel_variant(1);
     if (variant == 1) switch (CS) {
         case 16: return launch_panel_tma<false, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
         case 32: return launch_panel_tma<false, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
@@ -871,7 +877,7 @@ cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, 
                                    const double *ustream, const double *Xt, const double *Sp, double *Yt,
                                    int accumulate, cudaStream_t st)
 {
-    const int variant = panel_variant(CS);
+    const int variant = panel_variant(3);
     if (variant == 1) switch (CS) {
         case 16: return launch_panel_tma<true, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
         case 32: return launch_panel_tma<true, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);

@@ -14,6 +14,7 @@
 //   Sp[k][c]  stage-2 results                        Yt[i][c]  stage-3 results
 // so that the z rows an item needs are contiguous CS*8-byte pieces (cp.async friendly).
 #include <cstdlib>
+#include <type_traits>
 
 #include "hm_kernels.cuh"
 
@@ -111,29 +112,34 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
 #pragma unroll
             for (int n = 0; n < NB; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
 
-        for (int k0 = s_lo; k0 < s_hi; k0 += 4 * U) {
+        // One load batch = U k-steps (4 slab rows each).  Full batches run without row masks and
+        // with incrementing pointers (no 64-bit multiplies in the loop); the ragged end of the
+        // range takes the masked form once.
+        auto batch = [&](int k0, auto masked) {
+            constexpr bool MASK = decltype(masked)::value;
             double a0[U], a1[U], b[U][NB];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int row = k0 + 4 * u + tig;
-                const bool v = row < s_hi;
-                // software prefetch into L2, PD load batches ahead: the demand loads below then
-                // see L2 latency instead of HBM latency (no registers held)
-                const int prow = row + 4 * U * PD;
-                if (NB == 8 && prow < s_hi) { // measured: helps the MMA-bound 64-column case only
-                    if (c0ok) prefetch_l2(ap + (size_t)prow * Fp);
-                    if (c1ok) prefetch_l2(ap + (size_t)prow * Fp + 8);
-                    const double *pz;
-                    if (GATHER) {
-                        int zr = zrow[prow];
-                        pz = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
-                    } else {
-                        pz = Xt + (size_t)(it.zoff + prow) * CS;
+                const bool v = !MASK || row < s_hi;
+                if (NB == 8) { // software prefetch into L2, PD batches ahead (helps the MMA-bound case only)
+                    const int prow = row + 4 * U * PD;
+                    if (prow < s_hi) {
+                        if (c0ok) prefetch_l2(ap + (size_t)prow * Fp);
+                        if (c1ok) prefetch_l2(ap + (size_t)prow * Fp + 8);
+                        const double *pz;
+                        if (GATHER) {
+                            int zr = zrow[prow];
+                            pz = zr >= 0 ? Xt + (size_t)zr * CS : Sp + (size_t)(~zr) * CS;
+                        } else {
+                            pz = Xt + (size_t)(it.zoff + prow) * CS;
+                        }
+                        if (gid * 8 < CS) prefetch_l2(pz + gid * 8);
                     }
-                    if (gid * 8 < CS) prefetch_l2(pz + gid * 8);
                 }
-                a0[u] = (v && c0ok) ? __ldcs(ap + (size_t)row * Fp) : 0.0;
-                a1[u] = (v && c1ok) ? __ldcs(ap + (size_t)row * Fp + 8) : 0.0;
+                const double *arow = ap + (size_t)row * Fp;
+                a0[u] = (v && c0ok) ? __ldcs(arow) : 0.0;
+                a1[u] = (v && c1ok) ? __ldcs(arow + 8) : 0.0;
                 const double *zp = Xt;
                 if (v) {
                     if (GATHER) {
@@ -154,7 +160,10 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
                     if (two) dmma884(acc[1][n][0], acc[1][n][1], a1[u], b[u][n]);
                 }
             }
-        }
+        };
+        int k0 = s_lo;
+        for (; k0 + 4 * U <= s_hi; k0 += 4 * U) batch(k0, std::false_type{});
+        if (k0 < s_hi) batch(k0, std::true_type{});
 
         if (kgroups == 1) {
             // sole owner of the tile: write the C fragments straight out
@@ -671,7 +680,7 @@ cudaError_t launch_panel_mm(const HmItem *items, int64_t nitems, const HmRun *ru
 //   T[k][c] = sum of the leaf's partial panels (column order); S = F T | Sigma .* T
 // ---------------------------------------------------------------------------
 template <int NB>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__restrict__ plist,
                      const double *__restrict__ Pp, const double *__restrict__ core,
                      double *__restrict__ Sp, int max_r)
@@ -788,7 +797,7 @@ cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const 
         if (e != cudaSuccess) return e;
     }
     // small CTAs: the kernel is latency-bound, more leaves in flight per SM
-    hm_core_panel_kernel<NB><<<(unsigned)nblocks, 64, smem, st>>>(blocks, plist, Pp, core, Sp, max_r);
+    hm_core_panel_kernel<NB><<<(unsigned)nblocks, NB >= 8 ? 128 : 64, smem, st>>>(blocks, plist, Pp, core, Sp, max_r);
     return cudaGetLastError();
 }
 

@@ -833,7 +833,7 @@ cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1
 // register-streaming kernel and stage 3 (slow dimension ~1000-2000) the tiled GEMM --
 // measured per stage at N = 2^20, ms for 16 / 64 columns:
 //              stage 1        stage 3
-//   stream   1.98 / 6.05    2.48 / 6.17
+//   stream   1.92 / 5.50    2.48 / 6.17
 //   mm       2.64 / 6.39    2.10 / 5.19
 //   tma      5.70 / 7.79    5.00 / 6.85
 static int panel_variant(int stage)

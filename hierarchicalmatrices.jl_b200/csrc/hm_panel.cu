@@ -461,11 +461,11 @@ cudaError_t launch_panel_tma(const HmItem *items, int64_t nitems, const HmRun *r
 // tile, i.e. up to 16 independent MMA accumulators, so the tensor pipe stays busy across
 // the fragment loads; no split-K, C fragments go straight to global memory.
 // ---------------------------------------------------------------------------
-constexpr int MM_T = 256;   // threads: 4 row groups x 2 column groups of warps
+constexpr int MM_T = 128;   // threads
 constexpr int MM_ST = 3;    // stages
 constexpr int MM_KC = 16;   // slab rows per stage
-constexpr int MM_MT = 128;  // fast-dimension rows per pass (every stage-3 item is one pass)
-constexpr int MM_WPMAX = MM_MT + 8;
+constexpr int MM_MT = 64;   // fast-dimension rows per pass
+constexpr int MM_WP = MM_MT + 8;
 
 __device__ __forceinline__ void cp_async16_plain(void *smem_dst, const void *gsrc)
 {
@@ -478,33 +478,15 @@ template <int N> __device__ __forceinline__ void cp_async_wait_group()
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// the math of one chunk for a warp that owns RA row blocks x NBW column blocks (no masks)
-template <int RA, int NBW>
-__device__ __forceinline__ void mm_chunk(double (&acc)[4][NBW][2], const double *ap, const double *bp, int WP,
-                                         int ZP)
-{
-#pragma unroll
-    for (int ks = 0; ks < MM_KC / 4; ks++) {
-        double a[RA], b[NBW];
-#pragma unroll
-        for (int i = 0; i < RA; i++) a[i] = ap[ks * 4 * WP + i * 8];
-#pragma unroll
-        for (int n = 0; n < NBW; n++) b[n] = bp[ks * 4 * ZP + n * 8];
-#pragma unroll
-        for (int i = 0; i < RA; i++)
-#pragma unroll
-            for (int n = 0; n < NBW; n++) dmma884(acc[i][n][0], acc[i][n][1], a[i], b[n]);
-    }
-}
-
 template <bool GATHER, int NB>
-__global__ void __launch_bounds__(MM_T, 2)
+__global__ void __launch_bounds__(MM_T, 3)
 hm_panel_mm_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                    const double *__restrict__ W, const double *__restrict__ Xt,
                    const double *__restrict__ Sp, double *__restrict__ out, int accumulate)
 {
     constexpr int CS = NB * 8, ZP = CS + 8;
-    constexpr int NBW = NB >= 2 ? NB / 2 : 1; // column blocks per warp (two column groups)
+    constexpr int STAGE = MM_KC * (MM_WP + ZP);
+    constexpr int NBW = NB >= 4 ? NB / 2 : NB; // column blocks per warp in the 2 x 2 warp grid
     extern __shared__ __align__(16) double dsm[];
     __shared__ int zrow[GATHER ? HM_SMAX : 1];
     __shared__ int rpos[GATHER ? HM_MAXRUNS + 1 : 1];
@@ -542,48 +524,48 @@ hm_panel_mm_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ r
     const int nchunks = (S + MM_KC - 1) / MM_KC;
 
     for (int f0 = 0; f0 < Fp; f0 += MM_MT) {
-        const int mt = min(MM_MT, Fp - f0);        // even
-        const int nfb = (mt + 7) >> 3;             // 8-row blocks in this pass (<= 16)
-        const int ra = (nfb + 3) >> 2;             // row blocks per warp: 1..4
-        const int WP = ((mt + 15) & ~15) + 8;      // = 8 (mod 16): conflict-free fragment reads
-        const int STAGE = MM_KC * (WP + ZP);
-        const int wr = warp >> 1, wc = warp & 1;   // row group, column group
-        const int fb0 = wr * ra;
-        const int n0 = wc * NBW;
-        // a warp whose row blocks all exist runs mask-free; rows past Fp inside the last block
-        // hold stale shared memory, which only reaches output rows that are never stored
-        const int na = min(ra, nfb - fb0);
+        const int mt = min(MM_MT, Fp - f0); // even
+        const int nfb = (mt + 7) >> 3;      // 8-row blocks in this pass (<= 8)
+        // warp grid: rows beyond 32 exist -> 2 (rows) x 2 (columns); else 1 x 4
+        const bool tall = nfb > 4;
+        const int wr = tall ? (warp >> 1) : 0;                 // row half
+        const int wc = tall ? (warp & 1) : warp;               // column group
+        const int nbw = tall ? NBW : max(1, NB / 4);           // column blocks of this warp
+        const int n0 = wc * nbw;
+        const int fb0 = wr * 4;
+        const int na = min(4, nfb - fb0);                      // row blocks of this warp (<= 0: idle)
         const bool active = na > 0 && n0 < NB;
 
         double acc[4][NBW][2];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int a = 0; a < 4; a++)
 #pragma unroll
-            for (int n = 0; n < NBW; n++) acc[i][n][0] = acc[i][n][1] = 0.0;
+            for (int n = 0; n < NBW; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
 
-        // Each thread copies the same pieces of every chunk; offsets are computed once per pass
-        // (the copy code used to cost 4x the instructions of the math).
-        const int hw = mt >> 1;                    // 16-byte pieces per W row (<= 64)
-        constexpr int WPT = (MM_KC * (MM_MT / 2) + MM_T - 1) / MM_T; // 4
-        int w_s[WPT], w_r[WPT];
-        long long w_g[WPT];
+        // Each thread copies the same pieces of every chunk: up to 4 sixteen-byte pieces of W
+        // (row wr, column pair wp of the pass) and CS/64 * 4 of Z.  Their offsets are computed
+        // once per pass; per chunk only the base moves (keeps the copy code off the
+        // instruction budget: it used to cost 4x the instructions of the math).
+        const int hw = mt >> 1;
+        int w_s[4], w_r[4];
+        long long w_g[4];
 #pragma unroll
-        for (int j = 0; j < WPT; j++) {
+        for (int j = 0; j < 4; j++) {
             const int idx = t + j * MM_T;
             const int r = idx / hw, pp = idx - r * hw;
             w_r[j] = r < MM_KC ? r : MM_KC; // MM_KC: no such piece
-            w_s[j] = r * WP + 2 * pp;
+            w_s[j] = r * MM_WP + 2 * pp;
             w_g[j] = (long long)r * Fp + f0 + 2 * pp;
         }
-        constexpr int hz = CS / 2;                                // 16-byte pieces per z row
-        constexpr int ZPT = (MM_KC * hz + MM_T - 1) / MM_T;       // z pieces per thread
+        constexpr int hz = CS / 2;                    // 16-byte pieces per z row
+        constexpr int ZPT = (MM_KC * hz + MM_T - 1) / MM_T; // z pieces per thread
         auto issue = [&](int ch) {
             double *Wsm = dsm + (size_t)(ch % MM_ST) * STAGE;
-            double *Zsm = Wsm + MM_KC * WP;
+            double *Zsm = Wsm + MM_KC * MM_WP;
             const int s0 = ch * MM_KC, rows = min(MM_KC, S - s0);
             const double *wsrc = Wg + (size_t)s0 * Fp;
 #pragma unroll
-            for (int j = 0; j < WPT; j++)
+            for (int j = 0; j < 4; j++)
                 if (w_r[j] < rows) cp_async16_plain(Wsm + w_s[j], wsrc + w_g[j]);
 #pragma unroll
             for (int j = 0; j < ZPT; j++) {
@@ -601,7 +583,7 @@ hm_panel_mm_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ r
                 }
             }
             if (rows < MM_KC) { // zero the tail rows of the last chunk: 0 * stale NaN would poison the sums
-                for (int idx = t; idx < (MM_KC - rows) * WP; idx += MM_T) Wsm[rows * WP + idx] = 0.0;
+                for (int idx = t; idx < (MM_KC - rows) * MM_WP; idx += MM_T) Wsm[rows * MM_WP + idx] = 0.0;
                 for (int idx = t; idx < (MM_KC - rows) * ZP; idx += MM_T) Zsm[rows * ZP + idx] = 0.0;
             }
         };
@@ -618,14 +600,39 @@ hm_panel_mm_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ r
             cp_async_commit_group();
             if (active) {
                 const double *Wsm = dsm + (size_t)(ch % MM_ST) * STAGE;
-                const double *Zsm = Wsm + MM_KC * WP;
-                const double *ap = Wsm + tig * WP + fb0 * 8 + gid;
+                const double *Zsm = Wsm + MM_KC * MM_WP;
+                const double *ap = Wsm + tig * MM_WP + fb0 * 8 + gid;
                 const double *bp = Zsm + tig * ZP + n0 * 8 + gid;
-                switch (na) { // warp-uniform
-                case 1: mm_chunk<1, NBW>(acc, ap, bp, WP, ZP); break;
-                case 2: mm_chunk<2, NBW>(acc, ap, bp, WP, ZP); break;
-                case 3: mm_chunk<3, NBW>(acc, ap, bp, WP, ZP); break;
-                default: mm_chunk<4, NBW>(acc, ap, bp, WP, ZP); break;
+                if (na == 4 && nbw == NBW) { // full tile: no masking in the inner loop
+#pragma unroll
+                    for (int ks = 0; ks < MM_KC / 4; ks++) {
+                        double a[4], b[NBW];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) a[i] = ap[ks * 4 * MM_WP + i * 8];
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) b[n] = bp[ks * 4 * ZP + n * 8];
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int n = 0; n < NBW; n++) dmma884(acc[i][n][0], acc[i][n][1], a[i], b[n]);
+                    }
+                } else {
+#pragma unroll
+                    for (int ks = 0; ks < MM_KC / 4; ks++) {
+                        double a[4], b[NBW];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) a[i] = i < na ? ap[ks * 4 * MM_WP + i * 8] : 0.0;
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) b[n] = n < nbw ? bp[ks * 4 * ZP + n * 8] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            if (i < na) {
+#pragma unroll
+                                for (int n = 0; n < NBW; n++)
+                                    if (n < nbw) dmma884(acc[i][n][0], acc[i][n][1], a[i], b[n]);
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -639,13 +646,15 @@ hm_panel_mm_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ r
                     double2 *gp = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + n0 * 4 + tig;
 #pragma unroll
                     for (int n = 0; n < NBW; n++) {
-                        double2 v = make_double2(acc[i][n][0], acc[i][n][1]);
-                        if (GATHER && accumulate) {
-                            double2 o = gp[n * 4];
-                            v.x += o.x;
-                            v.y += o.y;
+                        if (n < nbw) {
+                            double2 v = make_double2(acc[i][n][0], acc[i][n][1]);
+                            if (GATHER && accumulate) {
+                                double2 o = gp[n * 4];
+                                v.x += o.x;
+                                v.y += o.y;
+                            }
+                            gp[n * 4] = v;
                         }
-                        gp[n * 4] = v;
                     }
                 }
             }
@@ -658,7 +667,7 @@ cudaError_t launch_panel_mm(const HmItem *items, int64_t nitems, const HmRun *ru
                             const double *Xt, const double *Sp, double *out, int accumulate, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
-    const size_t smem = (size_t)MM_ST * MM_KC * (MM_WPMAX + NB * 8 + 8) * sizeof(double);
+    const size_t smem = (size_t)MM_ST * MM_KC * (MM_WP + NB * 8 + 8) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(hm_panel_mm_kernel<GATHER, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;

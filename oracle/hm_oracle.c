@@ -784,6 +784,7 @@ typedef struct {
     int64_t nx, ny;
     int bs, r;
     int err;
+    int depth; /* a cluster of >= BLOCKSIZE coincident points never splits: StackOverflowError upstream */
 } asm_ctx;
 
 static int64_t rlen(int64_t a, int64_t b) { return b > a ? b - a : 0; }
@@ -820,10 +821,12 @@ static hmo_node *assemble(asm_ctx *c, int variant, int64_t i0, int64_t i1, int64
                           double a, double b, double cc, double d)
 {
     int64_t im, jm;
-    if (hmo_indsplit(c->x, c->nx, i0, i1, a, b, &im) || hmo_indsplit(c->y, c->ny, j0, j1, cc, d, &jm)) {
+    if (c->depth > 1200 || hmo_indsplit(c->x, c->nx, i0, i1, a, b, &im) ||
+        hmo_indsplit(c->y, c->ny, j0, j1, cc, d, &jm)) {
         c->err = 1;
         return NULL;
     }
+    c->depth++;
     double ab2 = 0.5 * (a + b), cd2 = 0.5 * (cc + d);
     int leaf = rlen(i0, im) < c->bs && rlen(im, i1) < c->bs && rlen(j0, jm) < c->bs &&
                rlen(jm, j1) < c->bs;
@@ -857,6 +860,7 @@ static hmo_node *assemble(asm_ctx *c, int variant, int64_t i0, int64_t i1, int64
         put_bary(c, h, 1, 0, ab2, b, cc, cd2, im, i1, j0, jm);
         put_bary(c, h, 1, 1, ab2, b, cd2, d, im, i1, jm, j1);
     }
+    c->depth--;
     return h;
 }
 
@@ -864,7 +868,7 @@ static hmo_node *assemble(asm_ctx *c, int variant, int64_t i0, int64_t i1, int64
 hmo_node *hmo_kernelmatrix(int kernel, const double *x, int64_t nx, const double *y, int64_t ny,
                            double a, double b, double c, double d)
 {
-    asm_ctx ctx = {kernel, x, y, nx, ny, hmo_blocksize_f64(), hmo_blockrank_f64(), 0};
+    asm_ctx ctx = {kernel, x, y, nx, ny, hmo_blocksize_f64(), hmo_blockrank_f64(), 0, 0};
     hmo_node *h = assemble(&ctx, 0, 0, nx, 0, ny, a, b, c, d);
     if (ctx.err) {
         hmo_node_free(h);

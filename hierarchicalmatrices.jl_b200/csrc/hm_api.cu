@@ -617,7 +617,7 @@ int32_t hm_plan_scale(hm_plan *p, const double *b, int64_t incb, int32_t side)
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
     if (side != 0 && side != 1) return fail(HM_ERR_INVALID, "side must be 0 (columns) or 1 (rows)");
-    if (incb == 0) return fail(HM_ERR_INVALID, "zero stride");
+    if (incb <= 0) return fail(HM_ERR_INVALID, "stride must be positive");
     const HmLayout &L = p->L;
     const int64_t n = side == 0 ? L.ncols : L.nrows;
     if (n == 0) return HM_OK;
@@ -814,7 +814,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
     const HmLayout &L = p->L;
     if ((!x && L.ncols > 0) || (!y && L.nrows > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
-    if (incx == 0 || incy == 0) return fail(HM_ERR_INVALID, "zero stride");
+    if (incx <= 0 || incy <= 0) return fail(HM_ERR_INVALID, "strides must be positive (INCX, INCY >= 1 as in the reference)");
     std::lock_guard<std::mutex> lock(p->mu);
     HM_DEVICE(p->device);
     const int64_t nc = L.ncols, r0 = L.row_begin, nr = L.row_end - L.row_begin;
@@ -917,7 +917,7 @@ int32_t hm_matvec_adjoint(hm_plan *p, const double *x, int64_t incx, double *y, 
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
     const HmLayout &L = p->L;
     if ((!x && L.nrows > 0) || (!y && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
-    if (incx == 0 || incy == 0) return fail(HM_ERR_INVALID, "zero stride");
+    if (incx <= 0 || incy <= 0) return fail(HM_ERR_INVALID, "strides must be positive (INCX, INCY >= 1 as in the reference)");
     std::lock_guard<std::mutex> lock(p->mu);
     HM_DEVICE(p->device);
     const int64_t nr = L.nrows, nc = L.ncols;

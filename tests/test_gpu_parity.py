@@ -351,6 +351,11 @@ def test_errors(hm):
         hm.mul_(np.zeros(2), H, np.zeros(3))
     with pytest.raises(TypeError):
         hm.mul_(np.zeros(3, dtype=np.float32), H, np.zeros(3))
+    xs, ys = np.zeros(3), np.zeros(3)
+    assert L.hm_matvec(H.plan().handle, xs.ctypes.data_as(dp), 0, ys.ctypes.data_as(dp), 1, 1) == 1   # HM_ERR_INVALID
+    assert L.hm_matvec(H.plan().handle, xs.ctypes.data_as(dp), 1, ys.ctypes.data_as(dp), -1, 1) == 1
+    assert L.hm_matvec(H.plan().handle, None, 1, ys.ctypes.data_as(dp), 1, 1) == 2                      # HM_ERR_NULL
+    assert L.hm_matmat(H.plan().handle, xs.ctypes.data_as(dp), 2, ys.ctypes.data_as(dp), 3, 1, 0) == 3  # ld < n
 
 
 # ------------------------------------------------------------------ many right-hand sides (DMMA panel kernels)

@@ -34,6 +34,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--npoints", "--size", dest="n", type=int, default=1 << 20,
                     help="points per side (default 2^20)")
+    ap.add_argument("--no-p2p", action="store_true",
+                    help="N > 1: gather y with an NCCL all-gather instead of the peer-memory stores fused into stage 3")
     ap.add_argument("--no-graph", action="store_true",
                     help="N > 1: launch every step from Python instead of one CUDA graph of the whole loop")
     ap.add_argument("--dist", default="cheb", choices=["cheb", "unif"],
@@ -395,6 +397,7 @@ def run_ours(args):
     x_bufs = [torch.from_numpy(v).to(dev) if rank == 0 else torch.zeros(n, dtype=torch.float64, device=dev)
               for _ in range(nbuf)]
     y_bufs = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+    p2p = None
     if dist_on:
         cuts = [None] * world
         dist.all_gather_object(cuts, (r0, r1))
@@ -406,6 +409,27 @@ def run_ours(args):
         xy_free = [torch.cuda.Event() for _ in range(nbuf)]
         y_ready = [torch.cuda.Event() for _ in range(nbuf)]
         y_done = [torch.cuda.Event() for _ in range(nbuf)]
+        if gather and not args.no_p2p:
+            # y lives in symmetric memory: every rank can store into every rank's buffer over
+            # NVLink, so stage 3 writes its rows to all of them (all-gather fused into the kernel)
+            # and only a device barrier remains on the second stream.
+            ok = torch.ones(1, device=dev)
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                ysym = [symm_mem.empty(n, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+                hdls = [symm_mem.rendezvous(t, dist.group.WORLD) for t in ysym]
+                for t in ysym:
+                    t.zero_()
+                p2p = {"bufs": ysym, "hdls": hdls, "ptrs": [[int(a) for a in h.buffer_ptrs] for h in hdls]}
+            except Exception as exc:  # symmetric memory unavailable: NCCL all-gather instead
+                ok.zero_()
+                if rank == 0:
+                    print(f"bench.py: symmetric memory unavailable ({exc!r}); using the NCCL all-gather", file=sys.stderr)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                p2p = None
+            else:
+                y_bufs = p2p["bufs"]
 
     def bcast(k, main):
         b = k % nbuf
@@ -429,8 +453,12 @@ def run_ours(args):
             b = k % nbuf
             main.wait_event(x_ready[b])
             main.wait_event(y_done[b])         # the all-gather that last read y_bufs[b] is done
-            plan.matvec_device(x_bufs[b].data_ptr(), y_bufs[b].data_ptr(), accumulate=False,
-                               stream=main.cuda_stream)
+            if p2p is not None:
+                plan.matvec_device_allgather(x_bufs[b].data_ptr(), p2p["ptrs"][b], rank, accumulate=False,
+                                             stream=main.cuda_stream)
+            else:
+                plan.matvec_device(x_bufs[b].data_ptr(), y_bufs[b].data_ptr(), accumulate=False,
+                                   stream=main.cuda_stream)
             xy_free[b].record(main)
             y_ready[b].record(main)
             if k + 1 < nsteps:
@@ -438,12 +466,15 @@ def run_ours(args):
             with torch.cuda.stream(cs):
                 if gather:
                     cs.wait_event(y_ready[b])
-                    # row parts are balanced by bytes, not rows: gather padded slices
-                    pad[: r1 - r0].copy_(y_bufs[b][r0:r1])
-                    dist.all_gather_into_tensor(gathered, pad)
-                    for q, (qa, qb) in enumerate(cuts):
-                        if q != rank:
-                            y_bufs[b][qa:qb].copy_(gathered[q * maxrows: q * maxrows + (qb - qa)])
+                    if p2p is not None:
+                        p2p["hdls"][b].barrier()   # every rank's rows have landed everywhere
+                    else:
+                        # row parts are balanced by bytes, not rows: gather padded slices
+                        pad[: r1 - r0].copy_(y_bufs[b][r0:r1])
+                        dist.all_gather_into_tensor(gathered, pad)
+                        for q, (qa, qb) in enumerate(cuts):
+                            if q != rank:
+                                y_bufs[b][qa:qb].copy_(gathered[q * maxrows: q * maxrows + (qb - qa)])
                 y_done[b].record(cs)
         main.wait_stream(cs)
 
@@ -543,7 +574,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(n, args.dist), "n": n, "dist": args.dist,
                        "partition": f"block-row x{world}" if world > 1 else "single GPU",
-                       "collectives": (("NCCL broadcast(x) + all-gather(y) per step, pipelined on a second stream"
+                       "collectives": ((("NCCL broadcast(x); all-gather(y) fused into stage 3 (stores into every rank's symmetric buffer "
+                                         "over NVLink) + device barrier, pipelined on a second stream" if p2p is not None else
+                                         "NCCL broadcast(x) + all-gather(y) per step, pipelined on a second stream")
                                         + (", whole loop replayed as one CUDA graph" if use_graph else "")) if gather else
                                        "NCCL broadcast(x) per step" if dist_on else "none"),
                        "l2": "inputs larger than L2 (%.1f GB streamed per step per GPU)" % (st["stored_bytes"] / 1e9),

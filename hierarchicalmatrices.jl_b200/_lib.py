@@ -74,6 +74,7 @@ SIGNATURES = {
                                      C.POINTER(TreeLeaf), _i64, C.POINTER(_i64)]),
     "hm_matvec": (_i32, [_vp, _dp, _i64, _dp, _i64, _i32]),
     "hm_matvec_device": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "hm_matvec_device_allgather": (_i32, [_vp, _vp, C.POINTER(C.c_uint64), _i32, _i32, _i32, _vp]),
     "hm_matvec_adjoint": (_i32, [_vp, _dp, _i64, _dp, _i64, _i32]),
     "hm_matvec_adjoint_device": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "hm_matmat": (_i32, [_vp, _dp, _i64, _dp, _i64, _i64, _i32]),

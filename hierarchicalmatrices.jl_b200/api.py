@@ -233,6 +233,12 @@ class Plan:
     def matvec_device(self, dx: int, dy: int, accumulate=False, stream: int = 0):
         _lib.check(_lib.lib().hm_matvec_device(self._h, dx, dy, 1 if accumulate else 0, stream))
 
+    # multi-GPU: owned rows of y are stored into every rank's y buffer (peer-mapped pointers)
+    def matvec_device_allgather(self, dx: int, ypeers, self_rank: int, accumulate=False, stream: int = 0):
+        arr = (C.c_uint64 * len(ypeers))(*[int(a) for a in ypeers])
+        _lib.check(_lib.lib().hm_matvec_device_allgather(self._h, dx, arr, len(ypeers), self_rank,
+                                                         1 if accumulate else 0, stream))
+
     def rmatvec_device(self, dx: int, dy: int, accumulate=False, stream: int = 0):
         _lib.check(_lib.lib().hm_matvec_adjoint_device(self._h, dx, dy, 1 if accumulate else 0, stream))
 

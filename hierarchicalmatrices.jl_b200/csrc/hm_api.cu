@@ -768,7 +768,31 @@ int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t
 // ---------------------------------------------------------------------------
 // mul!
 // ---------------------------------------------------------------------------
+static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream,
+                                  const HmPeers *peers);
+
 int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream)
+{
+    return matvec_device_impl(p, dx, dy, accumulate, stream, nullptr);
+}
+
+int32_t hm_matvec_device_allgather(hm_plan *p, const double *dx, const uint64_t *ypeers, int32_t npeers,
+                                   int32_t self, int32_t accumulate, void *stream)
+{
+    if (!p || !ypeers) return fail(HM_ERR_NULL, "NULL argument");
+    if (npeers < 1 || npeers > HM_MAX_PEERS) return fail(HM_ERR_INVALID, "npeers must be 1..%d", HM_MAX_PEERS);
+    if (self < 0 || self >= npeers) return fail(HM_ERR_INVALID, "self out of range");
+    HmPeers pe;
+    pe.n = npeers;
+    for (int i = 0; i < npeers; i++) {
+        if (!ypeers[i] && p->L.nrows > 0) return fail(HM_ERR_NULL, "peer pointer %d is NULL", i);
+        pe.y[i] = reinterpret_cast<double *>(ypeers[i]);
+    }
+    return matvec_device_impl(p, dx, pe.y[self], accumulate, stream, &pe);
+}
+
+static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream,
+                                  const HmPeers *peers)
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
     if ((!dx && p->L.ncols > 0) || (!dy && p->L.nrows > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
@@ -800,7 +824,7 @@ int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accum
     for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
         int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
         HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
-                                 r == 0 ? (accumulate != 0) : 1, st));
+                                 r == 0 ? (accumulate != 0) : 1, peers, st));
     }
     if (ev) {
         HM_CUDA(cudaEventRecord(ev[3], st));

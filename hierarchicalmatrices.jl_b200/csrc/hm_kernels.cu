@@ -175,11 +175,11 @@ hm_core_big_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
 // ---------------------------------------------------------------------------
 // stage 1 / stage 3
 // ---------------------------------------------------------------------------
-template <bool GATHER, bool FUSE>
+template <bool GATHER, bool FUSE, bool PEERS>
 __global__ void __launch_bounds__(HM_THREADS, 4)
 hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                  const double *__restrict__ W, const double *__restrict__ x,
-                 const double *__restrict__ svec, double *out, int accumulate, HmFuse fz)
+                 const double *__restrict__ svec, double *out, int accumulate, HmFuse fz, HmPeers pe)
 {
     constexpr int T = HM_THREADS;
     __shared__ double zs[HM_SMAX];
@@ -218,6 +218,23 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
     __syncthreads();
 
     const double2 *__restrict__ W2 = reinterpret_cast<const double2 *>(W + it.slab);
+
+    // one writer per output element.  Stage 3 with PEERS: the all-gather of y is fused into
+    // the kernel -- every owned row is stored straight into each rank's (symmetric, NVLink
+    // peer-mapped) y buffer instead of a local buffer followed by a collective.
+    auto put = [&](int f, double v) {
+        double *o = out + it.out + f;
+        if (GATHER) {
+            const double r = (accumulate ? *o : 0.0) + v;
+            if (PEERS) {
+                for (int q = 0; q < pe.n; q++) pe.y[q][it.out + f] = r;
+            } else {
+                *o = r;
+            }
+        } else {
+            *o = v;
+        }
+    };
 
     if (L <= T) {
         // ncg column groups of L threads; thread t reads double2 number t, t+TA, ...
@@ -261,14 +278,8 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
         }
         if (t < L) {
             int f = 2 * t;
-            double *o = out + it.out + f;
-            if (GATHER) {
-                if (f < F) o[0] = (accumulate ? o[0] : 0.0) + acc.x;
-                if (f + 1 < F) o[1] = (accumulate ? o[1] : 0.0) + acc.y;
-            } else {
-                if (f < F) o[0] = acc.x;
-                if (f + 1 < F) o[1] = acc.y;
-            }
+            if (f < F) put(f, acc.x);
+            if (f + 1 < F) put(f + 1, acc.y);
         }
     } else {
         // wide items: each thread owns whole columns of the slab
@@ -294,14 +305,8 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
                 acc.y = fma(w.y, z, acc.y);
             }
             int f = 2 * f2;
-            double *o = out + it.out + f;
-            if (GATHER) {
-                if (f < F) o[0] = (accumulate ? o[0] : 0.0) + acc.x;
-                if (f + 1 < F) o[1] = (accumulate ? o[1] : 0.0) + acc.y;
-            } else {
-                if (f < F) o[0] = acc.x;
-                if (f + 1 < F) o[1] = acc.y;
-            }
+            if (f < F) put(f, acc.x);
+            if (f + 1 < F) put(f + 1, acc.y);
         }
     }
 
@@ -819,11 +824,11 @@ cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *
 {
     if (nitems <= 0) return cudaSuccess;
     if (fuse && fuse->counters && (size_t)fuse->max_r * 8 <= HM_SMAX)
-        hm_stream_kernel<false, true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x, nullptr,
-                                                                               partial, 0, *fuse);
+        hm_stream_kernel<false, true, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x, nullptr,
+                                                                               partial, 0, *fuse, HmPeers{});
     else
-        hm_stream_kernel<false, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x,
-                                                                                nullptr, partial, 0, HmFuse{});
+        hm_stream_kernel<false, false, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x,
+                                                                                nullptr, partial, 0, HmFuse{}, HmPeers{});
     return cudaGetLastError();
 }
 
@@ -865,11 +870,15 @@ cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const i
 
 cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *runs,
                              const double *ustream, const double *x, const double *svec, double *y,
-                             int accumulate, cudaStream_t st)
+                             int accumulate, const HmPeers *peers, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
-    hm_stream_kernel<true, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec, y,
-                                                                           accumulate, HmFuse{});
+    if (peers && peers->n > 0)
+        hm_stream_kernel<true, false, true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec, y,
+                                                                                  accumulate, HmFuse{}, *peers);
+    else
+        hm_stream_kernel<true, false, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec,
+                                                                                   y, accumulate, HmFuse{}, HmPeers{});
     return cudaGetLastError();
 }
 

@@ -30,6 +30,14 @@ struct HmFuse {
     int max_r = 0;
 };
 
+// Stage 3 fused with the all-gather of y: every owned row is also stored into the y buffers of
+// the other ranks (peer-mapped device pointers, NVLink).  n == 0: plain local store.
+#define HM_MAX_PEERS 16
+struct HmPeers {
+    double *y[HM_MAX_PEERS] = {};
+    int n = 0;
+};
+
 // stage 1: partial[item.out + f] = sum_s V-slab[s][f] * x[item.zoff + s]
 cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *vstream,
                              const double *x, double *partial, const HmFuse *fuse, cudaStream_t st);
@@ -43,7 +51,7 @@ cudaError_t hm_launch_stage2_big(const HmCoreBlock *blocks, const int32_t *big, 
 // stage 3: y[item.out + f] (+)= sum_s U-slab[s][f] * z[s],  z gathered from x and s
 cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *runs,
                              const double *ustream, const double *x, const double *svec, double *y,
-                             int accumulate, cudaStream_t st);
+                             int accumulate, const HmPeers *peers, cudaStream_t st);
 
 // adjoint apply y (+)= H' x: four launches over the same streams (hm_kernels.cu)
 struct HmAdjoint {

@@ -177,6 +177,14 @@ HM_API int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, i
 HM_API int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate,
                          void *stream);
 
+/* Multi-GPU form of hm_matvec_device with the all-gather of y fused into stage 3: the rows
+ * this plan owns are stored into all `npeers` y buffers (`ypeers[i]` = device address, valid
+ * on this device, of rank i's full-length y: NVLink peer-mapped / symmetric memory) while
+ * they are computed; `self` is this rank's index (its buffer is read when accumulating).
+ * The caller synchronises the ranks afterwards (a device barrier) before anyone reads y. */
+HM_API int32_t hm_matvec_device_allgather(hm_plan *p, const double *dx, const uint64_t *ypeers, int32_t npeers,
+                                          int32_t self, int32_t accumulate, void *stream);
+
 /* Adjoint apply: y[j*incy] (+)= sum_i H[i,j] x[i*incx], x with nrows
  * entries, y with ncols.  The reference has no adjoint of its hierarchical types; the
  * leaf rules are those of its Transpose/Adjoint leaf methods (src/algebra.jl:52-82,

@@ -605,3 +605,39 @@ def test_panel_kernel_variants_agree(hm, O):
     Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
     X = np.asfortranarray(np.random.default_rng(0).standard_normal((6000, 40)))
     assert relinf(outs[1][:, 39], Kref.matvec(np.ascontiguousarray(X[:, 39]))) <= TOL
+
+
+def test_matvec_device_allgather_abi(hm, O):
+    """hm_matvec_device_allgather stores the owned rows into every peer buffer (here three
+    buffers on the same device stand in for the ranks' symmetric buffers); row parts written
+    by different plans tile each buffer exactly like the all-gather of y would."""
+    import torch
+    N = 4096
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
+    v = _vec(N, 9)
+    ref = Kref.matvec(v)
+    dev = torch.device("cuda", 0)
+    xd = torch.from_numpy(v).to(dev)
+    bufs = [torch.full((N,), float("nan"), dtype=torch.float64, device=dev) for _ in range(3)]
+    ptrs = [t.data_ptr() for t in bufs]
+    for p in range(3):  # rank p owns part p and writes its rows into all three buffers
+        Kp = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=p, nparts=3)
+        Kp.plan().matvec_device_allgather(xd.data_ptr(), ptrs, p, accumulate=False,
+                                          stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    for t in bufs:
+        assert relinf(t.cpu().numpy(), ref) <= TOL
+    # accumulate reads this rank's own buffer
+    K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0)
+    y0 = _vec(N, 10)
+    bufs[1].copy_(torch.from_numpy(y0))
+    K.plan().matvec_device_allgather(xd.data_ptr(), ptrs, 1, accumulate=True,
+                                     stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for t in bufs:
+        assert relinf(t.cpu().numpy(), y0 + ref) <= TOL
+    L = hm.lib()
+    arr = (C.c_uint64 * 1)(0)
+    assert L.hm_matvec_device_allgather(K.plan().handle, xd.data_ptr(), arr, 1, 0, 0, None) == 2   # NULL peer
+    assert L.hm_matvec_device_allgather(K.plan().handle, xd.data_ptr(), arr, 1, 3, 0, None) == 1   # self out of range

@@ -309,6 +309,11 @@ struct hm_plan {
     DevBuf<HmCoreBlock> cores;
     DevBuf<int32_t> plist, bigcores; // bigcores: leaves with more than HM_CORE_BIG partial sums
     int64_t nbig = 0;
+    // host-pointer path: chunked item orders, copy stream and events (allocated on first use)
+    DevBuf<HmItem> items1c, items3c;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_x[HM_NCHUNK] = {}, ev_y[HM_NCHUNK] = {}, ev_y0 = nullptr;
+    bool chunk_ready = false;
     // adjoint apply (allocated on first use)
     DevBuf<double> pq;
     DevBuf<int32_t> qlist, core_q0, core_qn, adjbig;
@@ -341,6 +346,12 @@ struct hm_plan {
     ~hm_plan()
     {
         for (cudaEvent_t e : tev) cudaEventDestroy(e);
+        for (int k = 0; k < HM_NCHUNK; k++) {
+            if (ev_x[k]) cudaEventDestroy(ev_x[k]);
+            if (ev_y[k]) cudaEventDestroy(ev_y[k]);
+        }
+        if (ev_y0) cudaEventDestroy(ev_y0);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         if (hx) cudaFreeHost(hx);
         if (hy) cudaFreeHost(hy);
         if (stream) cudaStreamDestroy(stream);
@@ -845,6 +856,54 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
     if (!p->dx.p) HM_CUDA(p->dx.alloc((size_t)std::max<int64_t>(nc, 1)));
     if (!p->dy.p) HM_CUDA(p->dy.alloc((size_t)std::max<int64_t>(L.nrows, 1)));
     cudaStream_t st = p->stream;
+    // Unit strides, one stage-3 round: pipeline the host copies against the kernels.  x goes up
+    // in HM_NCHUNK chunks on a copy stream and stage 1 starts on the items whose columns have
+    // arrived; y comes down in row chunks while stage 3 still computes the following ones.
+    if (incx == 1 && incy == 1 && nc > 0 && nr > 0 && L.round_begin.size() == 2 && !L.items3c.empty() &&
+        p->tcap == 0 && !getenv("HMB200_NO_COPY_PIPELINE")) {
+        if (!p->chunk_ready) {
+            HM_CUDA(p->items1c.upload(L.items1c, st));
+            HM_CUDA(p->items3c.upload(L.items3c, st));
+            HM_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+            for (int k = 0; k < HM_NCHUNK; k++) {
+                HM_CUDA(cudaEventCreateWithFlags(&p->ev_x[k], cudaEventDisableTiming));
+                HM_CUDA(cudaEventCreateWithFlags(&p->ev_y[k], cudaEventDisableTiming));
+            }
+            HM_CUDA(cudaEventCreateWithFlags(&p->ev_y0, cudaEventDisableTiming));
+            HM_CUDA(cudaStreamSynchronize(st));
+            p->chunk_ready = true;
+        }
+        cudaStream_t cst = p->copy_stream;
+        for (int k = 0; k < HM_NCHUNK; k++) {
+            const int64_t c0 = L.xchunk[(size_t)k], c1 = L.xchunk[(size_t)k + 1];
+            if (c1 > c0) HM_CUDA(cudaMemcpyAsync(p->dx.p + c0, x + c0, (size_t)(c1 - c0) * 8, cudaMemcpyHostToDevice, cst));
+            HM_CUDA(cudaEventRecord(p->ev_x[k], cst));
+        }
+        if (accumulate) HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, y + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, cst));
+        HM_CUDA(cudaEventRecord(p->ev_y0, cst));
+        for (int k = 0; k < HM_NCHUNK; k++) {
+            HM_CUDA(cudaStreamWaitEvent(st, p->ev_x[k], 0));
+            const int64_t i0 = L.c1_begin[(size_t)k], i1 = L.c1_begin[(size_t)k + 1];
+            HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st));
+        }
+        HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
+                                 p->svec.p, std::max(L.max_r, 1), st));
+        HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
+                                     p->svec.p, std::max(L.max_r, 1), st));
+        HM_CUDA(cudaStreamWaitEvent(st, p->ev_y0, 0));
+        for (int k = 0; k < HM_NCHUNK; k++) {
+            const int64_t i0 = L.c3_begin[(size_t)k], i1 = L.c3_begin[(size_t)k + 1];
+            HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
+                                     p->dy.p, accumulate != 0, nullptr, st));
+            HM_CUDA(cudaEventRecord(p->ev_y[k], st));
+            HM_CUDA(cudaStreamWaitEvent(cst, p->ev_y[k], 0));
+            const int64_t a0 = L.ychunk[(size_t)k], a1 = L.ychunk[(size_t)k + 1];
+            if (a1 > a0) HM_CUDA(cudaMemcpyAsync(y + a0, p->dy.p + a0, (size_t)(a1 - a0) * 8, cudaMemcpyDeviceToHost, cst));
+        }
+        HM_CUDA(cudaStreamSynchronize(cst));
+        HM_CUDA(cudaStreamSynchronize(st));
+        return HM_OK;
+    }
     // x -> device
     if (nc > 0) {
         if (incx == 1) {

@@ -472,6 +472,58 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         }
     }
 
+    // ---- chunked orderings for the host-pointer path ----
+    {
+        const int NC = HM_NCHUNK;
+        L.xchunk.assign((size_t)NC + 1, ncols);
+        L.ychunk.assign((size_t)NC + 1, rhi);
+        for (int k = 0; k < NC; k++) {
+            L.xchunk[(size_t)k] = (ncols * k / NC) & ~(int64_t)511;
+            L.ychunk[(size_t)k] = rlo;
+        }
+        auto chunk_of = [&](const std::vector<int64_t> &bnd, int64_t pos) {
+            int k = (int)(std::upper_bound(bnd.begin(), bnd.end() - 1, pos) - bnd.begin()) - 1;
+            return std::min(std::max(k, 0), NC - 1);
+        };
+        // stage 1: by the chunk that holds the last column the item reads
+        std::vector<std::pair<int, size_t>> key;
+        for (size_t i = 0; i < L.items1.size(); i++)
+            key.emplace_back(chunk_of(L.xchunk, (int64_t)L.items1[i].zoff + std::max(L.items1[i].S, 1) - 1), i);
+        std::stable_sort(key.begin(), key.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+        L.c1_begin.assign((size_t)NC + 1, 0);
+        for (auto &kv : key) {
+            L.items1c.push_back(L.items1[kv.second]);
+            L.c1_begin[(size_t)kv.first + 1]++;
+        }
+        for (int k = 0; k < NC; k++) L.c1_begin[(size_t)k + 1] += L.c1_begin[(size_t)k];
+        // stage 3 (only when everything fits one round): by row chunk; chunk boundaries sit on
+        // item boundaries so that each chunk's rows are one contiguous range of y
+        if (L.round_begin.size() == 2) {
+            std::vector<size_t> order(L.items3.size());
+            std::iota(order.begin(), order.end(), (size_t)0);
+            std::stable_sort(order.begin(), order.end(),
+                             [&](size_t a, size_t b) { return L.items3[a].out < L.items3[b].out; });
+            const int64_t rows = rhi - rlo;
+            size_t pos = 0;
+            std::vector<std::vector<size_t>> groups((size_t)NC);
+            for (int k = 0; k < NC; k++) {
+                const int64_t target = rlo + rows * (k + 1) / NC;
+                L.ychunk[(size_t)k] = pos < order.size() ? L.items3[order[pos]].out : rhi;
+                while (pos < order.size() && (k == NC - 1 || L.items3[order[pos]].out < target)) groups[(size_t)k].push_back(order[pos++]);
+            }
+            L.ychunk[0] = rlo;
+            L.c3_begin.assign((size_t)NC + 1, 0);
+            for (int k = 0; k < NC; k++) {
+                auto &g = groups[(size_t)k];
+                std::stable_sort(g.begin(), g.end(), [&](size_t a, size_t b) {
+                    return (int64_t)L.items3[a].Fp * L.items3[a].S > (int64_t)L.items3[b].Fp * L.items3[b].S;
+                });
+                for (size_t i : g) L.items3c.push_back(L.items3[i]);
+                L.c3_begin[(size_t)k + 1] = (int64_t)L.items3c.size();
+            }
+        }
+    }
+
     // ---- adjoint tables ----
     {
         if (L.pq_words >= ((int64_t)1 << 31) - 64) return "adjoint work buffer too long";

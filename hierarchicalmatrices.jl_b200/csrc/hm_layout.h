@@ -16,6 +16,8 @@ struct HmLayoutParams {
     int maxruns = 256; // max runs of a stage-3 item
 };
 
+constexpr int HM_NCHUNK = 4;
+
 struct HmLayout {
     int64_t nrows = 0, ncols = 0;
     int64_t row_begin = 0, row_end = 0; // owned rows
@@ -41,6 +43,12 @@ struct HmLayout {
     std::vector<HmFill> fill3;
     std::vector<int64_t> round_begin; // items3 index of each round start, plus end
     int64_t ustream_words = 0;
+    // host-pointer path (hm_matvec): the same items regrouped so that copies overlap compute --
+    // stage-1 items by the last chunk of x they read, stage-3 items (single round only) by
+    // the row chunk of y they write; HM_NCHUNK chunks each, sizes descending inside a chunk
+    std::vector<HmItem> items1c, items3c;
+    std::vector<int64_t> c1_begin, c3_begin; // item ranges per chunk (NCHUNK + 1 entries)
+    std::vector<int64_t> xchunk, ychunk;     // column / row boundaries of the chunks (NCHUNK + 1)
     // adjoint apply y = H' x: the same two streams, reduced over the fast index
     //   A'  q = (row dots of every U-stream slab row with x)      -> PQ[item3.aux + s]
     //   B'  t'_b = sum of the leaf's q pieces; s'_b = F_b' t'_b | Sigma_b .* t'_b

@@ -641,3 +641,86 @@ def test_matvec_device_allgather_abi(hm, O):
     arr = (C.c_uint64 * 1)(0)
     assert L.hm_matvec_device_allgather(K.plan().handle, xd.data_ptr(), arr, 1, 0, 0, None) == 2   # NULL peer
     assert L.hm_matvec_device_allgather(K.plan().handle, xd.data_ptr(), arr, 1, 3, 0, None) == 1   # self out of range
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_random_leaf_soup(hm, seed):
+    """Arbitrary leaves at arbitrary (overlapping) positions -- legal at the ABI, contributions
+    add -- against a dense numpy reference: matvec, accumulate, adjoint, panel, scaling, parts."""
+    rng = np.random.default_rng(100 + seed)
+    nr, ncol = int(rng.integers(50, 900)), int(rng.integers(50, 900))
+    D = np.zeros((nr, ncol))
+    L = hm.lib()
+    dp = C.POINTER(C.c_double)
+    leaves = []
+    for _ in range(int(rng.integers(1, 40))):
+        m, n = int(rng.integers(0, min(nr, 300) + 1)), int(rng.integers(0, min(ncol, 300) + 1))
+        r0, c0 = int(rng.integers(0, nr - m + 1)), int(rng.integers(0, ncol - n + 1))
+        kind = int(rng.integers(0, 3))
+        if kind == 0:
+            A = np.asfortranarray(rng.standard_normal((m, n)))
+            D[r0:r0 + m, c0:c0 + n] += A
+            leaves.append((3, r0, c0, A))
+        else:
+            r = int(rng.integers(1, 41))
+            U, V = np.asfortranarray(rng.standard_normal((m, r))), np.asfortranarray(rng.standard_normal((n, r)))
+            if kind == 1:
+                S = rng.standard_normal(r)
+                D[r0:r0 + m, c0:c0 + n] += (U * S) @ V.T
+                leaves.append((2, r0, c0, U, S, V))
+            else:
+                F = np.asfortranarray(rng.standard_normal((r, r)))
+                D[r0:r0 + m, c0:c0 + n] += U @ F @ V.T
+                leaves.append((4, r0, c0, U, F, V))
+
+    def build(part=0, nparts=1):
+        b = C.c_void_p()
+        hm._lib.check(L.hm_builder_create(C.byref(b), nr, ncol, 0, 0))
+        for lf in leaves:
+            if lf[0] == 3:
+                A = lf[3]
+                hm._lib.check(L.hm_builder_add_dense(b, A.ctypes.data_as(dp), A.shape[0], A.shape[1],
+                                                     max(A.shape[0], 1), lf[1], lf[2]))
+            elif lf[0] == 2:
+                U, S, V = lf[3:]
+                hm._lib.check(L.hm_builder_add_lowrank(b, U.ctypes.data_as(dp), max(U.shape[0], 1), S.ctypes.data_as(dp),
+                                                       V.ctypes.data_as(dp), max(V.shape[0], 1), U.shape[0],
+                                                       V.shape[0], U.shape[1], lf[1], lf[2]))
+            else:
+                U, F, V = lf[3:]
+                hm._lib.check(L.hm_builder_add_bary2d(b, U.ctypes.data_as(dp), max(U.shape[0], 1), F.ctypes.data_as(dp),
+                                                      F.shape[0], V.ctypes.data_as(dp), max(V.shape[0], 1),
+                                                      U.shape[0], V.shape[0], U.shape[1], lf[1], lf[2]))
+        h = C.c_void_p()
+        hm._lib.check(L.hm_plan_finalize_part(b, part, nparts, C.byref(h)))
+        L.hm_builder_destroy(b)
+        return hm.Plan(h.value, 0)
+
+    scale = max(np.abs(D).max(), 1.0)
+    tol = 1e-12 * scale * ncol  # entries of D are sums of products of O(1) numbers
+    plan = build()
+    v, w = rng.standard_normal(ncol), rng.standard_normal(nr)
+    out = np.zeros(nr)
+    plan.matvec(v, out, accumulate=False)
+    assert np.max(np.abs(out - D @ v)) <= tol
+    y0 = rng.standard_normal(nr)
+    out2 = y0.copy()
+    plan.matvec(v, out2, accumulate=True)
+    assert np.max(np.abs(out2 - (y0 + D @ v))) <= tol
+    adj = np.zeros(ncol)
+    plan.rmatvec(w, adj, accumulate=False)
+    assert np.max(np.abs(adj - D.T @ w)) <= tol * nr / ncol + tol
+    X = np.asfortranarray(rng.standard_normal((ncol, 19)))
+    Y = np.zeros((nr, 19), order="F")
+    plan.matmat(X, Y, accumulate=False)
+    assert np.max(np.abs(Y - D @ X)) <= tol
+    bc, br = rng.standard_normal(ncol), rng.standard_normal(nr)
+    plan.scale(bc, 0)
+    plan.scale(br, 1)
+    plan.matvec(v, out, accumulate=False)
+    assert np.max(np.abs(out - br * (D @ (bc * v)))) <= tol * 10
+    # row parts tile the product
+    res = np.full(nr, np.nan)
+    for p in range(3):
+        build(p, 3).matvec(v, res, accumulate=False)
+    assert np.max(np.abs(res - D @ v)) <= tol

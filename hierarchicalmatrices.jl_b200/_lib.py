@@ -61,6 +61,7 @@ SIGNATURES = {
     "hm_builder_add_dense": (_i32, [_vp, _dp, _i64, _i64, _i64, _i64, _i64]),
     "hm_builder_add_lowrank": (_i32, [_vp, _dp, _i64, _dp, _dp, _i64, _i64, _i64, _i64, _i64, _i64]),
     "hm_builder_add_bary2d": (_i32, [_vp, _dp, _i64, _dp, _i64, _dp, _i64, _i64, _i64, _i64, _i64, _i64]),
+    "hm_builder_add_evenbary": (_i32, [_vp, _dp, _i64, _dp, _i64, _i64, _i64, _i64, _i64, _i64, _i32]),
     "hm_builder_layout_stats": (_i32, [_vp, _i32, _i32, C.POINTER(Stats)]),
     "hm_plan_finalize": (_i32, [_vp, C.POINTER(_i32), _i32, C.POINTER(_vp)]),
     "hm_plan_finalize_part": (_i32, [_vp, _i32, _i32, C.POINTER(_vp)]),

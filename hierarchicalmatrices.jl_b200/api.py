@@ -11,6 +11,8 @@ The Julia shim that binds the same C ABI with `ccall` is in julia/.
     Block                     src/block.jl:8-10                 Block
     LowRankMatrix             src/LowRankMatrix.jl:28-38        LowRankMatrix
     BarycentricMatrix2D       src/BarycentricMatrix.jl:208-218  BarycentricMatrix2D
+    EvenBarycentricMatrix     src/BarycentricMatrix.jl:5-59     EvenBarycentricMatrix
+    barycentricmatrix         src/BarycentricMatrix.jl:61-89    barycentricmatrix
     @hierarchical             src/hierarchical.jl:4-232         hierarchical()
     HierarchicalMatrix        src/HierarchicalMatrix.jl:1       HierarchicalMatrix
     KernelMatrix              src/KernelMatrix.jl:1,47          KernelMatrix
@@ -37,6 +39,7 @@ __all__ = [
     "hierarchical", "HierarchicalMatrix", "KernelMatrix", "blocksize", "size", "mul_",
     "cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel", "Plan", "flatten",
     "chebyshevpoints", "HmError", "rmul_", "lmul_", "scale_", "adjoint", "Adjoint",
+    "chebyshevbarycentricweights", "EvenBarycentricMatrix", "barycentricmatrix",
 ]
 
 Matrix = np.ndarray  # the dense leaf type of the reference
@@ -60,17 +63,42 @@ def BLOCKSIZE(T=np.float64) -> int:
     return 4 * BLOCKRANK(T)
 
 
+def _sinpi(q: np.ndarray) -> np.ndarray:
+    """sinpi for 0 <= q <= 1: folded to [0, 1/4] and evaluated in long double."""
+    q = np.where(q > 0.5, 1.0 - q, q)
+    ql = q.astype(np.longdouble)
+    pi = np.longdouble("3.14159265358979323846264338327950288")
+    return np.where(q <= 0.25, np.sin(pi * ql), np.cos(pi * (np.longdouble(0.5) - ql))).astype(np.float64)
+
+
 def chebyshevpoints(n: int, kind: int = 1) -> np.ndarray:
     """chebyshevpoints(Float64, n; kind) -- BarycentricMatrix.jl:92-111 (sinpi in long double)."""
     k = np.arange(1, n // 2 + 1, dtype=np.float64)
     q = (n - 2 * k + 1.0) / (2.0 * n) if kind == 1 else (n - 2 * k + 1.0) / (2.0 * (n - 1))
-    ql = q.astype(np.longdouble)
-    pi = np.longdouble("3.14159265358979323846264338327950288")
-    v = np.where(q <= 0.25, np.sin(pi * ql), np.cos(pi * (np.longdouble(0.5) - ql))).astype(np.float64)
+    v = _sinpi(q)
     x = np.zeros(n)
     x[: n // 2] = v
     x[n - (n // 2):] = -v[::-1]
     return x
+
+
+def chebyshevbarycentricweights(n: int, kind: int = 1) -> np.ndarray:
+    """chebyshevbarycentricweights(Float64, n; kind) -- BarycentricMatrix.jl:114-136."""
+    lam = np.zeros(n)
+    if kind == 1:
+        h = n // 2
+        if n < 1:
+            raise IndexError("BoundsError: chebyshevbarycentricweights needs n >= 1")
+        k = np.arange(1, h + 2, dtype=np.float64)
+        lam[: h + 1] = _sinpi((2 * k - 1.0) / (2.0 * n))
+        lam[n - h:] = lam[:h][::-1]
+    else:
+        lam[:] = 1.0
+    lam[1::2] *= -1.0
+    if kind != 1:
+        lam[0] *= 0.5
+        lam[n - 1] *= 0.5
+    return lam
 
 
 class Block:
@@ -285,6 +313,104 @@ class Plan:
         return out
 
 
+class EvenBarycentricMatrix:
+    """`EvenBarycentricMatrix(T, f, a, b, c, d)` -- BarycentricMatrix.jl:5-45: the rank-BLOCKRANK
+    barycentric interpolant in i of f(i, j) on the integer grid i = a..b, j = c..d, whose `mul!`
+    (algebra.jl:168-239) keeps only the entries with even absolute i+j.  `f(x, j)` takes the real
+    abscissa and the integer column (the reference also passes the element type first)."""
+
+    def __init__(self, *args):
+        if len(args) == 6:
+            T, f, a, b, c, d = args
+            if np.dtype(T) != np.float64:
+                raise HmError(8, "only Float64 operators are supported")
+        elif len(args) == 5:
+            f, a, b, c, d = args
+        else:
+            raise TypeError("EvenBarycentricMatrix(T, f, a, b, c, d)")
+        for v in (a, b, c, d):
+            if not isinstance(v, (int, np.integer)):
+                raise TypeError("MethodError: a, b, c, d must be Int")
+        self.a, self.b, self.c, self.d = int(a), int(b), int(c), int(d)
+        n = BLOCKRANK()
+        self.x = chebyshevpoints(n)
+        self.λ = chebyshevbarycentricweights(n)
+        self.w, self.W = _bary1d_weights(self.a, self.b, self.x, self.λ)
+        self.β = np.zeros(n)
+        self.F = _bary1d_samples(f, self.a, self.b, self.c, self.d, self.x)
+        self._plans = {}
+
+    dtype = property(lambda self: self.W.dtype)
+    shape = property(lambda self: (self.b - self.a + 1, self.d - self.c + 1))
+
+    def size(self, k=None):
+        return self.shape if k is None else self.shape[k - 1]
+
+    # getindex -- BarycentricMatrix.jl:48-59 (1-based); its parity rule is the matrix's own
+    def __getitem__(self, key):
+        i, j = key
+        m, n = self.shape
+        if not (1 <= i <= m and 1 <= j <= n):
+            raise IndexError("BoundsError")
+        ret = 0.0
+        if (m + n + i + j) % 2 == 0:
+            for k in range(self.x.size):
+                ret += self.F[j - 1, k] * self.W[k, i - 1]
+        return ret
+
+    def plan(self, parity: int = 0, device=None) -> "Plan":
+        """Single-leaf plan serving mul! calls whose (istart-1)+(jstart-1) has this parity."""
+        key = (parity & 1, device)
+        if key not in self._plans:
+            self._plans[key] = _single_leaf_plan(self, parity & 1, _current_device() if device is None else device)
+        return self._plans[key]
+
+    def invalidate(self):
+        self._plans = {}
+
+    def __mul__(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        if v.ndim != 1 or v.size != self.shape[1]:
+            raise ValueError("DimensionMismatch")
+        return mul_(np.zeros(self.shape[0]), self, v)
+
+    __matmul__ = __mul__
+
+
+def _bary1d_weights(a: int, b: int, x: np.ndarray, lam: np.ndarray):
+    """w[i] = Σ_k λ_k inv(2i-a-b-(b-a)x_k) in k order; W[k,i] = λ_k inv((2i-a-b-(b-a)x_k) w[i])
+    -- BarycentricMatrix.jl:23-36, same operation order."""
+    m = max(b - a + 1, 0)
+    two_i = (2 * np.arange(a, b + 1, dtype=np.int64) - a - b).astype(np.float64)
+    den = two_i[None, :] - (float(b - a) * x)[:, None]  # n x m
+    w = np.zeros(m)
+    for k in range(x.size):
+        w += lam[k] * (1.0 / den[k])
+    W = np.asfortranarray(lam[:, None] * (1.0 / (den * w[None, :])))
+    return w, W
+
+
+def _bary1d_samples(f, a: int, b: int, c: int, d: int, x: np.ndarray) -> np.ndarray:
+    """F[j-c+1, k] = f((a+b)/2 + (b-a)x_k/2, j) -- BarycentricMatrix.jl:38-43."""
+    F = np.zeros((max(d - c + 1, 0), x.size), order="F")
+    for k in range(x.size):
+        node = (a + b) / 2 + (b - a) * x[k] / 2
+        for j in range(c, d + 1):
+            F[j - c, k] = f(node, j)
+    return F
+
+
+def barycentricmatrix(*args) -> LowRankMatrix:
+    """`barycentricmatrix(T, f, a, b, c, d)` -- BarycentricMatrix.jl:61-89: the unmasked
+    interpolant as LowRankMatrix(W', I, F)."""
+    if len(args) == 6:
+        args = args[1:]
+    f, a, b, c, d = args
+    x = chebyshevpoints(BLOCKRANK())
+    _, W = _bary1d_weights(int(a), int(b), x, chebyshevbarycentricweights(BLOCKRANK()))
+    return LowRankMatrix(np.asfortranarray(W.T), np.ones(x.size), _bary1d_samples(f, int(a), int(b), int(c), int(d), x))
+
+
 def _current_device() -> int:
     """The CUDA device of this process: LOCAL_RANK under torchrun, else 0."""
     import os
@@ -297,6 +423,8 @@ def _leaf_kind(A):
         return 2
     if isinstance(A, BarycentricMatrix2D):
         return 4
+    if isinstance(A, EvenBarycentricMatrix):
+        return 5
     if isinstance(A, np.ndarray):
         return 3
     return None
@@ -323,6 +451,7 @@ class _HierarchicalBase:
             setattr(self, f, np.empty((self.M, self.N), dtype=object))  # "#undef" slots
         self.assigned = np.zeros((self.M, self.N), dtype=np.int64)
         self._plan = None
+        self._has_parity = None
 
     dtype = property(lambda self: self.T)
 
@@ -341,6 +470,7 @@ class _HierarchicalBase:
         getattr(self, self._fields[code - 1])[m, n] = A
         self.assigned[m, n] = code
         self._plan = None
+        self._has_parity = None
 
     def _code_for(self, A):
         if type(A) is type(self):
@@ -410,6 +540,8 @@ class _HierarchicalBase:
             return A[i, j]
         if isinstance(A, np.ndarray):
             return A[i - 1, j - 1]
+        if isinstance(A, EvenBarycentricMatrix):
+            return A[i, j]
         if isinstance(A, LowRankMatrix):  # LowRankMatrix.jl:50-58, k = r..1
             ret = self.T.type(0)
             for k in range(A.rank() - 1, -1, -1):
@@ -438,21 +570,31 @@ class _HierarchicalBase:
             p += self.blocksize(m + 1, self.N, 1)
         return out
 
-    def plan(self, device=None, part=0, nparts=1) -> Plan:
+    def has_parity_leaves(self) -> bool:
+        """True when some leaf is an EvenBarycentricMatrix, whose active entries depend on the
+        parity of the offsets mul! is called with (algebra.jl:172)."""
+        if self._has_parity is None:
+            self._has_parity = any(kind == 5 for kind, _, _, _ in self.leaves())
+        return self._has_parity
+
+    def plan(self, device=None, part=0, nparts=1, parity=0) -> Plan:
         """Flatten the tree and pack it on the device.  The plan is a snapshot cached on
         this object: `H[Block(m), Block(n)] = A` on it drops the cache; after mutating a
-        nested block or a leaf's arrays in place call `invalidate()`."""
-        key = (device, part, nparts)
+        nested block or a leaf's arrays in place call `invalidate()`.  `parity` is that of
+        (istart-1)+(jstart-1) of the mul! calls to serve; it only matters for operators with
+        EvenBarycentricMatrix leaves."""
+        key = (device, part, nparts, parity & 1)
         if self._plan is not None and self._plan[0] == key:
             return self._plan[1]
         if self.T != np.float64:
             raise HmError(8, "only Float64 operators are supported")
-        P = flatten(self, _current_device() if device is None else device, part, nparts)
+        P = flatten(self, _current_device() if device is None else device, part, nparts, parity & 1)
         self._plan = (key, P)
         return P
 
     def invalidate(self):
         self._plan = None
+        self._has_parity = None
 
     def stats(self, part=0, nparts=1) -> dict:
         """Planner only (no GPU needed): sizes of the packed layout."""
@@ -489,7 +631,7 @@ def hierarchical(name: str, *types):
     """`@hierarchical Name T1 T2 ...` -- hierarchical.jl:4: a block-matrix type whose
     blocks are `Name` itself (code 1) or one of the listed leaf types (codes 2, 3, ...)."""
     for t in types:
-        if t is not Matrix and t not in (LowRankMatrix, BarycentricMatrix2D):
+        if t is not Matrix and t not in (LowRankMatrix, BarycentricMatrix2D, EvenBarycentricMatrix):
             raise HmError(8, f"leaf type {t!r} is not on the accelerated path")
     return type(name, (_HierarchicalBase,), {"_name": name, "_types": tuple(types)})
 
@@ -542,10 +684,10 @@ class KernelMatrix(_KernelMatrixBlocks):
 
     shape = property(lambda self: self.size())
 
-    def plan(self, device=None, part=0, nparts=1) -> Plan:
+    def plan(self, device=None, part=0, nparts=1, parity=0) -> Plan:
         if self._assembled is not None:
             return self._assembled
-        return super().plan(device, part, nparts)
+        return super().plan(device, part, nparts, parity)
 
     def stats(self, part=0, nparts=1):
         if self._assembled is not None:
@@ -564,10 +706,19 @@ class KernelMatrix(_KernelMatrixBlocks):
 
 
 # --------------------------------------------------------------------------- planner front end
-def _push_leaves(H, b):
+def _push_leaves(H, b, parity=0):
     L = _lib.lib()
     keep = []  # keep converted arrays alive until the builder has copied them
     for kind, row0, col0, A in H.leaves():
+        if kind == 5:
+            W = np.asfortranarray(A.W, dtype=np.float64)
+            F = np.asfortranarray(A.F, dtype=np.float64)
+            keep += [W, F]
+            r, m = W.shape
+            n = F.shape[0]
+            _lib.check(L.hm_builder_add_evenbary(b, W.ctypes.data_as(_dp), max(r, 1), F.ctypes.data_as(_dp),
+                                                 max(n, 1), m, n, r, row0, col0, parity))
+            continue
         if kind == 3:
             M = np.asfortranarray(A, dtype=np.float64)
             keep.append(M)
@@ -591,14 +742,31 @@ def _push_leaves(H, b):
     return keep
 
 
-def flatten(H, device: int, part=0, nparts=1) -> Plan:
+class _SingleLeaf:
+    """A leaf standing alone as an operator (the reference's leaf-level mul! methods)."""
+
+    def __init__(self, A):
+        self.A = A
+
+    def size(self):
+        return tuple(self.A.shape)
+
+    def leaves(self):
+        return [(_leaf_kind(self.A), 0, 0, self.A)]
+
+
+def _single_leaf_plan(A, parity: int, device: int) -> Plan:
+    return flatten(_SingleLeaf(A), device, 0, 1, parity)
+
+
+def flatten(H, device: int, part=0, nparts=1, parity=0) -> Plan:
     """Walk the block tree and pack it into device arrays (the planner)."""
     L = _lib.lib()
     nrows, ncols = H.size()
     b = C.c_void_p()
     _lib.check(L.hm_builder_create(C.byref(b), nrows, ncols, 0, device))
     try:
-        _push_leaves(H, b)
+        _push_leaves(H, b, parity)
         h = C.c_void_p()
         if nparts == 1:
             dev = (C.c_int32 * 1)(device)
@@ -671,6 +839,8 @@ def scale_(a, b, start: int = 1):
     n = H.size(2 if side == 0 else 1)
     if start < 1 or start - 1 + n > vec.size:
         raise IndexError("BoundsError: b is too short")
+    if getattr(H, "_assembled", None) is None and H.has_parity_leaves():
+        raise TypeError("MethodError: the reference defines no scale! for EvenBarycentricMatrix")
     assembled = getattr(H, "_assembled", None)
     if assembled is not None:
         assembled.scale(vec, side, start - 1)
@@ -734,6 +904,15 @@ def _linear(a: np.ndarray, name: str) -> np.ndarray:
     return a.reshape(-1, order="F")
 
 
+def _offset_parity(H, istart, jstart, INCX, INCY) -> int:
+    """Parity of (istart-1)+(jstart-1) when it matters (EvenBarycentricMatrix leaves), else 0."""
+    if getattr(H, "_assembled", None) is not None or not H.has_parity_leaves():
+        return 0
+    if INCX != 1 or INCY != 1:
+        raise TypeError("MethodError: EvenBarycentricMatrix has no strided mul! (algebra.jl:168)")
+    return (istart + jstart) & 1
+
+
 def mul_(y, H, x, istart: int = 1, jstart: int = 1, INCX: int = 1, INCY: int = 1):
     """`mul!(y, H, x, istart, jstart, INCX, INCY)`: y[istart+(i-1)INCY] += Σ_j H[i,j] x[jstart+(j-1)INCX]
     with 1-based linear indices (HierarchicalMatrix.jl:14-52, KernelMatrix.jl:14-45); returns y."""
@@ -749,7 +928,21 @@ def mul_(y, H, x, istart: int = 1, jstart: int = 1, INCX: int = 1, INCY: int = 1
             raise IndexError("BoundsError: y is too short")
         if nr and jstart - 1 + (nr - 1) * INCX >= xl.size:
             raise IndexError("BoundsError: x is too short")
-        Hp.plan().rmatvec(xl, yl, INCX, INCY, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
+        par = _offset_parity(Hp, istart, jstart, INCX, INCY)
+        Hp.plan(parity=par).rmatvec(xl, yl, INCX, INCY, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
+        return y
+    if isinstance(H, EvenBarycentricMatrix):  # leaf-level mul!(u, B, v, istart, jstart) -- algebra.jl:166-239
+        if INCX != 1 or INCY != 1:
+            raise TypeError("MethodError: mul!(u, ::EvenBarycentricMatrix, v, istart, jstart) has no strided form")
+        if not (isinstance(y, np.ndarray) and isinstance(x, np.ndarray) and y.dtype == x.dtype == np.float64):
+            raise TypeError("MethodError: u and v must be Float64 arrays")
+        if istart < 1 or jstart < 1:
+            raise IndexError("BoundsError: offsets are 1-based positive integers")
+        yl, xl = _linear(y, "u"), _linear(x, "v")
+        nr, nc = H.shape
+        if istart - 1 + nr > yl.size or jstart - 1 + nc > xl.size:
+            raise IndexError("BoundsError: u or v is too short")
+        H.plan((istart + jstart) & 1).matvec(xl, yl, 1, 1, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
         return y
     if not isinstance(H, _HierarchicalBase):
         raise TypeError("MethodError: H is not a hierarchical matrix")
@@ -767,5 +960,6 @@ def mul_(y, H, x, istart: int = 1, jstart: int = 1, INCX: int = 1, INCY: int = 1
         raise IndexError("BoundsError: y is too short")
     if nc and jstart - 1 + (nc - 1) * INCX >= xl.size:
         raise IndexError("BoundsError: x is too short")
-    H.plan().matvec(xl, yl, INCX, INCY, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
+    par = _offset_parity(H, istart, jstart, INCX, INCY)
+    H.plan(parity=par).matvec(xl, yl, INCX, INCY, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
     return y

@@ -562,6 +562,48 @@ int32_t hm_builder_add_bary2d(hm_builder *b, const double *U, int64_t ldu, const
     return add_factored(b, HM_LEAF_BARY2D, U, ldu, F, ldf, V, ldv, m, n, r, row0, col0);
 }
 
+// EvenBarycentricMatrix (reference src/BarycentricMatrix.jl:5-45, apply src/algebra.jl:168-239):
+// entry (i, j) = sum_k F[j,k] W[k,i] when (shift + row0 + i + col0 + j) is even, else 0.  Packed as a
+// rank-2r LowRankMatrix leaf with unit Sigma: factor columns [0, r) carry the rows with row0+i even
+// and the columns they pair with, [r, 2r) the other class; the masked-out entries are stored zeros.
+int32_t hm_builder_add_evenbary(hm_builder *b, const double *W, int64_t ldw, const double *F, int64_t ldf,
+                                int64_t m, int64_t n, int64_t r, int64_t row0, int64_t col0,
+                                int32_t shift_parity)
+{
+    if (!b) return fail(HM_ERR_NULL, "builder is NULL");
+    if (int32_t st = check_block(b, m, n, row0, col0)) return st;
+    if (r < 0) return fail(HM_ERR_SHAPE, "negative rank");
+    if (r > 1024) return fail(HM_ERR_UNSUPPORTED, "rank %lld > 1024", (long long)r);
+    if (shift_parity != 0 && shift_parity != 1) return fail(HM_ERR_INVALID, "shift_parity must be 0 or 1");
+    if (b->device >= 0 && m * r > 0 && !W) return fail(HM_ERR_NULL, "W is NULL");
+    if (b->device >= 0 && n * r > 0 && !F) return fail(HM_ERR_NULL, "F is NULL");
+    if (m * r > 0 && ldw < r) return fail(HM_ERR_SHAPE, "W: leading dimension %lld < rank %lld", (long long)ldw, (long long)r);
+    if (n * r > 0 && ldf < n) return fail(HM_ERR_SHAPE, "F: leading dimension %lld < rows %lld", (long long)ldf, (long long)n);
+    const int64_t r2 = 2 * r;
+    std::vector<double> U, V, S;
+    if (b->device >= 0) {
+        try {
+            U.assign((size_t)(m * r2), 0.0);
+            V.assign((size_t)(n * r2), 0.0);
+            S.assign((size_t)r2, 1.0);
+        } catch (const std::bad_alloc &) {
+            return fail(HM_ERR_NOMEM, "out of host memory");
+        }
+        for (int64_t i = 0; i < m; i++) {
+            const int64_t cls = (row0 + i) & 1;
+            for (int64_t k = 0; k < r; k++) U[(size_t)(i + (cls * r + k) * m)] = W[k + i * ldw];
+        }
+        for (int64_t j = 0; j < n; j++) {
+            const int64_t cls = (shift_parity + col0 + j) & 1;
+            for (int64_t k = 0; k < r; k++) V[(size_t)(j + (cls * r + k) * n)] = F[j + k * ldf];
+        }
+    }
+    int32_t st = add_factored(b, HM_LEAF_LOWRANK, U.data(), std::max<int64_t>(m, 1), S.data(), r2, V.data(),
+                              std::max<int64_t>(n, 1), m, n, r2, row0, col0);
+    if (st == HM_OK) b->leaves.back().extra_words = (m + n) * r + r2;
+    return st;
+}
+
 int32_t hm_builder_layout_stats(hm_builder *b, int32_t part, int32_t nparts, hm_stats *out)
 {
     if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");

@@ -160,7 +160,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         } else {
             (l.kind == HM_LEAF_BARY2D ? L.n_bary2d : L.n_lowrank)++;
             int64_t cw = core_words_of(l);
-            L.lowrank_words += std::max<int64_t>(l.m, 0) * l.ru + std::max<int64_t>(l.n, 0) * l.rv + cw;
+            L.lowrank_words += std::max<int64_t>(l.m, 0) * l.ru + std::max<int64_t>(l.n, 0) * l.rv + cw - l.extra_words;
             L.core_words_all += cw;
         }
     }

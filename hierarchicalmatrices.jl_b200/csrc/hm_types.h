@@ -33,6 +33,9 @@ struct HmLeaf {
     // HM_SRC_KERNEL
     int64_t xi0, yj0;  // first point index of the block's row / column range
     double a, b, c, d; // interpolation box of the block
+    // words stored here beyond what the reference stores for this leaf (EvenBarycentricMatrix
+    // is packed zero-interleaved at twice its rank); subtracted from the algorithmic count
+    int64_t extra_words;
 };
 
 // One CTA's work.  48 bytes.

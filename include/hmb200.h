@@ -118,6 +118,16 @@ HM_API int32_t hm_builder_add_bary2d(hm_builder *b, const double *U, int64_t ldu
                               int64_t ldf, const double *V, int64_t ldv, int64_t m, int64_t n,
                               int64_t r, int64_t row0, int64_t col0);
 
+/* EvenBarycentricMatrix leaf.  Replaces the apply of src/algebra.jl:168-239 on
+ * the factors src/BarycentricMatrix.jl:18-45 builds: W r x m (ld ldw), F n x r (ld ldf); entry
+ * (i, j) of the leaf is sum_k F[j,k] W[k,i] where shift_parity + row0 + i + col0 + j is even and 0
+ * elsewhere.  shift_parity is the parity of (istart-1)+(jstart-1) of the mul! calls the plan will
+ * serve (the reference decides the active class from the absolute offsets, algebra.jl:172).
+ * Stored zero-interleaved as a rank-2r LowRankMatrix leaf; hm_stats counts it at (m+n) r words. */
+HM_API int32_t hm_builder_add_evenbary(hm_builder *b, const double *W, int64_t ldw, const double *F,
+                                int64_t ldf, int64_t m, int64_t n, int64_t r, int64_t row0,
+                                int64_t col0, int32_t shift_parity);
+
 /* Planner only (no GPU needed): lay the operator out for row part `part` of
  * `nparts` and report the sizes. */
 HM_API int32_t hm_builder_layout_stats(hm_builder *b, int32_t part, int32_t nparts, hm_stats *out);

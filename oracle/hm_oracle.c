@@ -221,15 +221,94 @@ void hmo_mul_bary2d(double *u, const double *U, int64_t ldu, const double *F, in
 }
 
 /* ------------------------------------------------------------------ */
+/* EvenBarycentricMatrix                            */
+/* ------------------------------------------------------------------ */
+
+/* BarycentricMatrix.jl:18-37: w[i] = sum_k lambda_k * inv(2i-a-b-(b-a)x_k) (sequential
+ * in k), W[k,i] = lambda_k * inv((2i-a-b-(b-a)x_k) * w[i]).  The integer part 2i-a-b is
+ * exact; (b-a)*x_k is one rounded product.  barycentricmatrix (:61-89) builds the same
+ * numbers transposed. */
+void hmo_evenbary_weights(int64_t a, int64_t b, double *w, double *W)
+{
+    enum { RMAX = 64 };
+    int r = hmo_blockrank_f64();
+    double xk[RMAX], lam[RMAX];
+    hmo_chebyshevpoints(r, 1, xk);
+    hmo_chebyshevbarycentricweights(r, 1, lam);
+    const double span = (double)(b - a);
+    for (int64_t i = a; i <= b; i++) {
+        const double two_i = (double)(2 * i - a - b);
+        double acc = 0.0;
+        for (int k = 0; k < r; k++) acc += lam[k] * (1.0 / (two_i - span * xk[k]));
+        w[i - a] = acc;
+        for (int k = 0; k < r; k++) W[k + (i - a) * r] = lam[k] * (1.0 / ((two_i - span * xk[k]) * acc));
+    }
+}
+
+/* One half of algebra.jl:168-239: beta_k = sum over the columns j = jfirst, jfirst+2, ...
+ * of v[j0+j] F[j,k], then u[i0+i] += sum_k beta_k W[k,i] over the rows i = ifirst, ifirst+2, ... */
+static void evenbary_half(double *u, const double *W, int64_t ldw, const double *F, int64_t ldf,
+                          int64_t m, int64_t n, int64_t r, const double *v, int64_t i0, int64_t j0,
+                          int64_t ifirst, int64_t jfirst)
+{
+    double beta[64];
+    for (int64_t k = 0; k < r; k++) {
+        double bk = 0.0;
+        for (int64_t j = jfirst; j < n; j += 2) bk += v[j0 + j] * F[j + k * ldf];
+        beta[k] = bk;
+    }
+    for (int64_t i = ifirst; i < m; i += 2) {
+        double ui = 0.0;
+        for (int64_t k = 0; k < r; k++) ui += beta[k] * W[k + i * ldw];
+        u[i0 + i] += ui;
+    }
+}
+
+/* 0-based: the 1-based odd rows/columns are the even offsets here.  With an even total
+ * shift, odd columns feed odd rows then even columns feed even rows; with an odd shift the
+ * column classes swap (algebra.jl:172-236).  `shift_even` is passed separately so a walk
+ * that relocates u (hmo_mul_omp) keeps the reference's parity. */
+static void evenbary_apply(double *u, const double *W, int64_t ldw, const double *F, int64_t ldf,
+                           int64_t m, int64_t n, int64_t r, const double *v, int64_t i0, int64_t j0,
+                           int shift_even)
+{
+    if (shift_even) {
+        evenbary_half(u, W, ldw, F, ldf, m, n, r, v, i0, j0, 0, 0);
+        evenbary_half(u, W, ldw, F, ldf, m, n, r, v, i0, j0, 1, 1);
+    } else {
+        evenbary_half(u, W, ldw, F, ldf, m, n, r, v, i0, j0, 0, 1);
+        evenbary_half(u, W, ldw, F, ldf, m, n, r, v, i0, j0, 1, 0);
+    }
+}
+
+void hmo_mul_evenbary(double *u, const double *W, int64_t ldw, const double *F, int64_t ldf,
+                      int64_t m, int64_t n, int64_t r, const double *v, int64_t i0, int64_t j0)
+{
+    evenbary_apply(u, W, ldw, F, ldf, m, n, r, v, i0, j0, ((i0 + j0) & 1) == 0);
+}
+
+/* BarycentricMatrix.jl:48-59: nonzero iff size(B,1)+size(B,2)+i+j is even (1-based i, j;
+ * the +2 of the 0-based form does not change parity).  Note this is the matrix's own
+ * parity rule and differs from mul!'s when m+n is odd; both are restated as written. */
+double hmo_evenbary_getindex(const double *W, int64_t ldw, const double *F, int64_t ldf, int64_t m,
+                             int64_t n, int64_t r, int64_t i, int64_t j)
+{
+    double ret = 0.0;
+    if (((m + n + i + j) & 1) == 0)
+        for (int64_t k = 0; k < r; k++) ret += F[j + k * ldf] * W[k + i * ldw];
+    return ret;
+}
+
+/* ------------------------------------------------------------------ */
 /* @hierarchical container: src/hierarchical.jl:49-69                  */
 /* ------------------------------------------------------------------ */
 
 typedef struct hmo_block {
-    int kind;        /* HMO_NONE / NODE / LOWRANK / DENSE / BARY2D */
+    int kind;        /* HMO_NONE / NODE / LOWRANK / DENSE / BARY2D / EVENBARY */
     int64_t m, n, r; /* leaf extents */
-    double *U;       /* dense: A (ld m); low-rank families: U (ld m) */
+    double *U;       /* dense: A (ld m); low-rank families: U (ld m); EVENBARY: W (r x m, ld r) */
     double *S;       /* LOWRANK: Sigma (r); BARY2D: F (r x r) */
-    double *V;       /* n x r (ld n) */
+    double *V;       /* n x r (ld n); EVENBARY: F */
     hmo_node *child;
 } hmo_block;
 
@@ -350,13 +429,28 @@ int hmo_node_set_bary2d(hmo_node *h, int m, int n, const double *U, int64_t ldu,
     return 0;
 }
 
+int hmo_node_set_evenbary(hmo_node *h, int m, int n, const double *W, int64_t ldw, const double *F,
+                          int64_t ldf, int64_t rows, int64_t cols, int64_t r)
+{
+    hmo_block *b = slot(h, m, n);
+    if (!b || r > 64) return -1;
+    b->kind = HMO_EVENBARY;
+    b->m = rows;
+    b->n = cols;
+    b->r = r;
+    b->U = dupmat(W, r, rows, ldw);
+    b->V = dupmat(F, cols, r, ldf);
+    return 0;
+}
+
 /* the `assigned` code of hierarchical.jl:84-91 */
 int hmo_node_assigned(const hmo_node *h, int m, int n)
 {
     switch (blk(h, m, n)->kind) {
     case HMO_NODE: return 1;
     case HMO_LOWRANK:
-    case HMO_BARY2D: return 2;
+    case HMO_BARY2D:
+    case HMO_EVENBARY: return 2;
     case HMO_DENSE: return 3;
     default: return 0;
     }
@@ -428,6 +522,7 @@ double hmo_getindex(const hmo_node *h, int64_t i, int64_t j)
         }
         return ret;
     }
+    case HMO_EVENBARY: return hmo_evenbary_getindex(b->U, b->r, b->V, b->n, b->m, b->n, b->r, i, j);
     default: return 0.0;
     }
 }
@@ -464,6 +559,11 @@ static void leaf_apply(double *y, const hmo_block *b, const double *x, int64_t i
             for (int64_t k = 0; k < r; k++)
                 for (int64_t i = 0; i < b->m; i++) y[i0 + i * incy] += b->U[i + k * b->m] * t2[k];
         }
+        break;
+    case HMO_EVENBARY:
+        /* only the unit-stride 5-argument method exists (algebra.jl:168) */
+        if (incx == 1 && incy == 1)
+            hmo_mul_evenbary(y, b->U, b->r, b->V, b->n, b->m, b->n, b->r, x, i0, j0);
         break;
     default: break;
     }
@@ -512,6 +612,24 @@ void hmo_mul_adjoint(double *y, const hmo_node *h, const double *x, int64_t i0, 
                 hmo_mul_adjoint(y, b->child, x, i0 + p, j0 + q);
             } else if (b->kind == HMO_DENSE) {
                 hmo_mul_dense_t(y, b->U, b->m, b->n, b->m, x, j0 + q, i0 + p, 1, 1);
+            } else if (b->kind == HMO_EVENBARY) {
+                /* transpose of the masked interpolant: the row class that mul! pairs with a
+                 * column class feeds it back (beta = W x over the class, y += F beta) */
+                int even = ((i0 + p + j0 + q) & 1) == 0;
+                for (int64_t cls = 0; cls < 2; cls++) {
+                    int64_t jfirst = even ? cls : 1 - cls;
+                    double beta[64];
+                    for (int64_t k = 0; k < b->r; k++) {
+                        double t = 0.0;
+                        for (int64_t i = cls; i < b->m; i += 2) t += b->U[k + i * b->r] * x[i0 + p + i];
+                        beta[k] = t;
+                    }
+                    for (int64_t j = jfirst; j < b->n; j += 2) {
+                        double t = 0.0;
+                        for (int64_t k = 0; k < b->r; k++) t += b->V[j + k * b->n] * beta[k];
+                        y[j0 + q + j] += t;
+                    }
+                }
             } else if (b->kind != HMO_NONE) {
                 double t1[64], t2[64];
                 int64_t r = b->r;
@@ -557,7 +675,7 @@ void hmo_scale_cols(hmo_node *h, const double *b, int64_t j0)
             } else if (k->kind == HMO_DENSE) {
                 for (int64_t j = 0; j < k->n; j++)
                     for (int64_t i = 0; i < k->m; i++) k->U[i + j * k->m] = k->U[i + j * k->m] * b[j0 + q + j];
-            } else if (k->kind != HMO_NONE) {
+            } else if (k->kind != HMO_NONE) { /* EVENBARY (no reference method): rows of F, same loop */
                 for (int64_t c = 0; c < k->r; c++)
                     for (int64_t j = 0; j < k->n; j++) k->V[j + c * k->n] = k->V[j + c * k->n] * b[j0 + q + j];
             }
@@ -579,6 +697,9 @@ void hmo_scale_rows(const double *b, hmo_node *h, int64_t i0)
             } else if (k->kind == HMO_DENSE) {
                 for (int64_t j = 0; j < k->n; j++)
                     for (int64_t i = 0; i < k->m; i++) k->U[i + j * k->m] = k->U[i + j * k->m] * b[i0 + p + i];
+            } else if (k->kind == HMO_EVENBARY) { /* no reference method: columns of W */
+                for (int64_t i = 0; i < k->m; i++)
+                    for (int64_t c = 0; c < k->r; c++) k->U[c + i * k->r] = k->U[c + i * k->r] * b[i0 + p + i];
             } else if (k->kind != HMO_NONE) {
                 for (int64_t c = 0; c < k->r; c++)
                     for (int64_t i = 0; i < k->m; i++) k->U[i + c * k->m] = k->U[i + c * k->m] * b[i0 + p + i];
@@ -652,6 +773,7 @@ int64_t hmo_stored_words(const hmo_node *h)
         case HMO_DENSE: w += b->m * b->n; break;
         case HMO_LOWRANK: w += (b->m + b->n) * b->r + b->r; break;
         case HMO_BARY2D: w += (b->m + b->n) * b->r + b->r * b->r; break;
+        case HMO_EVENBARY: w += (b->m + b->n) * b->r; break; /* W and F; mul! reads nothing else */
         default: break;
         }
     }
@@ -713,6 +835,9 @@ void hmo_mul_omp(double *y, const hmo_node *h, const double *x, int64_t i0, int6
             else if (f->kind == HMO_LOWRANK)
                 hmo_mul_lowrank(yt, f->A, f->m, f->S, f->V, f->n, f->m, f->n, f->r, x, f->row0,
                                 j0 + f->col0, 1, 1);
+            else if (f->kind == HMO_EVENBARY)
+                evenbary_apply(yt, f->A, f->r, f->V, f->n, f->m, f->n, f->r, x, f->row0, j0 + f->col0,
+                               ((i0 + f->row0 + j0 + f->col0) & 1) == 0);
             else
                 hmo_mul_bary2d(yt, f->A, f->m, f->S, f->r, f->V, f->n, f->m, f->n, f->r, x,
                                f->row0, j0 + f->col0);

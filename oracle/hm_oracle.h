@@ -30,7 +30,7 @@ enum { HMO_CAUCHY = 0, HMO_COULOMB = 1, HMO_COULOMBPRIME = 2, HMO_LOG = 3 };
 
 /* block kinds; the `assigned` code of the reference (hierarchical.jl:84-91) is
  * 1 for NODE, 2 for LOWRANK/BARY2D (first listed leaf type), 3 for DENSE. */
-enum { HMO_NONE = 0, HMO_NODE = 1, HMO_LOWRANK = 2, HMO_DENSE = 3, HMO_BARY2D = 4 };
+enum { HMO_NONE = 0, HMO_NODE = 1, HMO_LOWRANK = 2, HMO_DENSE = 3, HMO_BARY2D = 4, HMO_EVENBARY = 5 };
 
 typedef struct hmo_node hmo_node;
 
@@ -65,6 +65,18 @@ void hmo_mul_bary2d(double *u, const double *U, int64_t ldu, const double *F, in
                     const double *V, int64_t ldv, int64_t m, int64_t n, int64_t r,
                     const double *v, int64_t i0, int64_t j0);
 
+/* ---- EvenBarycentricMatrix: BarycentricMatrix.jl:5-59, algebra.jl:166-239 ----
+ * 1-D barycentric interpolant on the integer grid a..b whose entries vanish on one
+ * parity class.  W is r x (b-a+1) (ld r), F is (d-c+1) x r: the caller evaluates the
+ * user kernel f(T, (a+b)/2 + (b-a)*x[k]/2, j) into F (BarycentricMatrix.jl:38-43). */
+void hmo_evenbary_weights(int64_t a, int64_t b, double *w, double *W);
+/* mul!(u, B, v, istart, jstart) -- algebra.jl:168-239; i0 = istart-1, j0 = jstart-1 */
+void hmo_mul_evenbary(double *u, const double *W, int64_t ldw, const double *F, int64_t ldf,
+                      int64_t m, int64_t n, int64_t r, const double *v, int64_t i0, int64_t j0);
+/* getindex(B, i, j) -- BarycentricMatrix.jl:48-59 (0-based i, j here) */
+double hmo_evenbary_getindex(const double *W, int64_t ldw, const double *F, int64_t ldf, int64_t m,
+                             int64_t n, int64_t r, int64_t i, int64_t j);
+
 /* ---- generic @hierarchical container: src/hierarchical.jl:49-69 ---- */
 hmo_node *hmo_node_create(int M, int N);
 void hmo_node_free(hmo_node *h); /* recursive; frees owned blocks */
@@ -77,6 +89,8 @@ int hmo_node_set_lowrank(hmo_node *h, int m, int n, const double *U, int64_t ldu
 int hmo_node_set_bary2d(hmo_node *h, int m, int n, const double *U, int64_t ldu, const double *F,
                         int64_t ldf, const double *V, int64_t ldv, int64_t rows, int64_t cols,
                         int64_t r);
+int hmo_node_set_evenbary(hmo_node *h, int m, int n, const double *W, int64_t ldw, const double *F,
+                          int64_t ldf, int64_t rows, int64_t cols, int64_t r);
 int hmo_node_assigned(const hmo_node *h, int m, int n); /* reference code 0..3 */
 /* blocksize(H,m,n,k) and size(H,k): hierarchical.jl:33-47, 76-97 (k = 1 rows, 2 cols) */
 int64_t hmo_blocksize(const hmo_node *h, int m, int n, int k);
@@ -114,7 +128,7 @@ void hmo_bary2d_build(int kernel, double a, double b, double c, double d, const 
 
 /* ---- leaf enumeration in walk order (feeds the GPU builder in tests) ---- */
 typedef struct hmo_leaf {
-    int32_t kind; /* HMO_DENSE / HMO_LOWRANK / HMO_BARY2D */
+    int32_t kind; /* HMO_DENSE / HMO_LOWRANK / HMO_BARY2D / HMO_EVENBARY (A = W, r x m, ld r; V = F) */
     int32_t depth;
     int64_t row0, col0, m, n, r;
     const double *A; /* dense (ld = m) or U (ld = m) */

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libhm_oracle.so")
 
 CAUCHY, COULOMB, COULOMBPRIME, LOG = 0, 1, 2, 3
-NONE, NODE, LOWRANK, DENSE, BARY2D = 0, 1, 2, 3, 4
+NONE, NODE, LOWRANK, DENSE, BARY2D, EVENBARY = 0, 1, 2, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
 _i64 = C.c_int64
@@ -71,6 +71,10 @@ def lib() -> C.CDLL:
         "hmo_mul_dense_t": (None, [_dp, _dp, _i64, _i64, _i64, _dp, _i64, _i64, _i64, _i64]),
         "hmo_mul_lowrank": (None, [_dp, _dp, _i64, _dp, _dp, _i64, _i64, _i64, _i64, _dp, _i64, _i64, _i64, _i64]),
         "hmo_mul_bary2d": (None, [_dp, _dp, _i64, _dp, _i64, _dp, _i64, _i64, _i64, _i64, _dp, _i64, _i64]),
+        "hmo_evenbary_weights": (None, [_i64, _i64, _dp, _dp]),
+        "hmo_mul_evenbary": (None, [_dp, _dp, _i64, _dp, _i64, _i64, _i64, _i64, _dp, _i64, _i64]),
+        "hmo_evenbary_getindex": (C.c_double, [_dp, _i64, _dp, _i64, _i64, _i64, _i64, _i64, _i64]),
+        "hmo_node_set_evenbary": (C.c_int, [vp, C.c_int, C.c_int, _dp, _i64, _dp, _i64, _i64, _i64, _i64]),
         "hmo_node_create": (vp, [C.c_int, C.c_int]),
         "hmo_node_free": (None, [vp]),
         "hmo_node_set_node": (C.c_int, [vp, C.c_int, C.c_int, vp]),
@@ -179,6 +183,40 @@ def bary2d_build(kernel, a, b, c, d, x, i0, i1, y, j0, j1):
     return U, F, V
 
 
+# ---------------------------------------------------------------- EvenBarycentricMatrix
+def evenbary_factors(f, a: int, b: int, c: int, d: int):
+    """EvenBarycentricMatrix(Float64, f, a, b, c, d) -- BarycentricMatrix.jl:18-45: returns
+    (w, W, F) with W r x (b-a+1) and F (d-c+1) x r; f(x, j) is the user kernel of a real
+    abscissa and an integer index (the reference passes the element type first)."""
+    r = blockrank()
+    m, n = b - a + 1, d - c + 1
+    w = np.zeros(max(m, 0))
+    W = np.zeros((r, max(m, 0)), order="F")
+    lib().hmo_evenbary_weights(a, b, _p(w), _p(W))
+    xk = chebyshevpoints(r, 1)
+    F = np.zeros((max(n, 0), r), order="F")
+    for k in range(r):
+        node = (a + b) / 2 + (b - a) * xk[k] / 2
+        for j in range(c, d + 1):
+            F[j - c, k] = f(node, j)
+    return w, W, F
+
+
+def mul_evenbary(u, W, F, v, i0=0, j0=0):
+    W, F = _f(W), _f(F)
+    r, m = W.shape
+    n = F.shape[0]
+    lib().hmo_mul_evenbary(_p(u), _p(W), max(r, 1), _p(F), max(n, 1), m, n, r, _p(v), i0, j0)
+    return u
+
+
+def evenbary_getindex(W, F, i, j) -> float:
+    W, F = _f(W), _f(F)
+    r, m = W.shape
+    n = F.shape[0]
+    return lib().hmo_evenbary_getindex(_p(W), max(r, 1), _p(F), max(n, 1), m, n, r, i, j)
+
+
 # ---------------------------------------------------------------- trees
 class Tree:
     """Owning handle on an oracle block tree (an `@hierarchical` instance)."""
@@ -220,6 +258,13 @@ class Tree:
         lib().hmo_node_set_bary2d(
             self.h, m, n, _p(U), max(U.shape[0], 1), _p(F), max(r, 1), _p(V), max(V.shape[0], 1),
             U.shape[0], V.shape[0], r)
+
+    def set_evenbary(self, m, n, W, F):
+        W, F = _f(W), _f(F)
+        r = W.shape[0]
+        rc = lib().hmo_node_set_evenbary(self.h, m, n, _p(W), max(r, 1), _p(F), max(F.shape[0], 1),
+                                         W.shape[1], F.shape[0], r)
+        assert rc == 0
 
     # -- queries
     @property

@@ -11,6 +11,11 @@ oracle/ and of the CUDA library:
                      kernel matrix applied densely at 60 digits -- the example's
                      own yardstick for the hierarchical product
 
+  evenbary_cauchy.json  EvenBarycentricMatrix(Float64, (x,j) -> 1/(x-j), 1, 96, 300, 420)
+                     (/root/reference/src/BarycentricMatrix.jl:18-45): sample entries of w
+                     and W, and the masked product of algebra.jl:168-239 for an even and an
+                     odd offset shift, all evaluated at 60 digits from the Float64 nodes/weights
+
 The reference ships no golden vectors (test/runtests.jl draws from Julia's RNG), and
 Julia is not installed here, so these are the strongest reference-independent pins
 available.
@@ -87,5 +92,36 @@ def main():
                   open(os.path.join(HERE, f"cauchy_dense_{n}.json"), "w"))
 
 
+def evenbary():
+    a, b, c, d, r = 1, 96, 300, 420, 20
+    xk = [mp.mpf(v) for v in chebpts(r)]
+    lam = [mp.mpf(v) for v in chebweights(r)]
+    m, n = b - a + 1, d - c + 1
+    den = [[mp.mpf(2 * i - a - b) - mp.mpf(b - a) * xk[k] for k in range(r)] for i in range(a, b + 1)]
+    w = [sum(lam[k] / den[i][k] for k in range(r)) for i in range(m)]
+    W = [[lam[k] / (den[i][k] * w[i]) for i in range(m)] for k in range(r)]  # W[k][i]
+    nodes = [float(mp.mpf(a + b) / 2 + mp.mpf(b - a) * xk[k] / 2) for k in range(r)]  # as Float64 ops would give
+    F = [[mp.mpf(1) / (mp.mpf(nodes[k]) - j) for k in range(r)] for j in range(c, d + 1)]  # F[j][k]
+    v = np.random.default_rng(20261018).standard_normal(n)
+    vm = [mp.mpf(float(t)) for t in v]
+    prods = {}
+    for shift in (0, 1):  # parity of (istart-1)+(jstart-1)
+        out = []
+        for i in range(m):
+            s = mp.mpf(0)
+            for j in range(n):
+                if (shift + i + j) % 2 == 0:
+                    s += sum(F[j][k] * W[k][i] for k in range(r)) * vm[j]
+            out.append(float(s))
+        prods[str(shift)] = hexlist(out)
+    idx = [0, 1, 17, 48, 95]
+    json.dump({"a": a, "b": b, "c": c, "d": d, "seed": 20261018, "v": hexlist(v),
+               "w_idx": idx, "w": hexlist([w[i] for i in idx]),
+               "W_cols": {str(i): hexlist([W[k][i] for k in range(r)]) for i in idx},
+               "u": prods},
+              open(os.path.join(HERE, "evenbary_cauchy.json"), "w"))
+
+
 if __name__ == "__main__":
+    evenbary()
     main()

@@ -15,13 +15,16 @@ def relinf(a, b):
 TOL = 1e-12  # BASELINE.json north_star: relative ∞-norm error in Float64
 
 
-def push_oracle_leaves(hm, O, tree, builder):
+def push_oracle_leaves(hm, O, tree, builder, parity=0):
     """hm_builder_add_* for every leaf of an oracle tree (pointers into the oracle's arrays)."""
     L = hm.lib()
     arr, n = tree.leaves()
     for i in range(n):
         f = arr[i]
-        if f.kind == O.DENSE:
+        if f.kind == O.EVENBARY:
+            st = L.hm_builder_add_evenbary(builder, f.A, max(f.r, 1), f.V, max(f.n, 1), f.m, f.n, f.r,
+                                           f.row0, f.col0, parity)
+        elif f.kind == O.DENSE:
             st = L.hm_builder_add_dense(builder, f.A, f.m, f.n, max(f.m, 1), f.row0, f.col0)
         elif f.kind == O.LOWRANK:
             st = L.hm_builder_add_lowrank(builder, f.A, max(f.m, 1), f.S, f.V, max(f.n, 1), f.m, f.n, f.r,
@@ -33,13 +36,13 @@ def push_oracle_leaves(hm, O, tree, builder):
     return n
 
 
-def plan_from_oracle_tree(hm, O, tree, device=0, part=0, nparts=1):
+def plan_from_oracle_tree(hm, O, tree, device=0, part=0, nparts=1, parity=0):
     L = hm.lib()
     nrows, ncols = tree.shape
     b = C.c_void_p()
     hm._lib.check(L.hm_builder_create(C.byref(b), nrows, ncols, 0, device))
     try:
-        push_oracle_leaves(hm, O, tree, b)
+        push_oracle_leaves(hm, O, tree, b, parity)
         h = C.c_void_p()
         if nparts == 1:
             hm._lib.check(L.hm_plan_finalize(b, (C.c_int32 * 1)(device), 1, C.byref(h)))
@@ -96,7 +99,9 @@ def oracle_tree_from_mirror(O, H):
                 T.set_node(m, n, oracle_tree_from_mirror(O, A))
             elif isinstance(A, np.ndarray):
                 T.set_dense(m, n, A)
-            elif hasattr(A, "F"):
+            elif hasattr(A, "W"):
+                T.set_evenbary(m, n, A.W, A.F)
+            elif hasattr(A, "U") and hasattr(A, "F"):
                 T.set_bary2d(m, n, A.U, A.F, A.V)
             else:
                 T.set_lowrank(m, n, A.U, A.S, A.V)

@@ -6,6 +6,8 @@ this image) -- see oracle/hm_oracle.h; it is itself checked against the dense ke
 product and the golden fixtures in tests/test_oracle.py.
 """
 import ctypes as C
+import json
+import os
 
 import numpy as np
 import pytest
@@ -724,3 +726,85 @@ def test_random_leaf_soup(hm, seed):
     for p in range(3):
         build(p, 3).matvec(v, res, accumulate=False)
     assert np.max(np.abs(res - D @ v)) <= tol
+
+
+# ---------------------------------------------------------------- EvenBarycentricMatrix
+def _cauchy_int(x, j):
+    return 1.0 / (x - j)
+
+
+def test_evenbary_leaf_mul_matches_oracle(hm, O):
+    """mul!(u, B::EvenBarycentricMatrix, v, istart, jstart) (algebra.jl:168-239) on the GPU: both
+    offset parities, ragged sizes, accumulation into u; also the golden 60-digit product."""
+    rng = np.random.default_rng(31)
+    for (a, b, c, d) in ((1, 100, 300, 420), (1, 333, 1000, 2501), (5, 6, 40, 40)):
+        B = hm.EvenBarycentricMatrix(np.float64, _cauchy_int, a, b, c, d)
+        m, n = B.shape
+        for (istart, jstart) in ((1, 1), (1, 2), (4, 2), (3, 3)):
+            v = rng.standard_normal(jstart - 1 + n)
+            u0 = rng.standard_normal(istart - 1 + m + 2)
+            ref = O.mul_evenbary(u0.copy(), B.W, B.F, v, istart - 1, jstart - 1)
+            got = hm.mul_(u0.copy(), B, v, istart, jstart)
+            assert relinf(got, ref) <= TOL
+            assert np.array_equal(got[:istart - 1], u0[:istart - 1]) and np.array_equal(got[-2:], u0[-2:])
+        assert relinf(B * v[-n:], O.mul_evenbary(np.zeros(m), B.W, B.F, v[-n:])) <= TOL
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "evenbary_cauchy.json")))
+    B = hm.EvenBarycentricMatrix(_cauchy_int, g["a"], g["b"], g["c"], g["d"])
+    v = np.array([float.fromhex(h) for h in g["v"]])
+    for shift in (0, 1):
+        ref = np.array([float.fromhex(h) for h in g["u"][str(shift)]])
+        vv = np.concatenate([np.zeros(shift), v])
+        assert relinf(hm.mul_(np.zeros(B.shape[0]), B, vv, 1, 1 + shift), ref) <= TOL
+
+
+def test_evenbary_in_block_tree(hm, O):
+    """A custom `@hierarchical` type with EvenBarycentricMatrix and Matrix leaves: the walk's
+    absolute offsets select each leaf's parity class; adjoint, panels and row parts follow."""
+    rng = np.random.default_rng(32)
+    T = hm.hierarchical("ParityMatrix", hm.EvenBarycentricMatrix, hm.Matrix)
+    H = T(np.float64, 2, 2)
+    H[hm.Block(1), hm.Block(1)] = hm.EvenBarycentricMatrix(_cauchy_int, 1, 161, 400, 690)     # 161 x 291
+    H[hm.Block(1), hm.Block(2)] = np.asfortranarray(rng.standard_normal((161, 33)))
+    H[hm.Block(2), hm.Block(1)] = hm.EvenBarycentricMatrix(_cauchy_int, 1, 245, -700, -410)   # 245 x 291
+    inner = T(np.float64, 1, 1)
+    inner[hm.Block(1), hm.Block(1)] = hm.EvenBarycentricMatrix(_cauchy_int, 1, 245, 300, 332)  # 245 x 33
+    H[hm.Block(2), hm.Block(2)] = inner
+    assert H.size() == (406, 324)
+    Tr = oracle_tree_from_mirror(O, H)
+    for (istart, jstart) in ((1, 1), (2, 1), (3, 6), (2, 2)):
+        x = rng.standard_normal(jstart - 1 + 324)
+        y0 = rng.standard_normal(istart - 1 + 406)
+        ref = Tr.mul(y0.copy(), x, istart - 1, jstart - 1)
+        got = hm.mul_(y0.copy(), H, x, istart, jstart)
+        assert relinf(got, ref) <= TOL
+    x = rng.standard_normal(324)
+    assert relinf(H * x, Tr.matvec(x)) <= TOL
+    w = rng.standard_normal(406)
+    assert relinf(hm.adjoint(H) * w, Tr.rmatvec(w)) <= TOL
+    X = np.asfortranarray(rng.standard_normal((324, 5)))
+    Y = H * X
+    for k in range(5):
+        assert relinf(Y[:, k], Tr.matvec(np.ascontiguousarray(X[:, k]))) <= TOL
+    res = np.full(406, np.nan)
+    for p in range(3):
+        hm.flatten(H, 0, p, 3).matvec(x, res, accumulate=False)
+    assert relinf(res, Tr.matvec(x)) <= TOL
+    # the plan counts the leaf at the reference's size; the zero-interleaved packing is 2x
+    st = H.plan().stats()
+    assert st["lowrank_words"] == ((161 + 291) + (245 + 291) + (245 + 33)) * 20
+
+
+def test_barycentricmatrix_lowrank_family(hm, O):
+    """barycentricmatrix (BarycentricMatrix.jl:61-89) gives a LowRankMatrix; in a
+    HierarchicalMatrix it applies like any other (algebra.jl:110-131)."""
+    rng = np.random.default_rng(33)
+    H = hm.HierarchicalMatrix(np.float64, 1, 2)
+    L1 = hm.barycentricmatrix(np.float64, _cauchy_int, 1, 300, 500, 900)
+    H[hm.Block(1), hm.Block(1)] = L1
+    H[hm.Block(1), hm.Block(2)] = np.asfortranarray(rng.standard_normal((300, 17)))
+    Tr = oracle_tree_from_mirror(O, H)
+    x = rng.standard_normal(401 + 17)
+    assert relinf(H * x, Tr.matvec(x)) <= TOL
+    i = np.arange(1, 301)[:, None]
+    j = np.arange(500, 901)[None, :]
+    assert relinf((H * x)[:300] - H[hm.Block(1), hm.Block(2)] @ x[401:], (1.0 / (i - j)) @ x[:401]) <= 1e-11

@@ -237,3 +237,100 @@ def test_adjoint_walk(O):
         D = 1.0 / (x[:, None] - y[None, :])
         assert np.linalg.norm(K.rmatvec(w) - D.T @ w) / np.linalg.norm(D.T @ w) < 1e-13
         assert abs(w @ K.matvec(v) - K.rmatvec(w) @ v) <= 1e-12 * np.linalg.norm(w) * np.linalg.norm(K.matvec(v))
+
+
+# ---------------------------------------------------------------- EvenBarycentricMatrix
+def _cauchy_int(x, j):
+    return 1.0 / (x - j)
+
+
+def test_evenbary_golden(O):
+    """w, W and the masked product against the 60-digit evaluation of BarycentricMatrix.jl:18-45
+    and algebra.jl:168-239 (tests/golden/make_golden.py: evenbary)."""
+    g = json.load(open(os.path.join(GOLD, "evenbary_cauchy.json")))
+    w, W, F = O.evenbary_factors(_cauchy_int, g["a"], g["b"], g["c"], g["d"])
+    idx = np.array(g["w_idx"])
+    assert np.max(np.abs(w[idx] / _hex(g["w"]) - 1)) <= 1e-14
+    for i in idx:
+        ref = _hex(g["W_cols"][str(i)])
+        assert np.max(np.abs(W[:, i] - ref)) <= 1e-14 * np.max(np.abs(ref))
+    v = _hex(g["v"])
+    m, n = W.shape[1], F.shape[0]
+    for shift in (0, 1):
+        u = np.zeros(m + 3)
+        vv = np.concatenate([np.zeros(2 + shift), v])
+        O.mul_evenbary(u, W, F, vv, 2, 2 + shift)   # mul!(u, B, v, 3, 3 + shift)
+        ref = _hex(g["u"][str(shift)])
+        assert np.all(u[:2] == 0) and u[-1] == 0
+        assert np.max(np.abs(u[2:2 + m] - ref)) <= 1e-13 * np.max(np.abs(ref))
+
+
+def test_evenbary_interpolates_and_masks(O):
+    """The factors reproduce f on the grid (well-separated ranges) and mul! keeps exactly the
+    entries whose absolute i+j is even, for either parity of the offsets and ragged sizes."""
+    rng = np.random.default_rng(5)
+    for (a, b, c, d) in ((1, 100, 300, 420), (7, 93, -250, -120), (1, 2, 50, 52), (10, 40, 100, 100)):
+        w, W, F = O.evenbary_factors(_cauchy_int, a, b, c, d)
+        M = (F @ W).T
+        i = np.arange(a, b + 1)[:, None]
+        j = np.arange(c, d + 1)[None, :]
+        assert np.max(np.abs(M - 1.0 / (i - j))) <= 1e-13 * np.max(np.abs(M))
+        m, n = M.shape
+        for (i0, j0) in ((0, 0), (3, 4), (5, 5), (0, 1)):
+            v = rng.standard_normal(j0 + n)
+            u0 = rng.standard_normal(i0 + m)
+            u = u0.copy()
+            O.mul_evenbary(u, W, F, v, i0, j0)
+            ii = np.arange(m)[:, None] + i0
+            jj = np.arange(n)[None, :] + j0
+            ref = (M * ((ii + jj) % 2 == 0)) @ v[j0:]
+            assert np.max(np.abs(u[i0:] - u0[i0:] - ref)) <= 1e-13 * max(np.max(np.abs(ref)), 1e-300)
+            assert np.array_equal(u[:i0], u0[:i0])
+        # getindex keeps its own rule: size-parity, not offset-parity (BarycentricMatrix.jl:51)
+        for (p, q) in ((0, 0), (0, 1), (m - 1, n - 1)):
+            val = O.evenbary_getindex(W, F, p, q)
+            assert val == (0.0 if (m + n + p + q) % 2 else float(np.dot(F[q, :], W[:, p]))) or \
+                abs(val - float(np.dot(F[q, :], W[:, p]))) <= 1e-15 * abs(val)
+
+
+def test_evenbary_tree_walks(O):
+    """EvenBarycentricMatrix leaves inside a block tree: the walk hands each leaf its absolute
+    offsets (KernelMatrix.jl:24-41), so the active parity class follows row0+col0; adjoint and the
+    threaded walk agree with the dense form."""
+    rng = np.random.default_rng(6)
+    _, W1, F1 = O.evenbary_factors(_cauchy_int, 1, 61, 200, 290)      # 61 x 91
+    _, W2, F2 = O.evenbary_factors(_cauchy_int, 1, 45, -300, -210)    # 45 x 91
+    D1 = rng.standard_normal((61, 33))
+    D2 = rng.standard_normal((45, 33))
+    T = O.Tree.create(2, 2)
+    T.set_evenbary(0, 0, W1, F1)
+    T.set_dense(0, 1, D1)
+    T.set_evenbary(1, 0, W2, F2)
+    T.set_dense(1, 1, D2)
+    assert T.shape == (106, 124) and T.assigned(0, 0) == 2 and T.assigned(0, 1) == 3
+    assert T.stored_words() == (61 + 91) * 20 + (45 + 91) * 20 + 61 * 33 + 45 * 33
+    M1, M2 = (F1 @ W1).T, (F2 @ W2).T
+
+    def dense(shift):
+        A = np.zeros((106, 124))
+        ii, jj = np.arange(106)[:, None], np.arange(124)[None, :]
+        A[:61, :91] = M1
+        A[61:, :91] = M2
+        A[:, :91] *= ((ii + jj[:, :91] + shift) % 2 == 0)
+        A[:61, 91:] = D1
+        A[61:, 91:] = D2
+        return A
+
+    for (i0, j0) in ((0, 0), (2, 3)):
+        A = dense((i0 + j0) % 2)
+        x = rng.standard_normal(j0 + 124)
+        y = np.zeros(i0 + 106)
+        T.mul(y, x, i0, j0)
+        ref = A @ x[j0:]
+        assert np.max(np.abs(y[i0:] - ref)) <= 1e-13 * np.max(np.abs(ref))
+        y2 = np.zeros(i0 + 106)
+        T.mul_omp(y2, x, 3, i0, j0)
+        assert np.max(np.abs(y2 - y)) <= 1e-13 * np.max(np.abs(ref))
+    xr = rng.standard_normal(106)
+    ref = dense(0).T @ xr
+    assert np.max(np.abs(T.rmatvec(xr) - ref)) <= 1e-13 * np.max(np.abs(ref))

@@ -255,3 +255,57 @@ def test_python_mirror_scale_host_side(hm, O):
         hm.scale_(H, bc[:100], 1)
     with pytest.raises(TypeError):
         hm.scale_(bc, br)
+
+
+# ---------------------------------------------------------------- EvenBarycentricMatrix
+def test_evenbary_host_factors_bit_identical_to_oracle(hm, O):
+    """The host mirror builds w, W, F with the reference's operation order
+    (BarycentricMatrix.jl:18-45) -- bit for bit what the oracle restatement builds."""
+    assert np.array_equal(hm.chebyshevbarycentricweights(20), O.chebyshevbarycentricweights(20))
+    assert np.array_equal(hm.chebyshevbarycentricweights(7), O.chebyshevbarycentricweights(7))
+    assert np.array_equal(hm.chebyshevbarycentricweights(6, kind=2), O.chebyshevbarycentricweights(6, 2))
+    f = lambda x, j: 1.0 / (x - j)  # noqa: E731
+    for (a, b, c, d) in ((1, 100, 300, 420), (-40, 37, 90, 91)):
+        B = hm.EvenBarycentricMatrix(np.float64, f, a, b, c, d)
+        w, W, F = O.evenbary_factors(f, a, b, c, d)
+        assert B.shape == (b - a + 1, d - c + 1) and B.size(2) == d - c + 1
+        assert np.array_equal(B.w, w) and np.array_equal(B.W, W) and np.array_equal(B.F, F)
+        for (i, j) in ((1, 1), (1, 2), (b - a + 1, d - c + 1)):
+            assert B[i, j] == O.evenbary_getindex(W, F, i - 1, j - 1)
+        L = hm.barycentricmatrix(np.float64, f, a, b, c, d)   # BarycentricMatrix.jl:61-89
+        assert isinstance(L, hm.LowRankMatrix) and np.array_equal(L.U, W.T) and np.array_equal(L.V, F)
+        assert np.array_equal(L.S, np.ones(20))
+    with pytest.raises(TypeError):
+        hm.EvenBarycentricMatrix(f, 1.0, 5, 1, 5)
+
+
+def test_evenbary_layout_accounting(hm):
+    """An EvenBarycentricMatrix leaf is counted at the reference's (m+n) r words although it is
+    packed zero-interleaved at rank 2r; parity and shapes are validated at the ABI."""
+    L = hm.lib()
+    b = C.c_void_p()
+    hm._lib.check(L.hm_builder_create(C.byref(b), 500, 400, 0, -1))
+    hm._lib.check(L.hm_builder_add_evenbary(b, None, 20, None, 300, 200, 300, 20, 10, 50, 1))
+    s = hm._lib.Stats()
+    hm._lib.check(L.hm_builder_layout_stats(b, 0, 1, C.byref(s)))
+    st = s.asdict()
+    assert st["lowrank_words"] == (200 + 300) * 20 and st["n_lowrank"] == 1
+    assert st["algorithmic_bytes"] == 8 * ((200 + 300) * 20 + 500 + 400)
+    assert st["v_stream_bytes"] + st["u_stream_bytes"] >= 2 * 8 * (200 + 300) * 20
+    assert L.hm_builder_add_evenbary(b, None, 20, None, 300, 200, 300, 20, 10, 50, 2) == 1     # HM_ERR_INVALID
+    assert L.hm_builder_add_evenbary(b, None, 20, None, 300, 200, 300, 20, 400, 50, 0) == 4    # HM_ERR_RANGE
+    assert L.hm_builder_add_evenbary(b, None, 20, None, 300, 200, 300, -1, 0, 0, 0) == 3     # HM_ERR_SHAPE
+    L.hm_builder_destroy(b)
+
+    T = hm.hierarchical("ParityMatrix", hm.EvenBarycentricMatrix, hm.Matrix)
+    H = T(np.float64, 1, 2)
+    f = lambda x, j: 1.0 / (x - j)  # noqa: E731
+    H[hm.Block(1), hm.Block(1)] = hm.EvenBarycentricMatrix(f, 1, 50, 100, 160)
+    H[hm.Block(1), hm.Block(2)] = np.ones((50, 9), order="F")
+    assert H.size() == (50, 70) and H.assigned.tolist() == [[2, 3]] and H.has_parity_leaves()
+    assert H[3, 5] == H[hm.Block(1), hm.Block(1)][3, 5] and H[1, 62] == 1.0
+    assert H.stats()["lowrank_words"] == (50 + 61) * 20
+    with pytest.raises(TypeError):
+        hm.rmul_(H, np.ones(70))       # the reference has no scale! for this leaf type
+    with pytest.raises(TypeError):
+        hm.mul_(np.zeros(100), H, np.ones(140), 1, 1, 2, 2)   # nor a strided mul!

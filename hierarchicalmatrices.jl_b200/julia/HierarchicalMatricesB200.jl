@@ -14,7 +14,7 @@ module HierarchicalMatricesB200
 using LinearAlgebra
 using HierarchicalMatrices
 import HierarchicalMatrices: KernelMatrix, HierarchicalMatrix, LowRankMatrix, BarycentricMatrix2D,
-                             blocksize
+                             EvenBarycentricMatrix, blocksize
 
 const libhm = get(ENV, "HMB200_LIB", joinpath(@__DIR__, "..", "lib", "libhmb200.so"))
 
@@ -178,6 +178,38 @@ HierarchicalMatrices.mul!(y::StridedVecOrMat{Float64}, H::HierarchicalMatrix{Flo
     HierarchicalMatrices.mul!(y, H, x, istart, jstart, 1, 1)
 LinearAlgebra.mul!(y::StridedVector{Float64}, H::HierarchicalMatrix{Float64}, x::StridedVector{Float64}) =
     HierarchicalMatrices.mul!(y, H, x, 1, 1, 1, 1)
+
+# EvenBarycentricMatrix: src/algebra.jl:166-239.  The active parity class depends on the absolute
+# offsets, so one single-leaf plan is kept per parity of (istart-1)+(jstart-1).
+const EVEN_PLANS = IdDict{Any,Vector{Union{Nothing,Plan}}}()
+
+function plan(B::EvenBarycentricMatrix{Float64}, parity::Int)
+    slots = get!(() -> Union{Nothing,Plan}[nothing, nothing], EVEN_PLANS, B)
+    slots[parity + 1] === nothing || return slots[parity + 1]
+    m, n = size(B)
+    W, F = B.W, B.F
+    b = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:hm_builder_create, libhm), Int32, (Ref{Ptr{Cvoid}}, Int64, Int64, Int32, Int32),
+                b, m, n, 0, device()))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    try
+        GC.@preserve W F check(ccall((:hm_builder_add_evenbary, libhm), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Int64, Int64, Int64, Int64, Int32),
+            b[], W, max(stride(W, 2), 1), F, max(stride(F, 2), 1), m, n, size(W, 1), 0, 0, parity))
+        dev = Int32[device()]
+        check(ccall((:hm_plan_finalize, libhm), Int32, (Ptr{Cvoid}, Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}),
+                    b[], dev, 1, out))
+    finally
+        ccall((:hm_builder_destroy, libhm), Int32, (Ptr{Cvoid},), b[])
+    end
+    slots[parity + 1] = Plan(out[])
+end
+
+function HierarchicalMatrices.mul!(u::Vector{Float64}, B::EvenBarycentricMatrix{Float64},
+                                   v::StridedVector{Float64}, istart::Int, jstart::Int)
+    checkbounds_mul(u, B, v, istart, jstart, 1, 1)
+    matvec!(u, plan(B, (istart + jstart) & 1), v, istart, jstart, 1, 1, true)
+end
 
 # rmul!(H, Diagonal(b)) / lmul!(Diagonal(b), H): src/HierarchicalMatrix.jl:15-16, 54-108.
 # The reference methods update the Julia blocks; afterwards the cached device plan (if any)

@@ -39,7 +39,7 @@ __all__ = [
     "hierarchical", "HierarchicalMatrix", "KernelMatrix", "blocksize", "size", "mul_",
     "cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel", "Plan", "flatten",
     "chebyshevpoints", "HmError", "rmul_", "lmul_", "scale_", "adjoint", "Adjoint",
-    "chebyshevbarycentricweights", "EvenBarycentricMatrix", "barycentricmatrix",
+    "chebyshevbarycentricweights", "EvenBarycentricMatrix", "barycentricmatrix", "Transpose", "transpose",
 ]
 
 Matrix = np.ndarray  # the dense leaf type of the reference
@@ -887,10 +887,26 @@ class Adjoint:
     __matmul__ = __mul__
 
 
+class Transpose:
+    """`transpose(A)` / `A'` of a leaf (Matrix or LowRankMatrix): the wrappers the reference's
+    leaf-level mul! methods take (algebra.jl:50-82, 133-159; test/runtests.jl:27-33)."""
+
+    def __init__(self, parent):
+        self.parent = parent
+
+    shape = property(lambda self: tuple(self.parent.shape[::-1]))
+
+
 def adjoint(H):
-    if not isinstance(H, _HierarchicalBase):
-        raise TypeError("MethodError: adjoint of a hierarchical matrix")
-    return Adjoint(H)
+    """`adjoint(H)`; all operators here are real, so this is the transpose."""
+    if isinstance(H, _HierarchicalBase):
+        return Adjoint(H)
+    if _leaf_kind(H) in (2, 3):
+        return Transpose(H)
+    raise TypeError("MethodError: adjoint of a hierarchical matrix, a Matrix or a LowRankMatrix")
+
+
+transpose = adjoint
 
 
 def _linear(a: np.ndarray, name: str) -> np.ndarray:
@@ -943,6 +959,30 @@ def mul_(y, H, x, istart: int = 1, jstart: int = 1, INCX: int = 1, INCY: int = 1
         if istart - 1 + nr > yl.size or jstart - 1 + nc > xl.size:
             raise IndexError("BoundsError: u or v is too short")
         H.plan((istart + jstart) & 1).matvec(xl, yl, 1, 1, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
+        return y
+    leaf, transposed = (H.parent, True) if isinstance(H, Transpose) else (H, False)
+    if _leaf_kind(leaf) in (2, 3, 4):
+        # leaf-level mul!(y, A, x, istart, jstart, INCX, INCY): Matrix algebra.jl:37-48, its
+        # transpose :52-82, LowRankMatrix :110-131 / :138-159, BarycentricMatrix2D :243-277.
+        # A one-leaf plan is packed for the call (leaves are plain arrays the caller may mutate).
+        if _leaf_kind(leaf) == 4 and (INCX != 1 or INCY != 1 or transposed):
+            raise TypeError("MethodError: BarycentricMatrix2D has only mul!(u, B, v, istart, jstart)")
+        if not (isinstance(y, np.ndarray) and isinstance(x, np.ndarray)
+                and y.dtype == x.dtype == leaf.dtype == np.float64):
+            raise TypeError("MethodError: y, A and x must all be Float64")
+        if isinstance(leaf, np.ndarray) and leaf.ndim != 2:
+            raise TypeError("MethodError: A must be a matrix")
+        if INCX < 1 or INCY < 1 or istart < 1 or jstart < 1:
+            raise IndexError("BoundsError: offsets and strides are 1-based positive integers")
+        yl, xl = _linear(y, "y"), _linear(x, "x")
+        nr, nc = leaf.shape[::-1] if transposed else leaf.shape
+        if nr and istart - 1 + (nr - 1) * INCY >= yl.size:
+            raise IndexError("BoundsError: y is too short")
+        if nc and jstart - 1 + (nc - 1) * INCX >= xl.size:
+            raise IndexError("BoundsError: x is too short")
+        P = _single_leaf_plan(leaf, 0, _current_device())
+        apply = P.rmatvec if transposed else P.matvec
+        apply(xl, yl, INCX, INCY, accumulate=True, xoff=jstart - 1, yoff=istart - 1)
         return y
     if not isinstance(H, _HierarchicalBase):
         raise TypeError("MethodError: H is not a hierarchical matrix")

@@ -808,3 +808,52 @@ def test_barycentricmatrix_lowrank_family(hm, O):
     i = np.arange(1, 301)[:, None]
     j = np.arange(500, 901)[None, :]
     assert relinf((H * x)[:300] - H[hm.Block(1), hm.Block(2)] @ x[401:], (1.0 / (i - j)) @ x[:401]) <= 1e-11
+
+
+def test_leaf_level_mul_reads_like_runtests(hm, O):
+    """test/runtests.jl:15-33 verbatim: mul!(y, A, x, ...) and mul!(y, transpose(A), x, ...) on a
+    bare Matrix; then the same call forms for LowRankMatrix (algebra.jl:110-159) and
+    BarycentricMatrix2D (algebra.jl:243-277) against the oracle's leaf applies."""
+    rng = np.random.default_rng(0)
+    eps = np.finfo(np.float64).eps
+    A = np.asfortranarray(rng.random((10, 5)))
+    x = rng.random(40)
+    y = np.zeros_like(x)
+    hm.mul_(y, A, x, 1, 1)
+    assert np.linalg.norm(y[0:10] - A @ x[0:5]) <= 4 * eps * np.linalg.norm(A @ x[0:5])
+    y[:] = 0
+    hm.mul_(y, A, x, 5, 5, 2, 2)
+    assert np.linalg.norm(y[4:23:2] - A @ x[4:13:2]) <= 4 * eps * np.linalg.norm(A @ x[4:13:2])
+    y[:] = 0
+    hm.mul_(y, hm.transpose(A), x, 1, 5, 2, 1)
+    assert np.linalg.norm(y[0:5] - A.T @ x[4:23:2]) <= 4 * eps * np.linalg.norm(A.T @ x[4:23:2])
+    y[:] = 0
+    hm.mul_(y, hm.transpose(A), x, 6, 3, 1, 3)
+    assert np.linalg.norm(y[5:18:3] - A.T @ x[2:12]) <= 4 * eps * np.linalg.norm(A.T @ x[2:12])
+    assert not y[:5].any() and not y[6:18:3].any() and not y[18:].any()
+    # exact on integer data, like the BigFloat block runtests.jl:35-52
+    Ai = np.asfortranarray(rng.integers(-8, 9, (10, 5)).astype(np.float64))
+    xi = rng.integers(-8, 9, 40).astype(np.float64)
+    yi = np.zeros(40)
+    hm.mul_(yi, hm.transpose(Ai), xi, 6, 3, 1, 3)
+    assert np.array_equal(yi[5:18:3], Ai.T @ xi[2:12])
+
+    U, V, S = rng.standard_normal((37, 6)), rng.standard_normal((23, 6)), rng.standard_normal(6)
+    Lr = hm.LowRankMatrix(np.asfortranarray(U), S, np.asfortranarray(V))
+    x = rng.standard_normal(200)
+    y0 = rng.standard_normal(200)
+    ref = O.mul_lowrank(y0.copy(), U, S, V, x, 3, 7, 2, 3)
+    assert relinf(hm.mul_(y0.copy(), Lr, x, 4, 8, 2, 3), ref) <= TOL
+    got = hm.mul_(y0.copy(), hm.adjoint(Lr), x, 2, 5, 3, 2)          # y[2 + 2k] += (V S U') x[5 + 3i]
+    ref = y0.copy()
+    ref[1:1 + 2 * 23:2] += (V * S) @ (U.T @ x[4:4 + 3 * 37:3])
+    assert relinf(got, ref) <= TOL
+
+    Ub, Fb, Vb = rng.standard_normal((50, 20)), rng.standard_normal((20, 20)), rng.standard_normal((31, 20))
+    B2 = hm.BarycentricMatrix2D(np.asfortranarray(Ub), np.asfortranarray(Fb), np.asfortranarray(Vb))
+    ref = O.mul_bary2d(y0.copy(), Ub, Fb, Vb, x, 9, 4)
+    assert relinf(hm.mul_(y0.copy(), B2, x, 10, 5), ref) <= TOL
+    with pytest.raises(TypeError):
+        hm.mul_(y0.copy(), B2, x, 1, 1, 2, 1)
+    with pytest.raises(IndexError):
+        hm.mul_(np.zeros(9), A, x, 1, 1)

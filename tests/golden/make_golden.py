@@ -16,6 +16,10 @@ oracle/ and of the CUDA library:
                      and W, and the masked product of algebra.jl:168-239 for an even and an
                      odd offset shift, all evaluated at 60 digits from the Float64 nodes/weights
 
+  bary2d_block.json  one BarycentricMatrix2D block (/root/reference/src/BarycentricMatrix.jl:147-178,
+                     236-297) for the Cauchy kernel on the box x in [0.5, 1], y in [-1, -0.5]:
+                     U, F, V from the formulas at 60 digits (row-normalised lambda/(x - node))
+
 The reference ships no golden vectors (test/runtests.jl draws from Julia's RNG), and
 Julia is not installed here, so these are the strongest reference-independent pins
 available.
@@ -122,6 +126,35 @@ def evenbary():
               open(os.path.join(HERE, "evenbary_cauchy.json"), "w"))
 
 
+def bary2d_block():
+    r = 20
+    a, b, c, d = 1.0, 0.5, -0.5, -1.0          # descending boxes, as KernelMatrix passes them
+    nodes = [mp.mpf(v) for v in chebpts(r)]
+    lam = [mp.mpf(v) for v in chebweights(r)]
+    rng = np.random.default_rng(20261019)
+    x = np.sort(rng.uniform(0.5, 1.0, 37))[::-1].copy()
+    y = np.sort(rng.uniform(-1.0, -0.5, 29))[::-1].copy()
+    # mapped nodes as Float64 arithmetic gives them: (a+b)/2 + (b-a)/2 * node
+    xn = [float(np.float64(0.5 * (a + b)) + np.float64(0.5 * (b - a)) * np.float64(float(t))) for t in nodes]
+    yn = [float(np.float64(0.5 * (c + d)) + np.float64(0.5 * (d - c)) * np.float64(float(t))) for t in nodes]
+
+    def factor(pts, nd):
+        out = []
+        for p in pts:
+            row = [lam[k] / (mp.mpf(float(p)) - mp.mpf(nd[k])) for k in range(r)]
+            tot = sum(row)
+            out.append([float(v / tot) for v in row])
+        return out
+    U = factor(x, xn)
+    V = factor(y, yn)
+    F = [[float(mp.mpf(1) / (mp.mpf(xn[p]) - mp.mpf(yn[q]))) for q in range(r)] for p in range(r)]
+    json.dump({"a": a, "b": b, "c": c, "d": d, "x": hexlist(x), "y": hexlist(y),
+               "U": [hexlist(row) for row in U], "V": [hexlist(row) for row in V],
+               "F": [hexlist(row) for row in F]},
+              open(os.path.join(HERE, "bary2d_block.json"), "w"))
+
+
 if __name__ == "__main__":
     evenbary()
+    bary2d_block()
     main()

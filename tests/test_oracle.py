@@ -334,3 +334,22 @@ def test_evenbary_tree_walks(O):
     xr = rng.standard_normal(106)
     ref = dense(0).T @ xr
     assert np.max(np.abs(T.rmatvec(xr) - ref)) <= 1e-13 * np.max(np.abs(ref))
+
+
+def test_bary2d_block_golden(O):
+    """U, F, V of one BarycentricMatrix2D block against the 60-digit evaluation of
+    BarycentricMatrix.jl:147-178 / 248-297 (tests/golden/make_golden.py: bary2d_block)."""
+    g = json.load(open(os.path.join(GOLD, "bary2d_block.json")))
+    x, y = _hex(g["x"]), _hex(g["y"])
+    U, F, V = O.bary2d_build(O.CAUCHY, g["a"], g["b"], g["c"], g["d"], x, 0, len(x), y, 0, len(y))
+    Ug = np.array([_hex(r) for r in g["U"]])
+    Vg = np.array([_hex(r) for r in g["V"]])
+    Fg = np.array([_hex(r) for r in g["F"]])
+    assert np.max(np.abs(F - Fg) / np.abs(Fg)) <= 4 * np.finfo(float).eps
+    # lambda/(x - node) loses digits only where x nearly hits a node; rows are normalised to sum 1
+    assert np.max(np.abs(U - Ug)) <= 1e-13 * np.max(np.abs(Ug))
+    assert np.max(np.abs(V - Vg)) <= 1e-13 * np.max(np.abs(Vg))
+    assert np.max(np.abs(U.sum(axis=1) - 1)) <= 1e-14 and np.max(np.abs(V.sum(axis=1) - 1)) <= 1e-14
+    # and the block it represents is the kernel: U F V' = 1/(x - y) to interpolation accuracy
+    K = 1.0 / (x[:, None] - y[None, :])
+    assert np.max(np.abs(U @ F @ V.T - K)) <= 1e-13 * np.max(np.abs(K))

@@ -595,14 +595,16 @@ def test_panel_kernel_variants_agree(hm, O):
         "x, y = hm.chebyshevpoints(6000), hm.chebyshevpoints(6000, 2);"
         "K = hm.KernelMatrix(hm.cauchykernel, x, y, 1.0, -1.0, 1.0, -1.0, device=0);"
         "X = np.asfortranarray(np.random.default_rng(0).standard_normal((6000, 40)));"
-        "np.save(sys.argv[1], K * X)"
+        "np.save(sys.argv[1], np.hstack([K * X, K * X[:, :10], K * X[:, 10:37]]))"   # 64-, 16- and 32-wide panels
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for flag in ("stream", "tma"):
+    for flag in ("stream", "tma", "mm"):
         path = f"/tmp/hm_panel_{flag}.npy"
         subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, HMB200_PANEL=flag))
         outs.append(np.load(path))
-    assert relinf(outs[0], outs[1]) <= 1e-13
+    for o in outs[1:]:
+        assert o.shape == (6000, 77) and relinf(outs[0], o) <= 1e-13
+    assert relinf(outs[2][:, 40:50], outs[2][:, :10]) <= 1e-13 and relinf(outs[2][:, 50:], outs[2][:, 10:37]) <= 1e-13
     x, y, (a, b, c, d) = O.example_points(6000, "cheb")
     Kref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d)
     X = np.asfortranarray(np.random.default_rng(0).standard_normal((6000, 40)))

@@ -938,6 +938,10 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
             HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
                                      p->dy.p, accumulate != 0, nullptr, st));
             HM_CUDA(cudaEventRecord(p->ev_y[k], st));
+        }
+        // all launches are queued before the first copy back: with pageable y the copies block
+        // the host, and must not hold up the launch of the following chunks
+        for (int k = 0; k < HM_NCHUNK; k++) {
             HM_CUDA(cudaStreamWaitEvent(cst, p->ev_y[k], 0));
             const int64_t a0 = L.ychunk[(size_t)k], a1 = L.ychunk[(size_t)k + 1];
             if (a1 > a0) HM_CUDA(cudaMemcpyAsync(y + a0, p->dy.p + a0, (size_t)(a1 - a0) * 8, cudaMemcpyDeviceToHost, cst));

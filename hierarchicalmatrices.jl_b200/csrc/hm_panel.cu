@@ -685,40 +685,58 @@ hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__re
                      const double *__restrict__ Pp, const double *__restrict__ core,
                      double *__restrict__ Sp, int max_r)
 {
-    constexpr int CS = NB * 8;
+    constexpr int CS = NB * 8, TP = CS + 4; // TP = 4 (mod 16): conflict-free B-fragment reads
     extern __shared__ double sm[];
-    double *Tsm = sm;                         // [rv][CS]
+    double *Tsm = sm;                         // [rv rounded up to 4][TP]
     const HmCoreBlock cb = blocks[blockIdx.x];
     const double *__restrict__ Fg = core + cb.core; // ru x rv (bary) or r (low rank); L1-resident
     (void)max_r;
     const int t = threadIdx.x, T = blockDim.x;
     const int32_t *pl = plist + cb.pl0;
-    const int nT = cb.rv * CS;
-    for (int e = t; e < nT; e += T) {
+    const int rv4 = (cb.rv + 3) & ~3;
+    for (int e = t; e < rv4 * CS; e += T) {
+        const int l = e / CS, c = e - l * CS;
         double a = 0.0;
-        int i = 0;
-        for (; i + 3 < cb.npl; i += 4) {
-            double p0 = Pp[(size_t)pl[i] * CS + e], p1 = Pp[(size_t)pl[i + 1] * CS + e];
-            double p2 = Pp[(size_t)pl[i + 2] * CS + e], p3 = Pp[(size_t)pl[i + 3] * CS + e];
-            a += p0;
-            a += p1;
-            a += p2;
-            a += p3;
+        if (l < cb.rv) {
+            int i = 0;
+            for (; i + 3 < cb.npl; i += 4) {
+                double p0 = Pp[(size_t)pl[i] * CS + e], p1 = Pp[(size_t)pl[i + 1] * CS + e];
+                double p2 = Pp[(size_t)pl[i + 2] * CS + e], p3 = Pp[(size_t)pl[i + 3] * CS + e];
+                a += p0;
+                a += p1;
+                a += p2;
+                a += p3;
+            }
+            for (; i < cb.npl; i++) a += Pp[(size_t)pl[i] * CS + e];
         }
-        for (; i < cb.npl; i++) a += Pp[(size_t)pl[i] * CS + e];
-        Tsm[e] = a;
+        Tsm[l * TP + c] = a; // rows rv .. rv4-1 are zero: the K padding of the MMAs below
     }
     __syncthreads();
     double *o = Sp + (size_t)cb.soff * CS;
-    const int nS = cb.ru * CS;
     if (cb.kind == HM_LEAF_LOWRANK) {
-        for (int e = t; e < nS; e += T) o[e] = Tsm[e] * __ldg(Fg + e / CS);
+        for (int e = t; e < cb.ru * CS; e += T) {
+            const int k = e / CS, c = e - k * CS;
+            o[e] = Tsm[k * TP + c] * __ldg(Fg + k);
+        }
     } else {
-        for (int e = t; e < nS; e += T) {
-            int k = e / CS, c = e - k * CS;
-            double a = 0.0;
-            for (int l = 0; l < cb.rv; l++) a = fma(__ldg(Fg + k + (size_t)l * cb.ru), Tsm[l * CS + c], a);
-            o[e] = a;
+        // S = F T on the FP64 tensor cores: a warp owns 8-column blocks of the panel; A fragments
+        // (F, column-major ru x rv) through L1, B fragments (T) from shared memory.  The plain-FMA
+        // form needed two memory instructions per FMA and was bound by L1 wavefronts.
+        const int lane = t & 31, warp = t >> 5, nw = T >> 5;
+        const int gid = lane >> 2, tig = lane & 3;
+        const int mb = (cb.ru + 7) >> 3, ks = rv4 >> 2;
+        for (int n = warp; n < NB; n += nw) {
+            for (int m = 0; m < mb; m++) {
+                const int row = m * 8 + gid;
+                double d0 = 0.0, d1 = 0.0;
+                for (int k = 0; k < ks; k++) {
+                    const int kk = k * 4 + tig;
+                    const double a = (row < cb.ru && kk < cb.rv) ? __ldg(Fg + row + (size_t)kk * cb.ru) : 0.0;
+                    dmma884(d0, d1, a, Tsm[kk * TP + n * 8 + gid]);
+                }
+                if (row < cb.ru)
+                    *reinterpret_cast<double2 *>(o + (size_t)row * CS + n * 8 + 2 * tig) = make_double2(d0, d1);
+            }
         }
     }
 }
@@ -789,7 +807,7 @@ cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const 
                               const double *core, double *Sp, int max_r, cudaStream_t st)
 {
     if (nblocks <= 0) return cudaSuccess;
-    const size_t smem = (size_t)max_r * NB * 8 * sizeof(double);
+    const size_t smem = (size_t)(max_r + 3) * (NB * 8 + 4) * sizeof(double);
     if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(hm_core_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,

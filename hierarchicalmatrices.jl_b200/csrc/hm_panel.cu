@@ -87,7 +87,13 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
 
     const double *__restrict__ Wg = W + it.slab;
     const int nfb = (Fp + 7) >> 3;  // 8-row blocks
-    const int nft = (nfb + 1) >> 1; // 16-row tiles
+    // 16-row tiles.  With TB3 an odd block count gives the last tile three blocks instead of
+    // opening a half-empty tile: the rank-20 slabs of stage 1 (most of its bytes) become one
+    // 24-row tile per warp, all eight warps splitting the slow dimension -- one B fragment load
+    // per three MMAs instead of per one and two, and no 2:1 imbalance between the warps.
+    constexpr bool TB3 = NB <= 4 && !GATHER; // stage 1 only: stage-3 row segments gain nothing (measured)
+    constexpr int TB = TB3 ? 3 : 2;
+    const int nft = TB3 ? max(nfb >> 1, nfb > 0 ? 1 : 0) : (nfb + 1) >> 1;
     if (nft == 0) return;
     const int kgroups = nft >= 8 ? 1 : 8 / nft;
     const int ntw = nft >= 8 ? 8 : nft; // warps per k-group
@@ -101,14 +107,16 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
     }
 
     for (int ft = warp % ntw; ft < nft && active; ft += ntw) {
-        const bool two = ft * 2 + 1 < nfb;
+        const int nblk = min(nfb - 2 * ft, (TB3 && ft == nft - 1) ? 3 : 2); // blocks of this tile
         const int col0 = ft * 16 + gid;
-        const bool c0ok = col0 < Fp, c1ok = two && (col0 + 8 < Fp);
+        bool cok[TB];
+#pragma unroll
+        for (int a = 0; a < TB; a++) cok[a] = a < nblk && col0 + 8 * a < Fp;
         const double *__restrict__ ap = Wg + col0;
 
-        double acc[2][NB][2];
+        double acc[TB][NB][2];
 #pragma unroll
-        for (int a = 0; a < 2; a++)
+        for (int a = 0; a < TB; a++)
 #pragma unroll
             for (int n = 0; n < NB; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
 
@@ -117,7 +125,7 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         // range takes the masked form once.
         auto batch = [&](int k0, auto masked) {
             constexpr bool MASK = decltype(masked)::value;
-            double a0[U], a1[U], b[U][NB];
+            double av[U][TB], b[U][NB];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const int row = k0 + 4 * u + tig;
@@ -125,8 +133,9 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
                 if (NB == 8) { // software prefetch into L2, PD batches ahead (helps the MMA-bound case only)
                     const int prow = row + 4 * U * PD;
                     if (prow < s_hi) {
-                        if (c0ok) prefetch_l2(ap + (size_t)prow * Fp);
-                        if (c1ok) prefetch_l2(ap + (size_t)prow * Fp + 8);
+#pragma unroll
+                        for (int a = 0; a < TB; a++)
+                            if (cok[a]) prefetch_l2(ap + (size_t)prow * Fp + 8 * a);
                         const double *pz;
                         if (GATHER) {
                             int zr = zrow[prow];
@@ -138,8 +147,8 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
                     }
                 }
                 const double *arow = ap + (size_t)row * Fp;
-                a0[u] = (v && c0ok) ? __ldcs(arow) : 0.0;
-                a1[u] = (v && c1ok) ? __ldcs(arow + 8) : 0.0;
+#pragma unroll
+                for (int a = 0; a < TB; a++) av[u][a] = (v && cok[a]) ? __ldcs(arow + 8 * a) : 0.0;
                 const double *zp = Xt;
                 if (v) {
                     if (GATHER) {
@@ -156,8 +165,9 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
             for (int u = 0; u < U; u++) {
 #pragma unroll
                 for (int n = 0; n < NB; n++) {
-                    dmma884(acc[0][n][0], acc[0][n][1], a0[u], b[u][n]);
-                    if (two) dmma884(acc[1][n][0], acc[1][n][1], a1[u], b[u][n]);
+                    dmma884(acc[0][n][0], acc[0][n][1], av[u][0], b[u][n]);
+                    if (nblk > 1) dmma884(acc[1][n][0], acc[1][n][1], av[u][1], b[u][n]);
+                    if (TB3 && nblk > 2) dmma884(acc[TB - 1][n][0], acc[TB - 1][n][1], av[u][TB - 1], b[u][n]);
                 }
             }
         };
@@ -168,9 +178,9 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         if (kgroups == 1) {
             // sole owner of the tile: write the C fragments straight out
 #pragma unroll
-            for (int a = 0; a < 2; a++) {
+            for (int a = 0; a < TB; a++) {
                 const int f = ft * 16 + a * 8 + gid;
-                if (f < F && (a == 0 || two)) {
+                if (f < F && a < nblk) {
                     double2 *g = reinterpret_cast<double2 *>(out + (size_t)(it.out + f) * CS) + tig;
 #pragma unroll
                     for (int n = 0; n < NB; n++) {
@@ -189,16 +199,18 @@ hm_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
             for (int g = 0; g < kgroups; g++) {
                 if (kg == g) {
 #pragma unroll
-                    for (int a = 0; a < 2; a++) {
-                        double *row = csm + ((size_t)ft * 16 + a * 8 + gid) * CP + 2 * tig;
+                    for (int a = 0; a < TB; a++) {
+                        if (a < nblk) {
+                            double *row = csm + ((size_t)ft * 16 + a * 8 + gid) * CP + 2 * tig;
 #pragma unroll
-                        for (int n = 0; n < NB; n++) {
-                            if (g == 0) {
-                                row[n * 8] = acc[a][n][0];
-                                row[n * 8 + 1] = acc[a][n][1];
-                            } else {
-                                row[n * 8] += acc[a][n][0];
-                                row[n * 8 + 1] += acc[a][n][1];
+                            for (int n = 0; n < NB; n++) {
+                                if (g == 0) {
+                                    row[n * 8] = acc[a][n][0];
+                                    row[n * 8 + 1] = acc[a][n][1];
+                                } else {
+                                    row[n * 8] += acc[a][n][0];
+                                    row[n * 8 + 1] += acc[a][n][1];
+                                }
                             }
                         }
                     }

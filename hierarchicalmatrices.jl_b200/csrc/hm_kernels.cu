@@ -642,9 +642,12 @@ hm_rowdot_kernel(const HmItem *__restrict__ items, const double *__restrict__ W,
     __syncthreads();
     const double2 *__restrict__ W2 = reinterpret_cast<const double2 *>(W + it.slab);
     double *__restrict__ o = PQ + it.aux;
-    if (L <= 8) {
+    // a group walks its rows in chunks of 2*LR words: the narrowest group that covers a row in one
+    // chunk keeps the most rows (and loads) in flight per warp -- rank-20 slabs (L = 10) run four
+    // groups of 8 lanes per warp
+    if (L <= 16) {
         rowdot_groups<8>(W2, zs, o, S, L, t);
-    } else if (L <= 16) {
+    } else if (L <= 32) {
         rowdot_groups<16>(W2, zs, o, S, L, t);
     } else {
         rowdot_groups<32>(W2, zs, o, S, L, t);
@@ -721,11 +724,45 @@ hm_core_adj_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks, cons
     double *Fs = tbuf + max_r; // F staged in shared memory when it fits (ru, rv <= 32)
     const HmCoreBlock cb = blocks[b];
     const double *c = core + cb.core;
+    const int32_t *ql = qlist + q0[b];
+    const int n = qn[b];
+    if (cb.kind == HM_LEAF_BARY2D && cb.ru == 20 && cb.rv == 20) {
+        // the rank the assembler produces: F goes to registers with coalesced loads that stay in
+        // flight while lane k walks the piece list; then F is laid out in shared memory with an odd
+        // pitch and lane l reads column l without bank conflicts
+        constexpr int R = 20, RP = 21, NJ = (R * R + 31) / 32;
+        double f[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; j++) f[j] = lane + 32 * j < R * R ? __ldcs(c + lane + 32 * j) : 0.0;
+        double t = 0.0;
+        if (lane < R) {
+            int i = 0;
+            for (; i + 3 < n; i += 4) {
+                double p0 = PQ[ql[i] + lane], p1 = PQ[ql[i + 1] + lane];
+                double p2 = PQ[ql[i + 2] + lane], p3 = PQ[ql[i + 3] + lane];
+                t += p0;
+                t += p1;
+                t += p2;
+                t += p3;
+            }
+            for (; i < n; i++) t += PQ[ql[i] + lane];
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+            const int idx = lane + 32 * j; // F[k + l*R] -> Fs[l*RP + k]
+            if (idx < R * R) Fs[(idx / R) * RP + idx % R] = f[j];
+        }
+        __syncwarp();
+        double a = 0.0;
+        const double *col = Fs + (lane < R ? lane : 0) * RP;
+#pragma unroll
+        for (int k = 0; k < R; k++) a = fma(col[k], __shfl_sync(0xffffffffu, t, k), a);
+        if (lane < R) svec[cb.soff + lane] = a;
+        return;
+    }
     const bool staged = cb.kind == HM_LEAF_BARY2D && cb.ru <= 32 && cb.rv <= 32;
     if (staged)
         for (int i = lane; i < cb.ru * cb.rv; i += 32) Fs[i] = __ldcs(c + i); // coalesced
-    const int32_t *ql = qlist + q0[b];
-    const int n = qn[b];
     for (int k = lane; k < cb.ru; k += 32) {
         double t = 0.0;
         int i = 0;

@@ -133,7 +133,10 @@ class _Kernel:
         self._fn = fn
 
     def __call__(self, x, y):
-        return self._fn(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64))
+        x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        if x.ndim == 1 and y.ndim == 1:  # f(X::Vector, Y::Vector) = [f(x, y) for x in X, y in Y] -- Kernel.jl:39-41
+            return self._fn(x[:, None], y[None, :])
+        return self._fn(x, y)
 
     def __repr__(self):
         return self.__name__

@@ -859,3 +859,17 @@ def test_leaf_level_mul_reads_like_runtests(hm, O):
         hm.mul_(y0.copy(), B2, x, 1, 1, 2, 1)
     with pytest.raises(IndexError):
         hm.mul_(np.zeros(9), A, x, 1, 1)
+
+
+def test_reference_example_runs(hm, capsys):
+    """test/runtests.jl:59 includes examples/Kernel.jl (and asserts nothing); the same script on
+    this engine, at its smaller size, with the error it prints bounded."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "kernel.py")
+    spec = importlib.util.spec_from_file_location("hm_example_kernel", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    worst = mod.main([1000])
+    out = capsys.readouterr().out
+    assert out.count("2-norm relative error") == 8     # 4 kernels x 2 point families
+    assert worst <= 1e-10

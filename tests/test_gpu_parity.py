@@ -873,3 +873,38 @@ def test_reference_example_runs(hm, capsys):
     out = capsys.readouterr().out
     assert out.count("2-norm relative error") == 8     # 4 kernels x 2 point families
     assert worst <= 1e-10
+
+
+def test_host_copy_pipeline_is_bit_identical(hm, O):
+    """hm_matvec pipelines its host copies against the kernels above ~2 MB of vector data (chunked
+    x upload ahead of chunk-ordered stage 1, chunked y download behind chunk-ordered stage 3).
+    Every output still has one writer and the same summation order: bit-identical to the plain
+    path, with accumulation, and for a row part."""
+    N = 1 << 19
+    x, y, (a, b, c, d) = O.example_points(N, "unif")
+    rng = np.random.default_rng(77)
+    v, y0 = rng.standard_normal(N), rng.standard_normal(N)
+    for part, nparts in ((0, 1), (1, 3)):
+        K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=part, nparts=nparts)
+        P = K.plan()
+        outs = []
+        for flag in (None, "1"):
+            if flag is None:
+                os.environ.pop("HMB200_NO_COPY_PIPELINE", None)
+            else:
+                os.environ["HMB200_NO_COPY_PIPELINE"] = flag
+            try:
+                u = y0.copy()
+                P.matvec(v, u, accumulate=True)
+                w = np.full(N, np.nan)
+                P.matvec(v, w, accumulate=False)
+            finally:
+                os.environ.pop("HMB200_NO_COPY_PIPELINE", None)
+            outs.append((u, w))
+        st = P.stats()
+        r0, r1 = st["row_begin"], st["row_end"]
+        assert np.array_equal(outs[0][0], outs[1][0])
+        assert np.array_equal(outs[0][1][r0:r1], outs[1][1][r0:r1])
+        assert np.isnan(outs[0][1][:r0]).all() and np.isnan(outs[0][1][r1:]).all()   # only owned rows are written
+        assert np.array_equal(outs[0][0][:r0], y0[:r0]) and np.array_equal(outs[0][0][r1:], y0[r1:])
+        assert relinf(outs[0][0][r0:r1] - y0[r0:r1], outs[0][1][r0:r1]) <= 1e-12

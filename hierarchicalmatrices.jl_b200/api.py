@@ -25,7 +25,6 @@ All arithmetic of `mul_` / `*` runs in the CUDA library (no CPU fallback).
 from __future__ import annotations
 
 import ctypes as C
-import math
 
 import numpy as np
 

@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--dist", default="cheb", choices=["cheb", "unif"],
                     help="cheb = examples/Kernel.jl:61-62 point sets; unif = uniform interlaced")
     ap.add_argument("--no-gather", action="store_true", help="skip the all-gather of y (N > 1)")
+    ap.add_argument("--matrix-free", action="store_true",
+                    help="hm_assemble_kernel_free: store no U/V/dense tiles, evaluate the entries inside every matvec "
+                         "(FP64-bound; not the headline configuration)")
     ap.add_argument("--nrhs", type=int, default=1,
                     help="> 1: time the multi-right-hand-side product (BASELINE configs[2]/[4]) instead")
     ap.add_argument("--adjoint", action="store_true",
@@ -352,7 +355,8 @@ def run_ours(args):
     n = args.n
     px, py = points(hm, n, args.dist)
     t0 = time.perf_counter()
-    K = hm.KernelMatrix(hm.cauchykernel, px, py, 1.0, -1.0, 1.0, -1.0, device=local, part=rank, nparts=world)
+    K = hm.KernelMatrix(hm.cauchykernel, px, py, 1.0, -1.0, 1.0, -1.0, device=local, part=rank, nparts=world,
+                        matrix_free=args.matrix_free)
     torch.cuda.synchronize()
     t_asm = time.perf_counter() - t0
     plan = K.plan()
@@ -580,11 +584,14 @@ def run_ours(args):
                                         + (", whole loop replayed as one CUDA graph" if use_graph else "")) if gather else
                                        "NCCL broadcast(x) per step" if dist_on else "none"),
                        "l2": "inputs larger than L2 (%.1f GB streamed per step per GPU)" % (st["stored_bytes"] / 1e9),
-                       "assembly_s": round(t_asm, 3)},
+                       "assembly_s": round(t_asm, 3), **({"matrix_free": True} if args.matrix_free else {})},
             "effective_gbs": st["algorithmic_bytes"] * value / 1e9,
             "algorithmic_bytes_per_matvec": st["algorithmic_bytes"],
             "roofline_frac_whole_step": st["algorithmic_bytes"] * value / 1e9 / (peak * world),
-            "roofline": {"bound": "hbm", "kernel": "hm_stream_kernel (stage 1 + stage 3 instantiations, rank 0)",
+            "roofline": {"bound": "hbm", "kernel": ("hm_free1/hm_free3 (matrix-free: entries evaluated on the fly; 'achieved' is "
+                                                   "the stored operator's algorithmic bytes per second, not HBM traffic)"
+                                                   if args.matrix_free else
+                                                   "hm_stream_kernel (stage 1 + stage 3 instantiations, rank 0)"),
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                          "peak_source": peak_src, "traffic": traffic,
                          "algorithmic_bytes_per_launch": {"stage1": b1, "stage3": b3},

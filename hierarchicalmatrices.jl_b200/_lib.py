@@ -69,6 +69,8 @@ SIGNATURES = {
     "hm_plan_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "hm_assemble_kernel": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                   _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "hm_assemble_kernel_free": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                       _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "hm_assemble_kernel_stats": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double,
                                         C.c_double, _i32, _i32, C.POINTER(Stats)]),
     "hm_kernel_tree_leaves": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,

@@ -654,7 +654,12 @@ class KernelMatrix(_KernelMatrixBlocks):
 
     _name = "KernelMatrix"
 
-    def __init__(self, *args, device=None, part=0, nparts=1):
+    def __init__(self, *args, device=None, part=0, nparts=1, matrix_free=False):
+        """`KernelMatrix(f, x, y, a, b, c, d)` assembles on the GPU.  `matrix_free=True` keeps no
+        U, V or dense tiles: every `mul!` evaluates the entries from the point sets while applying
+        them (FP64-bound instead of HBM-bound; the operator needs no memory beyond its r x r
+        cores, so sizes whose packed form exceeds the GPU still fit)."""
+        self.matrix_free = bool(matrix_free)
         if len(args) == 7:
             f, x, y, a, b, c, d = args
             if not isinstance(f, _Kernel):
@@ -664,12 +669,14 @@ class KernelMatrix(_KernelMatrixBlocks):
             y = np.ascontiguousarray(y, dtype=np.float64)
             dev = _current_device() if device is None else device
             h = C.c_void_p()
-            _lib.check(_lib.lib().hm_assemble_kernel(
-                x.ctypes.data_as(_dp), len(x), y.ctypes.data_as(_dp), len(y), a, b, c, d, f.id, dev,
-                part, nparts, C.byref(h)))
+            build = _lib.lib().hm_assemble_kernel_free if matrix_free else _lib.lib().hm_assemble_kernel
+            _lib.check(build(x.ctypes.data_as(_dp), len(x), y.ctypes.data_as(_dp), len(y), a, b, c, d, f.id, dev,
+                             part, nparts, C.byref(h)))
             self._assembled = Plan(h.value, dev)
             self.kernel = f
         else:
+            if matrix_free:
+                raise HmError(8, "matrix_free applies to KernelMatrix(f, x, y, a, b, c, d) only")
             super().__init__(*args)
             self._assembled = None
 

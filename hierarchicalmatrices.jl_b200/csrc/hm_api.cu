@@ -302,6 +302,13 @@ struct hm_plan {
     HmLayout L; // host metadata (tables are kept for the test hooks)
     int kernel_id = 0;
     HmCheb cheb{};
+    // matrix-free plans (hm_assemble_kernel_free): no streams; the tables the fill kernels use stay
+    // on the device together with the point sets, and the apply evaluates the entries itself
+    bool matrix_free = false;
+    DevBuf<HmLeaf> f_leaves;
+    DevBuf<HmFill> f_fill1, f_fill3;
+    DevBuf<double> f_px, f_py;
+    int free1_units = 1;
     // device arrays
     DevBuf<double> vstream, ustream, core, svec, partial;
     DevBuf<HmItem> items1, items3;
@@ -367,13 +374,17 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
     HmLayout &L = P->L;
     HM_CUDA(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
     cudaStream_t st = P->stream;
-    HM_CUDA(P->vstream.alloc((size_t)L.vstream_words));
-    HM_CUDA(P->ustream.alloc((size_t)L.ustream_words));
+    if (!P->matrix_free) {
+        HM_CUDA(P->vstream.alloc((size_t)L.vstream_words));
+        HM_CUDA(P->ustream.alloc((size_t)L.ustream_words));
+    }
     HM_CUDA(P->core.alloc((size_t)L.core_words));
     HM_CUDA(P->svec.alloc((size_t)std::max<int64_t>(L.s_words, 1)));
     HM_CUDA(P->partial.alloc((size_t)std::max<int64_t>(L.partial_words, 1)));
-    if (L.vstream_words) HM_CUDA(cudaMemsetAsync(P->vstream.p, 0, (size_t)L.vstream_words * 8, st));
-    if (L.ustream_words) HM_CUDA(cudaMemsetAsync(P->ustream.p, 0, (size_t)L.ustream_words * 8, st));
+    if (!P->matrix_free) {
+        if (L.vstream_words) HM_CUDA(cudaMemsetAsync(P->vstream.p, 0, (size_t)L.vstream_words * 8, st));
+        if (L.ustream_words) HM_CUDA(cudaMemsetAsync(P->ustream.p, 0, (size_t)L.ustream_words * 8, st));
+    }
     if (L.core_words) HM_CUDA(cudaMemsetAsync(P->core.p, 0, (size_t)L.core_words * 8, st));
     HM_CUDA(cudaMemsetAsync(P->partial.p, 0, P->partial.n * 8, st));
     HM_CUDA(P->items1.upload(L.items1, st));
@@ -386,7 +397,7 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
     HM_CUDA(cudaMemsetAsync(P->counters.p, 0, P->counters.n * sizeof(int), st));
     {
         const char *e = getenv("HMB200_FUSE_STAGE2");
-        P->fuse = (e && e[0] == '1') && (size_t)L.max_r * 8 <= HM_SMAX;
+        P->fuse = (e && e[0] == '1') && (size_t)L.max_r * 8 <= HM_SMAX && !P->matrix_free;
     }
     {
         std::vector<int32_t> big;
@@ -395,7 +406,29 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
         P->nbig = (int64_t)big.size();
         HM_CUDA(P->bigcores.upload(big, st));
     }
-    {
+    if (P->matrix_free) {
+        // the apply kernels read the fill tables themselves; only the cores are materialised
+        int units = 1;
+        for (const HmItem &it : L.items1) {
+            int nch, CH;
+            hm_free1_split(it.S, it.nrun, nch, CH);
+            units = std::max(units, it.nrun * nch);
+        }
+        if ((size_t)units * 20 * sizeof(double) > 160 * 1024)
+            return fail(HM_ERR_UNSUPPORTED, "matrix-free: a column segment is covered by too many leaves");
+        for (const HmItem &it : L.items3)
+            if (it.F > HM_THREADS || it.nrun > HM_MAXRUNS || it.S > HM_SMAX)
+                return fail(HM_ERR_UNSUPPORTED, "matrix-free: row segment outside the kernel limits");
+        P->free1_units = units;
+        DevBuf<int32_t> dcore_leaf;
+        HM_CUDA(P->f_leaves.upload(L.leaves, st));
+        HM_CUDA(P->f_fill1.upload(L.fill1, st));
+        HM_CUDA(P->f_fill3.upload(L.fill3, st));
+        HM_CUDA(dcore_leaf.upload(L.core_leaf, st));
+        HM_CUDA(hm_launch_fillcore(P->cores.p, dcore_leaf.p, (int64_t)L.cores.size(), P->f_leaves.p, P->core.p,
+                                   P->cheb, P->kernel_id, st));
+        HM_CUDA(cudaStreamSynchronize(st));
+    } else {
         // temporary tables for the fill kernels
         DevBuf<HmLeaf> dleaves;
         DevBuf<HmFill> dfill1, dfill3;
@@ -663,12 +696,17 @@ int32_t hm_plan_stats(const hm_plan *p, hm_stats *out)
 {
     if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
     fill_stats(p->L, out);
+    if (p->matrix_free) { // nothing but the cores is stored; the apply reads tables and points
+        out->v_stream_bytes = out->u_stream_bytes = 0;
+        out->stored_bytes = 8 * p->L.core_words;
+    }
     return HM_OK;
 }
 
 int32_t hm_plan_scale(hm_plan *p, const double *b, int64_t incb, int32_t side)
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
     if (side != 0 && side != 1) return fail(HM_ERR_INVALID, "side must be 0 (columns) or 1 (rows)");
     if (incb <= 0) return fail(HM_ERR_INVALID, "stride must be positive");
     const HmLayout &L = p->L;
@@ -780,9 +818,9 @@ int32_t hm_assemble_kernel_stats(const double *x, int64_t nx, const double *y, i
     return HM_OK;
 }
 
-int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
-                           double c, double d, int32_t kernel_id, int32_t device, int32_t part, int32_t nparts,
-                           hm_plan **out)
+static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                                    double c, double d, int32_t kernel_id, int32_t device, int32_t part,
+                                    int32_t nparts, bool matrix_free, hm_plan **out)
 {
     if (!out) return fail(HM_ERR_NULL, "out is NULL");
     *out = nullptr;
@@ -793,29 +831,47 @@ int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t
     if (!P) return fail(HM_ERR_NOMEM, "out of host memory");
     P->device = device;
     P->kernel_id = kernel_id;
+    P->matrix_free = matrix_free;
     if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, P->L)) {
         delete P;
         return st;
     }
     P->cheb.r = hm_blockrank_double();
     hm_cheb_nodes_weights(P->cheb.r, P->cheb.node, P->cheb.lam);
-    DevBuf<double> dpx, dpy;
-    cudaError_t e = dpx.alloc((size_t)std::max<int64_t>(nx, 1));
-    if (e == cudaSuccess) e = dpy.alloc((size_t)std::max<int64_t>(ny, 1));
-    if (e == cudaSuccess && nx) e = cudaMemcpy(dpx.p, x, (size_t)nx * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && ny) e = cudaMemcpy(dpy.p, y, (size_t)ny * 8, cudaMemcpyHostToDevice);
+    cudaError_t e = P->f_px.alloc((size_t)std::max<int64_t>(nx, 1));
+    if (e == cudaSuccess) e = P->f_py.alloc((size_t)std::max<int64_t>(ny, 1));
+    if (e == cudaSuccess && nx) e = cudaMemcpy(P->f_px.p, x, (size_t)nx * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ny) e = cudaMemcpy(P->f_py.p, y, (size_t)ny * 8, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         delete P;
         cudaGetLastError();
         return fail(HM_ERR_CUDA, "point upload failed: %s", cudaGetErrorString(e));
     }
-    int32_t st = materialize(P, dpx.p, dpy.p);
+    int32_t st = materialize(P, P->f_px.p, P->f_py.p);
     if (st != HM_OK) {
         delete P;
         return st;
     }
+    if (!matrix_free) { // the stored operator no longer needs the points
+        P->f_px.release();
+        P->f_py.release();
+    }
     *out = P;
     return HM_OK;
+}
+
+int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                           double c, double d, int32_t kernel_id, int32_t device, int32_t part, int32_t nparts,
+                           hm_plan **out)
+{
+    return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, kernel_id, device, part, nparts, false, out);
+}
+
+int32_t hm_assemble_kernel_free(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                                double c, double d, int32_t kernel_id, int32_t device, int32_t part,
+                                int32_t nparts, hm_plan **out)
+{
+    return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, kernel_id, device, part, nparts, true, out);
 }
 
 // ---------------------------------------------------------------------------
@@ -864,10 +920,14 @@ static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int3
         fz.svec = p->svec.p;
         fz.max_r = std::max(L.max_r, 1);
     }
-    HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p,
-                             p->fuse ? &fz : nullptr, st));
+    if (p->matrix_free)
+        HM_CUDA(hm_launch_free1(p->items1.p, (int64_t)L.items1.size(), p->f_fill1.p, p->f_leaves.p, p->f_py.p, dx,
+                                p->partial.p, p->cheb, p->free1_units, st));
+    else
+        HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p,
+                                 p->fuse ? &fz : nullptr, st));
     if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
-    if (!p->fuse) {
+    if (!p->fuse || p->matrix_free) {
         HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
                                  p->svec.p, std::max(L.max_r, 1), st));
         HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
@@ -876,8 +936,13 @@ static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int3
     if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
     for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
         int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
-        HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
-                                 r == 0 ? (accumulate != 0) : 1, peers, st));
+        if (p->matrix_free)
+            HM_CUDA(hm_launch_free3(p->items3.p + i0, i1 - i0, p->runs.p, p->f_fill3.p, p->f_leaves.p, p->f_px.p,
+                                    p->f_py.p, dx, p->svec.p, dy, r == 0 ? (accumulate != 0) : 1, p->cheb,
+                                    p->kernel_id, peers, st));
+        else
+            HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
+                                     r == 0 ? (accumulate != 0) : 1, peers, st));
     }
     if (ev) {
         HM_CUDA(cudaEventRecord(ev[3], st));
@@ -904,7 +969,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
     // Below ~2 MB of vector data the extra launches and events cost more than the overlap gains
     // (measured: N = 4096 48 vs 100 us, N = 65 536 175 vs 230 us, N = 262 144 600 vs 577 us).
     if (incx == 1 && incy == 1 && nc > 0 && nr > 0 && nc + nr >= 400000 && L.round_begin.size() == 2 &&
-        !L.items3c.empty() && p->tcap == 0 && !getenv("HMB200_NO_COPY_PIPELINE")) {
+        !L.items3c.empty() && p->tcap == 0 && !p->matrix_free && !getenv("HMB200_NO_COPY_PIPELINE")) {
         if (!p->chunk_ready) {
             HM_CUDA(p->items1c.upload(L.items1c, st));
             HM_CUDA(p->items3c.upload(L.items3c, st));
@@ -993,6 +1058,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
 int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream)
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
     const HmLayout &L = p->L;
     if ((!dx && L.nrows > 0) || (!dy && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
     if (L.adj_max_f > HM_SMAX) return fail(HM_ERR_UNSUPPORTED, "adjoint: a column segment is covered by too many ranks");
@@ -1076,6 +1142,7 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
                          int32_t accumulate, void *stream)
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
     if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
     if (nrhs == 0) return HM_OK;
     const HmLayout &L = p->L;
@@ -1130,6 +1197,7 @@ int32_t hm_matmat(hm_plan *p, const double *X, int64_t ldx, double *Y, int64_t l
                   int32_t accumulate)
 {
     if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
     if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
     if (nrhs == 0) return HM_OK;
     const HmLayout &L = p->L;
@@ -1188,6 +1256,7 @@ int32_t hm_plan_leaf_info(const hm_plan *p, int64_t leaf, int32_t *kind, int64_t
 int32_t hm_plan_read_leaf(hm_plan *p, int64_t leaf, int32_t which, double *out, int64_t cap)
 {
     if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
+    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
     if (leaf < 0 || leaf >= (int64_t)p->L.leaves.size()) return fail(HM_ERR_RANGE, "leaf index out of range");
     std::lock_guard<std::mutex> lock(p->mu);
     HM_DEVICE(p->device);

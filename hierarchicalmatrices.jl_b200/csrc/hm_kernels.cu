@@ -485,6 +485,176 @@ hm_fillcore_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
 }
 
 // ---------------------------------------------------------------------------
+// matrix-free apply ("fused assemble + apply")
+//
+// The same items, runs and fill tables as the stored operator, but the slabs are never
+// written: every U, V and dense entry is evaluated from the point sets at the moment it is
+// used (the arithmetic of the fill kernels above: src/BarycentricMatrix.jl:248-297,
+// src/KernelMatrix.jl:57-60) and consumed at once.  A barycentric row is used in its
+// unnormalised form, y_i += (sum_k w_k s_k) / (sum_k w_k), one divide per (row, leaf) instead of
+// one per entry.  The bound moves from HBM to the FP64 pipe (one reciprocal per entry); the
+// operator occupies no memory beyond its tables and the r x r cores, so N = 2^24 fits one GPU.
+// ---------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ double bary_raw(const HmCheb &cheb, double mid, double half, double p, double (&w)[R])
+{
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        const double node = __dadd_rn(mid, __dmul_rn(half, cheb.node[k]));
+        w[k] = __dmul_rn(cheb.lam[k], __drcp_rn(__dsub_rn(p, node)));
+        sum = __dadd_rn(sum, w[k]);
+    }
+    return sum;
+}
+
+// stage 1: partial[item.out + (leaf, k)] = sum_s V_leaf[s, k] x[zoff + s] with V evaluated on the
+// fly.  A warp owns a unit = (leaf of the item, chunk of its columns); lanes stride the columns
+// with R private accumulators, a butterfly adds them across the warp, and the chunks of a leaf
+// are combined in chunk order -- deterministic.
+template <int R>
+__global__ void __launch_bounds__(HM_THREADS, 2)
+hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fills,
+                const HmLeaf *__restrict__ leaves, const double *__restrict__ py,
+                const double *__restrict__ x, double *__restrict__ partial, const HmCheb cheb)
+{
+    constexpr int T = HM_THREADS;
+    extern __shared__ double ures[]; // [units][R]
+    const HmItem it = items[blockIdx.x];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int S = it.S;
+    int nch, CH;
+    hm_free1_split(S, it.nrun, nch, CH);
+    const int U = it.nrun * nch;
+    const double *__restrict__ xs = x + it.zoff;
+    for (int u = warp; u < U; u += T / 32) {
+        const int e = u / nch, c = u - e * nch;
+        const HmFill f = fills[it.run0 + e];
+        const HmLeaf *__restrict__ l = leaves + f.leaf;
+        const double lo = l->c, hi = l->d;
+        const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
+        const double *__restrict__ yc = py + l->yj0 + f.off;
+        double acc[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) acc[k] = 0.0;
+        const int s1 = min(S, (c + 1) * CH);
+        for (int s = c * CH + lane; s < s1; s += 32) {
+            double w[R];
+            const double sum = bary_raw<R>(cheb, mid, half, yc[s], w);
+            const double cf = __ddiv_rn(xs[s], sum);
+#pragma unroll
+            for (int k = 0; k < R; k++) acc[k] = fma(w[k], cf, acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++)
+            if (lane == k) ures[u * R + k] = acc[k];
+    }
+    __syncthreads();
+    for (int idx = t; idx < it.nrun * R; idx += T) {
+        const int e = idx / R, k = idx - e * R;
+        double sum = 0.0;
+        for (int c = 0; c < nch; c++) sum += ures[(e * nch + c) * R + k];
+        partial[it.out + (fills[it.run0 + e].dst - it.slab) + k] = sum;
+    }
+}
+
+// stage 3: y[item.out + f] (+)= sum over the item's runs, entries evaluated on the fly.  G = T / F
+// thread groups share the rows: low-rank runs go round-robin to the groups, the columns of a dense
+// run are dealt out over all of them; the group sums are combined in group order.
+template <int R, bool PEERS>
+__global__ void __launch_bounds__(HM_THREADS, 3)
+hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
+                const HmFill *__restrict__ fills, const HmLeaf *__restrict__ leaves,
+                const double *__restrict__ px, const double *__restrict__ py,
+                const double *__restrict__ x, const double *__restrict__ svec, double *y, int accumulate,
+                const HmCheb cheb, int kernel_id, HmPeers pe)
+{
+    constexpr int T = HM_THREADS;
+    __shared__ double zs[HM_SMAX];
+    __shared__ double red[T];
+    __shared__ int rpos[HM_MAXRUNS + 1];
+    __shared__ int rsrc[HM_MAXRUNS];
+    const HmItem it = items[blockIdx.x];
+    const int t = threadIdx.x;
+    const int S = it.S, F = it.F;
+
+    for (int r = t; r < it.nrun; r += T) {
+        HmRun rr = runs[it.run0 + r];
+        rpos[r] = rr.pos;
+        rsrc[r] = rr.src;
+    }
+    if (t == 0) rpos[it.nrun] = S;
+    __syncthreads();
+    for (int e = t; e < S; e += T) {
+        int lo = 0, hi = it.nrun; // rpos[lo] <= e < rpos[hi]
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (rpos[mid] <= e)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        int src = rsrc[lo], off = e - rpos[lo];
+        zs[e] = src >= 0 ? x[src + off] : svec[(~src) + off];
+    }
+    __syncthreads();
+
+    const int G = F > 0 ? T / F : 1; // F <= T (checked when the plan is built)
+    const int g = F > 0 ? t / F : G, f = t - g * F;
+    double acc = 0.0;
+    if (g < G) {
+        int lr = 0;
+        for (int r = 0; r < it.nrun; r++) {
+            const HmFill fl = fills[it.run0 + r];
+            const HmLeaf *__restrict__ l = leaves + fl.leaf;
+            const double *__restrict__ z = zs + rpos[r];
+            if (l->kind == HM_LEAF_DENSE) {
+                const double p = px[l->xi0 + fl.off + f];
+                const double *__restrict__ yc = py + l->yj0 + fl.k0;
+                for (int j = g; j < fl.kn; j += G) acc = fma(kernel_eval(kernel_id, p, yc[j]), z[j], acc);
+            } else {
+                if (lr % G == g) {
+                    const double p = px[l->xi0 + fl.off + f];
+                    const double lo = l->a, hi = l->b;
+                    const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
+                    double w[R];
+                    const double sum = bary_raw<R>(cheb, mid, half, p, w);
+                    double dot = 0.0;
+                    if (fl.k0 == 0 && fl.kn == R) {
+#pragma unroll
+                        for (int k = 0; k < R; k++) dot = fma(w[k], z[k], dot);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < R; k++)
+                            if (k >= fl.k0 && k < fl.k0 + fl.kn) dot = fma(w[k], z[k - fl.k0], dot);
+                    }
+                    acc += __ddiv_rn(dot, sum);
+                }
+                lr++;
+            }
+        }
+    }
+    red[t] = acc;
+    __syncthreads();
+    if (t < F) {
+        double v = red[t];
+        for (int gg = 1; gg < G; gg++) v += red[gg * F + t];
+        double *o = y + it.out + t;
+        const double r = (accumulate ? *o : 0.0) + v;
+        if (PEERS) {
+            for (int q = 0; q < pe.n; q++) pe.y[q][it.out + t] = r;
+        } else {
+            *o = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // operator updates on the packed streams: H <- H*Diagonal(b) and
 // H <- Diagonal(b)*H without re-planning.  Reference: rmul!/lmul! ->
 // scale! (/root/reference/src/HierarchicalMatrix.jl:15-16, 54-108) and its leaf methods
@@ -916,6 +1086,34 @@ cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *r
     else
         hm_stream_kernel<true, false, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec,
                                                                                    y, accumulate, HmFuse{}, HmPeers{});
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFill *fills, const HmLeaf *leaves,
+                            const double *py, const double *x, double *partial, const HmCheb &cheb,
+                            int max_units, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    const size_t smem = (size_t)std::max(max_units, 1) * 20 * sizeof(double);
+    if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(hm_free1_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hm_free1_kernel<20><<<(unsigned)nitems, HM_THREADS, smem, st>>>(items, fills, leaves, py, x, partial, cheb);
+    return cudaGetLastError();
+}
+
+cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFill *fills,
+                            const HmLeaf *leaves, const double *px, const double *py, const double *x,
+                            const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
+                            const HmPeers *peers, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    if (peers && peers->n > 0)
+        hm_free3_kernel<20, true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, fills, leaves, px, py, x, svec,
+                                                                        y, accumulate, cheb, kernel_id, *peers);
+    else
+        hm_free3_kernel<20, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, fills, leaves, px, py, x, svec,
+                                                                         y, accumulate, cheb, kernel_id, HmPeers{});
     return cudaGetLastError();
 }
 

@@ -86,6 +86,26 @@ cudaError_t hm_launch_fillcore(const HmCoreBlock *blocks, const int32_t *core_le
                                const HmLeaf *leaves, double *core, const HmCheb &cheb, int kernel_id,
                                cudaStream_t st);
 
+// matrix-free apply (the operator is evaluated on the fly from the point sets; hm_kernels.cu)
+// Work split of a stage-1 item: every leaf's S columns are cut into nch chunks of CH columns so
+// that the 8 warps of the CTA have about two units each (host and device must agree).
+__host__ __device__ inline void hm_free1_split(int S, int nrun, int &nch, int &CH)
+{
+    int want = nrun > 0 ? (16 + nrun - 1) / nrun : 1;
+    if (want < 1) want = 1;
+    CH = (S + want - 1) / want;
+    CH = (CH + 31) & ~31;
+    if (CH < 32) CH = 32;
+    nch = S > 0 ? (S + CH - 1) / CH : 1;
+}
+cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFill *fills, const HmLeaf *leaves,
+                            const double *py, const double *x, double *partial, const HmCheb &cheb,
+                            int max_units, cudaStream_t st);
+cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFill *fills,
+                            const HmLeaf *leaves, const double *px, const double *py, const double *x,
+                            const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
+                            const HmPeers *peers, cudaStream_t st);
+
 // many right-hand sides (hm_panel.cu): panels are row-major with pitch CS = hm_panel_width(nrhs)
 int hm_panel_width(int nrhs);
 cudaError_t hm_launch_panel_in(const double *X, int64_t ldx, int64_t n, int nrhs, int CS, double *Xt,

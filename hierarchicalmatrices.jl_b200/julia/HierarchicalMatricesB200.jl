@@ -12,6 +12,7 @@
 module HierarchicalMatricesB200
 
 using LinearAlgebra
+using Libdl
 using HierarchicalMatrices
 import HierarchicalMatrices: KernelMatrix, HierarchicalMatrix, LowRankMatrix, BarycentricMatrix2D,
                              EvenBarycentricMatrix, blocksize
@@ -130,10 +131,12 @@ invalidate!(H) = (delete!(PLANS, H); H)
 `KernelMatrix(f, x, y, a, b, c, d)` (KernelMatrix.jl:47) assembled on the GPU; `f` is one
 of the kernels of examples/Kernel.jl (`:cauchy`, `:coulomb`, `:coulombprime`, `:log`).
 """
-function assemble(f::Symbol, x::Vector{Float64}, y::Vector{Float64}, a, b, c, d)
+function assemble(f::Symbol, x::Vector{Float64}, y::Vector{Float64}, a, b, c, d; matrix_free::Bool = false)
     id = Dict(:cauchy => 0, :coulomb => 1, :coulombprime => 2, :log => 3)[f]
     out = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve x y check(ccall((:hm_assemble_kernel, libhm), Int32,
+    # matrix_free: nothing but the r x r cores is stored, entries are evaluated inside every mul!
+    entry = Libdl.dlsym(Libdl.dlopen(libhm), matrix_free ? :hm_assemble_kernel_free : :hm_assemble_kernel)
+    GC.@preserve x y check(ccall(entry, Int32,
         (Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Float64, Float64, Float64, Int32, Int32, Int32, Int32,
          Ref{Ptr{Cvoid}}),
         x, length(x), y, length(y), a, b, c, d, id, device(), 0, 1, out))

@@ -153,6 +153,17 @@ HM_API int32_t hm_plan_stats(const hm_plan *p, hm_stats *out);
 HM_API int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t ny, double a,
                            double b, double c, double d, int32_t kernel_id, int32_t device,
                            int32_t part, int32_t nparts, hm_plan **out);
+/* Matrix-free variant ("fused assemble + apply"): same arguments and the same
+ * operator as hm_assemble_kernel, but U, V and the dense tiles are never stored -- hm_matvec /
+ * hm_matvec_device / hm_matvec_device_allgather evaluate every entry from the point sets while
+ * applying it (the arithmetic of src/BarycentricMatrix.jl:248-297 and src/KernelMatrix.jl:57-60).
+ * The plan holds the r x r cores and the planner tables only, so an operator whose packed form
+ * exceeds the GPU memory still fits; the apply is bound by the FP64 pipe instead of HBM.
+ * hm_matmat, hm_matvec_adjoint, hm_plan_scale and hm_plan_read_leaf return HM_ERR_UNSUPPORTED. */
+HM_API int32_t hm_assemble_kernel_free(const double *x, int64_t nx, const double *y, int64_t ny, double a,
+                                double b, double c, double d, int32_t kernel_id, int32_t device,
+                                int32_t part, int32_t nparts, hm_plan **out);
+
 /* One leaf of the assembled tree, as the planner sees it (device-free). */
 typedef struct hm_tree_leaf {
     int32_t kind;          /* 3 = Matrix, 4 = BarycentricMatrix2D */

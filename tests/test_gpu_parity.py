@@ -908,3 +908,50 @@ def test_host_copy_pipeline_is_bit_identical(hm, O):
         assert np.isnan(outs[0][1][:r0]).all() and np.isnan(outs[0][1][r1:]).all()   # only owned rows are written
         assert np.array_equal(outs[0][0][:r0], y0[:r0]) and np.array_equal(outs[0][0][r1:], y0[r1:])
         assert relinf(outs[0][0][r0:r1] - y0[r0:r1], outs[0][1][r0:r1]) <= 1e-12
+
+
+# ---------------------------------------------------------------- matrix-free apply
+@pytest.mark.parametrize("kernel", ["cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel"])
+@pytest.mark.parametrize("dist,N", [("cheb", 4096), ("unif", 3000), ("quad", 1000), ("cheb", 77 * 2), ("unif", 20011)])
+def test_matrix_free_matches_oracle_and_stored(hm, O, kernel, dist, N):
+    """hm_assemble_kernel_free: nothing but the cores is stored, every U, V and dense entry is
+    evaluated inside mul!.  Same operator as the stored plan (and as the oracle's KernelMatrix)."""
+    x, y, (a, b, c, d) = O.example_points(N, dist)
+    f = getattr(hm, kernel)
+    Kf = hm.KernelMatrix(f, x, y, a, b, c, d, device=0, matrix_free=True)
+    Ks = hm.KernelMatrix(f, x, y, a, b, c, d, device=0)
+    Kref = O.kernelmatrix(getattr(O, kernel[:-6].upper()), x, y, a, b, c, d)
+    v = _vec(N, 5)
+    u = Kf * v
+    assert relinf(u, Kref.matvec(v)) <= TOL
+    assert relinf(u, Ks * v) <= 1e-13
+    y0 = _vec(N + 3, 6)
+    got = hm.mul_(y0.copy(), Kf, np.concatenate([np.zeros(2), v]), 4, 3)      # offsets, accumulate
+    ref = Kref.mul(y0.copy(), np.concatenate([np.zeros(2), v]), 3, 2)
+    assert relinf(got, ref) <= TOL
+    st = Kf.plan().stats()
+    assert st["u_stream_bytes"] == 0 and st["v_stream_bytes"] == 0 and st["stored_bytes"] == 8 * st["core_words"]
+    assert st["algorithmic_bytes"] == Ks.plan().stats()["algorithmic_bytes"]
+
+
+def test_matrix_free_parts_determinism_and_unsupported(hm, O):
+    N = 6000
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    v = _vec(N, 8)
+    full = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, matrix_free=True)
+    u1, u2 = full * v, full * v
+    assert np.array_equal(u1, u2)                                   # run-to-run deterministic
+    res = np.full(N, np.nan)
+    for p in range(3):
+        part = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=p, nparts=3, matrix_free=True)
+        part.plan().matvec(v, res, accumulate=False)
+    assert relinf(res, u1) <= 1e-13
+    P = full.plan()
+    with pytest.raises(hm.HmError):
+        P.rmatvec(v, np.zeros(N))
+    with pytest.raises(hm.HmError):
+        P.matmat(np.asfortranarray(np.ones((N, 2))), np.zeros((N, 2), order="F"))
+    with pytest.raises(hm.HmError):
+        P.scale(np.ones(N), 0)
+    with pytest.raises(hm.HmError):
+        P.read_leaf(0, 0)

@@ -495,23 +495,34 @@ hm_fillcore_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
 // one per entry.  The bound moves from HBM to the FP64 pipe (one reciprocal per entry); the
 // operator occupies no memory beyond its tables and the r x r cores, so N = 2^24 fits one GPU.
 // ---------------------------------------------------------------------------
-template <int R>
-__device__ __forceinline__ double bary_raw(const HmCheb &cheb, double mid, double half, double p, double (&w)[R])
+// 1/d to about one ulp: the hardware's 2^-23 approximation and two Newton steps (4 DFMA), against
+// the ~3x longer correctly rounded __drcp_rn.  The matrix-free kernels spend their time here.
+__device__ __forceinline__ double frcp(double d)
 {
-    double sum = 0.0;
-#pragma unroll
-    for (int k = 0; k < R; k++) {
-        const double node = __dadd_rn(mid, __dmul_rn(half, cheb.node[k]));
-        w[k] = __dmul_rn(cheb.lam[k], __drcp_rn(__dsub_rn(p, node)));
-        sum = __dadd_rn(sum, w[k]);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+}
+
+__device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)
+{
+    const double d = __dsub_rn(x, y);
+    switch (id) {
+    case 0: return frcp(d);
+    case 1: return frcp(__dmul_rn(d, d));
+    case 2: return frcp(__dmul_rn(__dmul_rn(d, d), d));
+    default: return log(fabs(d));
     }
-    return sum;
 }
 
 // stage 1: partial[item.out + (leaf, k)] = sum_s V_leaf[s, k] x[zoff + s] with V evaluated on the
-// fly.  A warp owns a unit = (leaf of the item, chunk of its columns); lanes stride the columns
-// with R private accumulators, a butterfly adds them across the warp, and the chunks of a leaf
-// are combined in chunk order -- deterministic.
+// fly: V[s,k] = lam_k r_sk / sigma_s, r_sk = 1/(y_s - node_k), sigma_s = sum_k lam_k r_sk.  A warp
+// owns a unit = (leaf of the item, chunk of its columns); the leaf's mapped nodes (exact
+// two-rounding form of BarycentricMatrix.jl:159-167) sit in shared memory, lanes stride the
+// columns with R private accumulators of r_sk x_s / sigma_s, a butterfly adds them across the
+// warp, and the chunks of a leaf are combined in chunk order -- deterministic.
 template <int R>
 __global__ void __launch_bounds__(HM_THREADS, 2)
 hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fills,
@@ -520,6 +531,8 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fil
 {
     constexpr int T = HM_THREADS;
     extern __shared__ double ures[]; // [units][R]
+    __shared__ double nodeW[T / 32][R];
+    __shared__ double wred[T / 32][32][R + 1];
     const HmItem it = items[blockIdx.x];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int S = it.S;
@@ -533,26 +546,38 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fil
         const HmLeaf *__restrict__ l = leaves + f.leaf;
         const double lo = l->c, hi = l->d;
         const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
+        __syncwarp();
+        if (lane < R) nodeW[warp][lane] = __dadd_rn(mid, __dmul_rn(half, cheb.node[lane]));
+        __syncwarp();
         const double *__restrict__ yc = py + l->yj0 + f.off;
         double acc[R];
 #pragma unroll
         for (int k = 0; k < R; k++) acc[k] = 0.0;
         const int s1 = min(S, (c + 1) * CH);
         for (int s = c * CH + lane; s < s1; s += 32) {
-            double w[R];
-            const double sum = bary_raw<R>(cheb, mid, half, yc[s], w);
-            const double cf = __ddiv_rn(xs[s], sum);
+            const double q = yc[s];
+            double r[R], sum = 0.0;
 #pragma unroll
-            for (int k = 0; k < R; k++) acc[k] = fma(w[k], cf, acc[k]);
+            for (int k = 0; k < R; k++) {
+                r[k] = frcp(__dsub_rn(q, nodeW[warp][k]));
+                sum = fma(cheb.lam[k], r[k], sum);
+            }
+            const double cf = xs[s] * frcp(sum);
+#pragma unroll
+            for (int k = 0; k < R; k++) acc[k] = fma(r[k], cf, acc[k]);
         }
+        // warp sum of the R accumulators through shared memory, in lane order (a butterfly costs
+        // 5 shuffles and adds per value; this is 20 stores and 32 loads per warp)
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < R; k++) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], d);
+        for (int k = 0; k < R; k++) wred[warp][lane][k] = acc[k];
+        __syncwarp();
+        if (lane < R) {
+            double tsum = 0.0;
+#pragma unroll 8
+            for (int j = 0; j < 32; j++) tsum += wred[warp][j][lane];
+            ures[u * R + lane] = cheb.lam[lane] * tsum;
         }
-#pragma unroll
-        for (int k = 0; k < R; k++)
-            if (lane == k) ures[u * R + k] = acc[k];
     }
     __syncthreads();
     for (int idx = t; idx < it.nrun * R; idx += T) {
@@ -564,8 +589,11 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fil
 }
 
 // stage 3: y[item.out + f] (+)= sum over the item's runs, entries evaluated on the fly.  G = T / F
-// thread groups share the rows: low-rank runs go round-robin to the groups, the columns of a dense
-// run are dealt out over all of them; the group sums are combined in group order.
+// thread groups share the rows.  Dense runs: the columns are dealt out over the groups.  Low-rank
+// runs go through shared-memory tables in batches of 12: per run the R exact nodes and lam_k s_k,
+// so that a thread spends one subtraction, one reciprocal and two FMAs per entry and one divide
+// per (row, leaf):  y_i += (sum_k lam_k s_k r_ik) / (sum_k lam_k r_ik).  The group sums are
+// combined in group order -- deterministic.
 template <int R, bool PEERS>
 __global__ void __launch_bounds__(HM_THREADS, 3)
 hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
@@ -574,13 +602,17 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
                 const double *__restrict__ x, const double *__restrict__ svec, double *y, int accumulate,
                 const HmCheb cheb, int kernel_id, HmPeers pe)
 {
-    constexpr int T = HM_THREADS;
+    constexpr int T = HM_THREADS, B = 12;
     __shared__ double zs[HM_SMAX];
     __shared__ double red[T];
+    __shared__ double2 tab[B][R];
+    __shared__ int64_t xoff[B];
     __shared__ int rpos[HM_MAXRUNS + 1];
     __shared__ int rsrc[HM_MAXRUNS];
+    __shared__ int lrlist[HM_MAXRUNS];
+    __shared__ int nlr_s;
     const HmItem it = items[blockIdx.x];
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31;
     const int S = it.S, F = it.F;
 
     for (int r = t; r < it.nrun; r += T) {
@@ -590,6 +622,17 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
     }
     if (t == 0) rpos[it.nrun] = S;
     __syncthreads();
+    if (t < 32) { // the low-rank runs (src < 0: they read the stage-2 vector), in order
+        int cnt = 0;
+        for (int base = 0; base < it.nrun; base += 32) {
+            const int r = base + lane;
+            const bool lrr = r < it.nrun && rsrc[r] < 0;
+            const unsigned m = __ballot_sync(0xffffffffu, lrr);
+            if (lrr) lrlist[cnt + __popc(m & ((1u << lane) - 1u))] = r;
+            cnt += __popc(m);
+        }
+        if (lane == 0) nlr_s = cnt;
+    }
     for (int e = t; e < S; e += T) {
         int lo = 0, hi = it.nrun; // rpos[lo] <= e < rpos[hi]
         while (hi - lo > 1) {
@@ -603,39 +646,50 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         zs[e] = src >= 0 ? x[src + off] : svec[(~src) + off];
     }
     __syncthreads();
+    const int nlr = nlr_s;
 
     const int G = F > 0 ? T / F : 1; // F <= T (checked when the plan is built)
     const int g = F > 0 ? t / F : G, f = t - g * F;
+    const bool active = g < G;
     double acc = 0.0;
-    if (g < G) {
-        int lr = 0;
+    if (active) {
         for (int r = 0; r < it.nrun; r++) {
+            if (rsrc[r] < 0) continue;
             const HmFill fl = fills[it.run0 + r];
             const HmLeaf *__restrict__ l = leaves + fl.leaf;
+            const double p = px[l->xi0 + fl.off + f];
+            const double *__restrict__ yc = py + l->yj0 + fl.k0;
             const double *__restrict__ z = zs + rpos[r];
-            if (l->kind == HM_LEAF_DENSE) {
-                const double p = px[l->xi0 + fl.off + f];
-                const double *__restrict__ yc = py + l->yj0 + fl.k0;
-                for (int j = g; j < fl.kn; j += G) acc = fma(kernel_eval(kernel_id, p, yc[j]), z[j], acc);
-            } else {
-                if (lr % G == g) {
-                    const double p = px[l->xi0 + fl.off + f];
-                    const double lo = l->a, hi = l->b;
-                    const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
-                    double w[R];
-                    const double sum = bary_raw<R>(cheb, mid, half, p, w);
-                    double dot = 0.0;
-                    if (fl.k0 == 0 && fl.kn == R) {
+            for (int j = g; j < fl.kn; j += G) acc = fma(kernel_eval_fast(kernel_id, p, yc[j]), z[j], acc);
+        }
+    }
+    for (int b0 = 0; b0 < nlr; b0 += B) {
+        const int nb = min(B, nlr - b0);
+        __syncthreads(); // the previous batch's tables are no longer read
+        for (int idx = t; idx < nb * R; idx += T) {
+            const int b = idx / R, k = idx - b * R;
+            const int r = lrlist[b0 + b];
+            const HmFill fl = fills[it.run0 + r];
+            const HmLeaf *__restrict__ l = leaves + fl.leaf;
+            const double lo = l->a, hi = l->b;
+            const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
+            const double zk = (k >= fl.k0 && k < fl.k0 + fl.kn) ? zs[rpos[r] + k - fl.k0] : 0.0;
+            tab[b][k] = make_double2(__dadd_rn(mid, __dmul_rn(half, cheb.node[k])), cheb.lam[k] * zk);
+            if (k == 0) xoff[b] = l->xi0 + fl.off;
+        }
+        __syncthreads();
+        if (active) {
+            for (int b = g; b < nb; b += G) {
+                const double p = px[xoff[b] + f];
+                double dot = 0.0, sum = 0.0;
 #pragma unroll
-                        for (int k = 0; k < R; k++) dot = fma(w[k], z[k], dot);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < R; k++)
-                            if (k >= fl.k0 && k < fl.k0 + fl.kn) dot = fma(w[k], z[k - fl.k0], dot);
-                    }
-                    acc += __ddiv_rn(dot, sum);
+                for (int k = 0; k < R; k++) {
+                    const double2 nz = tab[b][k];
+                    const double r = frcp(__dsub_rn(p, nz.x));
+                    dot = fma(nz.y, r, dot);
+                    sum = fma(cheb.lam[k], r, sum);
                 }
-                lr++;
+                acc = fma(dot, frcp(sum), acc);
             }
         }
     }

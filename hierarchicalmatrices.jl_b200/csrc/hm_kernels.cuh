@@ -91,7 +91,7 @@ cudaError_t hm_launch_fillcore(const HmCoreBlock *blocks, const int32_t *core_le
 // that the 8 warps of the CTA have about two units each (host and device must agree).
 __host__ __device__ inline void hm_free1_split(int S, int nrun, int &nch, int &CH)
 {
-    int want = nrun > 0 ? (16 + nrun - 1) / nrun : 1;
+    int want = nrun > 1 ? (16 + nrun - 1) / nrun : 8; // one leaf: one long chunk per warp
     if (want < 1) want = 1;
     CH = (S + want - 1) / want;
     CH = (CH + 31) & ~31;

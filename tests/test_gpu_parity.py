@@ -954,4 +954,4 @@ def test_matrix_free_parts_determinism_and_unsupported(hm, O):
     with pytest.raises(hm.HmError):
         P.scale(np.ones(N), 0)
     with pytest.raises(hm.HmError):
-        P.read_leaf(0, 0)
+        P.read_leaf(0, 3 if P.leaf_info(0)["kind"] == 3 else 0)

@@ -641,6 +641,16 @@ def test_matvec_device_allgather_abi(hm, O):
     torch.cuda.synchronize()
     for t in bufs:
         assert relinf(t.cpu().numpy(), y0 + ref) <= TOL
+    # the same through matrix-free plans (their stage 3 stores into the peer buffers as well)
+    for t in bufs:
+        t.fill_(float("nan"))
+    for p in range(3):
+        Kp = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=p, nparts=3, matrix_free=True)
+        Kp.plan().matvec_device_allgather(xd.data_ptr(), ptrs, p, accumulate=False,
+                                          stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    for t in bufs:
+        assert relinf(t.cpu().numpy(), ref) <= TOL
     L = hm.lib()
     arr = (C.c_uint64 * 1)(0)
     assert L.hm_matvec_device_allgather(K.plan().handle, xd.data_ptr(), arr, 1, 0, 0, None) == 2   # NULL peer

@@ -126,3 +126,22 @@ def test_builder_path_at_scale_matches_device_assembly(hm, O):
     sb, sd = plan.stats(), Kdev.plan().stats()
     for k in ("algorithmic_bytes", "stored_bytes", "n_stage1_items", "n_stage3_items", "partial_bytes"):
         assert sb[k] == sd[k]
+
+
+def test_fullsize_matrix_free(hm, K):
+    """The matrix-free plan (hm_assemble_kernel_free) is the same operator as the stored one at
+    full size: products agree to rounding, a unit vector reproduces a column of the kernel, and
+    nothing but the cores is resident."""
+    x, y = hm.chebyshevpoints(N), hm.chebyshevpoints(N, 2)
+    Kf = hm.KernelMatrix(hm.cauchykernel, x, y, 1.0, -1.0, 1.0, -1.0, device=0, matrix_free=True)
+    v = np.random.default_rng(9).standard_normal(N)
+    assert relinf(Kf * v, K * v) <= 1e-13
+    assert np.array_equal(Kf * v, Kf * v)
+    j = 777_777
+    e = np.zeros(N)
+    e[j] = 1.0
+    col = Kf * e
+    rows = np.array([0, 1, 5000, j - 1, j, j + 1, N // 2, N - 1])
+    assert relinf(col[rows], 1.0 / (x[rows] - y[j])) <= 1e-12
+    st = Kf.plan().stats()
+    assert st["stored_bytes"] == 8 * st["core_words"] < 0.04 * st["algorithmic_bytes"]

@@ -524,12 +524,12 @@ __device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)
 // columns with R private accumulators of r_sk x_s / sigma_s, a butterfly adds them across the
 // warp, and the chunks of a leaf are combined in chunk order -- deterministic.
 template <int R>
-__global__ void __launch_bounds__(HM_THREADS, 2)
+__global__ void __launch_bounds__(HM_FREE1_THREADS, 5)
 hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fills,
                 const HmLeaf *__restrict__ leaves, const double *__restrict__ py,
                 const double *__restrict__ x, double *__restrict__ partial, const HmCheb cheb)
 {
-    constexpr int T = HM_THREADS;
+    constexpr int T = HM_FREE1_THREADS; // small CTAs: ~100 registers per thread, 20 warps per SM
     extern __shared__ double ures[]; // [units][R]
     __shared__ double nodeW[T / 32][R];
     __shared__ double wred[T / 32][32][R + 1];
@@ -595,14 +595,14 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fil
 // per (row, leaf):  y_i += (sum_k lam_k s_k r_ik) / (sum_k lam_k r_ik).  The group sums are
 // combined in group order -- deterministic.
 template <int R, bool PEERS>
-__global__ void __launch_bounds__(HM_THREADS, 3)
+__global__ void __launch_bounds__(HM_THREADS, 4)
 hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                 const HmFill *__restrict__ fills, const HmLeaf *__restrict__ leaves,
                 const double *__restrict__ px, const double *__restrict__ py,
                 const double *__restrict__ x, const double *__restrict__ svec, double *y, int accumulate,
                 const HmCheb cheb, int kernel_id, HmPeers pe)
 {
-    constexpr int T = HM_THREADS, B = 12;
+    constexpr int T = HM_THREADS, B = 24;
     __shared__ double zs[HM_SMAX];
     __shared__ double red[T];
     __shared__ double2 tab[B][R];
@@ -1152,7 +1152,7 @@ cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFill *f
     if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(hm_free1_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hm_free1_kernel<20><<<(unsigned)nitems, HM_THREADS, smem, st>>>(items, fills, leaves, py, x, partial, cheb);
+    hm_free1_kernel<20><<<(unsigned)nitems, HM_FREE1_THREADS, smem, st>>>(items, fills, leaves, py, x, partial, cheb);
     return cudaGetLastError();
 }
 

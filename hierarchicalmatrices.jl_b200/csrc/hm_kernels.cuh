@@ -88,10 +88,12 @@ cudaError_t hm_launch_fillcore(const HmCoreBlock *blocks, const int32_t *core_le
 
 // matrix-free apply (the operator is evaluated on the fly from the point sets; hm_kernels.cu)
 // Work split of a stage-1 item: every leaf's S columns are cut into nch chunks of CH columns so
-// that the 8 warps of the CTA have about two units each (host and device must agree).
+// that the warps of the CTA have about two units each (host and device must agree).
+#define HM_FREE1_THREADS 128
 __host__ __device__ inline void hm_free1_split(int S, int nrun, int &nch, int &CH)
 {
-    int want = nrun > 1 ? (16 + nrun - 1) / nrun : 8; // one leaf: one long chunk per warp
+    constexpr int NW = HM_FREE1_THREADS / 32;
+    int want = nrun > 1 ? (2 * NW + nrun - 1) / nrun : NW; // one leaf: one long chunk per warp
     if (want < 1) want = 1;
     CH = (S + want - 1) / want;
     CH = (CH + 31) & ~31;

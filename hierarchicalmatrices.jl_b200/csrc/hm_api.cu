@@ -969,7 +969,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
     // Below ~2 MB of vector data the extra launches and events cost more than the overlap gains
     // (measured: N = 4096 48 vs 100 us, N = 65 536 175 vs 230 us, N = 262 144 600 vs 577 us).
     if (incx == 1 && incy == 1 && nc > 0 && nr > 0 && nc + nr >= 400000 && L.round_begin.size() == 2 &&
-        !L.items3c.empty() && p->tcap == 0 && !p->matrix_free && !getenv("HMB200_NO_COPY_PIPELINE")) {
+        !L.items3c.empty() && p->tcap == 0 && !getenv("HMB200_NO_COPY_PIPELINE")) {
         if (!p->chunk_ready) {
             HM_CUDA(p->items1c.upload(L.items1c, st));
             HM_CUDA(p->items3c.upload(L.items3c, st));
@@ -993,7 +993,11 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
         for (int k = 0; k < HM_NCHUNK; k++) {
             HM_CUDA(cudaStreamWaitEvent(st, p->ev_x[k], 0));
             const int64_t i0 = L.c1_begin[(size_t)k], i1 = L.c1_begin[(size_t)k + 1];
-            HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st));
+            if (p->matrix_free)
+                HM_CUDA(hm_launch_free1(p->items1c.p + i0, i1 - i0, p->f_fill1.p, p->f_leaves.p, p->f_py.p, p->dx.p,
+                                        p->partial.p, p->cheb, p->free1_units, st));
+            else
+                HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st));
         }
         HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
                                  p->svec.p, std::max(L.max_r, 1), st));
@@ -1002,8 +1006,13 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
         HM_CUDA(cudaStreamWaitEvent(st, p->ev_y0, 0));
         for (int k = 0; k < HM_NCHUNK; k++) {
             const int64_t i0 = L.c3_begin[(size_t)k], i1 = L.c3_begin[(size_t)k + 1];
-            HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
-                                     p->dy.p, accumulate != 0, nullptr, st));
+            if (p->matrix_free)
+                HM_CUDA(hm_launch_free3(p->items3c.p + i0, i1 - i0, p->runs.p, p->f_fill3.p, p->f_leaves.p, p->f_px.p,
+                                        p->f_py.p, p->dx.p, p->svec.p, p->dy.p, accumulate != 0, p->cheb,
+                                        p->kernel_id, nullptr, st));
+            else
+                HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
+                                         p->dy.p, accumulate != 0, nullptr, st));
             HM_CUDA(cudaEventRecord(p->ev_y[k], st));
         }
         // all launches are queued before the first copy back: with pageable y the copies block

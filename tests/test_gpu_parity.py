@@ -894,8 +894,8 @@ def test_host_copy_pipeline_is_bit_identical(hm, O):
     x, y, (a, b, c, d) = O.example_points(N, "unif")
     rng = np.random.default_rng(77)
     v, y0 = rng.standard_normal(N), rng.standard_normal(N)
-    for part, nparts in ((0, 1), (1, 3)):
-        K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=part, nparts=nparts)
+    for part, nparts, mfree in ((0, 1, False), (1, 3, False), (0, 1, True)):
+        K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=part, nparts=nparts, matrix_free=mfree)
         P = K.plan()
         outs = []
         for flag in (None, "1"):

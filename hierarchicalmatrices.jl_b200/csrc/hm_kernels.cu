@@ -524,17 +524,21 @@ __device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)
 // columns with R private accumulators of r_sk x_s / sigma_s, a butterfly adds them across the
 // warp, and the chunks of a leaf are combined in chunk order -- deterministic.
 template <int R>
-__global__ void __launch_bounds__(HM_FREE1_THREADS, 5)
+__global__ void __launch_bounds__(HM_FREE1_THREADS, 6)
 hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fills,
                 const HmLeaf *__restrict__ leaves, const double *__restrict__ py,
                 const double *__restrict__ x, double *__restrict__ partial, const HmCheb cheb)
 {
-    constexpr int T = HM_FREE1_THREADS; // small CTAs: ~100 registers per thread, 20 warps per SM
+    // Two lanes share a column, each taking half of the R ranks: half the accumulator registers per
+    // thread (more warps per SM) for one shuffle per column (the two halves of sigma).
+    constexpr int T = HM_FREE1_THREADS, H = R / 2;
+    static_assert(R % 2 == 0, "rank must be even");
     extern __shared__ double ures[]; // [units][R]
-    __shared__ double nodeW[T / 32][R];
-    __shared__ double wred[T / 32][32][R + 1];
+    __shared__ double2 nodeW[T / 32][R]; // (node_k, lam_k) of the warp's current leaf
+    __shared__ double wred[T / 32][32][H + 1];
     const HmItem it = items[blockIdx.x];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int h = lane & 1, cl = lane >> 1;
     const int S = it.S;
     int nch, CH;
     hm_free1_split(S, it.nrun, nch, CH);
@@ -547,35 +551,42 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fil
         const double lo = l->c, hi = l->d;
         const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
         __syncwarp();
-        if (lane < R) nodeW[warp][lane] = __dadd_rn(mid, __dmul_rn(half, cheb.node[lane]));
+        if (lane < R)
+            nodeW[warp][lane] = make_double2(__dadd_rn(mid, __dmul_rn(half, cheb.node[lane])), cheb.lam[lane]);
         __syncwarp();
+        const double2 *__restrict__ nw = nodeW[warp] + h * H;
         const double *__restrict__ yc = py + l->yj0 + f.off;
-        double acc[R];
+        double acc[H];
 #pragma unroll
-        for (int k = 0; k < R; k++) acc[k] = 0.0;
+        for (int k = 0; k < H; k++) acc[k] = 0.0;
         const int s1 = min(S, (c + 1) * CH);
-        for (int s = c * CH + lane; s < s1; s += 32) {
-            const double q = yc[s];
-            double r[R], sum = 0.0;
+        for (int s0 = c * CH; s0 < s1; s0 += 16) { // uniform trip count: every lane joins the shuffle
+            const int s = s0 + cl;
+            const bool valid = s < s1;
+            const double q = yc[valid ? s : s1 - 1];
+            const double xv = valid ? xs[s] : 0.0;
+            double r[H], sum = 0.0;
 #pragma unroll
-            for (int k = 0; k < R; k++) {
-                r[k] = frcp(__dsub_rn(q, nodeW[warp][k]));
-                sum = fma(cheb.lam[k], r[k], sum);
+            for (int k = 0; k < H; k++) {
+                const double2 nl = nw[k];
+                r[k] = frcp(__dsub_rn(q, nl.x));
+                sum = fma(nl.y, r[k], sum);
             }
-            const double cf = xs[s] * frcp(sum);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            const double cf = xv * frcp(sum);
 #pragma unroll
-            for (int k = 0; k < R; k++) acc[k] = fma(r[k], cf, acc[k]);
+            for (int k = 0; k < H; k++) acc[k] = fma(r[k], cf, acc[k]);
         }
-        // warp sum of the R accumulators through shared memory, in lane order (a butterfly costs
-        // 5 shuffles and adds per value; this is 20 stores and 32 loads per warp)
+        // warp sum through shared memory, in column-lane order
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < R; k++) wred[warp][lane][k] = acc[k];
+        for (int k = 0; k < H; k++) wred[warp][lane][k] = acc[k];
         __syncwarp();
         if (lane < R) {
+            const int kh = lane / H, kk = lane - kh * H;
             double tsum = 0.0;
 #pragma unroll 8
-            for (int j = 0; j < 32; j++) tsum += wred[warp][j][lane];
+            for (int j = 0; j < 16; j++) tsum += wred[warp][2 * j + kh][kk];
             ures[u * R + lane] = cheb.lam[lane] * tsum;
         }
     }

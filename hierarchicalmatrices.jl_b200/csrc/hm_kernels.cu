@@ -644,17 +644,11 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         }
         if (lane == 0) nlr_s = cnt;
     }
-    for (int e = t; e < S; e += T) {
-        int lo = 0, hi = it.nrun; // rpos[lo] <= e < rpos[hi]
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (rpos[mid] <= e)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        int src = rsrc[lo], off = e - rpos[lo];
-        zs[e] = src >= 0 ? x[src + off] : svec[(~src) + off];
+    // z: 32 lanes per run (the low-rank runs are R <= 32 long, the dense ones a few times that)
+    for (int idx = t; idx < it.nrun * 32; idx += T) {
+        const int r = idx >> 5;
+        const int pos = rpos[r], len = rpos[r + 1] - pos, src = rsrc[r];
+        for (int k = idx & 31; k < len; k += 32) zs[pos + k] = src >= 0 ? x[src + k] : svec[(~src) + k];
     }
     __syncthreads();
     const int nlr = nlr_s;

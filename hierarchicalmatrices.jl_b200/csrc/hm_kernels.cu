@@ -495,15 +495,15 @@ hm_fillcore_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
 // one per entry.  The bound moves from HBM to the FP64 pipe (one reciprocal per entry); the
 // operator occupies no memory beyond its tables and the r x r cores, so N = 2^24 fits one GPU.
 // ---------------------------------------------------------------------------
-// 1/d to about one ulp: the hardware's 2^-23 approximation and two Newton steps (4 DFMA), against
-// the ~3x longer correctly rounded __drcp_rn.  The matrix-free kernels spend their time here.
+// 1/d to about one ulp: the hardware's 2^-23 approximation r0 and one cubic (Halley) step,
+// 1/d = r0 (1 + e + e^2 + ...), e = 1 - d r0, truncated after e^2 (error e^3 ~ 2^-69): 3 DFMA,
+// against the ~3x longer correctly rounded __drcp_rn.  The matrix-free kernels spend their time here.
 __device__ __forceinline__ double frcp(double d)
 {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    r = fma(fma(-d, r, 1.0), r, r);
-    r = fma(fma(-d, r, 1.0), r, r);
-    return r;
+    const double e = fma(-d, r, 1.0);
+    return fma(r, fma(e, e, e), r);
 }
 
 __device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)

@@ -305,8 +305,8 @@ struct hm_plan {
     // matrix-free plans (hm_assemble_kernel_free): no streams; the tables the fill kernels use stay
     // on the device together with the point sets, and the apply evaluates the entries itself
     bool matrix_free = false;
-    DevBuf<HmLeaf> f_leaves;
-    DevBuf<HmFill> f_fill1, f_fill3;
+    DevBuf<HmFreeEnt> f_ent1;
+    DevBuf<HmFreeRun> f_run3;
     DevBuf<double> f_px, f_py;
     int free1_units = 1;
     // device arrays
@@ -420,12 +420,26 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
             if (it.F > HM_THREADS || it.nrun > HM_MAXRUNS || it.S > HM_SMAX)
                 return fail(HM_ERR_UNSUPPORTED, "matrix-free: row segment outside the kernel limits");
         P->free1_units = units;
+        std::vector<HmFreeEnt> ent1(L.fill1.size());
+        for (const HmItem &it : L.items1)
+            for (int32_t e = it.run0; e < it.run0 + it.nrun; e++) {
+                const HmFill &f = L.fill1[(size_t)e];
+                const HmLeaf &l = L.leaves[(size_t)f.leaf];
+                ent1[(size_t)e] = HmFreeEnt{0.5 * (l.c + l.d), 0.5 * (l.d - l.c), l.yj0 + f.off, f.dst - it.slab};
+            }
+        std::vector<HmFreeRun> run3(L.fill3.size());
+        for (size_t i = 0; i < L.fill3.size(); i++) {
+            const HmFill &f = L.fill3[i];
+            const HmLeaf &l = L.leaves[(size_t)f.leaf];
+            run3[i] = HmFreeRun{0.5 * (l.a + l.b), 0.5 * (l.b - l.a), l.xi0 + f.off, l.yj0 + f.k0, f.k0, f.kn};
+        }
+        DevBuf<HmLeaf> dleaves;
         DevBuf<int32_t> dcore_leaf;
-        HM_CUDA(P->f_leaves.upload(L.leaves, st));
-        HM_CUDA(P->f_fill1.upload(L.fill1, st));
-        HM_CUDA(P->f_fill3.upload(L.fill3, st));
+        HM_CUDA(dleaves.upload(L.leaves, st));
+        HM_CUDA(P->f_ent1.upload(ent1, st));
+        HM_CUDA(P->f_run3.upload(run3, st));
         HM_CUDA(dcore_leaf.upload(L.core_leaf, st));
-        HM_CUDA(hm_launch_fillcore(P->cores.p, dcore_leaf.p, (int64_t)L.cores.size(), P->f_leaves.p, P->core.p,
+        HM_CUDA(hm_launch_fillcore(P->cores.p, dcore_leaf.p, (int64_t)L.cores.size(), dleaves.p, P->core.p,
                                    P->cheb, P->kernel_id, st));
         HM_CUDA(cudaStreamSynchronize(st));
     } else {
@@ -921,8 +935,8 @@ static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int3
         fz.max_r = std::max(L.max_r, 1);
     }
     if (p->matrix_free)
-        HM_CUDA(hm_launch_free1(p->items1.p, (int64_t)L.items1.size(), p->f_fill1.p, p->f_leaves.p, p->f_py.p, dx,
-                                p->partial.p, p->cheb, p->free1_units, st));
+        HM_CUDA(hm_launch_free1(p->items1.p, (int64_t)L.items1.size(), p->f_ent1.p, p->f_py.p, dx, p->partial.p,
+                                p->cheb, p->free1_units, st));
     else
         HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p,
                                  p->fuse ? &fz : nullptr, st));
@@ -937,9 +951,9 @@ static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int3
     for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
         int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
         if (p->matrix_free)
-            HM_CUDA(hm_launch_free3(p->items3.p + i0, i1 - i0, p->runs.p, p->f_fill3.p, p->f_leaves.p, p->f_px.p,
-                                    p->f_py.p, dx, p->svec.p, dy, r == 0 ? (accumulate != 0) : 1, p->cheb,
-                                    p->kernel_id, peers, st));
+            HM_CUDA(hm_launch_free3(p->items3.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p, dx,
+                                    p->svec.p, dy, r == 0 ? (accumulate != 0) : 1, p->cheb, p->kernel_id, peers,
+                                    st));
         else
             HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
                                      r == 0 ? (accumulate != 0) : 1, peers, st));
@@ -994,8 +1008,8 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
             HM_CUDA(cudaStreamWaitEvent(st, p->ev_x[k], 0));
             const int64_t i0 = L.c1_begin[(size_t)k], i1 = L.c1_begin[(size_t)k + 1];
             if (p->matrix_free)
-                HM_CUDA(hm_launch_free1(p->items1c.p + i0, i1 - i0, p->f_fill1.p, p->f_leaves.p, p->f_py.p, p->dx.p,
-                                        p->partial.p, p->cheb, p->free1_units, st));
+                HM_CUDA(hm_launch_free1(p->items1c.p + i0, i1 - i0, p->f_ent1.p, p->f_py.p, p->dx.p, p->partial.p,
+                                        p->cheb, p->free1_units, st));
             else
                 HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st));
         }
@@ -1007,9 +1021,9 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
         for (int k = 0; k < HM_NCHUNK; k++) {
             const int64_t i0 = L.c3_begin[(size_t)k], i1 = L.c3_begin[(size_t)k + 1];
             if (p->matrix_free)
-                HM_CUDA(hm_launch_free3(p->items3c.p + i0, i1 - i0, p->runs.p, p->f_fill3.p, p->f_leaves.p, p->f_px.p,
-                                        p->f_py.p, p->dx.p, p->svec.p, p->dy.p, accumulate != 0, p->cheb,
-                                        p->kernel_id, nullptr, st));
+                HM_CUDA(hm_launch_free3(p->items3c.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p,
+                                        p->dx.p, p->svec.p, p->dy.p, accumulate != 0, p->cheb, p->kernel_id,
+                                        nullptr, st));
             else
                 HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
                                          p->dy.p, accumulate != 0, nullptr, st));

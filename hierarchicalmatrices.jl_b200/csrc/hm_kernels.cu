@@ -525,9 +525,9 @@ __device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)
 // warp, and the chunks of a leaf are combined in chunk order -- deterministic.
 template <int R>
 __global__ void __launch_bounds__(HM_FREE1_THREADS, 6)
-hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fills,
-                const HmLeaf *__restrict__ leaves, const double *__restrict__ py,
-                const double *__restrict__ x, double *__restrict__ partial, const HmCheb cheb)
+hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ ents,
+                const double *__restrict__ py, const double *__restrict__ x, double *__restrict__ partial,
+                const HmCheb cheb)
 {
     // Two lanes share a column, each taking half of the R ranks: half the accumulator registers per
     // thread (more warps per SM) for one shuffle per column (the two halves of sigma).
@@ -546,16 +546,13 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fil
     const double *__restrict__ xs = x + it.zoff;
     for (int u = warp; u < U; u += T / 32) {
         const int e = u / nch, c = u - e * nch;
-        const HmFill f = fills[it.run0 + e];
-        const HmLeaf *__restrict__ l = leaves + f.leaf;
-        const double lo = l->c, hi = l->d;
-        const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
+        const HmFreeEnt en = ents[it.run0 + e];
         __syncwarp();
         if (lane < R)
-            nodeW[warp][lane] = make_double2(__dadd_rn(mid, __dmul_rn(half, cheb.node[lane])), cheb.lam[lane]);
+            nodeW[warp][lane] = make_double2(__dadd_rn(en.mid, __dmul_rn(en.half, cheb.node[lane])), cheb.lam[lane]);
         __syncwarp();
         const double2 *__restrict__ nw = nodeW[warp] + h * H;
-        const double *__restrict__ yc = py + l->yj0 + f.off;
+        const double *__restrict__ yc = py + en.yoff;
         double acc[H];
 #pragma unroll
         for (int k = 0; k < H; k++) acc[k] = 0.0;
@@ -595,7 +592,7 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fil
         const int e = idx / R, k = idx - e * R;
         double sum = 0.0;
         for (int c = 0; c < nch; c++) sum += ures[(e * nch + c) * R + k];
-        partial[it.out + (fills[it.run0 + e].dst - it.slab) + k] = sum;
+        partial[it.out + ents[it.run0 + e].fofs + k] = sum;
     }
 }
 
@@ -608,7 +605,7 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFill *__restrict__ fil
 template <int R, bool PEERS>
 __global__ void __launch_bounds__(HM_THREADS, 4)
 hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
-                const HmFill *__restrict__ fills, const HmLeaf *__restrict__ leaves,
+                const HmFreeRun *__restrict__ frun,
                 const double *__restrict__ px, const double *__restrict__ py,
                 const double *__restrict__ x, const double *__restrict__ svec, double *y, int accumulate,
                 const HmCheb cheb, int kernel_id, HmPeers pe)
@@ -660,12 +657,11 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
     if (active) {
         for (int r = 0; r < it.nrun; r++) {
             if (rsrc[r] < 0) continue;
-            const HmFill fl = fills[it.run0 + r];
-            const HmLeaf *__restrict__ l = leaves + fl.leaf;
-            const double p = px[l->xi0 + fl.off + f];
-            const double *__restrict__ yc = py + l->yj0 + fl.k0;
+            const HmFreeRun fr = frun[it.run0 + r];
+            const double p = px[fr.xoff + f];
+            const double *__restrict__ yc = py + fr.yoff;
             const double *__restrict__ z = zs + rpos[r];
-            for (int j = g; j < fl.kn; j += G) acc = fma(kernel_eval_fast(kernel_id, p, yc[j]), z[j], acc);
+            for (int j = g; j < fr.kn; j += G) acc = fma(kernel_eval_fast(kernel_id, p, yc[j]), z[j], acc);
         }
     }
     for (int b0 = 0; b0 < nlr; b0 += B) {
@@ -674,13 +670,10 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         for (int idx = t; idx < nb * R; idx += T) {
             const int b = idx / R, k = idx - b * R;
             const int r = lrlist[b0 + b];
-            const HmFill fl = fills[it.run0 + r];
-            const HmLeaf *__restrict__ l = leaves + fl.leaf;
-            const double lo = l->a, hi = l->b;
-            const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
-            const double zk = (k >= fl.k0 && k < fl.k0 + fl.kn) ? zs[rpos[r] + k - fl.k0] : 0.0;
-            tab[b][k] = make_double2(__dadd_rn(mid, __dmul_rn(half, cheb.node[k])), cheb.lam[k] * zk);
-            if (k == 0) xoff[b] = l->xi0 + fl.off;
+            const HmFreeRun fr = frun[it.run0 + r];
+            const double zk = (k >= fr.k0 && k < fr.k0 + fr.kn) ? zs[rpos[r] + k - fr.k0] : 0.0;
+            tab[b][k] = make_double2(__dadd_rn(fr.mid, __dmul_rn(fr.half, cheb.node[k])), cheb.lam[k] * zk);
+            if (k == 0) xoff[b] = fr.xoff;
         }
         __syncthreads();
         if (active) {
@@ -1148,30 +1141,30 @@ cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *r
     return cudaGetLastError();
 }
 
-cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFill *fills, const HmLeaf *leaves,
-                            const double *py, const double *x, double *partial, const HmCheb &cheb,
-                            int max_units, cudaStream_t st)
+cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFreeEnt *ents, const double *py,
+                            const double *x, double *partial, const HmCheb &cheb, int max_units,
+                            cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
     const size_t smem = (size_t)std::max(max_units, 1) * 20 * sizeof(double);
     if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(hm_free1_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hm_free1_kernel<20><<<(unsigned)nitems, HM_FREE1_THREADS, smem, st>>>(items, fills, leaves, py, x, partial, cheb);
+    hm_free1_kernel<20><<<(unsigned)nitems, HM_FREE1_THREADS, smem, st>>>(items, ents, py, x, partial, cheb);
     return cudaGetLastError();
 }
 
-cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFill *fills,
-                            const HmLeaf *leaves, const double *px, const double *py, const double *x,
+cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun,
+                            const double *px, const double *py, const double *x,
                             const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
                             const HmPeers *peers, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
     if (peers && peers->n > 0)
-        hm_free3_kernel<20, true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, fills, leaves, px, py, x, svec,
+        hm_free3_kernel<20, true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, frun, px, py, x, svec,
                                                                         y, accumulate, cheb, kernel_id, *peers);
     else
-        hm_free3_kernel<20, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, fills, leaves, px, py, x, svec,
+        hm_free3_kernel<20, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, frun, px, py, x, svec,
                                                                          y, accumulate, cheb, kernel_id, HmPeers{});
     return cudaGetLastError();
 }

@@ -100,11 +100,11 @@ __host__ __device__ inline void hm_free1_split(int S, int nrun, int &nch, int &C
     if (CH < 32) CH = 32;
     nch = S > 0 ? (S + CH - 1) / CH : 1;
 }
-cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFill *fills, const HmLeaf *leaves,
-                            const double *py, const double *x, double *partial, const HmCheb &cheb,
-                            int max_units, cudaStream_t st);
-cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFill *fills,
-                            const HmLeaf *leaves, const double *px, const double *py, const double *x,
+cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFreeEnt *ents, const double *py,
+                            const double *x, double *partial, const HmCheb &cheb, int max_units,
+                            cudaStream_t st);
+cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun,
+                            const double *px, const double *py, const double *x,
                             const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
                             const HmPeers *peers, cudaStream_t st);
 

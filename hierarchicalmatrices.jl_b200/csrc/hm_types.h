@@ -86,6 +86,21 @@ struct HmFill {
     int32_t pad;
 };
 
+// Matrix-free apply: what a kernel needs about one stage-3 run / one (stage-1 item, leaf) entry,
+// precomputed at plan time so that the kernels do not chase fill -> leaf records.
+struct HmFreeRun {
+    double mid, half; // low-rank run: node_k = mid + half * cheb_k (box of the leaf's rows)
+    int64_t xoff;     // point index of the item's first row: leaf.xi0 + (item row - leaf.row0)
+    int64_t yoff;     // dense run: point index of its first column: leaf.yj0 + k0
+    int32_t k0, kn;   // low-rank: factor columns [k0, k0 + kn); dense: kn columns
+};
+
+struct HmFreeEnt {
+    double mid, half; // box of the leaf's columns
+    int64_t yoff;     // point index of the item's first column: leaf.yj0 + (item column - leaf.col0)
+    int64_t fofs;     // offset of the leaf's ranks inside the item's partial sums
+};
+
 struct HmLaunchParams {
     int threads = 256;
 };

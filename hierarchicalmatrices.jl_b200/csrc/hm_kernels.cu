@@ -524,7 +524,7 @@ __device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)
 // columns with R private accumulators of r_sk x_s / sigma_s, a butterfly adds them across the
 // warp, and the chunks of a leaf are combined in chunk order -- deterministic.
 template <int R>
-__global__ void __launch_bounds__(HM_FREE1_THREADS, 6)
+__global__ void __launch_bounds__(HM_FREE1_THREADS, 8)
 hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ ents,
                 const double *__restrict__ py, const double *__restrict__ x, double *__restrict__ partial,
                 const HmCheb cheb)
@@ -661,7 +661,11 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
             const double p = px[fr.xoff + f];
             const double *__restrict__ yc = py + fr.yoff;
             const double *__restrict__ z = zs + rpos[r];
-            for (int j = g; j < fr.kn; j += G) acc = fma(kernel_eval_fast(kernel_id, p, yc[j]), z[j], acc);
+            if (kernel_id == 0) { // Cauchy: the branch-free form of the common case
+                for (int j = g; j < fr.kn; j += G) acc = fma(frcp(__dsub_rn(p, yc[j])), z[j], acc);
+            } else {
+                for (int j = g; j < fr.kn; j += G) acc = fma(kernel_eval_fast(kernel_id, p, yc[j]), z[j], acc);
+            }
         }
     }
     for (int b0 = 0; b0 < nlr; b0 += B) {

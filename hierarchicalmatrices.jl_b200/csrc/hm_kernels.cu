@@ -520,9 +520,9 @@ __device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)
 // stage 1: partial[item.out + (leaf, k)] = sum_s V_leaf[s, k] x[zoff + s] with V evaluated on the
 // fly: V[s,k] = lam_k r_sk / sigma_s, r_sk = 1/(y_s - node_k), sigma_s = sum_k lam_k r_sk.  A warp
 // owns a unit = (leaf of the item, chunk of its columns); the leaf's mapped nodes (exact
-// two-rounding form of BarycentricMatrix.jl:159-167) sit in shared memory, lanes stride the
-// columns with R private accumulators of r_sk x_s / sigma_s, a butterfly adds them across the
-// warp, and the chunks of a leaf are combined in chunk order -- deterministic.
+// two-rounding form of BarycentricMatrix.jl:159-167) sit in shared memory, lane pairs stride the
+// columns with private accumulators of r_sk x_s / sigma_s, the warp sum goes through shared
+// memory in lane order, and the chunks of a leaf are combined in chunk order -- deterministic.
 template <int R>
 __global__ void __launch_bounds__(HM_FREE1_THREADS, 8)
 hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ ents,
@@ -598,7 +598,7 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ 
 
 // stage 3: y[item.out + f] (+)= sum over the item's runs, entries evaluated on the fly.  G = T / F
 // thread groups share the rows.  Dense runs: the columns are dealt out over the groups.  Low-rank
-// runs go through shared-memory tables in batches of 12: per run the R exact nodes and lam_k s_k,
+// runs go through shared-memory tables in batches of 24: per run the R exact nodes and lam_k s_k,
 // so that a thread spends one subtraction, one reciprocal and two FMAs per entry and one divide
 // per (row, leaf):  y_i += (sum_k lam_k s_k r_ik) / (sum_k lam_k r_ik).  The group sums are
 // combined in group order -- deterministic.

@@ -661,8 +661,18 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
             const double p = px[fr.xoff + f];
             const double *__restrict__ yc = py + fr.yoff;
             const double *__restrict__ z = zs + rpos[r];
-            if (kernel_id == 0) { // Cauchy: the branch-free form of the common case
-                for (int j = g; j < fr.kn; j += G) acc = fma(frcp(__dsub_rn(p, yc[j])), z[j], acc);
+            if (kernel_id == 0) { // Cauchy: the branch-free form of the common case, four columns in flight
+                int j = g;
+                for (; j + 3 * G < fr.kn; j += 4 * G) {
+                    const double y0 = yc[j], y1 = yc[j + G], y2 = yc[j + 2 * G], y3 = yc[j + 3 * G];
+                    const double r0 = frcp(__dsub_rn(p, y0)), r1 = frcp(__dsub_rn(p, y1));
+                    const double r2 = frcp(__dsub_rn(p, y2)), r3 = frcp(__dsub_rn(p, y3));
+                    acc = fma(r0, z[j], acc);
+                    acc = fma(r1, z[j + G], acc);
+                    acc = fma(r2, z[j + 2 * G], acc);
+                    acc = fma(r3, z[j + 3 * G], acc);
+                }
+                for (; j < fr.kn; j += G) acc = fma(frcp(__dsub_rn(p, yc[j])), z[j], acc);
             } else {
                 for (int j = g; j < fr.kn; j += G) acc = fma(kernel_eval_fast(kernel_id, p, yc[j]), z[j], acc);
             }

@@ -183,6 +183,11 @@ def test_no_cpu_fallback(hm):
     with pytest.raises(hm.HmError) as e:
         hm.KernelMatrix(hm.cauchykernel, x, x + 1e-3, 1.0, -1.0, 1.0, -1.0, device=0)
     assert e.value.status == 7
+    with pytest.raises(hm.HmError) as e:
+        hm.KernelMatrix(hm.cauchykernel, x, x + 1e-3, 1.0, -1.0, 1.0, -1.0, device=0, matrix_free=True)
+    assert e.value.status == 7
+    with pytest.raises(hm.HmError):     # matrix_free belongs to the assembling constructor only
+        hm.KernelMatrix(np.float64, 2, 2, matrix_free=True)
     H = hm.HierarchicalMatrix(np.float64, 1, 1)
     H[hm.Block(1), hm.Block(1)] = np.zeros((3, 3), order="F")
     with pytest.raises(hm.HmError):

@@ -308,7 +308,7 @@ struct hm_plan {
     DevBuf<HmFreeEnt> f_ent1;
     DevBuf<HmFreeRun> f_run3;
     DevBuf<double> f_px, f_py;
-    int free1_units = 1;
+    int free1_units = 1, free3_zcap = HM_SMAX;
     // device arrays
     DevBuf<double> vstream, ustream, core, svec, partial;
     DevBuf<HmItem> items1, items3;
@@ -420,6 +420,9 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
             if (it.F > HM_THREADS || it.nrun > HM_MAXRUNS || it.S > HM_SMAX)
                 return fail(HM_ERR_UNSUPPORTED, "matrix-free: row segment outside the kernel limits");
         P->free1_units = units;
+        int zcap = 2;
+        for (const HmItem &it : L.items3) zcap = std::max(zcap, (int)it.S);
+        P->free3_zcap = (zcap + 1) & ~1;
         std::vector<HmFreeEnt> ent1(L.fill1.size());
         for (const HmItem &it : L.items1)
             for (int32_t e = it.run0; e < it.run0 + it.nrun; e++) {
@@ -953,7 +956,7 @@ static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int3
         if (p->matrix_free)
             HM_CUDA(hm_launch_free3(p->items3.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p, dx,
                                     p->svec.p, dy, r == 0 ? (accumulate != 0) : 1, p->cheb, p->kernel_id, peers,
-                                    st));
+                                    p->free3_zcap, st));
         else
             HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
                                      r == 0 ? (accumulate != 0) : 1, peers, st));
@@ -1023,7 +1026,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
             if (p->matrix_free)
                 HM_CUDA(hm_launch_free3(p->items3c.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p,
                                         p->dx.p, p->svec.p, p->dy.p, accumulate != 0, p->cheb, p->kernel_id,
-                                        nullptr, st));
+                                        nullptr, p->free3_zcap, st));
             else
                 HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
                                          p->dy.p, accumulate != 0, nullptr, st));

@@ -611,13 +611,16 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
                 const HmCheb cheb, int kernel_id, HmPeers pe)
 {
     constexpr int T = HM_THREADS, B = 24;
-    __shared__ double zs[HM_SMAX];
+    extern __shared__ double zs[]; // the widest z of the launch (host-sized), not the 32 KB worst case
     __shared__ double red[T];
     __shared__ double2 tab[B][R];
     __shared__ int64_t xoff[B];
     __shared__ int rpos[HM_MAXRUNS + 1];
     __shared__ int rsrc[HM_MAXRUNS];
     __shared__ int lrlist[HM_MAXRUNS];
+    __shared__ double2 rbox[HM_MAXRUNS]; // (mid, half) of every low-rank run: read once, up front
+    __shared__ int64_t rxo[HM_MAXRUNS];
+    __shared__ int2 rk[HM_MAXRUNS];
     __shared__ int nlr_s;
     const HmItem it = items[blockIdx.x];
     const int t = threadIdx.x, lane = t & 31;
@@ -627,6 +630,12 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         HmRun rr = runs[it.run0 + r];
         rpos[r] = rr.pos;
         rsrc[r] = rr.src;
+        if (rr.src < 0) {
+            const HmFreeRun fr = frun[it.run0 + r];
+            rbox[r] = make_double2(fr.mid, fr.half);
+            rxo[r] = fr.xoff;
+            rk[r] = make_int2(fr.k0, fr.kn);
+        }
     }
     if (t == 0) rpos[it.nrun] = S;
     __syncthreads();
@@ -684,10 +693,11 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         for (int idx = t; idx < nb * R; idx += T) {
             const int b = idx / R, k = idx - b * R;
             const int r = lrlist[b0 + b];
-            const HmFreeRun fr = frun[it.run0 + r];
-            const double zk = (k >= fr.k0 && k < fr.k0 + fr.kn) ? zs[rpos[r] + k - fr.k0] : 0.0;
-            tab[b][k] = make_double2(__dadd_rn(fr.mid, __dmul_rn(fr.half, cheb.node[k])), cheb.lam[k] * zk);
-            if (k == 0) xoff[b] = fr.xoff;
+            const double2 box = rbox[r];
+            const int2 kr = rk[r];
+            const double zk = (k >= kr.x && k < kr.x + kr.y) ? zs[rpos[r] + k - kr.x] : 0.0;
+            tab[b][k] = make_double2(__dadd_rn(box.x, __dmul_rn(box.y, cheb.node[k])), cheb.lam[k] * zk);
+            if (k == 0) xoff[b] = rxo[r];
         }
         __syncthreads();
         if (active) {
@@ -1171,14 +1181,22 @@ cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFreeEnt
 cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun,
                             const double *px, const double *py, const double *x,
                             const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
-                            const HmPeers *peers, cudaStream_t st)
+                            const HmPeers *peers, int zcap, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
+    if (zcap < 2 || zcap > HM_SMAX) zcap = HM_SMAX;
+    const size_t smem = (size_t)zcap * sizeof(double);
+    {
+        cudaError_t e = cudaFuncSetAttribute(hm_free3_kernel<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(hm_free3_kernel<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     if (peers && peers->n > 0)
-        hm_free3_kernel<20, true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, frun, px, py, x, svec,
+        hm_free3_kernel<20, true><<<(unsigned)nitems, HM_THREADS, smem, st>>>(items, runs, frun, px, py, x, svec,
                                                                         y, accumulate, cheb, kernel_id, *peers);
     else
-        hm_free3_kernel<20, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, frun, px, py, x, svec,
+        hm_free3_kernel<20, false><<<(unsigned)nitems, HM_THREADS, smem, st>>>(items, runs, frun, px, py, x, svec,
                                                                          y, accumulate, cheb, kernel_id, HmPeers{});
     return cudaGetLastError();
 }

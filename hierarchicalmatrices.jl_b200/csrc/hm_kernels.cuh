@@ -106,7 +106,7 @@ cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFreeEnt
 cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun,
                             const double *px, const double *py, const double *x,
                             const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
-                            const HmPeers *peers, cudaStream_t st);
+                            const HmPeers *peers, int zcap, cudaStream_t st);
 
 // many right-hand sides (hm_panel.cu): panels are row-major with pitch CS = hm_panel_width(nrhs)
 int hm_panel_width(int nrhs);

@@ -603,7 +603,7 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ 
 // per (row, leaf):  y_i += (sum_k lam_k s_k r_ik) / (sum_k lam_k r_ik).  The group sums are
 // combined in group order -- deterministic.
 template <int R, bool PEERS>
-__global__ void __launch_bounds__(HM_THREADS, 4)
+__global__ void __launch_bounds__(HM_THREADS, 6)
 hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                 const HmFreeRun *__restrict__ frun,
                 const double *__restrict__ px, const double *__restrict__ py,

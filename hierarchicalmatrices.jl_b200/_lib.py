@@ -86,6 +86,7 @@ SIGNATURES = {
     "hm_plan_timing_begin": (_i32, [_vp, _i32]),
     "hm_plan_timing_end": (_i32, [_vp, _dp, C.POINTER(_i64)]),
     "hm_plan_launches_per_matvec": (_i32, [_vp]),
+    "hm_debug_fail_alloc": (_i32, [_i64]),
     "hm_plan_num_leaves": (_i32, [_vp, C.POINTER(_i64)]),
     "hm_plan_leaf_info": (_i32, [_vp, _i64, C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i64),
                                  C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),

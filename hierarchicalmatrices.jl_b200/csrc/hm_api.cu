@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <stdexcept>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -25,17 +26,32 @@
 // ---------------------------------------------------------------------------
 namespace {
 
-thread_local std::string g_err;
+thread_local char g_err[512] = ""; // fixed storage: reporting a failure must not allocate
 
-int32_t fail(hm_status st, const char *fmt, ...)
+int32_t fail(hm_status st, const char *fmt, ...) noexcept
 {
-    char buf[512];
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
-    g_err = buf;
     return (int32_t)st;
+}
+
+// No C++ exception may cross the extern "C" boundary (behind ccall / ctypes it would reach
+// std::terminate and kill the host process): every entry point runs its body through this.
+template <class Fn> int32_t guarded(Fn &&fn) noexcept
+{
+    try {
+        return fn();
+    } catch (const std::bad_alloc &) {
+        return fail(HM_ERR_NOMEM, "out of host memory");
+    } catch (const std::length_error &e) {
+        return fail(HM_ERR_NOMEM, "container size limit exceeded: %s", e.what());
+    } catch (const std::exception &e) {
+        return fail(HM_ERR_INVALID, "internal error: %s", e.what());
+    } catch (...) {
+        return fail(HM_ERR_INVALID, "internal error (unknown exception)");
+    }
 }
 
 #define HM_CUDA(call)                                                                              \
@@ -494,7 +510,7 @@ int32_t stage(hm_builder *b, const double *src, int64_t rows, int64_t cols, int6
 // ---------------------------------------------------------------------------
 extern "C" {
 
-const char *hm_last_error(void) { return g_err.c_str(); }
+const char *hm_last_error(void) { return g_err; }
 
 int32_t hm_version(void) { return 100; }
 
@@ -503,113 +519,125 @@ int32_t hm_blocksize_f64(void) { return hm_blocksize_double(); }
 
 int32_t hm_builder_create(hm_builder **out, int64_t nrows, int64_t ncols, int32_t dtype, int32_t device)
 {
-    if (!out) return fail(HM_ERR_NULL, "out is NULL");
-    *out = nullptr;
-    if (dtype != HM_F64) return fail(HM_ERR_UNSUPPORTED, "only Float64 (HM_F64) operators are supported");
-    if (nrows < 0 || ncols < 0) return fail(HM_ERR_SHAPE, "negative operator extent");
-    if (nrows >= ((int64_t)1 << 31) || ncols >= ((int64_t)1 << 31))
-        return fail(HM_ERR_UNSUPPORTED, "operator extent >= 2^31");
-    hm_builder *b = new (std::nothrow) hm_builder;
-    if (!b) return fail(HM_ERR_NOMEM, "out of host memory");
-    b->nrows = nrows;
-    b->ncols = ncols;
-    b->device = device;
-    if (device >= 0) {
-        DeviceGuard g(device);
-        if (!g.ok) {
-            delete b;
-            cudaGetLastError();
-            return fail(HM_ERR_CUDA, "cannot select CUDA device %d: %s", device, cudaGetErrorString(g.err));
+    return guarded([&]() -> int32_t {
+        if (!out) return fail(HM_ERR_NULL, "out is NULL");
+        *out = nullptr;
+        if (dtype != HM_F64) return fail(HM_ERR_UNSUPPORTED, "only Float64 (HM_F64) operators are supported");
+        if (nrows < 0 || ncols < 0) return fail(HM_ERR_SHAPE, "negative operator extent");
+        if (nrows >= ((int64_t)1 << 31) || ncols >= ((int64_t)1 << 31))
+            return fail(HM_ERR_UNSUPPORTED, "operator extent >= 2^31");
+        hm_builder *b = new (std::nothrow) hm_builder;
+        if (!b) return fail(HM_ERR_NOMEM, "out of host memory");
+        b->nrows = nrows;
+        b->ncols = ncols;
+        b->device = device;
+        if (device >= 0) {
+            DeviceGuard g(device);
+            if (!g.ok) {
+                delete b;
+                cudaGetLastError();
+                return fail(HM_ERR_CUDA, "cannot select CUDA device %d: %s", device, cudaGetErrorString(g.err));
+            }
+            b->up = new (std::nothrow) Uploader;
+            cudaError_t e = b->up ? b->up->init() : cudaErrorMemoryAllocation;
+            if (e != cudaSuccess) {
+                delete b;
+                cudaGetLastError();
+                return fail(HM_ERR_CUDA, "staging setup failed: %s", cudaGetErrorString(e));
+            }
         }
-        b->up = new (std::nothrow) Uploader;
-        cudaError_t e = b->up ? b->up->init() : cudaErrorMemoryAllocation;
-        if (e != cudaSuccess) {
-            delete b;
-            cudaGetLastError();
-            return fail(HM_ERR_CUDA, "staging setup failed: %s", cudaGetErrorString(e));
-        }
-    }
-    *out = b;
-    return HM_OK;
+        *out = b;
+        return HM_OK;
+    });
 }
 
 int32_t hm_builder_destroy(hm_builder *b)
 {
-    if (!b) return HM_OK;
-    if (b->device >= 0) {
-        DeviceGuard g(b->device);
-        delete b;
-    } else {
-        delete b;
-    }
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!b) return HM_OK;
+        if (b->device >= 0) {
+            DeviceGuard g(b->device);
+            delete b;
+        } else {
+            delete b;
+        }
+        return HM_OK;
+    });
 }
 
 int32_t hm_builder_add_dense(hm_builder *b, const double *A, int64_t m, int64_t n, int64_t lda, int64_t row0,
                              int64_t col0)
 {
-    if (!b) return fail(HM_ERR_NULL, "builder is NULL");
-    if (int32_t st = check_block(b, m, n, row0, col0)) return st;
-    HmLeaf l{};
-    l.kind = HM_LEAF_DENSE;
-    l.source = b->device >= 0 ? HM_SRC_COPY : HM_SRC_NONE;
-    l.row0 = row0;
-    l.col0 = col0;
-    l.m = m;
-    l.n = n;
-    if (b->device >= 0) {
-        HM_DEVICE(b->device);
-        if (int32_t st = stage(b, A, m, n, lda, "A", &l.dU)) return st;
-    }
-    l.ldu = m;
-    b->leaves.push_back(l);
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!b) return fail(HM_ERR_NULL, "builder is NULL");
+        if (int32_t st = check_block(b, m, n, row0, col0)) return st;
+        HmLeaf l{};
+        l.kind = HM_LEAF_DENSE;
+        l.source = b->device >= 0 ? HM_SRC_COPY : HM_SRC_NONE;
+        l.row0 = row0;
+        l.col0 = col0;
+        l.m = m;
+        l.n = n;
+        if (b->device >= 0) {
+            HM_DEVICE(b->device);
+            if (int32_t st = stage(b, A, m, n, lda, "A", &l.dU)) return st;
+        }
+        l.ldu = m;
+        b->leaves.push_back(l);
+        return HM_OK;
+    });
 }
 
 static int32_t add_factored(hm_builder *b, int32_t kind, const double *U, int64_t ldu, const double *C,
                             int64_t ldc, const double *V, int64_t ldv, int64_t m, int64_t n, int64_t r,
                             int64_t row0, int64_t col0)
 {
-    if (!b) return fail(HM_ERR_NULL, "builder is NULL");
-    if (int32_t st = check_block(b, m, n, row0, col0)) return st;
-    if (r < 0) return fail(HM_ERR_SHAPE, "negative rank");
-    if (r > 2048) return fail(HM_ERR_UNSUPPORTED, "rank %lld > 2048", (long long)r);
-    HmLeaf l{};
-    l.kind = kind;
-    l.source = b->device >= 0 ? HM_SRC_COPY : HM_SRC_NONE;
-    l.row0 = row0;
-    l.col0 = col0;
-    l.m = m;
-    l.n = n;
-    l.ru = l.rv = (int32_t)r;
-    if (b->device >= 0) {
-        HM_DEVICE(b->device);
-        if (int32_t st = stage(b, U, m, r, ldu, "U", &l.dU)) return st;
-        if (kind == HM_LEAF_LOWRANK) {
-            if (int32_t st = stage(b, C, r, 1, r, "S", &l.dC)) return st;
-        } else {
-            if (int32_t st = stage(b, C, r, r, ldc, "F", &l.dC)) return st;
+    return guarded([&]() -> int32_t {
+        if (!b) return fail(HM_ERR_NULL, "builder is NULL");
+        if (int32_t st = check_block(b, m, n, row0, col0)) return st;
+        if (r < 0) return fail(HM_ERR_SHAPE, "negative rank");
+        if (r > 2048) return fail(HM_ERR_UNSUPPORTED, "rank %lld > 2048", (long long)r);
+        HmLeaf l{};
+        l.kind = kind;
+        l.source = b->device >= 0 ? HM_SRC_COPY : HM_SRC_NONE;
+        l.row0 = row0;
+        l.col0 = col0;
+        l.m = m;
+        l.n = n;
+        l.ru = l.rv = (int32_t)r;
+        if (b->device >= 0) {
+            HM_DEVICE(b->device);
+            if (int32_t st = stage(b, U, m, r, ldu, "U", &l.dU)) return st;
+            if (kind == HM_LEAF_LOWRANK) {
+                if (int32_t st = stage(b, C, r, 1, r, "S", &l.dC)) return st;
+            } else {
+                if (int32_t st = stage(b, C, r, r, ldc, "F", &l.dC)) return st;
+            }
+            if (int32_t st = stage(b, V, n, r, ldv, "V", &l.dV)) return st;
         }
-        if (int32_t st = stage(b, V, n, r, ldv, "V", &l.dV)) return st;
-    }
-    l.ldu = m;
-    l.ldc = r;
-    l.ldv = n;
-    b->leaves.push_back(l);
-    return HM_OK;
+        l.ldu = m;
+        l.ldc = r;
+        l.ldv = n;
+        b->leaves.push_back(l);
+        return HM_OK;
+    });
 }
 
 int32_t hm_builder_add_lowrank(hm_builder *b, const double *U, int64_t ldu, const double *S, const double *V,
                                int64_t ldv, int64_t m, int64_t n, int64_t r, int64_t row0, int64_t col0)
 {
-    return add_factored(b, HM_LEAF_LOWRANK, U, ldu, S, r, V, ldv, m, n, r, row0, col0);
+    return guarded([&]() -> int32_t {
+        return add_factored(b, HM_LEAF_LOWRANK, U, ldu, S, r, V, ldv, m, n, r, row0, col0);
+    });
 }
 
 int32_t hm_builder_add_bary2d(hm_builder *b, const double *U, int64_t ldu, const double *F, int64_t ldf,
                               const double *V, int64_t ldv, int64_t m, int64_t n, int64_t r, int64_t row0,
                               int64_t col0)
 {
-    return add_factored(b, HM_LEAF_BARY2D, U, ldu, F, ldf, V, ldv, m, n, r, row0, col0);
+    return guarded([&]() -> int32_t {
+        return add_factored(b, HM_LEAF_BARY2D, U, ldu, F, ldf, V, ldv, m, n, r, row0, col0);
+    });
 }
 
 // EvenBarycentricMatrix (reference src/BarycentricMatrix.jl:5-45, apply src/algebra.jl:168-239):
@@ -620,166 +648,184 @@ int32_t hm_builder_add_evenbary(hm_builder *b, const double *W, int64_t ldw, con
                                 int64_t m, int64_t n, int64_t r, int64_t row0, int64_t col0,
                                 int32_t shift_parity)
 {
-    if (!b) return fail(HM_ERR_NULL, "builder is NULL");
-    if (int32_t st = check_block(b, m, n, row0, col0)) return st;
-    if (r < 0) return fail(HM_ERR_SHAPE, "negative rank");
-    if (r > 1024) return fail(HM_ERR_UNSUPPORTED, "rank %lld > 1024", (long long)r);
-    if (shift_parity != 0 && shift_parity != 1) return fail(HM_ERR_INVALID, "shift_parity must be 0 or 1");
-    if (b->device >= 0 && m * r > 0 && !W) return fail(HM_ERR_NULL, "W is NULL");
-    if (b->device >= 0 && n * r > 0 && !F) return fail(HM_ERR_NULL, "F is NULL");
-    if (m * r > 0 && ldw < r) return fail(HM_ERR_SHAPE, "W: leading dimension %lld < rank %lld", (long long)ldw, (long long)r);
-    if (n * r > 0 && ldf < n) return fail(HM_ERR_SHAPE, "F: leading dimension %lld < rows %lld", (long long)ldf, (long long)n);
-    const int64_t r2 = 2 * r;
-    std::vector<double> U, V, S;
-    if (b->device >= 0) {
-        try {
-            U.assign((size_t)(m * r2), 0.0);
-            V.assign((size_t)(n * r2), 0.0);
-            S.assign((size_t)r2, 1.0);
-        } catch (const std::bad_alloc &) {
-            return fail(HM_ERR_NOMEM, "out of host memory");
+    return guarded([&]() -> int32_t {
+        if (!b) return fail(HM_ERR_NULL, "builder is NULL");
+        if (int32_t st = check_block(b, m, n, row0, col0)) return st;
+        if (r < 0) return fail(HM_ERR_SHAPE, "negative rank");
+        if (r > 1024) return fail(HM_ERR_UNSUPPORTED, "rank %lld > 1024", (long long)r);
+        if (shift_parity != 0 && shift_parity != 1) return fail(HM_ERR_INVALID, "shift_parity must be 0 or 1");
+        if (b->device >= 0 && m * r > 0 && !W) return fail(HM_ERR_NULL, "W is NULL");
+        if (b->device >= 0 && n * r > 0 && !F) return fail(HM_ERR_NULL, "F is NULL");
+        if (m * r > 0 && ldw < r) return fail(HM_ERR_SHAPE, "W: leading dimension %lld < rank %lld", (long long)ldw, (long long)r);
+        if (n * r > 0 && ldf < n) return fail(HM_ERR_SHAPE, "F: leading dimension %lld < rows %lld", (long long)ldf, (long long)n);
+        const int64_t r2 = 2 * r;
+        std::vector<double> U, V, S;
+        if (b->device >= 0) {
+            try {
+                U.assign((size_t)(m * r2), 0.0);
+                V.assign((size_t)(n * r2), 0.0);
+                S.assign((size_t)r2, 1.0);
+            } catch (const std::bad_alloc &) {
+                return fail(HM_ERR_NOMEM, "out of host memory");
+            }
+            for (int64_t i = 0; i < m; i++) {
+                const int64_t cls = (row0 + i) & 1;
+                for (int64_t k = 0; k < r; k++) U[(size_t)(i + (cls * r + k) * m)] = W[k + i * ldw];
+            }
+            for (int64_t j = 0; j < n; j++) {
+                const int64_t cls = (shift_parity + col0 + j) & 1;
+                for (int64_t k = 0; k < r; k++) V[(size_t)(j + (cls * r + k) * n)] = F[j + k * ldf];
+            }
         }
-        for (int64_t i = 0; i < m; i++) {
-            const int64_t cls = (row0 + i) & 1;
-            for (int64_t k = 0; k < r; k++) U[(size_t)(i + (cls * r + k) * m)] = W[k + i * ldw];
-        }
-        for (int64_t j = 0; j < n; j++) {
-            const int64_t cls = (shift_parity + col0 + j) & 1;
-            for (int64_t k = 0; k < r; k++) V[(size_t)(j + (cls * r + k) * n)] = F[j + k * ldf];
-        }
-    }
-    int32_t st = add_factored(b, HM_LEAF_LOWRANK, U.data(), std::max<int64_t>(m, 1), S.data(), r2, V.data(),
-                              std::max<int64_t>(n, 1), m, n, r2, row0, col0);
-    if (st == HM_OK) b->leaves.back().extra_words = (m + n) * r + r2;
-    return st;
+        int32_t st = add_factored(b, HM_LEAF_LOWRANK, U.data(), std::max<int64_t>(m, 1), S.data(), r2, V.data(),
+                                  std::max<int64_t>(n, 1), m, n, r2, row0, col0);
+        if (st == HM_OK) b->leaves.back().extra_words = (m + n) * r + r2;
+        return st;
+    });
 }
 
 int32_t hm_builder_layout_stats(hm_builder *b, int32_t part, int32_t nparts, hm_stats *out)
 {
-    if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
-    HmLayout L;
-    std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, layout_params(), L);
-    if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
-    fill_stats(L, out);
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
+        HmLayout L;
+        std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, layout_params(), L);
+        if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
+        fill_stats(L, out);
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_finalize_part(hm_builder *b, int32_t part, int32_t nparts, hm_plan **out)
 {
-    if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
-    *out = nullptr;
-    if (b->device < 0) return fail(HM_ERR_STATE, "structure-only builder (device = -1) cannot be finalized");
-    HM_DEVICE(b->device);
-    HM_CUDA(b->up->finish());
-    hm_plan *P = new (std::nothrow) hm_plan;
-    if (!P) return fail(HM_ERR_NOMEM, "out of host memory");
-    P->device = b->device;
-    std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, layout_params(), P->L);
-    if (!err.empty()) {
-        delete P;
-        return fail(HM_ERR_INVALID, "%s", err.c_str());
-    }
-    P->cheb.r = 0;
-    int32_t st = materialize(P, nullptr, nullptr);
-    if (st != HM_OK) {
-        delete P;
-        return st;
-    }
-    *out = P;
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
+        *out = nullptr;
+        if (b->device < 0) return fail(HM_ERR_STATE, "structure-only builder (device = -1) cannot be finalized");
+        HM_DEVICE(b->device);
+        HM_CUDA(b->up->finish());
+        hm_plan *P = new (std::nothrow) hm_plan;
+        if (!P) return fail(HM_ERR_NOMEM, "out of host memory");
+        P->device = b->device;
+        std::string err = hm_build_layout(b->leaves, b->nrows, b->ncols, part, nparts, layout_params(), P->L);
+        if (!err.empty()) {
+            delete P;
+            return fail(HM_ERR_INVALID, "%s", err.c_str());
+        }
+        P->cheb.r = 0;
+        int32_t st = materialize(P, nullptr, nullptr);
+        if (st != HM_OK) {
+            delete P;
+            return st;
+        }
+        *out = P;
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_finalize(hm_builder *b, const int32_t *devices, int32_t ndev, hm_plan **out)
 {
-    if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
-    if (ndev != 1)
-        return fail(HM_ERR_UNSUPPORTED,
-                    "one plan drives one GPU; for multi-GPU run one process per GPU with hm_plan_finalize_part");
-    if (devices && devices[0] != b->device)
-        return fail(HM_ERR_INVALID, "devices[0] = %d but the builder staged its data on device %d", devices[0],
-                    b->device);
-    return hm_plan_finalize_part(b, 0, 1, out);
+    return guarded([&]() -> int32_t {
+        if (!b || !out) return fail(HM_ERR_NULL, "NULL argument");
+        if (ndev != 1)
+            return fail(HM_ERR_UNSUPPORTED,
+                        "one plan drives one GPU; for multi-GPU run one process per GPU with hm_plan_finalize_part");
+        if (devices && devices[0] != b->device)
+            return fail(HM_ERR_INVALID, "devices[0] = %d but the builder staged its data on device %d", devices[0],
+                        b->device);
+        return hm_plan_finalize_part(b, 0, 1, out);
+    });
 }
 
 int32_t hm_plan_destroy(hm_plan *p)
 {
-    if (!p) return HM_OK;
-    DeviceGuard g(p->device);
-    delete p;
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!p) return HM_OK;
+        DeviceGuard g(p->device);
+        delete p;
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_stats(const hm_plan *p, hm_stats *out)
 {
-    if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
-    fill_stats(p->L, out);
-    if (p->matrix_free) { // nothing but the cores is stored; the apply reads tables and points
-        out->v_stream_bytes = out->u_stream_bytes = 0;
-        out->stored_bytes = 8 * p->L.core_words;
-    }
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
+        fill_stats(p->L, out);
+        if (p->matrix_free) { // nothing but the cores is stored; the apply reads tables and points
+            out->v_stream_bytes = out->u_stream_bytes = 0;
+            out->stored_bytes = 8 * p->L.core_words;
+        }
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_scale(hm_plan *p, const double *b, int64_t incb, int32_t side)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
-    if (side != 0 && side != 1) return fail(HM_ERR_INVALID, "side must be 0 (columns) or 1 (rows)");
-    if (incb <= 0) return fail(HM_ERR_INVALID, "stride must be positive");
-    const HmLayout &L = p->L;
-    const int64_t n = side == 0 ? L.ncols : L.nrows;
-    if (n == 0) return HM_OK;
-    if (!b) return fail(HM_ERR_NULL, "b is NULL");
-    std::lock_guard<std::mutex> lock(p->mu);
-    HM_DEVICE(p->device);
-    std::vector<double> hb((size_t)n);
-    for (int64_t i = 0; i < n; i++) hb[(size_t)i] = b[i * incb];
-    DevBuf<double> db;
-    HM_CUDA(db.alloc((size_t)n));
-    cudaStream_t st = p->stream;
-    HM_CUDA(cudaMemcpyAsync(db.p, hb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    if (side == 1)
-        HM_CUDA(hm_launch_scale_rows(p->items3.p, (int64_t)L.items3.size(), p->ustream.p, db.p, st));
-    else
-        HM_CUDA(hm_launch_scale_cols(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->items3.p,
-                                     (int64_t)L.items3.size(), p->runs.p, p->ustream.p, db.p, st));
-    HM_CUDA(cudaStreamSynchronize(st));
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
+        if (side != 0 && side != 1) return fail(HM_ERR_INVALID, "side must be 0 (columns) or 1 (rows)");
+        if (incb <= 0) return fail(HM_ERR_INVALID, "stride must be positive");
+        const HmLayout &L = p->L;
+        const int64_t n = side == 0 ? L.ncols : L.nrows;
+        if (n == 0) return HM_OK;
+        if (!b) return fail(HM_ERR_NULL, "b is NULL");
+        std::lock_guard<std::mutex> lock(p->mu);
+        HM_DEVICE(p->device);
+        std::vector<double> hb((size_t)n);
+        for (int64_t i = 0; i < n; i++) hb[(size_t)i] = b[i * incb];
+        DevBuf<double> db;
+        HM_CUDA(db.alloc((size_t)n));
+        cudaStream_t st = p->stream;
+        HM_CUDA(cudaMemcpyAsync(db.p, hb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        if (side == 1)
+            HM_CUDA(hm_launch_scale_rows(p->items3.p, (int64_t)L.items3.size(), p->ustream.p, db.p, st));
+        else
+            HM_CUDA(hm_launch_scale_cols(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->items3.p,
+                                         (int64_t)L.items3.size(), p->runs.p, p->ustream.p, db.p, st));
+        HM_CUDA(cudaStreamSynchronize(st));
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_timing_begin(hm_plan *p, int32_t max_calls)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    if (max_calls < 0 || max_calls > 100000) return fail(HM_ERR_INVALID, "max_calls out of range");
-    HM_DEVICE(p->device);
-    while ((int)p->tev.size() < 4 * max_calls) {
-        cudaEvent_t e;
-        HM_CUDA(cudaEventCreate(&e));
-        p->tev.push_back(e);
-    }
-    p->tcap = max_calls;
-    p->tcount = 0;
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        if (max_calls < 0 || max_calls > 100000) return fail(HM_ERR_INVALID, "max_calls out of range");
+        HM_DEVICE(p->device);
+        while ((int)p->tev.size() < 4 * max_calls) {
+            cudaEvent_t e;
+            HM_CUDA(cudaEventCreate(&e));
+            p->tev.push_back(e);
+        }
+        p->tcap = max_calls;
+        p->tcount = 0;
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_timing_end(hm_plan *p, double *stage_ms3, int64_t *ncalls)
 {
-    if (!p || !stage_ms3 || !ncalls) return fail(HM_ERR_NULL, "NULL argument");
-    HM_DEVICE(p->device);
-    stage_ms3[0] = stage_ms3[1] = stage_ms3[2] = 0.0;
-    for (int c = 0; c < p->tcount; c++) {
-        cudaEvent_t *ev = &p->tev[(size_t)c * 4];
-        HM_CUDA(cudaEventSynchronize(ev[3]));
-        for (int s = 0; s < 3; s++) {
-            float ms = 0.f;
-            HM_CUDA(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
-            stage_ms3[s] += ms;
+    return guarded([&]() -> int32_t {
+        if (!p || !stage_ms3 || !ncalls) return fail(HM_ERR_NULL, "NULL argument");
+        HM_DEVICE(p->device);
+        stage_ms3[0] = stage_ms3[1] = stage_ms3[2] = 0.0;
+        for (int c = 0; c < p->tcount; c++) {
+            cudaEvent_t *ev = &p->tev[(size_t)c * 4];
+            HM_CUDA(cudaEventSynchronize(ev[3]));
+            for (int s = 0; s < 3; s++) {
+                float ms = 0.f;
+                HM_CUDA(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+                stage_ms3[s] += ms;
+            }
         }
-    }
-    *ncalls = p->tcount;
-    p->tcap = 0;
-    p->tcount = 0;
-    return HM_OK;
+        *ncalls = p->tcount;
+        p->tcap = 0;
+        p->tcount = 0;
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_launches_per_matvec(const hm_plan *p)
@@ -797,98 +843,110 @@ int32_t hm_plan_launches_per_matvec(const hm_plan *p)
 static int32_t kernel_tree_layout(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                                   double c, double d, int32_t part, int32_t nparts, HmLayout &L)
 {
-    if (!x || !y) return fail(HM_ERR_NULL, "point set is NULL");
-    if (nx < 0 || ny < 0) return fail(HM_ERR_SHAPE, "negative point count");
-    std::vector<HmLeaf> leaves;
-    int64_t nrows = 0, ncols = 0;
-    std::string err = hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
-    if (!err.empty()) return fail(HM_ERR_REFERENCE, "%s", err.c_str());
-    err = hm_build_layout(leaves, nrows, ncols, part, nparts, layout_params(), L);
-    if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!x || !y) return fail(HM_ERR_NULL, "point set is NULL");
+        if (nx < 0 || ny < 0) return fail(HM_ERR_SHAPE, "negative point count");
+        std::vector<HmLeaf> leaves;
+        int64_t nrows = 0, ncols = 0;
+        std::string err = hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
+        if (!err.empty()) return fail(HM_ERR_REFERENCE, "%s", err.c_str());
+        err = hm_build_layout(leaves, nrows, ncols, part, nparts, layout_params(), L);
+        if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
+        return HM_OK;
+    });
 }
 
 int32_t hm_kernel_tree_leaves(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                               double c, double d, hm_tree_leaf *out, int64_t cap, int64_t *count)
 {
-    if (!x || !y || !count) return fail(HM_ERR_NULL, "NULL argument");
-    if (nx < 0 || ny < 0) return fail(HM_ERR_SHAPE, "negative point count");
-    std::vector<HmLeaf> leaves;
-    int64_t nrows = 0, ncols = 0;
-    std::string err = hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
-    if (!err.empty()) return fail(HM_ERR_REFERENCE, "%s", err.c_str());
-    *count = (int64_t)leaves.size();
-    for (int64_t i = 0; out && i < cap && i < *count; i++) {
-        const HmLeaf &l = leaves[(size_t)i];
-        out[i] = hm_tree_leaf{l.kind, l.ru, l.row0, l.col0, l.m, l.n, l.xi0, l.yj0, l.a, l.b, l.c, l.d};
-    }
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!x || !y || !count) return fail(HM_ERR_NULL, "NULL argument");
+        if (nx < 0 || ny < 0) return fail(HM_ERR_SHAPE, "negative point count");
+        std::vector<HmLeaf> leaves;
+        int64_t nrows = 0, ncols = 0;
+        std::string err = hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
+        if (!err.empty()) return fail(HM_ERR_REFERENCE, "%s", err.c_str());
+        *count = (int64_t)leaves.size();
+        for (int64_t i = 0; out && i < cap && i < *count; i++) {
+            const HmLeaf &l = leaves[(size_t)i];
+            out[i] = hm_tree_leaf{l.kind, l.ru, l.row0, l.col0, l.m, l.n, l.xi0, l.yj0, l.a, l.b, l.c, l.d};
+        }
+        return HM_OK;
+    });
 }
 
 int32_t hm_assemble_kernel_stats(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                                  double c, double d, int32_t part, int32_t nparts, hm_stats *out)
 {
-    if (!out) return fail(HM_ERR_NULL, "out is NULL");
-    HmLayout L;
-    if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, L)) return st;
-    fill_stats(L, out);
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!out) return fail(HM_ERR_NULL, "out is NULL");
+        HmLayout L;
+        if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, L)) return st;
+        fill_stats(L, out);
+        return HM_OK;
+    });
 }
 
 static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                                     double c, double d, int32_t kernel_id, int32_t device, int32_t part,
                                     int32_t nparts, bool matrix_free, hm_plan **out)
 {
-    if (!out) return fail(HM_ERR_NULL, "out is NULL");
-    *out = nullptr;
-    if (kernel_id < 0 || kernel_id > 3) return fail(HM_ERR_INVALID, "unknown kernel id %d", kernel_id);
-    if (hm_blockrank_double() != 20) return fail(HM_ERR_UNSUPPORTED, "BLOCKRANK(Float64) != 20");
-    HM_DEVICE(device);
-    hm_plan *P = new (std::nothrow) hm_plan;
-    if (!P) return fail(HM_ERR_NOMEM, "out of host memory");
-    P->device = device;
-    P->kernel_id = kernel_id;
-    P->matrix_free = matrix_free;
-    if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, P->L)) {
-        delete P;
-        return st;
-    }
-    P->cheb.r = hm_blockrank_double();
-    hm_cheb_nodes_weights(P->cheb.r, P->cheb.node, P->cheb.lam);
-    cudaError_t e = P->f_px.alloc((size_t)std::max<int64_t>(nx, 1));
-    if (e == cudaSuccess) e = P->f_py.alloc((size_t)std::max<int64_t>(ny, 1));
-    if (e == cudaSuccess && nx) e = cudaMemcpy(P->f_px.p, x, (size_t)nx * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && ny) e = cudaMemcpy(P->f_py.p, y, (size_t)ny * 8, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        delete P;
-        cudaGetLastError();
-        return fail(HM_ERR_CUDA, "point upload failed: %s", cudaGetErrorString(e));
-    }
-    int32_t st = materialize(P, P->f_px.p, P->f_py.p);
-    if (st != HM_OK) {
-        delete P;
-        return st;
-    }
-    if (!matrix_free) { // the stored operator no longer needs the points
-        P->f_px.release();
-        P->f_py.release();
-    }
-    *out = P;
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!out) return fail(HM_ERR_NULL, "out is NULL");
+        *out = nullptr;
+        if (kernel_id < 0 || kernel_id > 3) return fail(HM_ERR_INVALID, "unknown kernel id %d", kernel_id);
+        if (hm_blockrank_double() != 20) return fail(HM_ERR_UNSUPPORTED, "BLOCKRANK(Float64) != 20");
+        HM_DEVICE(device);
+        hm_plan *P = new (std::nothrow) hm_plan;
+        if (!P) return fail(HM_ERR_NOMEM, "out of host memory");
+        P->device = device;
+        P->kernel_id = kernel_id;
+        P->matrix_free = matrix_free;
+        if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, P->L)) {
+            delete P;
+            return st;
+        }
+        P->cheb.r = hm_blockrank_double();
+        hm_cheb_nodes_weights(P->cheb.r, P->cheb.node, P->cheb.lam);
+        cudaError_t e = P->f_px.alloc((size_t)std::max<int64_t>(nx, 1));
+        if (e == cudaSuccess) e = P->f_py.alloc((size_t)std::max<int64_t>(ny, 1));
+        if (e == cudaSuccess && nx) e = cudaMemcpy(P->f_px.p, x, (size_t)nx * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && ny) e = cudaMemcpy(P->f_py.p, y, (size_t)ny * 8, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            delete P;
+            cudaGetLastError();
+            return fail(HM_ERR_CUDA, "point upload failed: %s", cudaGetErrorString(e));
+        }
+        int32_t st = materialize(P, P->f_px.p, P->f_py.p);
+        if (st != HM_OK) {
+            delete P;
+            return st;
+        }
+        if (!matrix_free) { // the stored operator no longer needs the points
+            P->f_px.release();
+            P->f_py.release();
+        }
+        *out = P;
+        return HM_OK;
+    });
 }
 
 int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                            double c, double d, int32_t kernel_id, int32_t device, int32_t part, int32_t nparts,
                            hm_plan **out)
 {
-    return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, kernel_id, device, part, nparts, false, out);
+    return guarded([&]() -> int32_t {
+        return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, kernel_id, device, part, nparts, false, out);
+    });
 }
 
 int32_t hm_assemble_kernel_free(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                                 double c, double d, int32_t kernel_id, int32_t device, int32_t part,
                                 int32_t nparts, hm_plan **out)
 {
-    return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, kernel_id, device, part, nparts, true, out);
+    return guarded([&]() -> int32_t {
+        return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, kernel_id, device, part, nparts, true, out);
+    });
 }
 
 // ---------------------------------------------------------------------------
@@ -899,267 +957,294 @@ static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int3
 
 int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream)
 {
-    return matvec_device_impl(p, dx, dy, accumulate, stream, nullptr);
+    return guarded([&]() -> int32_t {
+        return matvec_device_impl(p, dx, dy, accumulate, stream, nullptr);
+    });
 }
 
 int32_t hm_matvec_device_allgather(hm_plan *p, const double *dx, const uint64_t *ypeers, int32_t npeers,
                                    int32_t self, int32_t accumulate, void *stream)
 {
-    if (!p || !ypeers) return fail(HM_ERR_NULL, "NULL argument");
-    if (npeers < 1 || npeers > HM_MAX_PEERS) return fail(HM_ERR_INVALID, "npeers must be 1..%d", HM_MAX_PEERS);
-    if (self < 0 || self >= npeers) return fail(HM_ERR_INVALID, "self out of range");
-    HmPeers pe;
-    pe.n = npeers;
-    for (int i = 0; i < npeers; i++) {
-        if (!ypeers[i] && p->L.nrows > 0) return fail(HM_ERR_NULL, "peer pointer %d is NULL", i);
-        pe.y[i] = reinterpret_cast<double *>(ypeers[i]);
-    }
-    return matvec_device_impl(p, dx, pe.y[self], accumulate, stream, &pe);
+    return guarded([&]() -> int32_t {
+        if (!p || !ypeers) return fail(HM_ERR_NULL, "NULL argument");
+        if (npeers < 1 || npeers > HM_MAX_PEERS) return fail(HM_ERR_INVALID, "npeers must be 1..%d", HM_MAX_PEERS);
+        if (self < 0 || self >= npeers) return fail(HM_ERR_INVALID, "self out of range");
+        HmPeers pe;
+        pe.n = npeers;
+        for (int i = 0; i < npeers; i++) {
+            if (!ypeers[i] && p->L.nrows > 0) return fail(HM_ERR_NULL, "peer pointer %d is NULL", i);
+            pe.y[i] = reinterpret_cast<double *>(ypeers[i]);
+        }
+        return matvec_device_impl(p, dx, pe.y[self], accumulate, stream, &pe);
+    });
 }
 
 static int32_t matvec_device_impl(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream,
                                   const HmPeers *peers)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    if ((!dx && p->L.ncols > 0) || (!dy && p->L.nrows > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
-    HM_DEVICE(p->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const HmLayout &L = p->L;
-    cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
-    if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
-    HmFuse fz;
-    if (p->fuse) {
-        fz.s1ent = p->s1ent.p;
-        fz.counters = p->counters.p;
-        fz.blocks = p->cores.p;
-        fz.plist = p->plist.p;
-        fz.core = p->core.p;
-        fz.svec = p->svec.p;
-        fz.max_r = std::max(L.max_r, 1);
-    }
-    if (p->matrix_free)
-        HM_CUDA(hm_launch_free1(p->items1.p, (int64_t)L.items1.size(), p->f_ent1.p, p->f_py.p, dx, p->partial.p,
-                                p->cheb, p->free1_units, st));
-    else
-        HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p,
-                                 p->fuse ? &fz : nullptr, st));
-    if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
-    if (!p->fuse || p->matrix_free) {
-        HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
-                                 p->svec.p, std::max(L.max_r, 1), st));
-        HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
-                                     p->svec.p, std::max(L.max_r, 1), st));
-    }
-    if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
-    for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
-        int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        if ((!dx && p->L.ncols > 0) || (!dy && p->L.nrows > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+        HM_DEVICE(p->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        const HmLayout &L = p->L;
+        cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
+        if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
+        HmFuse fz;
+        if (p->fuse) {
+            fz.s1ent = p->s1ent.p;
+            fz.counters = p->counters.p;
+            fz.blocks = p->cores.p;
+            fz.plist = p->plist.p;
+            fz.core = p->core.p;
+            fz.svec = p->svec.p;
+            fz.max_r = std::max(L.max_r, 1);
+        }
         if (p->matrix_free)
-            HM_CUDA(hm_launch_free3(p->items3.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p, dx,
-                                    p->svec.p, dy, r == 0 ? (accumulate != 0) : 1, p->cheb, p->kernel_id, peers,
-                                    p->free3_zcap, st));
+            HM_CUDA(hm_launch_free1(p->items1.p, (int64_t)L.items1.size(), p->f_ent1.p, p->f_py.p, dx, p->partial.p,
+                                    p->cheb, p->free1_units, st));
         else
-            HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
-                                     r == 0 ? (accumulate != 0) : 1, peers, st));
-    }
-    if (ev) {
-        HM_CUDA(cudaEventRecord(ev[3], st));
-        p->tcount++;
-    }
-    return HM_OK;
+            HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p,
+                                     p->fuse ? &fz : nullptr, st));
+        if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
+        if (!p->fuse || p->matrix_free) {
+            HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
+                                     p->svec.p, std::max(L.max_r, 1), st));
+            HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
+                                         p->svec.p, std::max(L.max_r, 1), st));
+        }
+        if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
+        for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
+            int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
+            if (p->matrix_free)
+                HM_CUDA(hm_launch_free3(p->items3.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p, dx,
+                                        p->svec.p, dy, r == 0 ? (accumulate != 0) : 1, p->cheb, p->kernel_id, peers,
+                                        p->free3_zcap, st));
+            else
+                HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
+                                         r == 0 ? (accumulate != 0) : 1, peers, st));
+        }
+        if (ev) {
+            HM_CUDA(cudaEventRecord(ev[3], st));
+            p->tcount++;
+        }
+        return HM_OK;
+    });
 }
 
 int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy, int32_t accumulate)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    const HmLayout &L = p->L;
-    if ((!x && L.ncols > 0) || (!y && L.nrows > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
-    if (incx <= 0 || incy <= 0) return fail(HM_ERR_INVALID, "strides must be positive (INCX, INCY >= 1 as in the reference)");
-    std::lock_guard<std::mutex> lock(p->mu);
-    HM_DEVICE(p->device);
-    const int64_t nc = L.ncols, r0 = L.row_begin, nr = L.row_end - L.row_begin;
-    if (!p->dx.p) HM_CUDA(p->dx.alloc((size_t)std::max<int64_t>(nc, 1)));
-    if (!p->dy.p) HM_CUDA(p->dy.alloc((size_t)std::max<int64_t>(L.nrows, 1)));
-    cudaStream_t st = p->stream;
-    // Unit strides, one stage-3 round: pipeline the host copies against the kernels.  x goes up
-    // in HM_NCHUNK chunks on a copy stream and stage 1 starts on the items whose columns have
-    // arrived; y comes down in row chunks while stage 3 still computes the following ones.
-    // Below ~2 MB of vector data the extra launches and events cost more than the overlap gains
-    // (measured: N = 4096 48 vs 100 us, N = 65 536 175 vs 230 us, N = 262 144 600 vs 577 us).
-    if (incx == 1 && incy == 1 && nc > 0 && nr > 0 && nc + nr >= 400000 && L.round_begin.size() == 2 &&
-        !L.items3c.empty() && p->tcap == 0 && !getenv("HMB200_NO_COPY_PIPELINE")) {
-        if (!p->chunk_ready) {
-            HM_CUDA(p->items1c.upload(L.items1c, st));
-            HM_CUDA(p->items3c.upload(L.items3c, st));
-            HM_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
-            for (int k = 0; k < HM_NCHUNK; k++) {
-                HM_CUDA(cudaEventCreateWithFlags(&p->ev_x[k], cudaEventDisableTiming));
-                HM_CUDA(cudaEventCreateWithFlags(&p->ev_y[k], cudaEventDisableTiming));
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        const HmLayout &L = p->L;
+        if ((!x && L.ncols > 0) || (!y && L.nrows > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+        if (incx <= 0 || incy <= 0) return fail(HM_ERR_INVALID, "strides must be positive (INCX, INCY >= 1 as in the reference)");
+        std::lock_guard<std::mutex> lock(p->mu);
+        HM_DEVICE(p->device);
+        const int64_t nc = L.ncols, r0 = L.row_begin, nr = L.row_end - L.row_begin;
+        if (!p->dx.p) HM_CUDA(p->dx.alloc((size_t)std::max<int64_t>(nc, 1)));
+        if (!p->dy.p) HM_CUDA(p->dy.alloc((size_t)std::max<int64_t>(L.nrows, 1)));
+        cudaStream_t st = p->stream;
+        // Unit strides, one stage-3 round: pipeline the host copies against the kernels.  x goes up
+        // in HM_NCHUNK chunks on a copy stream and stage 1 starts on the items whose columns have
+        // arrived; y comes down in row chunks while stage 3 still computes the following ones.
+        // Below ~2 MB of vector data the extra launches and events cost more than the overlap gains
+        // (measured: N = 4096 48 vs 100 us, N = 65 536 175 vs 230 us, N = 262 144 600 vs 577 us).
+        if (incx == 1 && incy == 1 && nc > 0 && nr > 0 && nc + nr >= 400000 && L.round_begin.size() == 2 &&
+            !L.items3c.empty() && p->tcap == 0 && !getenv("HMB200_NO_COPY_PIPELINE")) {
+            if (!p->chunk_ready) {
+                HM_CUDA(p->items1c.upload(L.items1c, st));
+                HM_CUDA(p->items3c.upload(L.items3c, st));
+                HM_CUDA(cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking));
+                for (int k = 0; k < HM_NCHUNK; k++) {
+                    HM_CUDA(cudaEventCreateWithFlags(&p->ev_x[k], cudaEventDisableTiming));
+                    HM_CUDA(cudaEventCreateWithFlags(&p->ev_y[k], cudaEventDisableTiming));
+                }
+                HM_CUDA(cudaEventCreateWithFlags(&p->ev_y0, cudaEventDisableTiming));
+                HM_CUDA(cudaStreamSynchronize(st));
+                p->chunk_ready = true;
             }
-            HM_CUDA(cudaEventCreateWithFlags(&p->ev_y0, cudaEventDisableTiming));
-            HM_CUDA(cudaStreamSynchronize(st));
-            p->chunk_ready = true;
-        }
-        cudaStream_t cst = p->copy_stream;
-        for (int k = 0; k < HM_NCHUNK; k++) {
-            const int64_t c0 = L.xchunk[(size_t)k], c1 = L.xchunk[(size_t)k + 1];
-            if (c1 > c0) HM_CUDA(cudaMemcpyAsync(p->dx.p + c0, x + c0, (size_t)(c1 - c0) * 8, cudaMemcpyHostToDevice, cst));
-            HM_CUDA(cudaEventRecord(p->ev_x[k], cst));
-        }
-        if (accumulate) HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, y + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, cst));
-        HM_CUDA(cudaEventRecord(p->ev_y0, cst));
-        for (int k = 0; k < HM_NCHUNK; k++) {
-            HM_CUDA(cudaStreamWaitEvent(st, p->ev_x[k], 0));
-            const int64_t i0 = L.c1_begin[(size_t)k], i1 = L.c1_begin[(size_t)k + 1];
-            if (p->matrix_free)
-                HM_CUDA(hm_launch_free1(p->items1c.p + i0, i1 - i0, p->f_ent1.p, p->f_py.p, p->dx.p, p->partial.p,
-                                        p->cheb, p->free1_units, st));
-            else
-                HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st));
-        }
-        HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
-                                 p->svec.p, std::max(L.max_r, 1), st));
-        HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
+            cudaStream_t cst = p->copy_stream;
+            for (int k = 0; k < HM_NCHUNK; k++) {
+                const int64_t c0 = L.xchunk[(size_t)k], c1 = L.xchunk[(size_t)k + 1];
+                if (c1 > c0) HM_CUDA(cudaMemcpyAsync(p->dx.p + c0, x + c0, (size_t)(c1 - c0) * 8, cudaMemcpyHostToDevice, cst));
+                HM_CUDA(cudaEventRecord(p->ev_x[k], cst));
+            }
+            if (accumulate) HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, y + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, cst));
+            HM_CUDA(cudaEventRecord(p->ev_y0, cst));
+            for (int k = 0; k < HM_NCHUNK; k++) {
+                HM_CUDA(cudaStreamWaitEvent(st, p->ev_x[k], 0));
+                const int64_t i0 = L.c1_begin[(size_t)k], i1 = L.c1_begin[(size_t)k + 1];
+                if (p->matrix_free)
+                    HM_CUDA(hm_launch_free1(p->items1c.p + i0, i1 - i0, p->f_ent1.p, p->f_py.p, p->dx.p, p->partial.p,
+                                            p->cheb, p->free1_units, st));
+                else
+                    HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st));
+            }
+            HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
                                      p->svec.p, std::max(L.max_r, 1), st));
-        HM_CUDA(cudaStreamWaitEvent(st, p->ev_y0, 0));
-        for (int k = 0; k < HM_NCHUNK; k++) {
-            const int64_t i0 = L.c3_begin[(size_t)k], i1 = L.c3_begin[(size_t)k + 1];
-            if (p->matrix_free)
-                HM_CUDA(hm_launch_free3(p->items3c.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p,
-                                        p->dx.p, p->svec.p, p->dy.p, accumulate != 0, p->cheb, p->kernel_id,
-                                        nullptr, p->free3_zcap, st));
-            else
-                HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
-                                         p->dy.p, accumulate != 0, nullptr, st));
-            HM_CUDA(cudaEventRecord(p->ev_y[k], st));
+            HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
+                                         p->svec.p, std::max(L.max_r, 1), st));
+            HM_CUDA(cudaStreamWaitEvent(st, p->ev_y0, 0));
+            for (int k = 0; k < HM_NCHUNK; k++) {
+                const int64_t i0 = L.c3_begin[(size_t)k], i1 = L.c3_begin[(size_t)k + 1];
+                if (p->matrix_free)
+                    HM_CUDA(hm_launch_free3(p->items3c.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p,
+                                            p->dx.p, p->svec.p, p->dy.p, accumulate != 0, p->cheb, p->kernel_id,
+                                            nullptr, p->free3_zcap, st));
+                else
+                    HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
+                                             p->dy.p, accumulate != 0, nullptr, st));
+                HM_CUDA(cudaEventRecord(p->ev_y[k], st));
+            }
+            // all launches are queued before the first copy back: with pageable y the copies block
+            // the host, and must not hold up the launch of the following chunks
+            for (int k = 0; k < HM_NCHUNK; k++) {
+                HM_CUDA(cudaStreamWaitEvent(cst, p->ev_y[k], 0));
+                const int64_t a0 = L.ychunk[(size_t)k], a1 = L.ychunk[(size_t)k + 1];
+                if (a1 > a0) HM_CUDA(cudaMemcpyAsync(y + a0, p->dy.p + a0, (size_t)(a1 - a0) * 8, cudaMemcpyDeviceToHost, cst));
+            }
+            HM_CUDA(cudaStreamSynchronize(cst));
+            HM_CUDA(cudaStreamSynchronize(st));
+            return HM_OK;
         }
-        // all launches are queued before the first copy back: with pageable y the copies block
-        // the host, and must not hold up the launch of the following chunks
-        for (int k = 0; k < HM_NCHUNK; k++) {
-            HM_CUDA(cudaStreamWaitEvent(cst, p->ev_y[k], 0));
-            const int64_t a0 = L.ychunk[(size_t)k], a1 = L.ychunk[(size_t)k + 1];
-            if (a1 > a0) HM_CUDA(cudaMemcpyAsync(y + a0, p->dy.p + a0, (size_t)(a1 - a0) * 8, cudaMemcpyDeviceToHost, cst));
+        // x -> device
+        if (nc > 0) {
+            if (incx == 1) {
+                HM_CUDA(cudaMemcpyAsync(p->dx.p, x, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+            } else {
+                if (!p->hx) HM_CUDA(cudaMallocHost((void **)&p->hx, (size_t)nc * 8));
+                for (int64_t j = 0; j < nc; j++) p->hx[j] = x[j * incx];
+                HM_CUDA(cudaMemcpyAsync(p->dx.p, p->hx, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+            }
         }
-        HM_CUDA(cudaStreamSynchronize(cst));
-        HM_CUDA(cudaStreamSynchronize(st));
+        // y (owned rows) -> device when accumulating
+        if (nr > 0 && accumulate) {
+            if (incy == 1) {
+                HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, y + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, st));
+            } else {
+                if (!p->hy) HM_CUDA(cudaMallocHost((void **)&p->hy, (size_t)L.nrows * 8));
+                for (int64_t i = 0; i < nr; i++) p->hy[r0 + i] = y[(r0 + i) * incy];
+                HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, p->hy + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, st));
+            }
+        }
+        if (int32_t rc = hm_matvec_device(p, p->dx.p, p->dy.p, accumulate, st)) return rc;
+        if (nr > 0) {
+            if (incy == 1) {
+                HM_CUDA(cudaMemcpyAsync(y + r0, p->dy.p + r0, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
+                HM_CUDA(cudaStreamSynchronize(st));
+            } else {
+                if (!p->hy) HM_CUDA(cudaMallocHost((void **)&p->hy, (size_t)L.nrows * 8));
+                HM_CUDA(cudaMemcpyAsync(p->hy + r0, p->dy.p + r0, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
+                HM_CUDA(cudaStreamSynchronize(st));
+                for (int64_t i = 0; i < nr; i++) y[(r0 + i) * incy] = p->hy[r0 + i];
+            }
+        } else {
+            HM_CUDA(cudaStreamSynchronize(st));
+        }
         return HM_OK;
-    }
-    // x -> device
-    if (nc > 0) {
-        if (incx == 1) {
-            HM_CUDA(cudaMemcpyAsync(p->dx.p, x, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
-        } else {
-            if (!p->hx) HM_CUDA(cudaMallocHost((void **)&p->hx, (size_t)nc * 8));
-            for (int64_t j = 0; j < nc; j++) p->hx[j] = x[j * incx];
-            HM_CUDA(cudaMemcpyAsync(p->dx.p, p->hx, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
-        }
-    }
-    // y (owned rows) -> device when accumulating
-    if (nr > 0 && accumulate) {
-        if (incy == 1) {
-            HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, y + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, st));
-        } else {
-            if (!p->hy) HM_CUDA(cudaMallocHost((void **)&p->hy, (size_t)L.nrows * 8));
-            for (int64_t i = 0; i < nr; i++) p->hy[r0 + i] = y[(r0 + i) * incy];
-            HM_CUDA(cudaMemcpyAsync(p->dy.p + r0, p->hy + r0, (size_t)nr * 8, cudaMemcpyHostToDevice, st));
-        }
-    }
-    if (int32_t rc = hm_matvec_device(p, p->dx.p, p->dy.p, accumulate, st)) return rc;
-    if (nr > 0) {
-        if (incy == 1) {
-            HM_CUDA(cudaMemcpyAsync(y + r0, p->dy.p + r0, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
-            HM_CUDA(cudaStreamSynchronize(st));
-        } else {
-            if (!p->hy) HM_CUDA(cudaMallocHost((void **)&p->hy, (size_t)L.nrows * 8));
-            HM_CUDA(cudaMemcpyAsync(p->hy + r0, p->dy.p + r0, (size_t)nr * 8, cudaMemcpyDeviceToHost, st));
-            HM_CUDA(cudaStreamSynchronize(st));
-            for (int64_t i = 0; i < nr; i++) y[(r0 + i) * incy] = p->hy[r0 + i];
-        }
-    } else {
-        HM_CUDA(cudaStreamSynchronize(st));
-    }
-    return HM_OK;
+    });
 }
 
 // Adjoint apply y (+)= H' x.
 int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
-    const HmLayout &L = p->L;
-    if ((!dx && L.nrows > 0) || (!dy && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
-    if (L.adj_max_f > HM_SMAX) return fail(HM_ERR_UNSUPPORTED, "adjoint: a column segment is covered by too many ranks");
-    HM_DEVICE(p->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!p->adj_ready) {
-        HM_CUDA(cudaStreamSynchronize(st));
-        HM_CUDA(p->pq.alloc((size_t)std::max<int64_t>(L.pq_words, 1)));
-        HM_CUDA(p->qlist.upload(L.qlist, st));
-        HM_CUDA(p->core_q0.upload(L.core_q0, st));
-        HM_CUDA(p->core_qn.upload(L.core_qn, st));
-        HM_CUDA(p->colsegs.upload(L.colsegs, st));
-        HM_CUDA(p->colbases.upload(L.colbases, st));
-        {
-            std::vector<int32_t> big;
-            for (size_t c = 0; c < L.cores.size(); c++)
-                if (L.core_qn[c] > HM_CORE_BIG) big.push_back((int32_t)c);
-            p->nadjbig = (int)big.size();
-            HM_CUDA(p->adjbig.upload(big, st));
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
+        const HmLayout &L = p->L;
+        if ((!dx && L.nrows > 0) || (!dy && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+        if (L.adj_max_f > HM_SMAX) return fail(HM_ERR_UNSUPPORTED, "adjoint: a column segment is covered by too many ranks");
+        HM_DEVICE(p->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (!p->adj_ready) {
+            HM_CUDA(cudaStreamSynchronize(st));
+            HM_CUDA(p->pq.alloc((size_t)std::max<int64_t>(L.pq_words, 1)));
+            HM_CUDA(p->qlist.upload(L.qlist, st));
+            HM_CUDA(p->core_q0.upload(L.core_q0, st));
+            HM_CUDA(p->core_qn.upload(L.core_qn, st));
+            HM_CUDA(p->colsegs.upload(L.colsegs, st));
+            HM_CUDA(p->colbases.upload(L.colbases, st));
+            {
+                std::vector<int32_t> big;
+                for (size_t c = 0; c < L.cores.size(); c++)
+                    if (L.core_qn[c] > HM_CORE_BIG) big.push_back((int32_t)c);
+                p->nadjbig = (int)big.size();
+                HM_CUDA(p->adjbig.upload(big, st));
+            }
+            if (!p->s1ent.p) HM_CUDA(p->s1ent.upload(L.s1ent, st));
+            HM_CUDA(cudaStreamSynchronize(st));
+            p->adj_ready = true;
         }
-        if (!p->s1ent.p) HM_CUDA(p->s1ent.upload(L.s1ent, st));
-        HM_CUDA(cudaStreamSynchronize(st));
-        p->adj_ready = true;
-    }
-    HmAdjoint A;
-    A.items3 = p->items3.p;
-    A.items1 = p->items1.p;
-    A.n3 = (int64_t)L.items3.size();
-    A.n1 = (int64_t)L.items1.size();
-    A.ncores = (int64_t)L.cores.size();
-    A.nsegs = (int64_t)L.colsegs.size();
-    A.ustream = p->ustream.p;
-    A.vstream = p->vstream.p;
-    A.core = p->core.p;
-    A.blocks = p->cores.p;
-    A.q0 = p->core_q0.p;
-    A.qn = p->core_qn.p;
-    A.qlist = p->qlist.p;
-    A.s1ent = p->s1ent.p;
-    A.big = p->adjbig.p;
-    A.nbig = p->nadjbig;
-    A.segs = p->colsegs.p;
-    A.bases = p->colbases.p;
-    A.PQ = p->pq.p;
-    A.svec = p->svec.p;
-    A.max_r = std::max(L.max_r, 1);
-    HM_CUDA(hm_launch_adjoint(A, dx, dy, accumulate != 0, st));
-    return HM_OK;
+        HmAdjoint A;
+        A.items3 = p->items3.p;
+        A.items1 = p->items1.p;
+        A.n3 = (int64_t)L.items3.size();
+        A.n1 = (int64_t)L.items1.size();
+        A.ncores = (int64_t)L.cores.size();
+        A.nsegs = (int64_t)L.colsegs.size();
+        A.ustream = p->ustream.p;
+        A.vstream = p->vstream.p;
+        A.core = p->core.p;
+        A.blocks = p->cores.p;
+        A.q0 = p->core_q0.p;
+        A.qn = p->core_qn.p;
+        A.qlist = p->qlist.p;
+        A.s1ent = p->s1ent.p;
+        A.big = p->adjbig.p;
+        A.nbig = p->nadjbig;
+        A.segs = p->colsegs.p;
+        A.bases = p->colbases.p;
+        A.PQ = p->pq.p;
+        A.svec = p->svec.p;
+        A.max_r = std::max(L.max_r, 1);
+        HM_CUDA(hm_launch_adjoint(A, dx, dy, accumulate != 0, st));
+        return HM_OK;
+    });
 }
 
 int32_t hm_matvec_adjoint(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy, int32_t accumulate)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    const HmLayout &L = p->L;
-    if ((!x && L.nrows > 0) || (!y && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
-    if (incx <= 0 || incy <= 0) return fail(HM_ERR_INVALID, "strides must be positive (INCX, INCY >= 1 as in the reference)");
-    std::lock_guard<std::mutex> lock(p->mu);
-    HM_DEVICE(p->device);
-    const int64_t nr = L.nrows, nc = L.ncols;
-    // the forward path's staging buffers are reused with the roles of x and y swapped
-    if (!p->dx.p) HM_CUDA(p->dx.alloc((size_t)std::max<int64_t>(nc, 1)));
-    if (!p->dy.p) HM_CUDA(p->dy.alloc((size_t)std::max<int64_t>(nr, 1)));
-    cudaStream_t st = p->stream;
-    std::vector<double> hx((size_t)nr), hy((size_t)nc);
-    for (int64_t i = 0; i < nr; i++) hx[(size_t)i] = x[i * incx];
-    if (nr > 0) HM_CUDA(cudaMemcpyAsync(p->dy.p, hx.data(), (size_t)nr * 8, cudaMemcpyHostToDevice, st));
-    if (accumulate && nc > 0) {
-        for (int64_t j = 0; j < nc; j++) hy[(size_t)j] = y[j * incy];
-        HM_CUDA(cudaMemcpyAsync(p->dx.p, hy.data(), (size_t)nc * 8, cudaMemcpyHostToDevice, st));
-    }
-    if (int32_t rc = hm_matvec_adjoint_device(p, p->dy.p, p->dx.p, accumulate, st)) return rc;
-    if (nc > 0) HM_CUDA(cudaMemcpyAsync(hy.data(), p->dx.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
-    HM_CUDA(cudaStreamSynchronize(st));
-    for (int64_t j = 0; j < nc; j++) y[j * incy] = hy[(size_t)j];
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        const HmLayout &L = p->L;
+        if ((!x && L.nrows > 0) || (!y && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+        if (incx <= 0 || incy <= 0) return fail(HM_ERR_INVALID, "strides must be positive (INCX, INCY >= 1 as in the reference)");
+        std::lock_guard<std::mutex> lock(p->mu);
+        HM_DEVICE(p->device);
+        const int64_t nr = L.nrows, nc = L.ncols;
+        // the forward path's staging buffers are reused with the roles of x and y swapped
+        if (!p->dx.p) HM_CUDA(p->dx.alloc((size_t)std::max<int64_t>(nc, 1)));
+        if (!p->dy.p) HM_CUDA(p->dy.alloc((size_t)std::max<int64_t>(nr, 1)));
+        cudaStream_t st = p->stream;
+        // unit strides: straight from / to the caller's vectors; strided arguments are packed
+        // through the plan's pinned staging buffers (hy holds nrows words, hx ncols), as in hm_matvec
+        if (nr > 0) {
+            if (incx == 1) {
+                HM_CUDA(cudaMemcpyAsync(p->dy.p, x, (size_t)nr * 8, cudaMemcpyHostToDevice, st));
+            } else {
+                if (!p->hy) HM_CUDA(cudaMallocHost((void **)&p->hy, (size_t)nr * 8));
+                for (int64_t i = 0; i < nr; i++) p->hy[i] = x[i * incx];
+                HM_CUDA(cudaMemcpyAsync(p->dy.p, p->hy, (size_t)nr * 8, cudaMemcpyHostToDevice, st));
+            }
+        }
+        if (incy != 1 && nc > 0 && !p->hx) HM_CUDA(cudaMallocHost((void **)&p->hx, (size_t)nc * 8));
+        if (accumulate && nc > 0) {
+            if (incy == 1) {
+                HM_CUDA(cudaMemcpyAsync(p->dx.p, y, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+            } else {
+                for (int64_t j = 0; j < nc; j++) p->hx[j] = y[j * incy];
+                HM_CUDA(cudaMemcpyAsync(p->dx.p, p->hx, (size_t)nc * 8, cudaMemcpyHostToDevice, st));
+            }
+        }
+        if (int32_t rc = hm_matvec_adjoint_device(p, p->dy.p, p->dx.p, accumulate, st)) return rc;
+        if (nc > 0)
+            HM_CUDA(cudaMemcpyAsync(incy == 1 ? y : p->hx, p->dx.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, st));
+        HM_CUDA(cudaStreamSynchronize(st));
+        if (incy != 1)
+            for (int64_t j = 0; j < nc; j++) y[j * incy] = p->hx[j];
+        return HM_OK;
+    });
 }
 
 // Multi-RHS: Y[:, c] (+)= H X[:, c].  Columns are processed in panels of up to 64 with the
@@ -1167,169 +1252,185 @@ int32_t hm_matvec_adjoint(hm_plan *p, const double *x, int64_t incx, double *y, 
 int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t nrhs,
                          int32_t accumulate, void *stream)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
-    if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
-    if (nrhs == 0) return HM_OK;
-    const HmLayout &L = p->L;
-    if (ldx < std::max<int64_t>(L.ncols, 1) || ldy < std::max<int64_t>(L.nrows, 1))
-        return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
-    if ((!dX && L.ncols > 0) || (!dY && L.nrows > 0)) return fail(HM_ERR_NULL, "panel pointer is NULL");
-    if (nrhs == 1) return hm_matvec_device(p, dX, dY, accumulate, stream);
-    if ((size_t)L.max_r * 64 * sizeof(double) > 160 * 1024) {
-        // ranks beyond the panel kernels' shared-memory staging: column by column
-        for (int64_t c = 0; c < nrhs; c++)
-            if (int32_t rc = hm_matvec_device(p, dX + c * ldx, dY + c * ldy, accumulate, stream)) return rc;
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
+        if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
+        if (nrhs == 0) return HM_OK;
+        const HmLayout &L = p->L;
+        if (ldx < std::max<int64_t>(L.ncols, 1) || ldy < std::max<int64_t>(L.nrows, 1))
+            return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
+        if ((!dX && L.ncols > 0) || (!dY && L.nrows > 0)) return fail(HM_ERR_NULL, "panel pointer is NULL");
+        if (nrhs == 1) return hm_matvec_device(p, dX, dY, accumulate, stream);
+        if (!hm_panel_supports_rank(L.max_r, (int)std::min<int64_t>(nrhs, 64))) {
+            // ranks beyond the panel kernels' shared-memory staging: column by column
+            for (int64_t c = 0; c < nrhs; c++)
+                if (int32_t rc = hm_matvec_device(p, dX + c * ldx, dY + c * ldy, accumulate, stream)) return rc;
+            return HM_OK;
+        }
+        HM_DEVICE(p->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        for (int64_t c0 = 0; c0 < nrhs; c0 += 64) {
+            const int nc = (int)std::min<int64_t>(64, nrhs - c0);
+            const int CS = hm_panel_width(nc);
+            if (CS > p->ws_cs) {
+                HM_CUDA(cudaStreamSynchronize(st));
+                HM_CUDA(p->wXt.alloc((size_t)std::max<int64_t>(L.ncols, 1) * CS));
+                HM_CUDA(p->wPp.alloc((size_t)std::max<int64_t>(L.partial_words, 1) * CS));
+                HM_CUDA(p->wSp.alloc((size_t)std::max<int64_t>(L.s_words, 1) * CS));
+                HM_CUDA(p->wYt.alloc((size_t)std::max<int64_t>(L.nrows, 1) * CS));
+                p->ws_cs = CS;
+            }
+            cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
+            if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
+            HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st));
+            HM_CUDA(hm_launch_panel_stage1(CS, p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->wXt.p,
+                                           p->wPp.p, st));
+            if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
+            HM_CUDA(hm_launch_panel_stage2(CS, p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->wPp.p, p->core.p,
+                                           p->wSp.p, std::max(L.max_r, 1), st));
+            if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
+            for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
+                int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
+                HM_CUDA(hm_launch_panel_stage3(CS, p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->wXt.p,
+                                               p->wSp.p, p->wYt.p, r == 0 ? 0 : 1, st));
+            }
+            HM_CUDA(hm_launch_panel_out(p->wYt.p, CS, L.row_begin, L.row_end, nc, dY + c0 * ldy, ldy,
+                                        accumulate != 0, st));
+            if (ev) {
+                HM_CUDA(cudaEventRecord(ev[3], st));
+                p->tcount++;
+            }
+        }
         return HM_OK;
-    }
-    HM_DEVICE(p->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    for (int64_t c0 = 0; c0 < nrhs; c0 += 64) {
-        const int nc = (int)std::min<int64_t>(64, nrhs - c0);
-        const int CS = hm_panel_width(nc);
-        if (CS > p->ws_cs) {
-            HM_CUDA(cudaStreamSynchronize(st));
-            HM_CUDA(p->wXt.alloc((size_t)std::max<int64_t>(L.ncols, 1) * CS));
-            HM_CUDA(p->wPp.alloc((size_t)std::max<int64_t>(L.partial_words, 1) * CS));
-            HM_CUDA(p->wSp.alloc((size_t)std::max<int64_t>(L.s_words, 1) * CS));
-            HM_CUDA(p->wYt.alloc((size_t)std::max<int64_t>(L.nrows, 1) * CS));
-            p->ws_cs = CS;
-        }
-        cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
-        if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
-        HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st));
-        HM_CUDA(hm_launch_panel_stage1(CS, p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->wXt.p,
-                                       p->wPp.p, st));
-        if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
-        HM_CUDA(hm_launch_panel_stage2(CS, p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->wPp.p, p->core.p,
-                                       p->wSp.p, std::max(L.max_r, 1), st));
-        if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
-        for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
-            int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
-            HM_CUDA(hm_launch_panel_stage3(CS, p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->wXt.p,
-                                           p->wSp.p, p->wYt.p, r == 0 ? 0 : 1, st));
-        }
-        HM_CUDA(hm_launch_panel_out(p->wYt.p, CS, L.row_begin, L.row_end, nc, dY + c0 * ldy, ldy,
-                                    accumulate != 0, st));
-        if (ev) {
-            HM_CUDA(cudaEventRecord(ev[3], st));
-            p->tcount++;
-        }
-    }
-    return HM_OK;
+    });
 }
 
 int32_t hm_matmat(hm_plan *p, const double *X, int64_t ldx, double *Y, int64_t ldy, int64_t nrhs,
                   int32_t accumulate)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
-    if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
-    if (nrhs == 0) return HM_OK;
-    const HmLayout &L = p->L;
-    if (ldx < std::max<int64_t>(L.ncols, 1) || ldy < std::max<int64_t>(L.nrows, 1))
-        return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
-    if ((!X && L.ncols > 0) || (!Y && L.nrows > 0)) return fail(HM_ERR_NULL, "panel pointer is NULL");
-    std::lock_guard<std::mutex> lock(p->mu);
-    HM_DEVICE(p->device);
-    cudaStream_t st = p->stream;
-    const int64_t nc = std::max<int64_t>(L.ncols, 1), nr = std::max<int64_t>(L.nrows, 1);
-    if (nrhs > p->nrhs_cap) {
-        HM_CUDA(p->dX.alloc((size_t)nc * nrhs));
-        HM_CUDA(p->dY.alloc((size_t)nr * nrhs));
-        p->nrhs_cap = nrhs;
-    }
-    const int64_t r0 = L.row_begin, rows = L.row_end - L.row_begin;
-    if (L.ncols > 0)
-        HM_CUDA(cudaMemcpy2DAsync(p->dX.p, (size_t)nc * 8, X, (size_t)ldx * 8, (size_t)L.ncols * 8, (size_t)nrhs,
-                                  cudaMemcpyHostToDevice, st));
-    if (accumulate && rows > 0)
-        HM_CUDA(cudaMemcpy2DAsync(p->dY.p + r0, (size_t)nr * 8, Y + r0, (size_t)ldy * 8, (size_t)rows * 8,
-                                  (size_t)nrhs, cudaMemcpyHostToDevice, st));
-    if (int32_t rc = hm_matmat_device(p, p->dX.p, nc, p->dY.p, nr, nrhs, accumulate, st)) return rc;
-    if (rows > 0)
-        HM_CUDA(cudaMemcpy2DAsync(Y + r0, (size_t)ldy * 8, p->dY.p + r0, (size_t)nr * 8, (size_t)rows * 8,
-                                  (size_t)nrhs, cudaMemcpyDeviceToHost, st));
-    HM_CUDA(cudaStreamSynchronize(st));
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
+        if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
+        if (nrhs == 0) return HM_OK;
+        const HmLayout &L = p->L;
+        if (ldx < std::max<int64_t>(L.ncols, 1) || ldy < std::max<int64_t>(L.nrows, 1))
+            return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
+        if ((!X && L.ncols > 0) || (!Y && L.nrows > 0)) return fail(HM_ERR_NULL, "panel pointer is NULL");
+        std::lock_guard<std::mutex> lock(p->mu);
+        HM_DEVICE(p->device);
+        cudaStream_t st = p->stream;
+        const int64_t nc = std::max<int64_t>(L.ncols, 1), nr = std::max<int64_t>(L.nrows, 1);
+        if (nrhs > p->nrhs_cap) {
+            HM_CUDA(p->dX.alloc((size_t)nc * nrhs));
+            HM_CUDA(p->dY.alloc((size_t)nr * nrhs));
+            p->nrhs_cap = nrhs;
+        }
+        const int64_t r0 = L.row_begin, rows = L.row_end - L.row_begin;
+        if (L.ncols > 0)
+            HM_CUDA(cudaMemcpy2DAsync(p->dX.p, (size_t)nc * 8, X, (size_t)ldx * 8, (size_t)L.ncols * 8, (size_t)nrhs,
+                                      cudaMemcpyHostToDevice, st));
+        if (accumulate && rows > 0)
+            HM_CUDA(cudaMemcpy2DAsync(p->dY.p + r0, (size_t)nr * 8, Y + r0, (size_t)ldy * 8, (size_t)rows * 8,
+                                      (size_t)nrhs, cudaMemcpyHostToDevice, st));
+        if (int32_t rc = hm_matmat_device(p, p->dX.p, nc, p->dY.p, nr, nrhs, accumulate, st)) return rc;
+        if (rows > 0)
+            HM_CUDA(cudaMemcpy2DAsync(Y + r0, (size_t)ldy * 8, p->dY.p + r0, (size_t)nr * 8, (size_t)rows * 8,
+                                      (size_t)nrhs, cudaMemcpyDeviceToHost, st));
+        HM_CUDA(cudaStreamSynchronize(st));
+        return HM_OK;
+    });
 }
 
 // ---------------------------------------------------------------------------
 // test hooks
 // ---------------------------------------------------------------------------
+int32_t hm_debug_fail_alloc(int64_t nth)
+{
+    hm_fault_arm(nth);
+    return HM_OK;
+}
+
 int32_t hm_plan_num_leaves(const hm_plan *p, int64_t *out)
 {
-    if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
-    *out = (int64_t)p->L.leaves.size();
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
+        *out = (int64_t)p->L.leaves.size();
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_leaf_info(const hm_plan *p, int64_t leaf, int32_t *kind, int64_t *row0, int64_t *col0,
                           int64_t *m, int64_t *n, int64_t *r)
 {
-    if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-    if (leaf < 0 || leaf >= (int64_t)p->L.leaves.size()) return fail(HM_ERR_RANGE, "leaf index out of range");
-    const HmLeaf &l = p->L.leaves[(size_t)leaf];
-    if (kind) *kind = l.kind;
-    if (row0) *row0 = l.row0;
-    if (col0) *col0 = l.col0;
-    if (m) *m = l.m;
-    if (n) *n = l.n;
-    if (r) *r = l.ru;
-    return HM_OK;
+    return guarded([&]() -> int32_t {
+        if (!p) return fail(HM_ERR_NULL, "plan is NULL");
+        if (leaf < 0 || leaf >= (int64_t)p->L.leaves.size()) return fail(HM_ERR_RANGE, "leaf index out of range");
+        const HmLeaf &l = p->L.leaves[(size_t)leaf];
+        if (kind) *kind = l.kind;
+        if (row0) *row0 = l.row0;
+        if (col0) *col0 = l.col0;
+        if (m) *m = l.m;
+        if (n) *n = l.n;
+        if (r) *r = l.ru;
+        return HM_OK;
+    });
 }
 
 int32_t hm_plan_read_leaf(hm_plan *p, int64_t leaf, int32_t which, double *out, int64_t cap)
 {
-    if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
-    if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
-    if (leaf < 0 || leaf >= (int64_t)p->L.leaves.size()) return fail(HM_ERR_RANGE, "leaf index out of range");
-    std::lock_guard<std::mutex> lock(p->mu);
-    HM_DEVICE(p->device);
-    HmLayout &L = p->L;
-    if (!p->indexed) {
-        for (size_t i = 0; i < L.fill1.size(); i++) p->idx1.emplace(L.fill1[i].leaf, i);
-        for (size_t i = 0; i < L.fill3.size(); i++) p->idx3.emplace(L.fill3[i].leaf, i);
-        p->indexed = true;
-    }
-    const HmLeaf &l = L.leaves[(size_t)leaf];
-    const bool dense = l.kind == HM_LEAF_DENSE;
-    int64_t need = 0;
-    if (which == 0) need = dense ? -1 : l.m * l.ru;
-    else if (which == 1) need = dense ? -1 : (l.kind == HM_LEAF_BARY2D ? (int64_t)l.ru * l.rv : l.ru);
-    else if (which == 2) need = dense ? -1 : l.n * l.rv;
-    else if (which == 3) need = dense ? l.m * l.n : -1;
-    else return fail(HM_ERR_INVALID, "which must be 0..3");
-    if (need < 0) return fail(HM_ERR_INVALID, "leaf kind has no such factor");
-    if (cap < need) return fail(HM_ERR_SHAPE, "output capacity %lld < %lld", (long long)cap, (long long)need);
-    for (int64_t i = 0; i < need; i++) out[i] = 0.0; // rows outside this part stay 0
-    if (which == 1) {
-        for (size_t c = 0; c < L.cores.size(); c++)
-            if (L.core_leaf[c] == (int32_t)leaf)
-                HM_CUDA(cudaMemcpy(out, p->core.p + L.cores[c].core, (size_t)need * 8, cudaMemcpyDeviceToHost));
-        return HM_OK;
-    }
-    if (which == 0 || which == 3) {
-        auto range = p->idx3.equal_range((int32_t)leaf);
+    return guarded([&]() -> int32_t {
+        if (!p || !out) return fail(HM_ERR_NULL, "NULL argument");
+        if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
+        if (leaf < 0 || leaf >= (int64_t)p->L.leaves.size()) return fail(HM_ERR_RANGE, "leaf index out of range");
+        std::lock_guard<std::mutex> lock(p->mu);
+        HM_DEVICE(p->device);
+        HmLayout &L = p->L;
+        if (!p->indexed) {
+            for (size_t i = 0; i < L.fill1.size(); i++) p->idx1.emplace(L.fill1[i].leaf, i);
+            for (size_t i = 0; i < L.fill3.size(); i++) p->idx3.emplace(L.fill3[i].leaf, i);
+            p->indexed = true;
+        }
+        const HmLeaf &l = L.leaves[(size_t)leaf];
+        const bool dense = l.kind == HM_LEAF_DENSE;
+        int64_t need = 0;
+        if (which == 0) need = dense ? -1 : l.m * l.ru;
+        else if (which == 1) need = dense ? -1 : (l.kind == HM_LEAF_BARY2D ? (int64_t)l.ru * l.rv : l.ru);
+        else if (which == 2) need = dense ? -1 : l.n * l.rv;
+        else if (which == 3) need = dense ? l.m * l.n : -1;
+        else return fail(HM_ERR_INVALID, "which must be 0..3");
+        if (need < 0) return fail(HM_ERR_INVALID, "leaf kind has no such factor");
+        if (cap < need) return fail(HM_ERR_SHAPE, "output capacity %lld < %lld", (long long)cap, (long long)need);
+        for (int64_t i = 0; i < need; i++) out[i] = 0.0; // rows outside this part stay 0
+        if (which == 1) {
+            for (size_t c = 0; c < L.cores.size(); c++)
+                if (L.core_leaf[c] == (int32_t)leaf)
+                    HM_CUDA(cudaMemcpy(out, p->core.p + L.cores[c].core, (size_t)need * 8, cudaMemcpyDeviceToHost));
+            return HM_OK;
+        }
+        if (which == 0 || which == 3) {
+            auto range = p->idx3.equal_range((int32_t)leaf);
+            for (auto it = range.first; it != range.second; ++it) {
+                const HmFill &f = L.fill3[it->second];
+                // kn columns of F rows (ld Fp) -> out[(off + i) + (k0 + k) * m]
+                HM_CUDA(cudaMemcpy2D(out + f.off + (int64_t)f.k0 * l.m, (size_t)l.m * 8, p->ustream.p + f.dst,
+                                     (size_t)f.Fp * 8, (size_t)f.F * 8, (size_t)f.kn, cudaMemcpyDeviceToHost));
+            }
+            return HM_OK;
+        }
+        auto range = p->idx1.equal_range((int32_t)leaf);
+        std::vector<double> tmp;
         for (auto it = range.first; it != range.second; ++it) {
-            const HmFill &f = L.fill3[it->second];
-            // kn columns of F rows (ld Fp) -> out[(off + i) + (k0 + k) * m]
-            HM_CUDA(cudaMemcpy2D(out + f.off + (int64_t)f.k0 * l.m, (size_t)l.m * 8, p->ustream.p + f.dst,
-                                 (size_t)f.Fp * 8, (size_t)f.F * 8, (size_t)f.kn, cudaMemcpyDeviceToHost));
+            const HmFill &f = L.fill1[it->second];
+            tmp.resize((size_t)f.S * f.kn);
+            HM_CUDA(cudaMemcpy2D(tmp.data(), (size_t)f.kn * 8, p->vstream.p + f.dst, (size_t)f.Fp * 8,
+                                 (size_t)f.kn * 8, (size_t)f.S, cudaMemcpyDeviceToHost));
+            for (int s = 0; s < f.S; s++)
+                for (int k = 0; k < f.kn; k++) out[(f.off + s) + (int64_t)(f.k0 + k) * l.n] = tmp[(size_t)s * f.kn + k];
         }
         return HM_OK;
-    }
-    auto range = p->idx1.equal_range((int32_t)leaf);
-    std::vector<double> tmp;
-    for (auto it = range.first; it != range.second; ++it) {
-        const HmFill &f = L.fill1[it->second];
-        tmp.resize((size_t)f.S * f.kn);
-        HM_CUDA(cudaMemcpy2D(tmp.data(), (size_t)f.kn * 8, p->vstream.p + f.dst, (size_t)f.Fp * 8,
-                             (size_t)f.kn * 8, (size_t)f.S, cudaMemcpyDeviceToHost));
-        for (int s = 0; s < f.S; s++)
-            for (int k = 0; k < f.kn; k++) out[(f.off + s) + (int64_t)(f.k0 + k) * l.n] = tmp[(size_t)s * f.kn + k];
-    }
-    return HM_OK;
+    });
 }
 
 } // extern "C"

@@ -110,6 +110,7 @@ cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *ru
 
 // many right-hand sides (hm_panel.cu): panels are row-major with pitch CS = hm_panel_width(nrhs)
 int hm_panel_width(int nrhs);
+bool hm_panel_supports_rank(int max_r, int nrhs);
 cudaError_t hm_launch_panel_in(const double *X, int64_t ldx, int64_t n, int nrhs, int CS, double *Xt,
                                cudaStream_t st);
 cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1, int nrhs, double *Y,

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <new>
 #include <numeric>
 
 namespace {
@@ -90,12 +91,25 @@ Cover cover_pieces(const std::vector<int64_t> &starts, size_t nleaves, RangeFn r
 
 } // namespace
 
+namespace {
+thread_local int64_t g_fault_countdown = -1;
+}
+
+void hm_fault_arm(int64_t nth) { g_fault_countdown = nth; }
+
+void hm_fault_checkpoint()
+{
+    if (g_fault_countdown < 0) return;
+    if (g_fault_countdown-- == 0) throw std::bad_alloc();
+}
+
 std::vector<int64_t> hm_partition_rows(const std::vector<HmLeaf> &leaves, int64_t nrows,
                                        int nparts)
 {
     std::vector<int64_t> cuts((size_t)nparts + 1, nrows);
     cuts[0] = 0;
     if (nparts <= 1 || nrows <= 0) return cuts;
+    hm_fault_checkpoint();
     // candidate cut points: block-row boundaries, refined every 128 rows
     std::vector<int64_t> b{0, nrows};
     for (const HmLeaf &l : leaves) {
@@ -109,35 +123,75 @@ std::vector<int64_t> hm_partition_rows(const std::vector<HmLeaf> &leaves, int64_
     for (size_t i = 0; i + 1 < b.size(); i++)
         for (int64_t p = b[i]; p < b[i + 1]; p += 128) cand.push_back(p);
     cand.push_back(nrows);
-    // words per row on each candidate interval (difference array)
-    std::vector<double> diff(cand.size() + 1, 0.0);
+    const size_t nc = cand.size();
+    // cost of the part [cand[i], cand[j]) = rowc[j] - rowc[i]      (U rows, dense tile rows, y)
+    //                                     + vbeg[j] - vend[i]      (V + core of every low-rank leaf
+    //                                                               with row0 < cand[j] and row end > cand[i])
+    //                                     + ncols                  (x)
+    std::vector<double> diff(nc + 1, 0.0), vbeg(nc, 0.0), vend(nc, 0.0);
+    double ncols_seen = 0.0;
     for (const HmLeaf &l : leaves) {
         if (!leaf_live(l)) continue;
-        double w = (double)zlen(l);
-        if (l.kind != HM_LEAF_DENSE) w += ((double)l.n * l.rv + (double)core_words_of(l)) / (double)l.m;
         int64_t lo = std::max<int64_t>(l.row0, 0), hi = std::min(l.row0 + l.m, nrows);
         if (hi <= lo) continue;
+        ncols_seen = std::max(ncols_seen, (double)(l.col0 + l.n));
         size_t ilo = (size_t)(std::lower_bound(cand.begin(), cand.end(), lo) - cand.begin());
         size_t ihi = (size_t)(std::lower_bound(cand.begin(), cand.end(), hi) - cand.begin());
-        diff[ilo] += w;
-        diff[ihi] -= w;
+        diff[ilo] += (double)zlen(l);
+        diff[ihi] -= (double)zlen(l);
+        if (l.kind != HM_LEAF_DENSE) {
+            const double vw = (double)l.n * l.rv + (double)core_words_of(l);
+            if (ilo + 1 < nc) vbeg[ilo + 1] += vw; // counted by every cut j > ilo (row0 < cand[j])
+            vend[ihi] += vw;                       // dropped by every cut i >= ihi (row end <= cand[i])
+        }
     }
-    std::vector<double> cum(cand.size(), 0.0);
+    std::vector<double> rowc(nc, 0.0);
     double w = 0.0;
-    for (size_t i = 0; i + 1 < cand.size(); i++) {
+    for (size_t i = 0; i + 1 < nc; i++) {
         w += diff[i];
-        cum[i + 1] = cum[i] + (w + 2.0) * (double)(cand[i + 1] - cand[i]); // +2: x and y words
+        rowc[i + 1] = rowc[i] + (w + 1.0) * (double)(cand[i + 1] - cand[i]); // +1: the y word
     }
-    double total = cum.back();
-    size_t last = 0;
-    for (int p = 1; p < nparts; p++) {
-        double target = total * (double)p / (double)nparts;
-        size_t i = (size_t)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
-        if (i > 0 && i < cum.size() && target - cum[i - 1] < cum[i] - target) i -= 1;
-        i = std::min(std::max(i, last), cand.size() - 1);
-        cuts[(size_t)p] = cand[i];
-        last = i;
+    for (size_t i = 1; i < nc; i++) {
+        vbeg[i] += vbeg[i - 1];
+        vend[i] += vend[i - 1];
     }
+    auto cost = [&](size_t i, size_t j) { return rowc[j] - rowc[i] + vbeg[j] - vend[i] + ncols_seen; };
+    // the farthest j > i with cost(i, j) <= T (cost grows with j); at least i + 1
+    auto reach = [&](size_t i, double T) {
+        size_t lo = i + 1, hi = nc - 1;
+        if (cost(i, lo) > T) return lo;
+        while (lo < hi) {
+            size_t mid = (lo + hi + 1) / 2;
+            if (cost(i, mid) <= T)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        return lo;
+    };
+    auto parts_needed = [&](double T) {
+        size_t i = 0;
+        int k = 0;
+        while (i < nc - 1) {
+            if (cost(i, i + 1) > T) return nparts + 1; // a single candidate interval exceeds T
+            i = reach(i, T);
+            if (++k > nparts) return k;
+        }
+        return k;
+    };
+    double tlo = 0.0, thi = cost(0, nc - 1);
+    for (int it = 0; it < 60; it++) {
+        double mid = 0.5 * (tlo + thi);
+        if (parts_needed(mid) <= nparts)
+            thi = mid;
+        else
+            tlo = mid;
+    }
+    // greedy cuts for the bound thi: every part but the last is filled up to the bound
+    std::vector<size_t> ci((size_t)nparts + 1, nc - 1);
+    ci[0] = 0;
+    for (int p = 1; p < nparts; p++) ci[(size_t)p] = ci[(size_t)p - 1] < nc - 1 ? reach(ci[(size_t)p - 1], thi) : nc - 1;
+    for (int p = 1; p < nparts; p++) cuts[(size_t)p] = cand[ci[(size_t)p]];
     return cuts;
 }
 
@@ -148,6 +202,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
     if (nrows < 0 || ncols < 0) return "negative matrix extent";
     if (nrows >= (int64_t)1 << 31 || ncols >= (int64_t)1 << 31) return "matrix extent >= 2^31";
     if (prm.cmax1 > prm.smax || prm.cmax0 > prm.smax) return "layout parameters: cmax > smax";
+    hm_fault_checkpoint();
     L = HmLayout();
     L.nrows = nrows;
     L.ncols = ncols;
@@ -333,6 +388,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
     }
 
     // ---- stage 1: column segments ----
+    hm_fault_checkpoint();
     {
         std::vector<int32_t> npl(L.cores.size(), 0);
         struct Pending {

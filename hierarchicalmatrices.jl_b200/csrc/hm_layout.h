@@ -68,9 +68,18 @@ struct HmLayout {
 };
 
 // Row cut points [0 = c_0 <= c_1 <= ... <= c_nparts = nrows], on block-row
-// boundaries, balancing the stored words per part.
+// boundaries, minimising the largest number of words any part streams per matvec: its U
+// rows and dense tile rows, plus the whole V and core of every low-rank leaf it touches
+// (a leaf that straddles a cut has V and F replicated on both sides), plus x and its y rows.
 std::vector<int64_t> hm_partition_rows(const std::vector<HmLeaf> &leaves, int64_t nrows,
                                        int nparts);
+
+// Fault injection for the C ABI's exception barrier (tests only): after hm_fault_arm(n) the
+// n-th checkpoint passed on the calling thread (n = 0: the next one) throws std::bad_alloc, as a
+// failed container allocation at that point would; n < 0 disarms.  Checkpoints sit at the
+// allocation-heavy steps of the planner and the tree builder.
+void hm_fault_arm(int64_t nth);
+void hm_fault_checkpoint();
 
 // Returns "" on success, else an error message.
 std::string hm_build_layout(const std::vector<HmLeaf> &all_leaves, int64_t nrows, int64_t ncols,

@@ -814,13 +814,17 @@ cudaError_t launch_panel(const HmItem *items, int64_t nitems, const HmRun *runs,
     return cudaGetLastError();
 }
 
+// shared memory of the stage-2 panel kernel: (max_r + 3) rows of NB*8 columns, pitch padded by 4
+constexpr size_t HM_PANEL_SMEM_CAP = 160 * 1024;
+inline size_t core_panel_smem(int max_r, int NB) { return (size_t)(max_r + 3) * (NB * 8 + 4) * sizeof(double); }
+
 template <int NB>
 cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist, const double *Pp,
                               const double *core, double *Sp, int max_r, cudaStream_t st)
 {
     if (nblocks <= 0) return cudaSuccess;
-    const size_t smem = (size_t)(max_r + 3) * (NB * 8 + 4) * sizeof(double);
-    if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
+    const size_t smem = core_panel_smem(max_r, NB);
+    if (smem > HM_PANEL_SMEM_CAP) return cudaErrorInvalidConfiguration;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(hm_core_panel_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
@@ -834,6 +838,13 @@ cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const 
 } // namespace
 
 int hm_panel_width(int nrhs) { return nrhs <= 16 ? 16 : nrhs <= 32 ? 32 : 64; }
+
+// The panel kernels stage a leaf's rank in shared memory; beyond this the caller applies the
+// columns one by one (the same formula the stage-2 launcher checks).
+bool hm_panel_supports_rank(int max_r, int nrhs)
+{
+    return core_panel_smem(std::max(max_r, 1), hm_panel_width(nrhs) / 8) <= HM_PANEL_SMEM_CAP;
+}
 
 cudaError_t hm_launch_panel_in(const double *X, int64_t ldx, int64_t n, int nrhs, int CS, double *Xt,
                                cudaStream_t st)

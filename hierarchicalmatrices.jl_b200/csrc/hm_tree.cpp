@@ -9,6 +9,7 @@
 // block column, columns from the first block row), not from the index ranges,
 // so degenerate splits land where the reference's walk would put them.
 #include "hm_tree.h"
+#include "hm_layout.h"
 
 #include <cfloat>
 #include <cmath>
@@ -218,6 +219,7 @@ std::string hm_kernel_tree(const double *x, int64_t nx, const double *y, int64_t
                            double b, double c, double d, std::vector<HmLeaf> &leaves,
                            int64_t &nrows, int64_t &ncols)
 {
+    hm_fault_checkpoint();
     Builder bld;
     bld.x = x;
     bld.y = y;
@@ -232,6 +234,7 @@ std::string hm_kernel_tree(const double *x, int64_t nx, const double *y, int64_t
     nrows = bld.nodes[(size_t)root].rows;
     ncols = bld.nodes[(size_t)root].cols;
     leaves.clear();
+    hm_fault_checkpoint();
     bld.emit(root, 0, 0, leaves);
     // the leaves address points by their own ranges; they must exist
     for (const HmLeaf &l : leaves)

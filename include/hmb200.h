@@ -247,6 +247,12 @@ HM_API int32_t hm_plan_timing_end(hm_plan *p, double *stage_ms3, int64_t *ncalls
 /* Number of kernel launches one hm_matvec_device enqueues (bench bookkeeping). */
 HM_API int32_t hm_plan_launches_per_matvec(const hm_plan *p);
 
+/* Test hook for the exception barrier: every entry point catches C++ exceptions and returns
+ * HM_ERR_NOMEM (std::bad_alloc / std::length_error) or HM_ERR_INVALID.  After
+ * hm_debug_fail_alloc(n) the n-th allocation checkpoint of the planner / tree builder passed on
+ * the calling thread (0 = the next) fails as an exhausted host would; n < 0 disarms. */
+HM_API int32_t hm_debug_fail_alloc(int64_t nth);
+
 /* Test hooks: copy packed factors back to the host to compare the on-device
  * assembly with the oracle's factors.  which: 0 = U (m x ru), 1 = core
  * (F ru x rv | Sigma), 2 = V (n x rv), 3 = dense A (m x n); tight column-major. */

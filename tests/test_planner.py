@@ -146,6 +146,62 @@ def test_row_partition(hm, O, nparts):
     assert sum(p["part_u_words"] + p["part_dense_words"] for p in parts) == whole["part_u_words"] + whole["part_dense_words"]
 
 
+@pytest.mark.parametrize("dist", ["cheb", "unif"])
+def test_row_partition_balances_true_bytes_2pow20(hm, dist):
+    """hm_partition_rows minimises the largest per-part byte count *including* the V / F
+    replicas of leaves that straddle a cut."""
+    n = 1 << 20
+    if dist == "cheb":
+        x, y = hm.chebyshevpoints(n), hm.chebyshevpoints(n, 2)
+    else:
+        i = np.arange(1, n + 1, dtype=np.float64)
+        x, y = 1.0 - 2.0 * (i - 0.5) / n, 1.0 - 2.0 * (i - 0.25) / n
+    whole = hm.KernelMatrix.layout_stats(x, y, 1.0, -1.0, 1.0, -1.0)["algorithmic_bytes"]
+    for nparts in (2, 4, 8):
+        b = [hm.KernelMatrix.layout_stats(x, y, 1.0, -1.0, 1.0, -1.0, p, nparts)["part_algorithmic_bytes"]
+             for p in range(nparts)]
+        # (the uniform tree on 4 parts has its optimum at the clean quarter cuts, 2.4 % apart:
+        # moving a cut into a block replicates more V words than it moves)
+        assert max(b) <= 1.03 * (sum(b) / nparts), (nparts, b)
+        # against the unreplicated ideal: the round-1 cuts were at 1.131 (cheb) / 1.122 (unif) for 8
+        assert max(b) <= (1.0 + 0.01 * (nparts + 1)) * whole / nparts, (nparts, b)
+
+
+def test_no_exception_crosses_the_abi(hm, O):
+    """every entry point returns a status; a host allocation failure inside the
+    planner or the tree builder becomes HM_ERR_NOMEM, not std::terminate."""
+    L = hm.lib()
+    dp = C.POINTER(C.c_double)
+    x, y, (a, b, c, d) = O.example_points(3000, "cheb")
+    s = hm._lib.Stats()
+    args = (x.ctypes.data_as(dp), 3000, y.ctypes.data_as(dp), 3000, a, b, c, d)
+    assert L.hm_assemble_kernel_stats(*args, 0, 2, C.byref(s)) == 0
+    hit = 0
+    for nth in range(8):
+        L.hm_debug_fail_alloc(nth)
+        rc = L.hm_assemble_kernel_stats(*args, 0, 2, C.byref(s))
+        L.hm_debug_fail_alloc(-1)
+        if rc != 0:
+            assert rc == 6 and b"memory" in L.hm_last_error()  # HM_ERR_NOMEM
+            hit += 1
+    assert hit >= 4  # tree entry, leaf emission, layout entry, partition, stage-1 tables
+    cnt = C.c_int64()
+    L.hm_debug_fail_alloc(0)
+    assert L.hm_kernel_tree_leaves(*args, None, 0, C.byref(cnt)) == 6
+    L.hm_debug_fail_alloc(-1)
+    # structure-only builder: the layout of pushed leaves
+    bld = C.c_void_p()
+    hm._lib.check(L.hm_builder_create(C.byref(bld), 100, 100, 0, -1))
+    hm._lib.check(L.hm_builder_add_dense(bld, None, 100, 100, 100, 0, 0))
+    L.hm_debug_fail_alloc(0)
+    assert L.hm_builder_layout_stats(bld, 0, 1, C.byref(s)) == 6
+    L.hm_debug_fail_alloc(-1)
+    assert L.hm_builder_layout_stats(bld, 0, 1, C.byref(s)) == 0 and s.n_dense == 1
+    L.hm_builder_destroy(bld)
+    # the library is still usable afterwards
+    assert L.hm_assemble_kernel_stats(*args, 0, 1, C.byref(s)) == 0 and s.nrows == 3000
+
+
 def test_builder_validation_and_structure_only_mode(hm):
     L = hm.lib()
     b = C.c_void_p()

@@ -78,6 +78,14 @@ SIGNATURES = {
     "hm_matvec": (_i32, [_vp, _dp, _i64, _dp, _i64, _i32]),
     "hm_matvec_device": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "hm_matvec_device_allgather": (_i32, [_vp, _vp, C.POINTER(C.c_uint64), _i32, _i32, _i32, _vp]),
+    "hm_dist_get_id": (_i32, [_vp]),
+    "hm_dist_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "hm_dist_buffers": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "hm_dist_bcast_x": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "hm_dist_matvec_device": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "hm_dist_barrier": (_i32, [_vp, _vp]),
+    "hm_dist_check": (_i32, [_vp]),
+    "hm_dist_matvec": (_i32, [_vp, _dp, _i64, _dp, _i64, _i32, _i32]),
     "hm_matvec_adjoint": (_i32, [_vp, _dp, _i64, _dp, _i64, _i32]),
     "hm_matvec_adjoint_device": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "hm_matmat": (_i32, [_vp, _dp, _i64, _dp, _i64, _i64, _i32]),

@@ -39,6 +39,7 @@ __all__ = [
     "cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel", "Plan", "flatten",
     "chebyshevpoints", "HmError", "rmul_", "lmul_", "scale_", "adjoint", "Adjoint",
     "chebyshevbarycentricweights", "EvenBarycentricMatrix", "barycentricmatrix", "Transpose", "transpose",
+    "dist_unique_id",
 ]
 
 Matrix = np.ndarray  # the dense leaf type of the reference
@@ -195,6 +196,13 @@ class BarycentricMatrix2D:
 
 
 # --------------------------------------------------------------------------- plan handle
+def dist_unique_id() -> bytes:
+    """128-byte id for `Plan.dist_init` (ncclGetUniqueId); create on one rank, send to all."""
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.lib().hm_dist_get_id(buf))
+    return buf.raw
+
+
 class Plan:
     """Owning handle on an `hm_plan` (immutable packed operator on one GPU)."""
 
@@ -230,29 +238,50 @@ class Plan:
     def launches_per_matvec(self) -> int:
         return int(_lib.lib().hm_plan_launches_per_matvec(self._h))
 
+    @staticmethod
+    def _check_vec(a, nm, n, inc, off):
+        """The raw pointer handed to the C ABI must cover off + (n-1)*inc (cudaMemcpy has no bounds)."""
+        if not isinstance(a, np.ndarray) or a.dtype != np.float64:
+            raise TypeError(f"{nm} must be a Float64 array (MethodError in the reference: all eltypes equal)")
+        if a.ndim != 1 or (a.size > 1 and a.strides[0] != 8):
+            raise ValueError(f"{nm} must be a contiguous vector (use incx/incy for strides)")
+        if inc < 1 or off < 0:
+            raise ValueError(f"{nm}: stride must be >= 1 and offset >= 0")
+        if n > 0 and off + (n - 1) * inc >= a.size:
+            raise ValueError(f"{nm} has {a.size} elements; offset {off} + ({n}-1)*{inc} is out of range "
+                             f"(BoundsError in the reference)")
+
     # y[i*incy] (+)= (H x)[i]; host arrays, strides in elements
     def matvec(self, x: np.ndarray, y: np.ndarray, incx=1, incy=1, accumulate=True, xoff=0, yoff=0):
-        for a, nm in ((x, "x"), (y, "y")):
-            if a.dtype != np.float64:
-                raise TypeError(f"{nm} must be Float64 (MethodError in the reference: all eltypes equal)")
-        isz = 8
-        px = C.cast(x.ctypes.data + xoff * isz, _dp)
-        py = C.cast(y.ctypes.data + yoff * isz, _dp)
+        nr, nc = self.shape
+        self._check_vec(x, "x", nc, incx, xoff)
+        self._check_vec(y, "y", nr, incy, yoff)
+        px = C.cast(x.ctypes.data + xoff * 8, _dp)
+        py = C.cast(y.ctypes.data + yoff * 8, _dp)
         _lib.check(_lib.lib().hm_matvec(self._h, px, incx, py, incy, 1 if accumulate else 0))
         return y
 
     # y[j*incy] (+)= (H' x)[j]
     def rmatvec(self, x: np.ndarray, y: np.ndarray, incx=1, incy=1, accumulate=True, xoff=0, yoff=0):
-        for a, nm in ((x, "x"), (y, "y")):
-            if a.dtype != np.float64:
-                raise TypeError(f"{nm} must be Float64")
+        nr, nc = self.shape
+        self._check_vec(x, "x", nr, incx, xoff)
+        self._check_vec(y, "y", nc, incy, yoff)
         px = C.cast(x.ctypes.data + xoff * 8, _dp)
         py = C.cast(y.ctypes.data + yoff * 8, _dp)
         _lib.check(_lib.lib().hm_matvec_adjoint(self._h, px, incx, py, incy, 1 if accumulate else 0))
         return y
 
     def matmat(self, X: np.ndarray, Y: np.ndarray, accumulate=True):
-        assert X.flags.f_contiguous and Y.flags.f_contiguous and X.dtype == Y.dtype == np.float64
+        nr, nc = self.shape
+        for a, nm, rows in ((X, "X", nc), (Y, "Y", nr)):
+            if not isinstance(a, np.ndarray) or a.dtype != np.float64 or a.ndim != 2:
+                raise TypeError(f"{nm} must be a Float64 matrix")
+            if not a.flags.f_contiguous:
+                raise ValueError(f"{nm} must be column-major (Fortran order)")
+            if a.shape[0] != rows:
+                raise ValueError(f"{nm} has {a.shape[0]} rows, the operator needs {rows}")
+        if X.shape[1] != Y.shape[1]:
+            raise ValueError("X and Y must have the same number of columns")
         nrhs = X.shape[1]
         _lib.check(_lib.lib().hm_matmat(
             self._h, X.ctypes.data_as(_dp), max(X.shape[0], 1), Y.ctypes.data_as(_dp), max(Y.shape[0], 1),
@@ -268,6 +297,54 @@ class Plan:
         arr = (C.c_uint64 * len(ypeers))(*[int(a) for a in ypeers])
         _lib.check(_lib.lib().hm_matvec_device_allgather(self._h, dx, arr, len(ypeers), self_rank,
                                                          1 if accumulate else 0, stream))
+
+    # ---- multi-GPU: this plan is block-row part `rank` of `nranks`, one process per GPU ----
+    def dist_init(self, uid: bytes, nranks: int, rank: int):
+        """Collective.  `uid` = `dist_unique_id()` of one rank, distributed by the caller."""
+        if len(uid) != 128:
+            raise ValueError("uid must be the 128 bytes of dist_unique_id()")
+        buf = C.create_string_buffer(bytes(uid), 128)
+        _lib.check(_lib.lib().hm_dist_init(self._h, buf, nranks, rank))
+        self.nranks, self.rank = nranks, rank
+
+    def dist_init_torch(self, group=None):
+        """`dist_init` with the id broadcast over an initialised `torch.distributed` group."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.dist_init(box[0], world, rank)
+
+    def dist_buffers(self):
+        """((x slot 0, x slot 1), (y slot 0, y slot 1)) device addresses; y slots are full length."""
+        x2, y2 = (C.c_void_p * 2)(), (C.c_void_p * 2)()
+        _lib.check(_lib.lib().hm_dist_buffers(self._h, x2, y2))
+        return (int(x2[0]), int(x2[1])), (int(y2[0]), int(y2[1]))
+
+    def dist_bcast_x(self, dx_root: int, root: int = 0, slot: int = 0, stream: int = 0):
+        _lib.check(_lib.lib().hm_dist_bcast_x(self._h, dx_root or None, root, slot, stream))
+
+    def dist_matvec_device(self, dx: int, yslot: int = 0, accumulate=False, stream: int = 0):
+        _lib.check(_lib.lib().hm_dist_matvec_device(self._h, dx, yslot, 1 if accumulate else 0, stream))
+
+    def dist_barrier(self, stream: int = 0):
+        _lib.check(_lib.lib().hm_dist_barrier(self._h, stream))
+
+    def dist_check(self):
+        _lib.check(_lib.lib().hm_dist_check(self._h))
+
+    def dist_matvec(self, x, y, root: int = 0, accumulate=False, incx=1, incy=1):
+        """Host arrays: x is read on `root` only (pass None elsewhere), y (or None) gets the whole
+        result on every rank that passes one."""
+        nr, nc = self.shape
+        if x is not None:
+            self._check_vec(x, "x", nc, incx, 0)
+        if y is not None:
+            self._check_vec(y, "y", nr, incy, 0)
+        px = x.ctypes.data_as(_dp) if x is not None else None
+        py = y.ctypes.data_as(_dp) if y is not None else None
+        _lib.check(_lib.lib().hm_dist_matvec(self._h, px, incx, py, incy, root, 1 if accumulate else 0))
+        return y
 
     def rmatvec_device(self, dx: int, dy: int, accumulate=False, stream: int = 0):
         _lib.check(_lib.lib().hm_matvec_adjoint_device(self._h, dx, dy, 1 if accumulate else 0, stream))

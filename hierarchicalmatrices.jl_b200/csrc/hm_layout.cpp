@@ -206,6 +206,8 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
     L = HmLayout();
     L.nrows = nrows;
     L.ncols = ncols;
+    L.part = part;
+    L.nparts = nparts;
 
     // ---- accounting over the whole operator (SURVEY 8d formula) ----
     for (const HmLeaf &l : all) {

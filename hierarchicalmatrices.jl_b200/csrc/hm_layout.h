@@ -21,6 +21,7 @@ constexpr int HM_NCHUNK = 4;
 struct HmLayout {
     int64_t nrows = 0, ncols = 0;
     int64_t row_begin = 0, row_end = 0; // owned rows
+    int part = 0, nparts = 1;           // which block-row part this is
     // leaves of this part (those intersecting the owned rows), in walk order
     std::vector<HmLeaf> leaves;
     std::vector<int64_t> leaf_global; // index in the full leaf list

@@ -134,8 +134,9 @@ HM_API int32_t hm_builder_layout_stats(hm_builder *b, int32_t part, int32_t npar
 
 /* ------------------------------------------------------------------------
  * Plan: immutable packed operator on one device.
- * hm_plan_finalize      -- whole operator on devices[0] (ndev must be 1; one
- *                          process drives one GPU, multi-GPU = one part per process)
+ * hm_plan_finalize      -- whole operator on devices[0].  ndev must be 1: a plan lives on one
+ *                          GPU; the multi-GPU form is one process per GPU, each with
+ *                          hm_plan_finalize_part + hm_dist_init (below)
  * hm_plan_finalize_part -- block-row part `part` of `nparts` (rows balanced by
  *                          stored bytes); y rows outside the part are not touched.
  * The builder can be destroyed afterwards.
@@ -194,7 +195,10 @@ HM_API int32_t hm_assemble_kernel_stats(const double *x, int64_t nx, const doubl
 HM_API int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy,
                   int32_t accumulate);
 /* Device pointers (contiguous), enqueued on `stream` (a cudaStream_t; NULL =
- * default stream); returns without synchronising. */
+ * default stream); returns without synchronising.  The *_device entry points use the plan's
+ * scratch buffers (partial sums, stage-2 vector, panel workspace) without locking: a plan admits
+ * ONE in-flight device call at a time, all on one stream (or ordered by events); the host-pointer
+ * entry points (hm_matvec, hm_matmat, ...) serialise themselves on the plan's mutex. */
 HM_API int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate,
                          void *stream);
 
@@ -205,6 +209,42 @@ HM_API int32_t hm_matvec_device(hm_plan *p, const double *dx, double *dy, int32_
  * The caller synchronises the ranks afterwards (a device barrier) before anyone reads y. */
 HM_API int32_t hm_matvec_device_allgather(hm_plan *p, const double *dx, const uint64_t *ypeers, int32_t npeers,
                                           int32_t self, int32_t accumulate, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Multi-GPU mul!: one process per GPU, rank r holds block-row part r of nranks
+ * (hm_plan_finalize_part / hm_assemble_kernel with part = r, nparts = nranks).  The plan owns the
+ * exchange: an NCCL communicator (bound at run time, dlopen of libnccl.so.2) for the broadcast of
+ * x, and one peer-mapped (cudaIpc, NVLink) exchange region per rank through which stage 3 stores
+ * the rows it owns into the y buffer of every rank -- the all-gather of y is fused into the
+ * kernel -- followed by a cross-rank barrier kernel.  After hm_dist_matvec* every rank holds the
+ * whole y.
+ *
+ * hm_dist_get_id   one rank creates the 128-byte id (ncclGetUniqueId); the caller distributes it
+ *                  to all ranks (MPI, torch.distributed, a file).
+ * hm_dist_init     collective over all ranks.
+ * x and y live in plan-owned, double-buffered device buffers ("slots" 0 / 1, hm_dist_buffers): a
+ * call writing y slot s may overlap peers reading slot 1 - s; calls alternate slots.
+ * ------------------------------------------------------------------------ */
+#define HM_DIST_ID_BYTES 128
+HM_API int32_t hm_dist_get_id(void *id_out);
+HM_API int32_t hm_dist_init(hm_plan *p, const void *id, int32_t nranks, int32_t rank);
+/* device addresses of this rank's x slots and (full-length, replicated) y slots */
+HM_API int32_t hm_dist_buffers(hm_plan *p, double **x2, double **y2);
+/* ncclBroadcast of x (ncols words) from `root` into x slot `slot` of every rank, enqueued on
+ * `stream`.  dx_root: device pointer on the root (NULL = the root's slot already holds x). */
+HM_API int32_t hm_dist_bcast_x(hm_plan *p, const double *dx_root, int32_t root, int32_t slot, void *stream);
+/* y slot `yslot` (+)= H x on every rank: the three stages of this rank's part with the all-gather
+ * fused into stage 3, then the barrier; enqueued on `stream`, no host synchronisation (may be
+ * captured into a CUDA graph).  dx: any device vector of ncols words -- an x slot after
+ * hm_dist_bcast_x, or the other y slot (x_{k+1} = y_k: a dependent iteration needs no broadcast). */
+HM_API int32_t hm_dist_matvec_device(hm_plan *p, const double *dx, int32_t yslot, int32_t accumulate, void *stream);
+HM_API int32_t hm_dist_barrier(hm_plan *p, void *stream);
+/* HM_ERR_CUDA if a barrier timed out since hm_dist_init (a peer died); synchronous. */
+HM_API int32_t hm_dist_check(hm_plan *p);
+/* Host pointers: x (ncols, stride incx) is read on `root` only; y (nrows, stride incy) receives the
+ * whole result on every rank that passes a non-NULL pointer.  Collective; copies are part of the call. */
+HM_API int32_t hm_dist_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy,
+                              int32_t root, int32_t accumulate);
 
 /* Adjoint apply: y[j*incy] (+)= sum_i H[i,j] x[i*incx], x with nrows
  * entries, y with ncols.  The reference has no adjoint of its hierarchical types; the

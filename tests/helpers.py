@@ -15,6 +15,17 @@ def relinf(a, b):
 TOL = 1e-12  # BASELINE.json north_star: relative ∞-norm error in Float64
 
 
+class _DevArr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr, n, device=0):
+    """torch view (no copy) of n Float64 words at a raw device address the library handed out."""
+    import torch
+    return torch.as_tensor(_DevArr(ptr, n), device=f"cuda:{device}")
+
+
 def push_oracle_leaves(hm, O, tree, builder, parity=0):
     """hm_builder_add_* for every leaf of an oracle tree (pointers into the oracle's arrays)."""
     L = hm.lib()

@@ -34,13 +34,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--npoints", "--size", dest="n", type=int, default=1 << 20,
                     help="points per side (default 2^20)")
-    ap.add_argument("--no-p2p", action="store_true",
-                    help="N > 1: gather y with an NCCL all-gather instead of the peer-memory stores fused into stage 3")
     ap.add_argument("--no-graph", action="store_true",
                     help="N > 1: launch every step from Python instead of one CUDA graph of the whole loop")
     ap.add_argument("--dist", default="cheb", choices=["cheb", "unif"],
                     help="cheb = examples/Kernel.jl:61-62 point sets; unif = uniform interlaced")
-    ap.add_argument("--no-gather", action="store_true", help="skip the all-gather of y (N > 1)")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the secondary configurations (64-RHS product, 2^22 assembly + 16 RHS, 2^24 multi-GPU)")
     ap.add_argument("--no-matrix-free", action="store_true", help="skip the secondary matrix-free measurement")
     ap.add_argument("--matrix-free", action="store_true",
                     help="hm_assemble_kernel_free: store no U/V/dense tiles, evaluate the entries inside every matvec "
@@ -239,87 +238,316 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-# --------------------------------------------------------------------------- multi-RHS mode (single GPU)
-def run_matmat(args, hm, torch, plan, st, px, py, dev, t_asm):
-    """Y = K X with X of `nrhs` columns (BASELINE configs[2]: N = 2^20, 64 right-hand sides; FP64
-    tensor-core panel kernels).  A step is one product; value = columns per second."""
-    n, nrhs = args.n, args.nrhs
+# --------------------------------------------------------------------------- helpers
+class _DevArr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(torch, ptr, n, dev):
+    """torch view (no copy) of n Float64 words at a device address handed out by the library."""
+    return torch.as_tensor(_DevArr(ptr, n), device=dev)
+
+
+_DGEMM = {}
+
+
+def dgemm_peak(torch, dev):
+    """cuBLAS DGEMM 8192^3 measured in this run (best of 5): the FP64-pipe denominator, which
+    MEASURED_PEAKS.json does not carry."""
+    if "tf" not in _DGEMM:
+        A = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        B = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            torch.matmul(A, B)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            torch.matmul(A, B)
+            a1.record()
+            torch.cuda.synchronize()
+            best = min(best, a0.elapsed_time(a1))
+        _DGEMM["tf"] = 2 * 8192 ** 3 / (best / 1e3) / 1e12
+        del A, B
+        torch.cuda.empty_cache()
+    return _DGEMM["tf"]
+
+
+def sampled_rows_check(px, py, v, y_host, nrows_sampled, seed=1):
+    """examples/Kernel.jl:78 on sampled rows: dense Cauchy rows in long double."""
+    n = len(px)
+    rows = np.unique(np.random.default_rng(seed).integers(0, n, nrows_sampled))
+    xl, yl, vl = px.astype(np.longdouble), py.astype(np.longdouble), v.astype(np.longdouble)
+    dense = np.array([np.sum(vl / (xl[i] - yl)) for i in rows], dtype=np.float64)
+    return float(np.max(np.abs(y_host[rows] - dense)) / np.max(np.abs(dense)))
+
+
+# --------------------------------------------------------------------------- multi-RHS product
+def measure_matmat(torch, plan, st, px, py, dev, nrhs, steps, warmup):
+    """Y = K X with X of `nrhs` columns through hm_matmat_device (FP64 tensor-core panel kernels,
+    hm_panel.cu).  A step is one product; value = columns per second."""
+    n = st["ncols"]
     rng = np.random.default_rng(0)
     X = torch.from_numpy(rng.standard_normal((nrhs, n))).to(dev)   # column-major n x nrhs
-    Y = torch.zeros((nrhs, n), dtype=torch.float64, device=dev)
+    Y = torch.zeros((nrhs, st["nrows"]), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
 
     def run(k):
         for _ in range(k):
-            plan.matmat_device(X.data_ptr(), n, Y.data_ptr(), n, nrhs, accumulate=False, stream=stream.cuda_stream)
+            plan.matmat_device(X.data_ptr(), n, Y.data_ptr(), st["nrows"], nrhs, accumulate=False,
+                               stream=stream.cuda_stream)
 
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
-    run(max(args.warmup, 3))
+    run(max(warmup, 3))
     torch.cuda.synchronize()
-    plan.timing_begin(args.steps * ((nrhs + 63) // 64))
+    npanels = (nrhs + 63) // 64
+    plan.timing_begin(steps * npanels)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record(stream)
-    run(args.steps)
+    run(steps)
     e1.record(stream)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = e0.elapsed_time(e1) / steps
     stage_ms, ncalls = plan.timing_end()
     clocks = sampler.stop(t_wall0)
-    # measured FP64 GEMM peak on this box (cuBLAS DGEMM 8192^3), the FP64-pipe denominator
-    A = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
-    B = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
-    for _ in range(2):
-        torch.matmul(A, B)
-    torch.cuda.synchronize()
-    best = 1e9
-    for _ in range(5):
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        torch.matmul(A, B)
-        a1.record()
-        torch.cuda.synchronize()
-        best = min(best, a0.elapsed_time(a1))
-    dgemm_tflops = 2 * 8192 ** 3 / (best / 1e3) / 1e12
-    del A, B
+    dgemm_tflops = dgemm_peak(torch, dev)
     words = st["dense_words"] + st["lowrank_words"]
     flops = 2.0 * words * nrhs
-    cs = 16 if nrhs <= 16 else 32 if nrhs <= 32 else 64
-    bytes_alg = 8 * words + 16 * n * nrhs
+    bytes_alg = 8 * words + 8 * (st["ncols"] + st["nrows"]) * nrhs
     peak, peak_src = measured_peak()
-    # spot check of a few entries against dense kernel rows in long double
+    # spot check of two columns against dense kernel rows in long double
     Yh = Y.cpu().numpy()
     Xh = X.cpu().numpy()
-    rows = np.unique(rng.integers(0, n, 12))
-    cols = [0, nrhs - 1]
-    xl, yl = px.astype(np.longdouble), py.astype(np.longdouble)
-    err = 0.0
-    for c in cols:
-        dense = np.array([np.sum(Xh[c].astype(np.longdouble) / (xl[i] - yl)) for i in rows], dtype=np.float64)
-        err = max(err, float(np.max(np.abs(Yh[c, rows] - dense)) / np.max(np.abs(dense))))
+    err = max(sampled_rows_check(px, py, Xh[c], Yh[c], 12, seed=2 + c) for c in (0, nrhs - 1))
     tf = flops / (ms / 1e3) / 1e12
     gbs = bytes_alg / (ms / 1e3) / 1e9
-    line = {
-        "metric": "H-matmat columns/s", "value": nrhs / (ms / 1e3), "unit": "columns/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n, args.dist).replace("single-vector mul!", f"{nrhs} right-hand sides"),
-                   "n": n, "dist": args.dist, "nrhs": nrhs, "panel_width": cs, "assembly_s": round(t_asm, 3),
-                   "l2": "inputs larger than L2"},
-        "tflops": tf, "effective_gbs": gbs,
-        "roofline": {"bound": "tensor" if tf / dgemm_tflops > gbs / peak else "hbm",
-                     "kernel": "hm_panel_kernel (DMMA m8n8k4, stage 1 + stage 3)",
-                     "achieved_tflops": tf, "peak_tflops": dgemm_tflops,
+    bound = "tensor" if flops / (dgemm_tflops * 1e12) > bytes_alg / (peak * 1e9) else "hbm"
+    out = {
+        "value": nrhs / (ms / 1e3), "unit": "columns/s", "ms_per_step": ms, "steps": steps, "nrhs": nrhs,
+        "panel_width": 16 if nrhs <= 16 else 32 if nrhs <= 32 else 64,
+        "tflops": tf, "effective_gbs": gbs, "algorithmic_flops": flops, "algorithmic_bytes": bytes_alg,
+        "roofline": {"bound": bound,
+                     "kernel": "hm_panel kernels (FP64 DMMA m8n8k4; stage 1 + stage 2 + stage 3)",
+                     "achieved": tf if bound == "tensor" else gbs,
+                     "peak": dgemm_tflops if bound == "tensor" else peak,
+                     "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                     "frac": tf / dgemm_tflops if bound == "tensor" else gbs / peak,
+                     "frac_fp64": tf / dgemm_tflops, "frac_hbm": gbs / peak,
                      "peak_tflops_source": "cuBLAS DGEMM 8192^3 measured in this run (best of 5)",
-                     "frac_fp64": tf / dgemm_tflops, "achieved_gbs": gbs, "peak_gbs": peak, "peak_gbs_source": peak_src,
-                     "frac_hbm": gbs / peak, "traffic": None,
+                     "peak_gbs_source": peak_src, "traffic": None,
                      "ms_per_launch": {"stage1+in": stage_ms[0] / max(ncalls, 1), "stage2": stage_ms[1] / max(ncalls, 1),
                                        "stage3+out": stage_ms[2] / max(ncalls, 1)}},
-        "gpu_launches": args.steps * ((nrhs + 63) // 64) * (plan.launches_per_matvec + 2), "clocks": clocks,
-        "check_sampled_dense_entries_relerr": err,
+        "gpu_launches": steps * npanels * (plan.launches_per_matvec + 2), "clocks": clocks,
+        "check_sampled_dense_entries_relerr": err, "api": "hm_matmat_device",
+    }
+    del X, Y
+    return out
+
+
+def run_matmat(args, torch, plan, st, px, py, dev, t_asm):
+    """--nrhs mode: the product as the headline line (BASELINE configs[2])."""
+    n, nrhs = args.n, args.nrhs
+    o = measure_matmat(torch, plan, st, px, py, dev, nrhs, args.steps, args.warmup)
+    line = {
+        "metric": "H-matmat columns/s", "value": o["value"], "unit": "columns/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": o["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n, args.dist).replace("single-vector mul!", f"{nrhs} right-hand sides"),
+                   "n": n, "dist": args.dist, "nrhs": nrhs, "panel_width": o["panel_width"],
+                   "assembly_s": round(t_asm, 3), "l2": "inputs larger than L2"},
+        "tflops": o["tflops"], "effective_gbs": o["effective_gbs"], "roofline": o["roofline"],
+        "gpu_launches": o["gpu_launches"], "clocks": o["clocks"],
+        "check_sampled_dense_entries_relerr": o["check_sampled_dense_entries_relerr"],
     }
     print(json.dumps(line), flush=True)
+
+
+def measure_cfg5(hm, torch, dev, local, dist_name, steps):
+    """BASELINE configs[4]: KernelMatrix assembly of a 2^22-point Cauchy operator on the GPU
+    (hm_assemble_kernel: host builds the range tree, device fills U, V, F and the dense tiles)
+    followed by a 16-column product."""
+    n = 1 << 22
+    free, _total = torch.cuda.mem_get_info(dev)
+    if free < 80e9:
+        return {"skipped": f"needs ~70 GB of free device memory, {free / 1e9:.0f} GB available"}
+    px, py = points(hm, n, dist_name)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    K = hm.KernelMatrix(hm.cauchykernel, px, py, 1.0, -1.0, 1.0, -1.0, device=local)
+    torch.cuda.synchronize()
+    t_asm = time.perf_counter() - t0
+    plan = K.plan()
+    st = plan.stats()
+    o = measure_matmat(torch, plan, st, px, py, dev, 16, steps, 3)
+    o["workload"] = (f"on-GPU KernelMatrix assembly, N={n} ({dist_name}), then a 16-column product "
+                     f"(BASELINE configs[4])")
+    o["assembly_s"] = round(t_asm, 3)
+    o["assembly_note"] = "wall clock of hm_assemble_kernel: host range tree + planner + device fill kernels"
+    o["assembled_bytes"] = st["stored_bytes"]
+    o["leaves"] = {"dense": st["n_dense"], "bary2d": st["n_bary2d"]}
+    # the assembled operator also as a single-vector matvec (its HBM roofline)
+    x1 = torch.from_numpy(np.random.default_rng(5).standard_normal(n)).to(dev)
+    y1 = torch.zeros(n, dtype=torch.float64, device=dev)
+    sm = torch.cuda.current_stream()
+    for _ in range(3):
+        plan.matvec_device(x1.data_ptr(), y1.data_ptr(), False, sm.cuda_stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(sm)
+    for _ in range(steps):
+        plan.matvec_device(x1.data_ptr(), y1.data_ptr(), False, sm.cuda_stream)
+    e1.record(sm)
+    torch.cuda.synchronize()
+    ms1 = e0.elapsed_time(e1) / steps
+    peak, _ = measured_peak()
+    o["matvec"] = {"ms_per_step": ms1, "value": 1e3 / ms1, "unit": "matvecs/s",
+                   "effective_gbs": st["algorithmic_bytes"] / ms1 / 1e6,
+                   "frac_hbm": st["algorithmic_bytes"] / ms1 / 1e6 / peak,
+                   "check_sampled_dense_rows_relerr": sampled_rows_check(px, py, x1.cpu().numpy(), y1.cpu().numpy(), 12)}
+    del K, plan, x1, y1
+    torch.cuda.empty_cache()
+    return o
+
+
+# --------------------------------------------------------------------------- multi-GPU pipeline (product API)
+class DistLoop:
+    """K steps of y = K x over all ranks through the product's hm_dist_* entry points.
+    independent: every step gets a fresh x, replicated by the NCCL broadcast (hm_dist_bcast_x) on
+        a second stream while the previous step computes.
+    dependent: x_{k+1} = y_k (a Krylov-style iteration): y is already replicated by the fused
+        all-gather, so no broadcast at all; chains of `chain` steps restart from the broadcast x."""
+
+    def __init__(self, torch, plan, dev, rank, v):
+        self.torch, self.plan, self.rank = torch, plan, rank
+        (self.x0, self.x1), (self.y0, self.y1) = plan.dist_buffers()
+        self.xs, self.ys = (self.x0, self.x1), (self.y0, self.y1)
+        self.xd = torch.from_numpy(v).to(dev) if rank == 0 else None
+        self.cs = torch.cuda.Stream(device=dev)
+        self.x_ready = [torch.cuda.Event() for _ in range(2)]
+        self.x_free = [torch.cuda.Event() for _ in range(2)]
+
+    def _bcast(self, slot):
+        torch = self.torch
+        with torch.cuda.stream(self.cs):
+            self.cs.wait_event(self.x_free[slot])  # the matvec that last read this x slot is done
+            self.plan.dist_bcast_x(self.xd.data_ptr() if self.rank == 0 else 0, 0, slot, self.cs.cuda_stream)
+            self.x_ready[slot].record(self.cs)
+
+    def independent(self, nsteps):
+        main = self.torch.cuda.current_stream()
+        for b in range(2):
+            self.x_free[b].record(main)
+        self._bcast(0)
+        for k in range(nsteps):
+            b = k & 1
+            main.wait_event(self.x_ready[b])
+            self.plan.dist_matvec_device(self.xs[b], b, False, main.cuda_stream)
+            self.x_free[b].record(main)
+            if k + 1 < nsteps:
+                self._bcast((k + 1) & 1)
+        main.wait_stream(self.cs)
+        return self.ys[(nsteps - 1) & 1]
+
+    def dependent(self, nsteps, chain=8):
+        main = self.torch.cuda.current_stream()
+        self.plan.dist_bcast_x(self.xd.data_ptr() if self.rank == 0 else 0, 0, 0, main.cuda_stream)
+        for k in range(nsteps):
+            j = k % chain
+            src = self.xs[0] if j == 0 else self.ys[(j - 1) & 1]
+            self.plan.dist_matvec_device(src, j & 1, False, main.cuda_stream)
+        return self.ys[((nsteps - 1) % chain) & 1]
+
+
+def timed_graph(torch, fn, barrier, stream):
+    """Capture fn() once, replay it untimed (graph upload, NCCL warm-up), then time one replay."""
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ret = fn()
+    barrier()
+    g.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    g.replay()
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1), t_wall0, g, ret
+
+
+def measure_cfg4(hm, torch, dist, dev, rank, world, local, steps):
+    """BASELINE configs[3]: N = 2^24 uniform points, stored operator (289 GB) partitioned by block
+    rows over the GPUs of the box, x replicated by the NCCL broadcast, y gathered by the fused
+    stores.  Needs >= 2 GPUs to fit."""
+    n = 1 << 24
+    px, py = points(hm, n, "unif")
+    whole = hm.KernelMatrix.layout_stats(px, py, 1.0, -1.0, 1.0, -1.0, rank, world)
+    free, _total = torch.cuda.mem_get_info(dev)
+    ok = torch.tensor([1.0 if whole["stored_bytes"] + 3e9 < free else 0.0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if ok.item() == 0:
+        return {"skipped": f"part of {whole['stored_bytes'] / 1e9:.0f} GB does not fit {free / 1e9:.0f} GB free"}
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    K = hm.KernelMatrix(hm.cauchykernel, px, py, 1.0, -1.0, 1.0, -1.0, device=local, part=rank, nparts=world)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_asm = time.perf_counter() - t0
+    plan = K.plan()
+    st = plan.stats()
+    plan.dist_init_torch()
+    v = np.random.default_rng(0).standard_normal(n)
+    loop = DistLoop(torch, plan, dev, rank, v)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    loop.independent(3)
+    barrier()
+    ms, t_wall0, g, ydev = timed_graph(torch, lambda: loop.independent(steps), barrier, torch.cuda.current_stream())
+    plan.timing_begin(steps)
+    loop.independent(steps)
+    barrier()
+    stage_ms, ncalls = plan.timing_end()
+    clocks = sampler.stop(t_wall0) if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    pb = torch.tensor([float(st["part_algorithmic_bytes"])], dtype=torch.float64, device=dev)
+    dist.all_reduce(pb, op=dist.ReduceOp.MAX)
+    plan.dist_check()
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        yh = device_view(torch, ydev, n, dev).cpu().numpy()
+        gbs = st["algorithmic_bytes"] / ms / 1e6
+        s1, s2, s3 = (m / max(ncalls, 1) for m in stage_ms)
+        out = {"workload": f"Cauchy KernelMatrix N={n} uniform interlaced points, stored operator "
+                           f"({st['algorithmic_bytes'] / 1e9:.0f} GB) block-row x{world}, NCCL x-broadcast, fused y gather "
+                           f"(BASELINE configs[3])",
+               "value": 1e3 / ms, "unit": "matvecs/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+               "assembly_s": round(t_asm, 3), "effective_gbs": gbs,
+               "roofline": {"bound": "hbm", "kernel": "hm_stream_kernel (stage 1 + stage 3), all ranks",
+                            "achieved": gbs, "peak": peak * world, "unit": "GB/s", "frac": gbs / (peak * world),
+                            "peak_source": f"{world} x {peak_src}", "traffic": None,
+                            "ms_per_launch_rank0": {"stage1": s1, "stage2": s2, "stage3": s3}},
+               "part_bytes_max_over_mean": float(pb.item()) * world / (st["algorithmic_bytes"] + 8 * n * (world - 1)),
+               "check_sampled_dense_rows_relerr": sampled_rows_check(px, py, v, yh, 12),
+               "clocks": clocks, "api": "hm_assemble_kernel(part) + hm_dist_init + hm_dist_bcast_x + hm_dist_matvec_device"}
+    g.reset()
+    del loop, K, plan
+    torch.cuda.empty_cache()
+    barrier()
+    return out
 
 
 # --------------------------------------------------------------------------- our arm
@@ -348,6 +576,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist_on = world > 1
+    dist = None
     if dist_on:
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
@@ -365,7 +594,7 @@ def run_ours(args):
     r0, r1 = st["row_begin"], st["row_end"]
 
     if args.nrhs > 1:
-        return run_matmat(args, hm, torch, plan, st, px, py, dev, t_asm)
+        return run_matmat(args, torch, plan, st, px, py, dev, t_asm)
     if args.adjoint:
         xa = torch.from_numpy(np.random.default_rng(0).standard_normal(n)).to(dev)
         ya = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -394,94 +623,7 @@ def run_ours(args):
         return
 
     v = np.random.default_rng(0).standard_normal(n)
-    gather = dist_on and not args.no_gather
     stream = torch.cuda.current_stream()
-    # two x / y buffers: the NCCL broadcast of x for step k+1 and the all-gather of y from
-    # step k-1 run on a second stream while step k computes
-    nbuf = 2 if dist_on else 1
-    x_bufs = [torch.from_numpy(v).to(dev) if rank == 0 else torch.zeros(n, dtype=torch.float64, device=dev)
-              for _ in range(nbuf)]
-    y_bufs = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(nbuf)]
-    p2p = None
-    if dist_on:
-        cuts = [None] * world
-        dist.all_gather_object(cuts, (r0, r1))
-        maxrows = max(b - a for a, b in cuts)
-        pad = torch.zeros(maxrows, dtype=torch.float64, device=dev)
-        gathered = torch.zeros(world * maxrows, dtype=torch.float64, device=dev)
-        cs = torch.cuda.Stream(device=dev)
-        x_ready = [torch.cuda.Event() for _ in range(nbuf)]
-        xy_free = [torch.cuda.Event() for _ in range(nbuf)]
-        y_ready = [torch.cuda.Event() for _ in range(nbuf)]
-        y_done = [torch.cuda.Event() for _ in range(nbuf)]
-        if gather and not args.no_p2p:
-            # y lives in symmetric memory: every rank can store into every rank's buffer over
-            # NVLink, so stage 3 writes its rows to all of them (all-gather fused into the kernel)
-            # and only a device barrier remains on the second stream.
-            ok = torch.ones(1, device=dev)
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-                ysym = [symm_mem.empty(n, dtype=torch.float64, device=dev) for _ in range(nbuf)]
-                hdls = [symm_mem.rendezvous(t, dist.group.WORLD) for t in ysym]
-                for t in ysym:
-                    t.zero_()
-                p2p = {"bufs": ysym, "hdls": hdls, "ptrs": [[int(a) for a in h.buffer_ptrs] for h in hdls]}
-            except Exception as exc:  # symmetric memory unavailable: NCCL all-gather instead
-                ok.zero_()
-                if rank == 0:
-                    print(f"bench.py: symmetric memory unavailable ({exc!r}); using the NCCL all-gather", file=sys.stderr)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() == 0:
-                p2p = None
-            else:
-                y_bufs = p2p["bufs"]
-
-    def bcast(k, main):
-        b = k % nbuf
-        with torch.cuda.stream(cs):
-            cs.wait_event(xy_free[b])          # the matvec that last read x_bufs[b] is done
-            dist.broadcast(x_bufs[b], src=0)
-            x_ready[b].record(cs)
-
-    def run(nsteps):
-        main = torch.cuda.current_stream()
-        if not dist_on:
-            for _ in range(nsteps):
-                plan.matvec_device(x_bufs[0].data_ptr(), y_bufs[0].data_ptr(), accumulate=False,
-                                   stream=main.cuda_stream)
-            return
-        for b in range(nbuf):
-            xy_free[b].record(main)
-            y_done[b].record(main)
-        bcast(0, main)
-        for k in range(nsteps):
-            b = k % nbuf
-            main.wait_event(x_ready[b])
-            main.wait_event(y_done[b])         # the all-gather that last read y_bufs[b] is done
-            if p2p is not None:
-                plan.matvec_device_allgather(x_bufs[b].data_ptr(), p2p["ptrs"][b], rank, accumulate=False,
-                                             stream=main.cuda_stream)
-            else:
-                plan.matvec_device(x_bufs[b].data_ptr(), y_bufs[b].data_ptr(), accumulate=False,
-                                   stream=main.cuda_stream)
-            xy_free[b].record(main)
-            y_ready[b].record(main)
-            if k + 1 < nsteps:
-                bcast(k + 1, main)
-            with torch.cuda.stream(cs):
-                if gather:
-                    cs.wait_event(y_ready[b])
-                    if p2p is not None:
-                        p2p["hdls"][b].barrier()   # every rank's rows have landed everywhere
-                    else:
-                        # row parts are balanced by bytes, not rows: gather padded slices
-                        pad[: r1 - r0].copy_(y_bufs[b][r0:r1])
-                        dist.all_gather_into_tensor(gathered, pad)
-                        for q, (qa, qb) in enumerate(cuts):
-                            if q != rank:
-                                y_bufs[b][qa:qb].copy_(gathered[q * maxrows: q * maxrows + (qb - qa)])
-                y_done[b].record(cs)
-        main.wait_stream(cs)
 
     def barrier():
         if dist_on:
@@ -491,43 +633,88 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    run(max(args.warmup, 3))
-    barrier()
-    use_graph = dist_on and not args.no_graph
+    dependent = comm = None
+    graph = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if use_graph:
-        # the whole K-step pipeline (our kernels + the NCCL collectives, two streams) as ONE
-        # CUDA graph: at 0.3 ms of GPU work per step the Python/NCCL launch path is the bottleneck
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            run(args.steps)
+    if not dist_on:
+        x_dev = torch.from_numpy(v).to(dev)
+        y_dev = torch.zeros(n, dtype=torch.float64, device=dev)
+
+        def run(k):
+            for _ in range(k):
+                plan.matvec_device(x_dev.data_ptr(), y_dev.data_ptr(), accumulate=False, stream=stream.cuda_stream)
+
+        run(max(args.warmup, 3))
         barrier()
-        graph.replay()                          # untimed replay (graph upload, NCCL warm-up)
-        barrier()
+        plan.timing_begin(args.steps)
         t_wall0 = time.time()
         e0.record(stream)
-        graph.replay()
+        run(args.steps)
         e1.record(stream)
         barrier()
+        ms = e0.elapsed_time(e1)
+        stage_ms, ncalls = plan.timing_end()
+    else:
+        # the exchange is the product's: communicator, peer-mapped y / x buffers and barrier belong to the plan
+        plan.dist_init_torch()
+        loop = DistLoop(torch, plan, dev, rank, v)
+        loop.independent(max(args.warmup, 3))
+        barrier()
+        if args.no_graph:
+            t_wall0 = time.time()
+            e0.record(stream)
+            yptr = loop.independent(args.steps)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1)
+        else:
+            # the whole K-step pipeline (our kernels, barrier kernels, the NCCL broadcasts on the second
+            # stream) as ONE CUDA graph: at 0.3 ms of GPU work per step the launch path would dominate
+            ms, t_wall0, graph, yptr = timed_graph(torch, lambda: loop.independent(args.steps), barrier, stream)
         # per-stage kernel times for the roofline: the same steps launched eagerly
         plan.timing_begin(args.steps)
-        run(args.steps)
+        loop.independent(args.steps)
         barrier()
-    else:
-        plan.timing_begin(args.steps)
+        stage_ms, ncalls = plan.timing_end()
+        y_dev = device_view(torch, yptr, n, dev)
+        y_indep = y_dev.clone()
+        # dependent iteration x_{k+1} = y_k: no broadcast on the critical path at all
+        loop.dependent(8)
         barrier()
-        t_wall0 = time.time()
-        e0.record(stream)
-        run(args.steps)
-        e1.record(stream)
+        ms_dep, _, gdep, _ = timed_graph(torch, lambda: loop.dependent(args.steps), barrier, stream)
+        gdep.reset()
+        # the exchange pieces alone
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for _ in range(5):
+            plan.dist_barrier(stream.cuda_stream)
+            plan.dist_bcast_x(loop.xd.data_ptr() if rank == 0 else 0, 0, 0, stream.cuda_stream)
         barrier()
-    y_dev = y_bufs[(args.steps - 1) % nbuf]
-    ms = e0.elapsed_time(e1)
-    stage_ms, ncalls = plan.timing_end()
+        ev[0].record(stream)
+        for _ in range(50):
+            plan.dist_barrier(stream.cuda_stream)
+        ev[1].record(stream)
+        for _ in range(50):
+            plan.dist_bcast_x(loop.xd.data_ptr() if rank == 0 else 0, 0, 0, stream.cuda_stream)
+        ev[2].record(stream)
+        barrier()
+        tt = torch.tensor([ms_dep, ev[0].elapsed_time(ev[1]) / 50, ev[1].elapsed_time(ev[2]) / 50],
+                          dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dep, t_bar, t_bc = (float(a) for a in tt.tolist())
+        dependent = {"value": args.steps / (ms_dep / 1e3), "unit": "matvecs/s", "ms_per_step": ms_dep / args.steps,
+                     "what": "x_{k+1} = y_k (chains of 8 from the broadcast x): y is already on every rank after the "
+                             "fused gather + barrier, so the step has no broadcast"}
+        comm = {"barrier_kernel_ms": t_bar, "nccl_bcast_x_ms": t_bc,
+                "note": "back-to-back on one stream, max over ranks; in the step the broadcast of x(k+1) runs on a "
+                        "second stream under step k, the barrier is in line after stage 3"}
+        plan.dist_check()
+        y_dev = y_indep
     clocks = sampler.stop(t_wall0) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    pbytes = torch.tensor([float(st["part_algorithmic_bytes"])], dtype=torch.float64, device=dev)
     if dist_on:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pbytes, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = args.steps / (ms / 1e3)
 
@@ -539,56 +726,78 @@ def run_ours(args):
 
     # ---- end to end through the host-pointer C ABI call (pinned host buffers) ----
     e2e = None
+    xn = yn = None
     if not args.no_e2e:
-        xh = torch.from_numpy(v.copy()).pin_memory()
-        yh = torch.zeros(n, dtype=torch.float64).pin_memory()
-        xn, yn = xh.numpy(), yh.numpy()
+        if rank == 0:
+            xh = torch.from_numpy(v.copy()).pin_memory()
+            yh = torch.zeros(n, dtype=torch.float64).pin_memory()
+            xn, yn = xh.numpy(), yh.numpy()
+
+        def call():
+            if dist_on:   # x is read on rank 0 only, the whole y lands in rank 0's host vector
+                plan.dist_matvec(xn, yn, root=0, accumulate=False)
+            else:
+                plan.matvec(xn, yn, accumulate=False)  # H2D x, 3 stages, D2H y, sync
+
         for _ in range(3):
-            plan.matvec(xn, yn, accumulate=False)
+            call()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            plan.matvec(xn, yn, accumulate=False)  # H2D x, 3 stages, D2H y rows, sync
+            call()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if dist_on:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        e2e = {"value": args.steps / dt, "unit": "matvecs/s", "h2d_bytes_per_step": 8 * st["ncols"] * world,
+        e2e = {"value": args.steps / dt, "unit": "matvecs/s", "h2d_bytes_per_step": 8 * st["ncols"],
                "d2h_bytes_per_step": 8 * st["nrows"], "ms_per_step": dt / args.steps * 1e3,
-               "api": "hm_matvec (C ABI, host pointers)"}
+               "api": ("hm_dist_matvec (C ABI, host pointers: x from rank 0's host memory, NCCL broadcast, whole y "
+                       "back into rank 0's host memory)" if dist_on else "hm_matvec (C ABI, host pointers)")}
+        if rank == 0 and dist_on:
+            e2e["relinf_vs_device_loop"] = float(np.max(np.abs(yn - y_dev.cpu().numpy())) / np.max(np.abs(yn)))
 
-    # ---- the same operator applied matrix-free (hm_assemble_kernel_free), measured beside the
-    # headline stored path: nothing but the r x r cores is resident, the entries are evaluated
-    # inside the matvec (FP64-bound).  Reported, not the headline: the roofline above is the
-    # stored path's. ----
-    mfree = None
+    # ---- secondary objects, single GPU ----
+    mfree = matmat64 = cfg5 = None
     if world == 1 and not args.matrix_free and not args.no_matrix_free:
+        # the same operator applied matrix-free (hm_assemble_kernel_free): nothing but the r x r cores is
+        # resident, the entries are evaluated inside the matvec (FP64-bound).  Reported, not the headline.
         t0 = time.perf_counter()
         Kf = hm.KernelMatrix(hm.cauchykernel, px, py, 1.0, -1.0, 1.0, -1.0, device=local, matrix_free=True)
         pf = Kf.plan()
         t_setup = time.perf_counter() - t0
         yf = torch.zeros(n, dtype=torch.float64, device=dev)
-        main = torch.cuda.current_stream()
         for _ in range(5):
-            pf.matvec_device(x_bufs[0].data_ptr(), yf.data_ptr(), accumulate=False, stream=main.cuda_stream)
+            pf.matvec_device(x_dev.data_ptr(), yf.data_ptr(), accumulate=False, stream=stream.cuda_stream)
         torch.cuda.synchronize()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         nmf = max(10, min(args.steps, 50))
-        f0.record(main)
+        pf.timing_begin(nmf)
+        f0.record(stream)
         for _ in range(nmf):
-            pf.matvec_device(x_bufs[0].data_ptr(), yf.data_ptr(), accumulate=False, stream=main.cuda_stream)
-        f1.record(main)
+            pf.matvec_device(x_dev.data_ptr(), yf.data_ptr(), accumulate=False, stream=stream.cuda_stream)
+        f1.record(stream)
         torch.cuda.synchronize()
         ms_f = f0.elapsed_time(f1) / nmf
-        ref_y = y_bufs[0]
-        plan.matvec_device(x_bufs[0].data_ptr(), ref_y.data_ptr(), accumulate=False, stream=main.cuda_stream)
-        torch.cuda.synchronize()
-        dev_rel = float((yf - ref_y).abs().max() / ref_y.abs().max())
+        fst, fn = pf.timing_end()
+        dev_rel = float((yf - y_dev).abs().max() / y_dev.abs().max())
+        # FP64 work of one matrix-free matvec: per stored U / V / dense word one subtraction, one
+        # reciprocal (rcp.approx + 3 DFMA refinement) and two FMAs -- counted as 6 FP64-pipe issues;
+        # peak = the DFMA issue rate measured by profiles/microbench/fp64_pipes.cu (34.2 TFLOP/s = 17.1e12 issues/s)
+        words = st["dense_words"] + st["lowrank_words"] - st["core_words"]
+        issues = 6.0 * words
         mfree = {"value": 1e3 / ms_f, "unit": "matvecs/s", "ms_per_step": ms_f, "steps": nmf,
                  "resident_bytes": pf.stats()["stored_bytes"], "setup_s": round(t_setup, 3),
-                 "relinf_vs_stored": dev_rel, "api": "hm_assemble_kernel_free + hm_matvec_device"}
+                 "relinf_vs_stored": dev_rel, "api": "hm_assemble_kernel_free + hm_matvec_device",
+                 "ms_per_launch": {"stage1": fst[0] / max(fn, 1), "stage2": fst[1] / max(fn, 1), "stage3": fst[2] / max(fn, 1)},
+                 "roofline": {"bound": "fp64", "kernel": "hm_free1_kernel + hm_free3_kernel",
+                              "achieved": issues / (ms_f / 1e3) / 1e12, "peak": 17.1,
+                              "unit": "10^12 FP64-pipe instructions/s (lane-level)",
+                              "frac": issues / (ms_f / 1e3) / 1e12 / 17.1,
+                              "how": "6 FP64-pipe issues per evaluated entry (sub, rcp.approx, 3 refinement DFMA "
+                                     "incl. the use, 1 accumulate DFMA); peak = DFMA rate of "
+                                     "profiles/microbench/fp64_pipes.cu (34.2 TFLOP/s / 2)"}}
         if not args.no_e2e:
             for _ in range(3):
                 pf.matvec(xn, yn, accumulate=False)
@@ -599,16 +808,16 @@ def run_ours(args):
             mfree["e2e"] = {"value": nmf / (time.perf_counter() - t0), "unit": "matvecs/s",
                             "api": "hm_matvec (C ABI, host pointers)"}
         del Kf, pf, yf
+    if world == 1 and not args.matrix_free and not args.no_secondary:
+        # BASELINE configs[2]: the same operator applied to 64 right-hand sides
+        matmat64 = measure_matmat(torch, plan, st, px, py, dev, 64, 10, 3)
+        matmat64["workload"] = workload_name(n, args.dist).replace("single-vector mul!", "64 right-hand sides") + \
+            " (BASELINE configs[2])"
 
-    y_host = y_dev.cpu().numpy() if (rank == 0 and (gather or not dist_on)) else None
-    sampled = None
-    if y_host is not None:
-        # independent spot check (examples/Kernel.jl:78 on sampled rows): dense kernel rows in long double
-        rows = np.unique(np.random.default_rng(1).integers(0, n, 48 if n <= (1 << 21) else 12))
-        xl, yl, vl = px.astype(np.longdouble), py.astype(np.longdouble), v.astype(np.longdouble)
-        dense = np.array([np.sum(vl / (xl[i] - yl)) for i in rows], dtype=np.float64)
-        sampled = float(np.max(np.abs(y_host[rows] - dense)) / np.max(np.abs(dense)))
+    y_host = y_dev.cpu().numpy() if rank == 0 else None
+    sampled = sampled_rows_check(px, py, v, y_host, 48 if n <= (1 << 21) else 12) if rank == 0 else None
 
+    line = None
     if rank == 0:
         peak, peak_src = measured_peak()
         ach = (b1 + b3) / ((s1 + s3) / 1e3) / 1e9 if (s1 + s3) > 0 else None
@@ -620,11 +829,10 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(n, args.dist), "n": n, "dist": args.dist,
                        "partition": f"block-row x{world}" if world > 1 else "single GPU",
-                       "collectives": ((("NCCL broadcast(x); all-gather(y) fused into stage 3 (stores into every rank's symmetric buffer "
-                                         "over NVLink) + device barrier, pipelined on a second stream" if p2p is not None else
-                                         "NCCL broadcast(x) + all-gather(y) per step, pipelined on a second stream")
-                                        + (", whole loop replayed as one CUDA graph" if use_graph else "")) if gather else
-                                       "NCCL broadcast(x) per step" if dist_on else "none"),
+                       "collectives": (("product API hm_dist_*: NCCL broadcast(x) per step on a second stream; all-gather(y) "
+                                        "fused into stage 3 (stores into every rank's peer-mapped buffer over NVLink) + barrier "
+                                        "kernel" + ("" if args.no_graph else "; whole loop replayed as one CUDA graph"))
+                                       if dist_on else "none"),
                        "l2": "inputs larger than L2 (%.1f GB streamed per step per GPU)" % (st["stored_bytes"] / 1e9),
                        "assembly_s": round(t_asm, 3), **({"matrix_free": True} if args.matrix_free else {})},
             "effective_gbs": st["algorithmic_bytes"] * value / 1e9,
@@ -641,23 +849,41 @@ def run_ours(args):
             "stages": {"stage1_gbs": b1 / (s1 / 1e3) / 1e9 if s1 > 0 else None,
                        "stage2_gbs": b2 / (s2 / 1e3) / 1e9 if s2 > 0 else None,
                        "stage3_gbs": b3 / (s3 / 1e3) / 1e9 if s3 > 0 else None},
-            "e2e": e2e, "matrix_free": mfree, "gpu_launches": plan.launches_per_matvec * args.steps, "clocks": clocks,
+            "e2e": e2e, "matrix_free": mfree, "matmat64": matmat64,
+            "gpu_launches": (plan.launches_per_matvec + (1 if dist_on else 0)) * args.steps, "clocks": clocks,
             "leaves": {"dense": st["n_dense"], "bary2d": st["n_bary2d"]},
             "check_sampled_dense_rows_relerr": sampled,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            del K, plan
-            torch.cuda.empty_cache()
+        if dist_on:
+            line["dependent_iteration"] = dependent
+            line["comm"] = comm
+            line["partition_balance"] = {"max_part_bytes": float(pbytes.item()),
+                                         "ideal_part_bytes": st["algorithmic_bytes"] / world,
+                                         "max_over_ideal": float(pbytes.item()) * world / st["algorithmic_bytes"]}
+    if graph is not None:
+        graph.reset()
+    # release the headline operator before the large secondary configurations
+    del K, plan
+    if dist_on:
+        del loop
+    torch.cuda.empty_cache()
+    if world == 1 and not args.matrix_free and not args.no_secondary:
+        cfg5 = measure_cfg5(hm, torch, dev, local, args.dist, 10)
+        line["cfg5_assemble_2p22_matmat16"] = cfg5
+    if dist_on and not args.no_secondary:
+        cfg4 = measure_cfg4(hm, torch, dist, dev, rank, world, local, 10)
+        if rank == 0:
+            line["cfg4_2p24_multi_gpu"] = cfg4
+    if rank == 0:
+        if not args.no_cpu_baseline and host_mem_ok(n):
+            # the oracle on the host cores: baseline at N = 1, and the full-vector parity check at every N
             cb, parity = cpu_baseline(n, args.dist, v, y_host)
-            line["cpu_baseline"] = cb
+            if world == 1:
+                line["cpu_baseline"] = cb
             line["parity_relinf_vs_oracle"] = parity
         print(json.dumps(line), flush=True)
     if dist_on:
-        # Tearing NCCL down while a captured graph still references its streams can hang:
-        # release the graph, make sure every rank is done, then leave without the
-        # communicator destructor.
-        if use_graph:
-            graph.reset()
+        # leave without the communicator destructors (NCCL teardown order at exit can hang)
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()

@@ -50,6 +50,9 @@ class TreeLeaf(C.Structure):
                 ("d", C.c_double)]
 
 
+# hm_kernel_fn: out[i] = f(x[i], y[i]) for i < n
+KERNEL_FN = C.CFUNCTYPE(None, _dp, _dp, _i64, _dp, _vp)
+
 # name -> (restype, argtypes); must list every symbol include/hmb200.h declares
 SIGNATURES = {
     "hm_last_error": (C.c_char_p, []),
@@ -69,6 +72,8 @@ SIGNATURES = {
     "hm_plan_stats": (_i32, [_vp, C.POINTER(Stats)]),
     "hm_assemble_kernel": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                   _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "hm_assemble_kernel_fn": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                     KERNEL_FN, _vp, _i32, _i32, _i32, C.POINTER(_vp)]),
     "hm_assemble_kernel_free": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                        _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "hm_assemble_kernel_stats": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double,

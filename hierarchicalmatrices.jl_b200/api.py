@@ -725,8 +725,9 @@ class KernelMatrix(_KernelMatrixBlocks):
     KernelMatrix(T, M, N)            empty container, blocks set with H[Block(m), Block(n)] = A
     KernelMatrix(f, x, y, a, b, c, d) the assembling constructor (KernelMatrix.jl:47-116):
         the tree of index ranges is built on the host, U, V, F and the dense leaves
-        are evaluated on the GPU straight into the packed streams; `f` must be one
-        of the four kernels of examples/Kernel.jl.
+        are evaluated on the GPU straight into the packed streams when `f` is one of the
+        four kernels of examples/Kernel.jl; for any other function f(x, y) (called with
+        arrays) the cores and dense leaves are evaluated by f on the host, U and V on the GPU.
     """
 
     _name = "KernelMatrix"
@@ -739,16 +740,39 @@ class KernelMatrix(_KernelMatrixBlocks):
         self.matrix_free = bool(matrix_free)
         if len(args) == 7:
             f, x, y, a, b, c, d = args
-            if not isinstance(f, _Kernel):
-                raise HmError(8, "device assembly knows cauchykernel, coulombkernel, coulombprimekernel, logkernel")
+            if not callable(f):
+                raise TypeError("MethodError: f must be a function f(x, y)")
             super().__init__(np.float64, 0, 0)
             x = np.ascontiguousarray(x, dtype=np.float64)
             y = np.ascontiguousarray(y, dtype=np.float64)
             dev = _current_device() if device is None else device
             h = C.c_void_p()
-            build = _lib.lib().hm_assemble_kernel_free if matrix_free else _lib.lib().hm_assemble_kernel
-            _lib.check(build(x.ctypes.data_as(_dp), len(x), y.ctypes.data_as(_dp), len(y), a, b, c, d, f.id, dev,
-                             part, nparts, C.byref(h)))
+            if isinstance(f, _Kernel):
+                build = _lib.lib().hm_assemble_kernel_free if matrix_free else _lib.lib().hm_assemble_kernel
+                _lib.check(build(x.ctypes.data_as(_dp), len(x), y.ctypes.data_as(_dp), len(y), a, b, c, d, f.id, dev,
+                                 part, nparts, C.byref(h)))
+            else:
+                # any f::Function (KernelMatrix.jl:47): the cores and the dense leaves are evaluated by f on
+                # the host in large batches (f is called with two equally long arrays), U and V on the device
+                if matrix_free:
+                    raise HmError(8, "matrix_free needs one of the kernels the device can evaluate")
+                err = []
+
+                def batch(px, py, n, pout, _user):
+                    try:
+                        xa = np.ctypeslib.as_array(px, shape=(n,))
+                        ya = np.ctypeslib.as_array(py, shape=(n,))
+                        np.ctypeslib.as_array(pout, shape=(n,))[:] = np.asarray(f(xa, ya), dtype=np.float64)
+                    except BaseException as exc:  # must not propagate through the C frames
+                        err.append(exc)
+                        np.ctypeslib.as_array(pout, shape=(n,))[:] = np.nan
+
+                cb = _lib.KERNEL_FN(batch)
+                _lib.check(_lib.lib().hm_assemble_kernel_fn(x.ctypes.data_as(_dp), len(x), y.ctypes.data_as(_dp), len(y),
+                                                            a, b, c, d, cb, None, dev, part, nparts, C.byref(h)))
+                if err:
+                    Plan(h.value, dev).close()
+                    raise err[0]
             self._assembled = Plan(h.value, dev)
             self.kernel = f
         else:

@@ -738,14 +738,132 @@ int32_t hm_assemble_kernel_stats(const double *x, int64_t nx, const double *y, i
     });
 }
 
+// hm_assemble_kernel_fn: the parts of the operator that depend on f -- the r x r cores
+// F[m,n] = f(x_m, y_n) at the mapped Chebyshev nodes (BarycentricMatrix.jl:159-175) and the dense
+// leaves T[f(x[i], y[j])] (KernelMatrix.jl:57-60) -- are evaluated by the caller's f on the host, in
+// large batches, and copied into the packed streams; U and V (88 % of the bytes) do not depend on f
+// and were filled by the device kernels.
+static int32_t host_fill(hm_plan *P, const double *x, const double *y, hm_kernel_fn fn, void *user)
+{
+    HmLayout &L = P->L;
+    cudaStream_t st = P->stream;
+    constexpr size_t BATCH = (size_t)1 << 21; // evaluations per callback
+    std::vector<double> xs, ys;
+    xs.reserve(BATCH + 4096);
+    ys.reserve(BATCH + 4096);
+    double *pin = nullptr; // results of one batch, in stream layout
+    size_t pin_cap = 0;
+    struct Piece {
+        double *dst;
+        size_t off, words;
+    };
+    std::vector<Piece> pieces;
+    auto ensure = [&](size_t words) -> cudaError_t {
+        if (words <= pin_cap) return cudaSuccess;
+        if (pin) cudaFreeHost(pin);
+        pin = nullptr;
+        pin_cap = 0;
+        cudaError_t e = cudaMallocHost((void **)&pin, words * 8);
+        if (e == cudaSuccess) pin_cap = words;
+        return e;
+    };
+    struct PinGuard {
+        double *&p;
+        ~PinGuard()
+        {
+            if (p) cudaFreeHost(p);
+        }
+    } pin_guard{pin};
+    // ---- cores ----
+    {
+        size_t c = 0;
+        const size_t nc = L.cores.size();
+        while (c < nc) {
+            xs.clear();
+            ys.clear();
+            pieces.clear();
+            size_t words = 0;
+            const size_t c_begin = c;
+            for (; c < nc && xs.size() < BATCH; c++) {
+                const HmCoreBlock &cb = L.cores[c];
+                const HmLeaf &l = L.leaves[(size_t)L.core_leaf[c]];
+                if (l.source != HM_SRC_KERNEL || cb.kind != HM_LEAF_BARY2D) continue;
+                const double xm = 0.5 * (l.a + l.b), xh = 0.5 * (l.b - l.a);
+                const double ym = 0.5 * (l.c + l.d), yh = 0.5 * (l.d - l.c);
+                for (int n = 0; n < cb.rv; n++)
+                    for (int m = 0; m < cb.ru; m++) {
+                        xs.push_back(xm + xh * P->cheb.node[m]);
+                        ys.push_back(ym + yh * P->cheb.node[n]);
+                    }
+                pieces.push_back(Piece{P->core.p + cb.core, words, (size_t)cb.ru * cb.rv});
+                words += (size_t)cb.ru * cb.rv;
+            }
+            if (words == 0) continue;
+            (void)c_begin;
+            HM_CUDA(ensure(words));
+            fn(xs.data(), ys.data(), (int64_t)words, pin, user);
+            for (const Piece &pc : pieces)
+                HM_CUDA(cudaMemcpyAsync(pc.dst, pin + pc.off, pc.words * 8, cudaMemcpyHostToDevice, st));
+            HM_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    // ---- dense tiles (stage-3 fill entries of dense leaves: kn slab columns of F rows, pitch Fp) ----
+    {
+        size_t i = 0;
+        const size_t nf = L.fill3.size();
+        std::vector<double> vals;
+        while (i < nf) {
+            xs.clear();
+            ys.clear();
+            pieces.clear();
+            size_t words = 0;
+            const size_t i_begin = i;
+            for (; i < nf && xs.size() < BATCH; i++) {
+                const HmFill &f = L.fill3[i];
+                const HmLeaf &l = L.leaves[(size_t)f.leaf];
+                if (l.source != HM_SRC_KERNEL || l.kind != HM_LEAF_DENSE) continue;
+                const double *xr = x + l.xi0 + f.off, *yc = y + l.yj0 + f.k0;
+                for (int k = 0; k < f.kn; k++)
+                    for (int r = 0; r < f.F; r++) {
+                        xs.push_back(xr[r]);
+                        ys.push_back(yc[k]);
+                    }
+                pieces.push_back(Piece{P->ustream.p + f.dst, words, (size_t)f.kn * f.Fp});
+                words += (size_t)f.kn * f.Fp;
+            }
+            if (xs.empty()) continue;
+            vals.resize(xs.size());
+            fn(xs.data(), ys.data(), (int64_t)xs.size(), vals.data(), user);
+            HM_CUDA(ensure(words));
+            size_t src = 0, pi = 0;
+            for (size_t j = i_begin; j < i; j++) {
+                const HmFill &f = L.fill3[j];
+                const HmLeaf &l = L.leaves[(size_t)f.leaf];
+                if (l.source != HM_SRC_KERNEL || l.kind != HM_LEAF_DENSE) continue;
+                double *dstp = pin + pieces[pi++].off;
+                for (int k = 0; k < f.kn; k++) {
+                    for (int r = 0; r < f.F; r++) dstp[(size_t)k * f.Fp + r] = vals[src++];
+                    for (int r = f.F; r < f.Fp; r++) dstp[(size_t)k * f.Fp + r] = 0.0;
+                }
+            }
+            for (const Piece &pc : pieces)
+                HM_CUDA(cudaMemcpyAsync(pc.dst, pin + pc.off, pc.words * 8, cudaMemcpyHostToDevice, st));
+            HM_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return HM_OK;
+}
+
 static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                                     double c, double d, int32_t kernel_id, int32_t device, int32_t part,
-                                    int32_t nparts, bool matrix_free, hm_plan **out)
+                                    int32_t nparts, bool matrix_free, hm_plan **out, hm_kernel_fn fn = nullptr,
+                                    void *user = nullptr)
 {
     return guarded([&]() -> int32_t {
         if (!out) return fail(HM_ERR_NULL, "out is NULL");
         *out = nullptr;
-        if (kernel_id < 0 || kernel_id > 3) return fail(HM_ERR_INVALID, "unknown kernel id %d", kernel_id);
+        if (fn) kernel_id = HM_KERNEL_HOST_FN;
+        else if (kernel_id < 0 || kernel_id > 3) return fail(HM_ERR_INVALID, "unknown kernel id %d", kernel_id);
         if (hm_blockrank_double() != 20) return fail(HM_ERR_UNSUPPORTED, "BLOCKRANK(Float64) != 20");
         HM_DEVICE(device);
         hm_plan *P = new (std::nothrow) hm_plan;
@@ -773,6 +891,13 @@ static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y
             delete P;
             return st;
         }
+        if (fn) {
+            st = host_fill(P, x, y, fn, user);
+            if (st != HM_OK) {
+                delete P;
+                return st;
+            }
+        }
         if (!matrix_free) { // the stored operator no longer needs the points
             P->f_px.release();
             P->f_py.release();
@@ -788,6 +913,17 @@ int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t
 {
     return guarded([&]() -> int32_t {
         return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, kernel_id, device, part, nparts, false, out);
+    });
+}
+
+int32_t hm_assemble_kernel_fn(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                              double c, double d, hm_kernel_fn f, void *user, int32_t device, int32_t part,
+                              int32_t nparts, hm_plan **out)
+{
+    return guarded([&]() -> int32_t {
+        if (!f) return fail(HM_ERR_NULL, "kernel function is NULL");
+        return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, HM_KERNEL_HOST_FN, device, part, nparts, false, out, f,
+                                    user);
     });
 }
 

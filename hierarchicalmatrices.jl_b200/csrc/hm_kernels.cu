@@ -406,6 +406,7 @@ hm_fill3_kernel(const HmFill *__restrict__ fills, const HmLeaf *__restrict__ lea
         }
     } else if (l->kind == HM_LEAF_DENSE) {
         // T[f(x[i], y[j]) for i in ir, j in jr] -- src/KernelMatrix.jl:57-60
+        if (kernel_id == HM_KERNEL_HOST_FN) return; // evaluated on the host (hm_assemble_kernel_fn)
         const double *xr = px + l->xi0 + f.off;
         const double *yc = py + l->yj0 + f.k0;
         for (int idx = t; idx < f.kn * f.F; idx += T) {
@@ -473,6 +474,7 @@ hm_fillcore_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
         }
     } else {
         // F[m,n] = f(x_m, y_n) at the mapped Chebyshev nodes -- BarycentricMatrix.jl:159-175
+        if (kernel_id == HM_KERNEL_HOST_FN) return; // evaluated on the host (hm_assemble_kernel_fn)
         const double xm = __dmul_rn(0.5, __dadd_rn(l->a, l->b)), xh = __dmul_rn(0.5, __dsub_rn(l->b, l->a));
         const double ym = __dmul_rn(0.5, __dadd_rn(l->c, l->d)), yh = __dmul_rn(0.5, __dsub_rn(l->d, l->c));
         for (int idx = t; idx < cb.ru * cb.rv; idx += T) {

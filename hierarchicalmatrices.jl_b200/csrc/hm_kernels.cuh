@@ -9,6 +9,7 @@
 #define HM_MAXRUNS 256  // run-table capacity of a stage-3 item
 #define HM_RMAX_ASM 32  // max interpolation rank of on-device assembly
 #define HM_CORE_BIG 128 // stage 2: leaves with more partial sums than this get a whole CTA
+#define HM_KERNEL_HOST_FN 4 // kernel id of hm_assemble_kernel_fn: f is a host callback
 
 // Chebyshev nodes / barycentric weights of the reference's BarycentricPoly2D
 // (src/BarycentricMatrix.jl:147-156), computed once on the host.

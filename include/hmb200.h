@@ -154,6 +154,18 @@ HM_API int32_t hm_plan_stats(const hm_plan *p, hm_stats *out);
 HM_API int32_t hm_assemble_kernel(const double *x, int64_t nx, const double *y, int64_t ny, double a,
                            double b, double c, double d, int32_t kernel_id, int32_t device,
                            int32_t part, int32_t nparts, hm_plan **out);
+/* KernelMatrix(f, x, y, a, b, c, d) for ANY kernel function (src/KernelMatrix.jl:47 takes any
+ * `f::Function`): f is a host callback evaluating a batch, out[i] = f(x[i], y[i]), i < n.  Only the
+ * r x r cores F[m,n] = f(x_m, y_n) (src/BarycentricMatrix.jl:159-175; 2.9 % of the bytes at
+ * N = 2^20) and the dense leaves (src/KernelMatrix.jl:57-60; 9.3 %) depend on f: they are evaluated
+ * through the callback in batches of ~2 M points and copied into the packed streams, while U and V
+ * are filled on the device exactly as in hm_assemble_kernel.  The callback is used during this
+ * call only. */
+typedef void (*hm_kernel_fn)(const double *x, const double *y, int64_t n, double *out, void *user);
+HM_API int32_t hm_assemble_kernel_fn(const double *x, int64_t nx, const double *y, int64_t ny, double a,
+                              double b, double c, double d, hm_kernel_fn f, void *user, int32_t device,
+                              int32_t part, int32_t nparts, hm_plan **out);
+
 /* Matrix-free variant ("fused assemble + apply"): same arguments and the same
  * operator as hm_assemble_kernel, but U, V and the dense tiles are never stored -- hm_matvec /
  * hm_matvec_device / hm_matvec_device_allgather evaluate every entry from the point sets while

@@ -118,10 +118,16 @@ int hmo_indsplit(const double *x, int64_t nx, int64_t i0, int64_t i1, double a, 
     return 0;
 }
 
+/* KernelMatrix.jl:47 takes any f::Function: kernel id HMO_USER calls the function registered
+ * here, element by element, exactly where the reference calls f(x, y). */
+static double (*hmo_user_kernel)(double, double) = 0;
+void hmo_set_user_kernel(double (*f)(double, double)) { hmo_user_kernel = f; }
+
 /* examples/Kernel.jl:34-37.  `^2`/`^3` are literal powers (x*x, x*x*x). */
 double hmo_kernel_eval(int kernel, double x, double y)
 {
     double d = x - y;
+    if (kernel == HMO_USER) return hmo_user_kernel ? hmo_user_kernel(x, y) : NAN;
     switch (kernel) {
     case HMO_CAUCHY: return 1.0 / d;
     case HMO_COULOMB: return 1.0 / (d * d);

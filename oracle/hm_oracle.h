@@ -26,7 +26,9 @@ extern "C" {
 #endif
 
 /* kernel ids -- examples/Kernel.jl:34-37 */
-enum { HMO_CAUCHY = 0, HMO_COULOMB = 1, HMO_COULOMBPRIME = 2, HMO_LOG = 3 };
+enum { HMO_CAUCHY = 0, HMO_COULOMB = 1, HMO_COULOMBPRIME = 2, HMO_LOG = 3, HMO_USER = 4 };
+/* any f::Function (KernelMatrix.jl:47): kernel id HMO_USER evaluates this scalar callback */
+void hmo_set_user_kernel(double (*f)(double, double));
 
 /* block kinds; the `assigned` code of the reference (hierarchical.jl:84-91) is
  * 1 for NODE, 2 for LOWRANK/BARY2D (first listed leaf type), 3 for DENSE. */

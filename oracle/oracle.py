@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libhm_oracle.so")
 
-CAUCHY, COULOMB, COULOMBPRIME, LOG = 0, 1, 2, 3
+CAUCHY, COULOMB, COULOMBPRIME, LOG, USER = 0, 1, 2, 3, 4
 NONE, NODE, LOWRANK, DENSE, BARY2D, EVENBARY = 0, 1, 2, 3, 4, 5
 
 _dp = C.POINTER(C.c_double)
@@ -324,6 +324,19 @@ class Tree:
     def matvec(self, x):
         y = np.zeros(self.shape[0])
         return self.mul(y, np.ascontiguousarray(x, dtype=np.float64))
+
+
+_USER_KERNEL_T = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double)
+_user_kernel_keep = None
+
+
+def set_user_kernel(f):
+    """Register a scalar Python function f(x, y) as kernel id USER (any f::Function, KernelMatrix.jl:47)."""
+    global _user_kernel_keep
+    _user_kernel_keep = _USER_KERNEL_T(lambda a, b: float(f(a, b)))
+    lib().hmo_set_user_kernel.argtypes = [_USER_KERNEL_T]
+    lib().hmo_set_user_kernel.restype = None
+    lib().hmo_set_user_kernel(_user_kernel_keep)
 
 
 def kernelmatrix(kernel, x, y, a, b, c, d) -> Tree:

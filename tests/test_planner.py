@@ -242,6 +242,9 @@ def test_no_cpu_fallback(hm):
     with pytest.raises(hm.HmError) as e:
         hm.KernelMatrix(hm.cauchykernel, x, x + 1e-3, 1.0, -1.0, 1.0, -1.0, device=0, matrix_free=True)
     assert e.value.status == 7
+    with pytest.raises(hm.HmError) as e:   # any-f constructor (host callback): no CPU path either
+        hm.KernelMatrix(lambda p, q: np.exp(-np.abs(p - q)), x, x + 1e-3, 1.0, -1.0, 1.0, -1.0, device=0)
+    assert e.value.status == 7
     with pytest.raises(hm.HmError):     # matrix_free belongs to the assembling constructor only
         hm.KernelMatrix(np.float64, 2, 2, matrix_free=True)
     H = hm.HierarchicalMatrix(np.float64, 1, 1)

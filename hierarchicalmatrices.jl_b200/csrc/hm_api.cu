@@ -1255,14 +1255,22 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
         }
         HM_DEVICE(p->device);
         cudaStream_t st = (cudaStream_t)stream;
+        if (p->panel_zcap == 0) {
+            int zc = 4;
+            for (const HmItem &it : L.items3) zc = std::max(zc, (int)it.S);
+            p->panel_zcap = zc;
+        }
         for (int64_t c0 = 0; c0 < nrhs; c0 += 64) {
             const int nc = (int)std::min<int64_t>(64, nrhs - c0);
             const int CS = hm_panel_width(nc);
             if (CS > p->ws_cs) {
                 HM_CUDA(cudaStreamSynchronize(st));
-                HM_CUDA(p->wXt.alloc((size_t)std::max<int64_t>(L.ncols, 1) * CS));
+                // Xt and Sp share one allocation (Sp right behind Xt): the stage-3 kernel addresses the z
+                // rows of both through one base pointer and a 32-bit row index
+                const size_t xt_rows = (size_t)std::max<int64_t>(L.ncols, 1);
+                HM_CUDA(p->wXt.alloc((xt_rows + (size_t)std::max<int64_t>(L.s_words, 1)) * CS));
+                p->wSp = p->wXt.p + xt_rows * CS;
                 HM_CUDA(p->wPp.alloc((size_t)std::max<int64_t>(L.partial_words, 1) * CS));
-                HM_CUDA(p->wSp.alloc((size_t)std::max<int64_t>(L.s_words, 1) * CS));
                 HM_CUDA(p->wYt.alloc((size_t)std::max<int64_t>(L.nrows, 1) * CS));
                 p->ws_cs = CS;
             }
@@ -1273,12 +1281,12 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
                                            p->wPp.p, st));
             if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
             HM_CUDA(hm_launch_panel_stage2(CS, p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->wPp.p, p->core.p,
-                                           p->wSp.p, std::max(L.max_r, 1), st));
+                                           p->wSp, std::max(L.max_r, 1), st));
             if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
             for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
                 int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
                 HM_CUDA(hm_launch_panel_stage3(CS, p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->wXt.p,
-                                               p->wSp.p, p->wYt.p, r == 0 ? 0 : 1, st));
+                                               p->wSp, p->wYt.p, r == 0 ? 0 : 1, p->panel_zcap, st));
             }
             HM_CUDA(hm_launch_panel_out(p->wYt.p, CS, L.row_begin, L.row_end, nc, dY + c0 * ldy, ldy,
                                         accumulate != 0, st));

@@ -154,7 +154,9 @@ struct hm_plan {
     DevBuf<double> dX, dY;
     // panel workspace of the multi-RHS path (row pitch ws_cs)
     int ws_cs = 0;
-    DevBuf<double> wXt, wPp, wSp, wYt;
+    int panel_zcap = 0; // largest z length of a stage-3 item
+    DevBuf<double> wXt, wPp, wYt;
+    double *wSp = nullptr; // inside wXt's allocation, behind the x panel
     std::mutex mu;
     // per-stage timing (bench bookkeeping)
     std::vector<cudaEvent_t> tev;

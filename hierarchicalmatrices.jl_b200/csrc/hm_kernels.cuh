@@ -120,6 +120,13 @@ cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, 
                                    const double *Xt, double *Pp, cudaStream_t st);
 cudaError_t hm_launch_panel_stage2(int CS, const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
                                    const double *Pp, const double *core, double *Sp, int max_r, cudaStream_t st);
+// zcap: largest S of the items (sizes the z row table of the pipelined kernel)
 cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, const HmRun *runs,
                                    const double *ustream, const double *Xt, const double *Sp, double *Yt,
-                                   int accumulate, cudaStream_t st);
+                                   int accumulate, int zcap, cudaStream_t st);
+// pipelined DMMA implementation of the two panel stages (hm_panel_mma.cu)
+cudaError_t hm_launch_panelm_stage1(int CS, const HmItem *items, int64_t nitems, const double *vstream,
+                                    const double *Xt, double *Pp, cudaStream_t st);
+cudaError_t hm_launch_panelm_stage3(int CS, const HmItem *items, int64_t nitems, const HmRun *runs,
+                                    const double *ustream, const double *Xt, const double *Sp, double *Yt,
+                                    int accumulate, int zcap, cudaStream_t st);

@@ -877,12 +877,14 @@ cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1
 //   stream   1.92 / 5.50    2.48 / 6.17
 //   mm       2.64 / 6.39    2.10 / 5.19
 //   tma      5.70 / 7.79    5.00 / 6.85
+//   fma (default)     hm_panelf_kernel (hm_panel_mma.cu): register-tiled FMA-pipe GEMM behind a cp.async ring
+//   dmma              the per-stage DMMA choice above
 static int panel_variant(int stage)
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("HMB200_PANEL");
-        v = !e ? 3 : e[0] == 't' ? 1 : e[0] == 'm' ? 2 : e[0] == 's' ? 0 : 3;
+        v = !e ? 4 : e[0] == 't' ? 1 : e[0] == 'm' ? 2 : e[0] == 's' ? 0 : e[0] == 'd' ? 3 : 4;
     }
     if (v == 3) return stage == 3 ? 2 : 0;
     return v;
@@ -892,6 +894,7 @@ cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, 
                                    const double *Xt, double *Pp, cudaStream_t st)
 {
     const int variant = panel_variant(1);
+    if (variant == 4) return hm_launch_panelm_stage1(CS, items, nitems, vstream, Xt, Pp, st);
     if (variant == 1) switch (CS) {
         case 16: return launch_panel_tma<false, 2>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
         case 32: return launch_panel_tma<false, 4>(items, nitems, nullptr, vstream, Xt, nullptr, Pp, 0, st);
@@ -925,9 +928,10 @@ cudaError_t hm_launch_panel_stage2(int CS, const HmCoreBlock *blocks, int64_t nb
 
 cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, const HmRun *runs,
                                    const double *ustream, const double *Xt, const double *Sp, double *Yt,
-                                   int accumulate, cudaStream_t st)
+                                   int accumulate, int zcap, cudaStream_t st)
 {
     const int variant = panel_variant(3);
+    if (variant == 4) return hm_launch_panelm_stage3(CS, items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, zcap, st);
     if (variant == 1) switch (CS) {
         case 16: return launch_panel_tma<true, 2>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);
         case 32: return launch_panel_tma<true, 4>(items, nitems, runs, ustream, Xt, Sp, Yt, accumulate, st);

@@ -969,29 +969,40 @@ def test_matrix_free_parts_determinism_and_unsupported(hm, O):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("dist,N", [("cheb", 3000), ("unif", 2048), ("quad", 1000)])
-def test_arbitrary_kernel_function_matches_oracle(hm, O, dist, N):
-    """KernelMatrix(f, x, y, a, b, c, d) takes any f::Function (KernelMatrix.jl:47): a fifth kernel,
-    exp(-|x - y|), through hm_assemble_kernel_fn (cores and dense leaves evaluated by the host
-    callback, U and V on the device) against the oracle given the same function."""
+@pytest.mark.parametrize("kname", ["exp", "lorentz"])
+def test_arbitrary_kernel_function_matches_oracle(hm, O, dist, N, kname):
+    """KernelMatrix(f, x, y, a, b, c, d) takes any f::Function (KernelMatrix.jl:47): a fifth and a
+    sixth kernel, exp(-|x - y|) and 1/(1 + (x - y)^2), through hm_assemble_kernel_fn (cores and dense
+    leaves evaluated by the host callback, U and V on the device) against the oracle given the same
+    function."""
     import math
     x, y, (a, b, c, d) = O.example_points(N, dist)
-    K = hm.KernelMatrix(lambda p, q: np.exp(-np.abs(p - q)), x, y, a, b, c, d, device=0)
-    O.set_user_kernel(lambda p, q: math.exp(-abs(p - q)))
+    if kname == "exp":
+        fv, fs = (lambda p, q: np.exp(-np.abs(p - q))), (lambda p, q: math.exp(-abs(p - q)))
+    else:
+        fv = fs = lambda p, q: 1.0 / (1.0 + (p - q) * (p - q))
+    K = hm.KernelMatrix(fv, x, y, a, b, c, d, device=0)
+    O.set_user_kernel(fs)
     Kref = O.kernelmatrix(O.USER, x, y, a, b, c, d)
     v = np.random.default_rng(11).standard_normal(N)
     assert relinf(K * v, Kref.matvec(v)) <= TOL
-    # the factors themselves: cores and dense leaves bit-identical (same libm exp on the host), U and V
-    # bit-identical as for the built-in kernels
+    # the factors themselves: U and V bit-identical as for the built-in kernels; cores and dense leaves
+    # bit-identical for the rational kernel (IEEE arithmetic on both sides), to an ulp or two for exp
+    # (numpy's vectorised exp vs libm's)
     plan = K.plan()
     arr, n = Kref.leaves()
     assert plan.num_leaves() == n
+    same = np.array_equal if kname == "lorentz" else (lambda p, q: np.allclose(p, q, rtol=4e-16, atol=0))
     for i in range(0, n, max(1, n // 40)):
         o = arr[i]
         if o.kind == O.DENSE:
-            assert np.array_equal(plan.read_leaf(i, 3), np.ctypeslib.as_array(o.A, shape=(o.n, o.m)).T)
+            assert same(plan.read_leaf(i, 3), np.ctypeslib.as_array(o.A, shape=(o.n, o.m)).T)
         else:
-            assert np.array_equal(plan.read_leaf(i, 1), np.ctypeslib.as_array(o.S, shape=(o.r, o.r)).T)
+            assert same(plan.read_leaf(i, 1), np.ctypeslib.as_array(o.S, shape=(o.r, o.r)).T)
             assert np.array_equal(plan.read_leaf(i, 0), np.ctypeslib.as_array(o.A, shape=(o.r, o.m)).T)
+            assert np.array_equal(plan.read_leaf(i, 2), np.ctypeslib.as_array(o.V, shape=(o.r, o.n)).T)
+    if kname == "exp":
+        return
     # a failing callback surfaces as its Python exception, not as a crash
     with pytest.raises(ZeroDivisionError):
         hm.KernelMatrix(lambda p, q: 1 / 0, x, y, a, b, c, d, device=0)

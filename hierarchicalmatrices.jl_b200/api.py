@@ -213,8 +213,9 @@ class Plan:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h and _lib._lib is not None:
-            _lib._lib.hm_plan_destroy(h)
+        lib = getattr(_lib, "_lib", None) if _lib is not None else None  # module globals vanish at interpreter exit
+        if h and lib is not None:
+            lib.hm_plan_destroy(h)
 
     close = __del__
 

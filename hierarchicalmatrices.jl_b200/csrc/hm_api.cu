@@ -1064,12 +1064,13 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
                     HM_CUDA(hm_launch_free1(p->items1c.p + i0, i1 - i0, p->f_ent1.p, p->f_py.p, p->dx.p, p->partial.p,
                                             p->cheb, p->free1_units, st));
                 else
-                    HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st));
+                    HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st,
+                                             false));
             }
             HM_CUDA(hm_launch_stage2(p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->partial.p, p->core.p,
-                                     p->svec.p, std::max(L.max_r, 1), st));
+                                     p->svec.p, std::max(L.max_r, 1), st, false));
             HM_CUDA(hm_launch_stage2_big(p->cores.p, p->bigcores.p, p->nbig, p->plist.p, p->partial.p, p->core.p,
-                                         p->svec.p, std::max(L.max_r, 1), st));
+                                         p->svec.p, std::max(L.max_r, 1), st, false));
             HM_CUDA(cudaStreamWaitEvent(st, p->ev_y0, 0));
             for (int k = 0; k < HM_NCHUNK; k++) {
                 const int64_t i0 = L.c3_begin[(size_t)k], i1 = L.c3_begin[(size_t)k + 1];
@@ -1079,7 +1080,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
                                             nullptr, p->free3_zcap, st));
                 else
                     HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
-                                             p->dy.p, accumulate != 0, nullptr, st));
+                                             p->dy.p, accumulate != 0, nullptr, st, false));
                 HM_CUDA(cudaEventRecord(p->ev_y[k], st));
             }
             // all launches are queued before the first copy back: with pageable y the copies block

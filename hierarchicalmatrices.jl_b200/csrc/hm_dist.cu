@@ -20,6 +20,7 @@
 #include <nccl.h> // types and prototypes only; the entry points are resolved with dlsym
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "hm_internal.h"
@@ -30,6 +31,7 @@ struct NcclApi {
     void *h = nullptr;
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommInitRankConfig) CommInitRankConfig = nullptr; // optional (NCCL >= 2.17)
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
     decltype(&ncclBroadcast) Broadcast = nullptr;
     decltype(&ncclAllGather) AllGather = nullptr;
@@ -65,6 +67,7 @@ struct NcclApi {
         HM_SYM(GetErrorString, "ncclGetErrorString")
         HM_SYM(GetVersion, "ncclGetVersion")
 #undef HM_SYM
+        CommInitRankConfig = reinterpret_cast<decltype(CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
         return true;
     }
 };
@@ -94,6 +97,10 @@ struct BarrierArgs {
 __global__ void __launch_bounds__(32) hm_barrier_kernel(BarrierArgs b)
 {
     __shared__ unsigned es;
+    // programmatic dependent launch: the next kernel (stage 1 of the following matvec) may begin its
+    // prologue while this one spins; this kernel itself must not signal before stage 3 has finished
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) es = ++(*b.epoch);
     __syncwarp();
     const unsigned e = es;
@@ -155,8 +162,17 @@ int32_t launch_barrier(hm_plan *p, cudaStream_t st)
     b.n = d->nranks;
     b.self = d->rank;
     b.timeout_cycles = 20LL * 1000 * 1000 * 1000; // ~10 s at 2 GHz: a dead peer must not hang the GPU
-    hm_barrier_kernel<<<1, 32, 0, st>>>(b);
-    HM_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    const char *e = getenv("HMB200_PDL");
+    cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+    HM_CUDA(cudaLaunchKernelEx(&cfg, hm_barrier_kernel, b));
     return HM_OK;
 }
 
@@ -209,7 +225,20 @@ int32_t hm_dist_init(hm_plan *p, const void *id, int32_t nranks, int32_t rank)
         d->ncols = p->L.ncols;
         ncclUniqueId uid;
         memcpy(&uid, id, sizeof uid);
-        HM_NCCL(g_nccl.CommInitRank(&d->comm, nranks, uid, rank));
+        // The only collective on the data path is the broadcast of x (8 N bytes), issued on a second
+        // stream underneath the previous matvec: it is latency-tolerant, so the communicator is
+        // limited to a few CTAs -- NCCL's default channel count takes SMs (and HBM bandwidth) away
+        // from the stream kernels it overlaps with.  HMB200_NCCL_MAX_CTAS overrides (0 = NCCL default).
+        int max_ctas = 2;
+        if (const char *e = getenv("HMB200_NCCL_MAX_CTAS")) max_ctas = atoi(e);
+        if (g_nccl.CommInitRankConfig && max_ctas > 0) {
+            ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+            cfg.minCTAs = 1;
+            cfg.maxCTAs = max_ctas;
+            HM_NCCL(g_nccl.CommInitRankConfig(&d->comm, nranks, uid, rank, &cfg));
+        } else {
+            HM_NCCL(g_nccl.CommInitRank(&d->comm, nranks, uid, rank));
+        }
         // exchange region: [flag rows | epoch | err | x0 | x1 | y0 | y1], identical layout on all ranks
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
         size_t off = 0;

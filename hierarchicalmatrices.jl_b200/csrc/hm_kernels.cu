@@ -15,10 +15,18 @@
 //
 // HBM-bound: 8 B of stream per FMA.  No tensor-core use on the single-vector path.
 #include <algorithm>
+#include <cstdlib>
 
 #include "hm_kernels.cuh"
 
 namespace {
+
+// Programmatic dependent launch (PDL).  A kernel launched with the programmatic-stream-
+// serialization attribute may begin before its predecessor in the stream has finished;
+// griddepcontrol.wait blocks until that predecessor has completed and its writes are visible.
+// Without the attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ double2 ld_stream(const double2 *p)
 {
@@ -55,6 +63,7 @@ __device__ __noinline__ void core_apply_warp(const HmCoreBlock &cb, const int32_
 #pragma unroll
             for (int l = 0; l < R; l++) f[l] = __ldcs(c + lane + l * R);
         }
+        pdl_wait(); // the core does not depend on stage 1; the partial sums below do
         double t = 0.0;
         if (act) {
             int i = 0;
@@ -78,6 +87,7 @@ __device__ __noinline__ void core_apply_warp(const HmCoreBlock &cb, const int32_
         if (act) svec[cb.soff + lane] = a;
         return;
     }
+    pdl_wait();
     for (int k = lane; k < cb.rv; k += 32) {
         double t = 0.0;
         int i = 0;
@@ -114,6 +124,7 @@ __device__ __noinline__ void core_apply_cta(const HmCoreBlock &cb, const int32_t
 {
     const int lane = tid & 31, w = tid >> 5;
     const int32_t *pl = plist + cb.pl0;
+    pdl_wait();
     for (int k = lane; k < cb.rv; k += 32) {
         double t = 0.0;
         int i = w;
@@ -155,6 +166,7 @@ hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
                const double *__restrict__ core, double *__restrict__ svec, int max_r)
 {
     extern __shared__ double tbuf_all[];
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     if (b >= nblocks) return;
@@ -169,6 +181,7 @@ hm_core_big_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
                    const double *__restrict__ core, double *__restrict__ svec, int max_r)
 {
     extern __shared__ double sm[]; // [8][max_r] warp sums, then [max_r] t
+    pdl_launch_dependents();
     core_apply_cta(blocks[big[blockIdx.x]], plist, partial, core, svec, sm, max_r, threadIdx.x);
 }
 
@@ -190,6 +203,36 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
     const HmItem it = items[blockIdx.x];
     const int t = threadIdx.x;
     const int S = it.S, F = it.F, L = it.Fp >> 1;
+    // programmatic dependent launch: the next kernel of the stream may start its own prologue while
+    // this grid runs (it blocks in griddepcontrol.wait until this grid has completed)
+    pdl_launch_dependents();
+
+    const double2 *__restrict__ W2 = reinterpret_cast<const double2 *>(W + it.slab);
+
+    // ---- first batch of the slab: issued before z is staged.  The slab does not depend on the
+    // previous kernel, so these loads are in flight during the prologue (and, under programmatic
+    // dependent launch, while the previous kernel is still finishing) ----
+    const bool narrow = L <= T;
+    const int ncg = narrow ? (L > 0 ? T / L : 1) : 1; // column groups of L threads (narrow items)
+    const int TA = ncg * L;
+    const int nvec = S * L;
+    double2 w0[8];
+    bool pre = false;
+    if (narrow) {
+        if (t < TA && t + 7 * TA < nvec) {
+            pre = true;
+#pragma unroll
+            for (int u = 0; u < 8; u++) w0[u] = ld_stream(W2 + t + u * TA);
+        }
+    } else if (S >= 8) {
+        pre = true; // t < T < L: the thread's first column exists
+#pragma unroll
+        for (int u = 0; u < 8; u++) w0[u] = ld_stream(W2 + t + (size_t)u * L);
+    }
+
+    // everything below reads what the previous kernel wrote (x / the stage-2 vector) or writes
+    // what it may still be reading
+    pdl_wait();
 
     // ---- stage z in shared memory ----
     if (GATHER) {
@@ -217,8 +260,6 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
     }
     __syncthreads();
 
-    const double2 *__restrict__ W2 = reinterpret_cast<const double2 *>(W + it.slab);
-
     // one writer per output element.  Stage 3 with PEERS: the all-gather of y is fused into
     // the kernel -- every owned row is stored straight into each rank's (symmetric, NVLink
     // peer-mapped) y buffer instead of a local buffer followed by a collective.
@@ -236,15 +277,22 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
         }
     };
 
-    if (L <= T) {
+    if (narrow) {
         // ncg column groups of L threads; thread t reads double2 number t, t+TA, ...
-        const int ncg = L > 0 ? T / L : 1;
-        const int TA = ncg * L;
         double2 acc = make_double2(0.0, 0.0);
         if (t < TA) {
             const int cg = t / L;
-            const int nvec = S * L;
             int i = t, si = cg;
+            if (pre) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    double z = zs[si + u * ncg];
+                    acc.x = fma(w0[u].x, z, acc.x);
+                    acc.y = fma(w0[u].y, z, acc.y);
+                }
+                i += 8 * TA;
+                si += 8 * ncg;
+            }
             for (; i + 7 * TA < nvec; i += 8 * TA, si += 8 * ncg) {
                 double2 w[8];
 #pragma unroll
@@ -287,6 +335,15 @@ hm_stream_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ run
             double2 acc = make_double2(0.0, 0.0);
             const double2 *p = W2 + f2;
             int s = 0;
+            if (pre && f2 == t) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    double z = zs[u];
+                    acc.x = fma(w0[u].x, z, acc.x);
+                    acc.y = fma(w0[u].y, z, acc.y);
+                }
+                s = 8;
+            }
             for (; s + 7 < S; s += 8) {
                 double2 w[8];
 #pragma unroll
@@ -1104,22 +1161,50 @@ cudaError_t hm_launch_scale_cols(const HmItem *items1, int64_t n1, double *vstre
 // ---------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------
+// Launch with the programmatic-stream-serialization attribute (PDL): the kernel may start while the
+// previous kernel of the stream is still running; it synchronises itself with griddepcontrol.wait.
+// Only kernels that contain pdl_wait() may be launched this way.  HMB200_PDL=0 disables it.
+static bool pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HMB200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <class... KArgs, class... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                            bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *vstream,
-                             const double *x, double *partial, const HmFuse *fuse, cudaStream_t st)
+                             const double *x, double *partial, const HmFuse *fuse, cudaStream_t st, bool pdl)
 {
     if (nitems <= 0) return cudaSuccess;
     if (fuse && fuse->counters && (size_t)fuse->max_r * 8 <= HM_SMAX)
-        hm_stream_kernel<false, true, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x, nullptr,
-                                                                               partial, 0, *fuse, HmPeers{});
-    else
-        hm_stream_kernel<false, false, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, nullptr, vstream, x,
-                                                                                nullptr, partial, 0, HmFuse{}, HmPeers{});
-    return cudaGetLastError();
+        return launch_k(hm_stream_kernel<false, true, false>, (unsigned)nitems, HM_THREADS, 0, st, pdl, items,
+                        (const HmRun *)nullptr, vstream, x, (const double *)nullptr, partial, 0, *fuse, HmPeers{});
+    return launch_k(hm_stream_kernel<false, false, false>, (unsigned)nitems, HM_THREADS, 0, st, pdl, items,
+                    (const HmRun *)nullptr, vstream, x, (const double *)nullptr, partial, 0, HmFuse{}, HmPeers{});
 }
 
 cudaError_t hm_launch_stage2_big(const HmCoreBlock *blocks, const int32_t *big, int64_t nbig,
                                  const int32_t *plist, const double *partial, const double *core,
-                                 double *svec, int max_r, cudaStream_t st)
+                                 double *svec, int max_r, cudaStream_t st, bool pdl)
 {
     if (nbig <= 0) return cudaSuccess;
     size_t smem = (size_t)9 * max_r * sizeof(double);
@@ -1131,13 +1216,13 @@ cudaError_t hm_launch_stage2_big(const HmCoreBlock *blocks, const int32_t *big, 
             if (e != cudaSuccess) return e;
         }
     }
-    hm_core_big_kernel<<<(unsigned)nbig, 256, smem, st>>>(blocks, big, plist, partial, core, svec, max_r);
-    return cudaGetLastError();
+    return launch_k(hm_core_big_kernel, (unsigned)nbig, 256, smem, st, pdl, blocks, big, plist, partial, core, svec,
+                    max_r);
 }
 
 cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
                              const double *partial, const double *core, double *svec, int max_r,
-                             cudaStream_t st)
+                             cudaStream_t st, bool pdl)
 {
     if (nblocks <= 0) return cudaSuccess;
     int threads = 256;
@@ -1149,22 +1234,20 @@ cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const i
     if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
     int wpb = threads / 32;
     unsigned grid = (unsigned)((nblocks + wpb - 1) / wpb);
-    hm_core_kernel<<<grid, threads, smem, st>>>(blocks, nblocks, plist, partial, core, svec, max_r);
-    return cudaGetLastError();
+    return launch_k(hm_core_kernel, grid, (unsigned)threads, smem, st, pdl, blocks, nblocks, plist, partial, core,
+                    svec, max_r);
 }
 
 cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *runs,
                              const double *ustream, const double *x, const double *svec, double *y,
-                             int accumulate, const HmPeers *peers, cudaStream_t st)
+                             int accumulate, const HmPeers *peers, cudaStream_t st, bool pdl)
 {
     if (nitems <= 0) return cudaSuccess;
     if (peers && peers->n > 0)
-        hm_stream_kernel<true, false, true><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec, y,
-                                                                                  accumulate, HmFuse{}, *peers);
-    else
-        hm_stream_kernel<true, false, false><<<(unsigned)nitems, HM_THREADS, 0, st>>>(items, runs, ustream, x, svec,
-                                                                                   y, accumulate, HmFuse{}, HmPeers{});
-    return cudaGetLastError();
+        return launch_k(hm_stream_kernel<true, false, true>, (unsigned)nitems, HM_THREADS, 0, st, pdl, items, runs,
+                        ustream, x, svec, y, accumulate, HmFuse{}, *peers);
+    return launch_k(hm_stream_kernel<true, false, false>, (unsigned)nitems, HM_THREADS, 0, st, pdl, items, runs,
+                    ustream, x, svec, y, accumulate, HmFuse{}, HmPeers{});
 }
 
 cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFreeEnt *ents, const double *py,

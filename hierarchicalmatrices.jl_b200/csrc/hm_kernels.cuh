@@ -40,19 +40,22 @@ struct HmPeers {
 };
 
 // stage 1: partial[item.out + f] = sum_s V-slab[s][f] * x[item.zoff + s]
+// pdl: launch with the programmatic-stream-serialization attribute (the kernel may start while the
+// previous kernel of the stream still runs and synchronises itself); false where a launch follows
+// an event wait on another stream's copy.
 cudaError_t hm_launch_stage1(const HmItem *items, int64_t nitems, const double *vstream,
-                             const double *x, double *partial, const HmFuse *fuse, cudaStream_t st);
+                             const double *x, double *partial, const HmFuse *fuse, cudaStream_t st, bool pdl = true);
 // stage 2: s_b = F_b * (sum of partials) | Sigma_b .* (sum of partials)
 cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
                              const double *partial, const double *core, double *svec, int max_r,
-                             cudaStream_t st);
+                             cudaStream_t st, bool pdl = true);
 cudaError_t hm_launch_stage2_big(const HmCoreBlock *blocks, const int32_t *big, int64_t nbig,
                                  const int32_t *plist, const double *partial, const double *core,
-                                 double *svec, int max_r, cudaStream_t st);
+                                 double *svec, int max_r, cudaStream_t st, bool pdl = true);
 // stage 3: y[item.out + f] (+)= sum_s U-slab[s][f] * z[s],  z gathered from x and s
 cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *runs,
                              const double *ustream, const double *x, const double *svec, double *y,
-                             int accumulate, const HmPeers *peers, cudaStream_t st);
+                             int accumulate, const HmPeers *peers, cudaStream_t st, bool pdl = true);
 
 // adjoint apply y (+)= H' x: four launches over the same streams (hm_kernels.cu)
 struct HmAdjoint {

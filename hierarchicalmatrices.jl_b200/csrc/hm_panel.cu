@@ -877,14 +877,18 @@ cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1
 //   stream   1.92 / 5.50    2.48 / 6.17
 //   mm       2.64 / 6.39    2.10 / 5.19
 //   tma      5.70 / 7.79    5.00 / 6.85
-//   fma (default)     hm_panelf_kernel (hm_panel_mma.cu): register-tiled FMA-pipe GEMM behind a cp.async ring
-//   dmma              the per-stage DMMA choice above
+//   pipe     hm_panelm_kernel (hm_panel_mma.cu, HMB200_PANEL=pipe): 32 x 32 DMMA warp tiles behind a
+//            multi-stage cp.async ring with conflict-free padded pitches.  Round 2, measured at N = 2^20:
+//            12.0 ms (64 columns) and 5.7 ms (16) against 11.65 / 4.3 ms of the default pair -- its DMMA
+//            pipe is 58-67 % active at 8-12 executed instructions per MMA (per-chunk barrier + copy
+//            issue), i.e. the same plateau as the kernels above; not the default.
+//   dmma     (default) the per-stage choice measured above: stage 1 register streaming, stage 3 tiled GEMM
 static int panel_variant(int stage)
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("HMB200_PANEL");
-        v = !e ? 4 : e[0] == 't' ? 1 : e[0] == 'm' ? 2 : e[0] == 's' ? 0 : e[0] == 'd' ? 3 : 4;
+        v = !e ? 3 : e[0] == 't' ? 1 : e[0] == 'm' ? 2 : e[0] == 's' ? 0 : e[0] == 'p' ? 4 : 3;
     }
     if (v == 3) return stage == 3 ? 2 : 0;
     return v;

@@ -452,6 +452,20 @@ class DistLoop:
         main.wait_stream(self.cs)
         return self.ys[(nsteps - 1) & 1]
 
+    def independent_push(self, nsteps):
+        """Same as `independent`, but x is replicated by the root's copy engines (hm_dist_push_x:
+        peer cudaMemcpyAsync over NVLink, joined into the barrier of the step it overlaps) instead
+        of an NCCL kernel: nothing but our own kernels occupies the SMs."""
+        main = self.torch.cuda.current_stream()
+        xp = self.xd.data_ptr() if self.rank == 0 else 0
+        self.plan.dist_push_x(xp, 0, 0, main.cuda_stream)
+        self.plan.dist_barrier(main.cuda_stream)
+        for k in range(nsteps):
+            if k + 1 < nsteps:
+                self.plan.dist_push_x(xp, 0, (k + 1) & 1, main.cuda_stream)
+            self.plan.dist_matvec_device(self.xs[k & 1], k & 1, False, main.cuda_stream)
+        return self.ys[(nsteps - 1) & 1]
+
     def dependent(self, nsteps, chain=8):
         main = self.torch.cuda.current_stream()
         self.plan.dist_bcast_x(self.xd.data_ptr() if self.rank == 0 else 0, 0, 0, main.cuda_stream)
@@ -633,7 +647,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dependent = comm = None
+    dependent = comm = x_push = None
     graph = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if not dist_on:
@@ -678,6 +692,12 @@ def run_ours(args):
         stage_ms, ncalls = plan.timing_end()
         y_dev = device_view(torch, yptr, n, dev)
         y_indep = y_dev.clone()
+        # the same loop with x replicated by the copy engines instead of the NCCL kernel
+        loop.independent_push(3)
+        barrier()
+        ms_push, _, gpush, ypush = timed_graph(torch, lambda: loop.independent_push(args.steps), barrier, stream)
+        push_rel = float((device_view(torch, ypush, n, dev) - y_indep).abs().max() / y_indep.abs().max())
+        gpush.reset()
         # dependent iteration x_{k+1} = y_k: no broadcast on the critical path at all
         loop.dependent(8)
         barrier()
@@ -697,10 +717,15 @@ def run_ours(args):
             plan.dist_bcast_x(loop.xd.data_ptr() if rank == 0 else 0, 0, 0, stream.cuda_stream)
         ev[2].record(stream)
         barrier()
-        tt = torch.tensor([ms_dep, ev[0].elapsed_time(ev[1]) / 50, ev[1].elapsed_time(ev[2]) / 50],
+        tt = torch.tensor([ms_dep, ev[0].elapsed_time(ev[1]) / 50, ev[1].elapsed_time(ev[2]) / 50, ms_push],
                           dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_dep, t_bar, t_bc = (float(a) for a in tt.tolist())
+        ms_dep, t_bar, t_bc, ms_push = (float(a) for a in tt.tolist())
+        x_push = {"value": args.steps / (ms_push / 1e3), "unit": "matvecs/s", "ms_per_step": ms_push / args.steps,
+                  "relinf_vs_nccl_loop": push_rel,
+                  "what": "independent right-hand sides with x replicated by hm_dist_push_x (the root's copy engines "
+                          "write x(k+1) into every rank's buffer over NVLink during step k; joined into step k's barrier) "
+                          "instead of the NCCL broadcast kernel"}
         dependent = {"value": args.steps / (ms_dep / 1e3), "unit": "matvecs/s", "ms_per_step": ms_dep / args.steps,
                      "what": "x_{k+1} = y_k (chains of 8 from the broadcast x): y is already on every rank after the "
                              "fused gather + barrier, so the step has no broadcast"}
@@ -856,6 +881,7 @@ def run_ours(args):
         }
         if dist_on:
             line["dependent_iteration"] = dependent
+            line["x_push_copy_engines"] = x_push
             line["comm"] = comm
             line["partition_balance"] = {"max_part_bytes": float(pbytes.item()),
                                          "ideal_part_bytes": st["algorithmic_bytes"] / world,

@@ -87,6 +87,7 @@ SIGNATURES = {
     "hm_dist_init": (_i32, [_vp, _vp, _i32, _i32]),
     "hm_dist_buffers": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "hm_dist_bcast_x": (_i32, [_vp, _vp, _i32, _i32, _vp]),
+    "hm_dist_push_x": (_i32, [_vp, _vp, _i32, _i32, _vp]),
     "hm_dist_matvec_device": (_i32, [_vp, _vp, _i32, _i32, _vp]),
     "hm_dist_barrier": (_i32, [_vp, _vp]),
     "hm_dist_check": (_i32, [_vp]),

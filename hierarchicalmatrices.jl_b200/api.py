@@ -325,6 +325,11 @@ class Plan:
     def dist_bcast_x(self, dx_root: int, root: int = 0, slot: int = 0, stream: int = 0):
         _lib.check(_lib.lib().hm_dist_bcast_x(self._h, dx_root or None, root, slot, stream))
 
+    def dist_push_x(self, dx_root: int, root: int = 0, slot: int = 0, stream: int = 0):
+        """Copy-engine replication of x from the root into every rank's x slot; complete on a rank once
+        the next barrier (the next `dist_matvec_device`) has completed there."""
+        _lib.check(_lib.lib().hm_dist_push_x(self._h, dx_root or None, root, slot, stream))
+
     def dist_matvec_device(self, dx: int, yslot: int = 0, accumulate=False, stream: int = 0):
         _lib.check(_lib.lib().hm_dist_matvec_device(self._h, dx, yslot, 1 if accumulate else 0, stream))
 

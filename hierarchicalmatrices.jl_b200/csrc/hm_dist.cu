@@ -134,6 +134,10 @@ struct HmDist {
     int64_t nrows = 0, ncols = 0;
     double *hx = nullptr, *hy = nullptr; // pinned staging of hm_dist_matvec
     uint64_t calls = 0;                  // hm_dist_matvec calls so far
+    // hm_dist_push_x: copy-engine replication of x (root side)
+    cudaStream_t push_stream[HM_MAX_PEERS] = {};
+    cudaEvent_t push_start = nullptr, push_done[HM_MAX_PEERS] = {};
+    bool push_pending = false;
     double *x(int s) const { return reinterpret_cast<double *>(base + off_x[s]); }
     double *y(int q, int s) const { return reinterpret_cast<double *>(peer[q] + off_y[s]); }
 };
@@ -147,6 +151,11 @@ void hm_dist_release(HmDist *d) noexcept
     if (d->base) cudaFree(d->base);
     if (d->hx) cudaFreeHost(d->hx);
     if (d->hy) cudaFreeHost(d->hy);
+    for (int q = 0; q < HM_MAX_PEERS; q++) {
+        if (d->push_stream[q]) cudaStreamDestroy(d->push_stream[q]);
+        if (d->push_done[q]) cudaEventDestroy(d->push_done[q]);
+    }
+    if (d->push_start) cudaEventDestroy(d->push_start);
     delete d;
 }
 
@@ -155,6 +164,12 @@ namespace {
 int32_t launch_barrier(hm_plan *p, cudaStream_t st)
 {
     HmDist *d = p->dist;
+    if (d->push_pending) {
+        // x pushed by hm_dist_push_x must have landed on every rank before this rank signals
+        for (int q = 0; q < d->nranks; q++)
+            if (d->push_done[q]) HM_CUDA(cudaStreamWaitEvent(st, d->push_done[q], 0));
+        d->push_pending = false;
+    }
     BarrierArgs b{};
     for (int q = 0; q < d->nranks; q++) b.flags[q] = reinterpret_cast<unsigned *>(d->peer[q] + d->off_flags);
     b.epoch = reinterpret_cast<unsigned *>(d->base + d->off_epoch);
@@ -225,11 +240,10 @@ int32_t hm_dist_init(hm_plan *p, const void *id, int32_t nranks, int32_t rank)
         d->ncols = p->L.ncols;
         ncclUniqueId uid;
         memcpy(&uid, id, sizeof uid);
-        // The only collective on the data path is the broadcast of x (8 N bytes), issued on a second
-        // stream underneath the previous matvec: it is latency-tolerant, so the communicator is
-        // limited to a few CTAs -- NCCL's default channel count takes SMs (and HBM bandwidth) away
-        // from the stream kernels it overlaps with.  HMB200_NCCL_MAX_CTAS overrides (0 = NCCL default).
-        int max_ctas = 2;
+        // HMB200_NCCL_MAX_CTAS > 0 limits the communicator's CTAs.  Measured on 8 B200 at N = 2^20: the
+        // 8 MB broadcast takes 33 us with NCCL's default, 62 us with 8 CTAs and 190 us with 2 -- it stops
+        // hiding under the 0.3 ms step, so the default is left alone.
+        int max_ctas = 0;
         if (const char *e = getenv("HMB200_NCCL_MAX_CTAS")) max_ctas = atoi(e);
         if (g_nccl.CommInitRankConfig && max_ctas > 0) {
             ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
@@ -309,6 +323,38 @@ int32_t hm_dist_bcast_x(hm_plan *p, const double *dx_root, int32_t root, int32_t
         HM_DEVICE(p->device);
         const double *src = d->rank == root ? (dx_root ? dx_root : d->x(slot)) : d->x(slot);
         HM_NCCL(g_nccl.Broadcast(src, d->x(slot), (size_t)d->ncols, ncclDouble, root, d->comm, (cudaStream_t)stream));
+        return HM_OK;
+    });
+}
+
+int32_t hm_dist_push_x(hm_plan *p, const double *dx_root, int32_t root, int32_t slot, void *stream)
+{
+    return guarded([&]() -> int32_t {
+        if (int32_t st = need_dist(p)) return st;
+        HmDist *d = p->dist;
+        if (root < 0 || root >= d->nranks) return fail(HM_ERR_INVALID, "root out of range");
+        if (slot != 0 && slot != 1) return fail(HM_ERR_INVALID, "slot must be 0 or 1");
+        if (d->rank != root || d->ncols == 0) return HM_OK; // the root's copy engines do all the work
+        if (!dx_root) return fail(HM_ERR_NULL, "x is NULL on the root");
+        HM_DEVICE(p->device);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (!d->push_start) {
+            HM_CUDA(cudaEventCreateWithFlags(&d->push_start, cudaEventDisableTiming));
+            for (int q = 0; q < d->nranks; q++) {
+                HM_CUDA(cudaStreamCreateWithFlags(&d->push_stream[q], cudaStreamNonBlocking));
+                HM_CUDA(cudaEventCreateWithFlags(&d->push_done[q], cudaEventDisableTiming));
+            }
+        }
+        // fork: one copy stream per destination, so the copies spread over the copy engines
+        HM_CUDA(cudaEventRecord(d->push_start, st));
+        const size_t bytes = (size_t)d->ncols * 8;
+        for (int q = 0; q < d->nranks; q++) {
+            double *dst = reinterpret_cast<double *>(d->peer[q] + d->off_x[slot]);
+            HM_CUDA(cudaStreamWaitEvent(d->push_stream[q], d->push_start, 0));
+            if (dst != dx_root) HM_CUDA(cudaMemcpyAsync(dst, dx_root, bytes, cudaMemcpyDeviceToDevice, d->push_stream[q]));
+            HM_CUDA(cudaEventRecord(d->push_done[q], d->push_stream[q]));
+        }
+        d->push_pending = true; // joined by the next barrier enqueued on this plan
         return HM_OK;
     });
 }

@@ -245,6 +245,14 @@ HM_API int32_t hm_dist_buffers(hm_plan *p, double **x2, double **y2);
 /* ncclBroadcast of x (ncols words) from `root` into x slot `slot` of every rank, enqueued on
  * `stream`.  dx_root: device pointer on the root (NULL = the root's slot already holds x). */
 HM_API int32_t hm_dist_bcast_x(hm_plan *p, const double *dx_root, int32_t root, int32_t slot, void *stream);
+/* The same replication without a collective kernel: the root's copy engines write x into x slot
+ * `slot` of every rank through the peer mappings (one cudaMemcpyAsync per destination on internal
+ * streams, forked from `stream`); no SM is taken from the matvec it overlaps with.  Completion is
+ * joined into the NEXT barrier this plan enqueues on the root (hm_dist_matvec_device /
+ * hm_dist_barrier): once that barrier has completed on a rank, its slot holds x.  So, pipelined:
+ *   push_x(x[k+1] -> slot (k+1)&1);  matvec_device(x slot k&1 -> y slot k&1);  ...
+ * Non-root ranks return immediately.  The root must not overwrite dx_root before that barrier. */
+HM_API int32_t hm_dist_push_x(hm_plan *p, const double *dx_root, int32_t root, int32_t slot, void *stream);
 /* y slot `yslot` (+)= H x on every rank: the three stages of this rank's part with the all-gather
  * fused into stage 3, then the barrier; enqueued on `stream`, no host synchronisation (may be
  * captured into a CUDA graph).  dx: any device vector of ncols words -- an x slot after

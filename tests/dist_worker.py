@@ -68,6 +68,18 @@ def main():
     out["dev"] = relinf(device_view(y0, n, local).cpu().numpy(), ref)
     out["dev_dependent"] = relinf(device_view(y1, n, local).cpu().numpy(), ref2)
 
+    # x replicated by the root's copy engines instead of the NCCL broadcast (hm_dist_push_x): complete
+    # once the next barrier has passed
+    xd2 = torch.from_numpy(2.0 * v).to(dev) if rank == 0 else None
+    plan.dist_push_x(xd2.data_ptr() if rank == 0 else 0, root=0, slot=1, stream=st.cuda_stream)
+    plan.dist_barrier(st.cuda_stream)
+    plan.dist_push_x(xd.data_ptr() if rank == 0 else 0, root=0, slot=0, stream=st.cuda_stream)  # joins the next barrier
+    plan.dist_matvec_device(x1, yslot=0, accumulate=False, stream=st.cuda_stream)
+    plan.dist_matvec_device(x0, yslot=1, accumulate=False, stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    out["push"] = max(relinf(device_view(y0, n, local).cpu().numpy(), 2.0 * ref),
+                      relinf(device_view(y1, n, local).cpu().numpy(), ref))
+
     # the same sequence captured once and replayed (the barrier epoch lives on the device)
     g = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream(device=dev)

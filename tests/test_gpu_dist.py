@@ -41,7 +41,7 @@ def test_two_rank_mul_matches_oracle(free):
     res = _run_workers(world, {"HM_TEST_FREE": free})
     assert len(res) == world
     for r in res:
-        for k in ("host", "host_acc", "host_strided", "dev", "dev_dependent", "graph"):
+        for k in ("host", "host_acc", "host_strided", "dev", "dev_dependent", "push", "graph"):
             assert r[k] <= TOL, (k, r)
         assert r["identical"]
 

@@ -1234,6 +1234,8 @@ cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const i
     if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
     int wpb = threads / 32;
     unsigned grid = (unsigned)((nblocks + wpb - 1) / wpb);
+    // (a persistent variant with two leaves in flight per warp was measured in round 2: 0.204 ms vs
+    // 0.108 ms at N = 2^20 -- 16 warps per SM hide less latency than 32 one-leaf warps)
     return launch_k(hm_core_kernel, grid, (unsigned)threads, smem, st, pdl, blocks, nblocks, plist, partial, core,
                     svec, max_r);
 }

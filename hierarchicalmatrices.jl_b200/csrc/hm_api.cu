@@ -1154,7 +1154,7 @@ int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32
             {
                 std::vector<int32_t> big;
                 for (size_t c = 0; c < L.cores.size(); c++)
-                    if (L.core_qn[c] > HM_CORE_BIG) big.push_back((int32_t)c);
+                    if (L.core_qn[c] > HM_ADJ_BIG) big.push_back((int32_t)c);
                 p->nadjbig = (int)big.size();
                 HM_CUDA(p->adjbig.upload(big, st));
             }

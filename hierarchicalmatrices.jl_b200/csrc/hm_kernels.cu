@@ -933,16 +933,45 @@ hm_rowdot_kernel(const HmItem *__restrict__ items, const double *__restrict__ W,
     if (MODE == 0) {
         for (int f = t; f < it.Fp; f += T) zs[f] = f < F ? zsrc[it.out + f] : 0.0;
     } else {
-        // z[f], f = (leaf, k) in the order of the item's leaf list
-        if (warp == 0) {
-            int fofs = 0;
-            for (int e = 0; e < it.nrun; e++) {
-                const HmCoreBlock cb = blocks[s1ent[it.run0 + e]];
-                for (int k = lane; k < cb.rv; k += 32) zs[fofs + k] = zsrc[cb.soff + k];
-                fofs += cb.rv;
+        // z[f], f = (leaf, k) in the order of the item's leaf list.  The leaf records are fetched by
+        // all threads at once (one dependent round trip for the whole list instead of one per leaf:
+        // with a single warp walking it the other seven waited at the barrier, 8.4 stalled warps per
+        // issue in round 1's profile), offsets by a short scan, the copies spread over the warps.
+        __shared__ int e_soff[T], e_fofs[T + 1];
+        int fbase = 0;
+        for (int e0 = 0; e0 < it.nrun; e0 += T) {
+            const int ne = min(T, it.nrun - e0);
+            int rv = 0;
+            if (t < ne) {
+                const HmCoreBlock cb = blocks[s1ent[it.run0 + e0 + t]];
+                e_soff[t] = cb.soff;
+                rv = cb.rv;
             }
-            if (lane == 0 && fofs < it.Fp) zs[fofs] = 0.0;
+            // inclusive scan of rv over the chunk (warp scans + warp totals)
+            int incl = rv;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            __shared__ int wtot[T / 32];
+            if (lane == 31) wtot[warp] = incl;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < warp; w++) woff += wtot[w];
+            if (t < ne) e_fofs[t] = fbase + woff + incl - rv;
+            int total = 0;
+            for (int w = 0; w < T / 32; w++) total += wtot[w];
+            if (t == 0) e_fofs[ne] = fbase + total;
+            __syncthreads();
+            for (int e = warp; e < ne; e += T / 32) {
+                const int f0 = e_fofs[e], n = e_fofs[e + 1] - f0, so = e_soff[e];
+                for (int k = lane; k < n; k += 32) zs[f0 + k] = zsrc[so + k];
+            }
+            fbase += total;
+            __syncthreads();
         }
+        if (t == 0 && fbase < it.Fp) zs[fbase] = 0.0;
     }
     __syncthreads();
     const double2 *__restrict__ W2 = reinterpret_cast<const double2 *>(W + it.slab);
@@ -1023,9 +1052,10 @@ hm_core_adj_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks, cons
     } else {
         b = (int64_t)(blockIdx.x - nbig) * (blockDim.x >> 5) + wib;
         if (b >= nblocks) return;
-        if (qn[b] > HM_CORE_BIG) return; // handled by a "big" CTA
+        if (qn[b] > HM_ADJ_BIG) return; // handled by a "big" CTA
     }
-    double *tbuf = sm + (size_t)wib * (max_r + 32 * 32);
+    const int fs_words = max_r <= 20 ? 20 * 21 : 32 * 32; // must match hm_launch_adjoint
+    double *tbuf = sm + (size_t)wib * (max_r + fs_words);
     double *Fs = tbuf + max_r; // F staged in shared memory when it fits (ru, rv <= 32)
     const HmCoreBlock cb = blocks[b];
     const double *c = core + cb.core;
@@ -1123,8 +1153,10 @@ cudaError_t hm_launch_adjoint(const HmAdjoint &A, const double *x, double *y, in
     if (A.n3 > 0)
         hm_rowdot_kernel<0><<<(unsigned)A.n3, HM_THREADS, 0, st>>>(A.items3, A.ustream, x, nullptr, nullptr, A.PQ);
     if (A.ncores > 0) {
-        // per warp: t' (max_r) + staged F (32 x 32); big CTAs: 13 * max_r at most
-        size_t smem = (size_t)8 * ((size_t)A.max_r + 32 * 32) * sizeof(double);
+        // per warp: t' (max_r) + staged F (32 x 32, or 20 x 21 when no rank exceeds 20: the kernel is
+        // latency-bound and shared memory limits its occupancy); big CTAs: 13 * max_r at most
+        const size_t fs_words = A.max_r <= 20 ? 20 * 21 : 32 * 32;
+        size_t smem = (size_t)8 * ((size_t)A.max_r + fs_words) * sizeof(double);
         smem = std::max(smem, (size_t)(256 + A.max_r) * 2 * sizeof(double));
         if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
         if (smem > 48 * 1024) {

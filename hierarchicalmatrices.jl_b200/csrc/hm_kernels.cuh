@@ -9,6 +9,7 @@
 #define HM_MAXRUNS 256  // run-table capacity of a stage-3 item
 #define HM_RMAX_ASM 32  // max interpolation rank of on-device assembly
 #define HM_CORE_BIG 128 // stage 2: leaves with more partial sums than this get a whole CTA
+#define HM_ADJ_BIG 32   // adjoint stage B': leaves with more q pieces than this get a whole CTA
 #define HM_KERNEL_HOST_FN 4 // kernel id of hm_assemble_kernel_fn: f is a host callback
 
 // Chebyshev nodes / barycentric weights of the reference's BarycentricPoly2D
@@ -64,7 +65,7 @@ struct HmAdjoint {
     const double *ustream = nullptr, *vstream = nullptr, *core = nullptr;
     const HmCoreBlock *blocks = nullptr;
     const int32_t *q0 = nullptr, *qn = nullptr, *qlist = nullptr, *s1ent = nullptr;
-    const int32_t *big = nullptr; // leaves with more than HM_CORE_BIG q pieces
+    const int32_t *big = nullptr; // leaves with more than HM_ADJ_BIG q pieces
     int nbig = 0;
     const HmColSeg *segs = nullptr;
     const int64_t *bases = nullptr;

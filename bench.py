@@ -647,7 +647,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dependent = comm = x_push = None
+    dependent = comm = x_push = nccl_loop = None
+    x_exchange = None
     graph = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if not dist_on:
@@ -734,6 +735,17 @@ def run_ours(args):
                         "second stream under step k, the barrier is in line after stage 3"}
         plan.dist_check()
         y_dev = y_indep
+        # headline = the faster of the two ways the product replicates a fresh x every step
+        nccl_loop = {"value": None, "unit": "matvecs/s", "ms_per_step": None,
+                     "what": "independent right-hand sides with x replicated by hm_dist_bcast_x (ncclBroadcast on a "
+                             "second stream under the previous step)"}
+        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+        nccl_loop["value"], nccl_loop["ms_per_step"] = args.steps / (ms / 1e3), ms / args.steps
+        x_exchange = "nccl"
+        if ms_push < ms:
+            ms, x_exchange = ms_push, "copy_engines"
     clocks = sampler.stop(t_wall0) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     pbytes = torch.tensor([float(st["part_algorithmic_bytes"])], dtype=torch.float64, device=dev)
@@ -854,9 +866,13 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(n, args.dist), "n": n, "dist": args.dist,
                        "partition": f"block-row x{world}" if world > 1 else "single GPU",
-                       "collectives": (("product API hm_dist_*: NCCL broadcast(x) per step on a second stream; all-gather(y) "
-                                        "fused into stage 3 (stores into every rank's peer-mapped buffer over NVLink) + barrier "
-                                        "kernel" + ("" if args.no_graph else "; whole loop replayed as one CUDA graph"))
+                       "collectives": (("product API hm_dist_*: a fresh x replicated from rank 0 every step "
+                                        + ("by the root's copy engines over the NVLink peer mappings (hm_dist_push_x), under the "
+                                           "previous step" if x_exchange == "copy_engines" else
+                                           "by ncclBroadcast (hm_dist_bcast_x) on a second stream under the previous step")
+                                        + "; all-gather(y) fused into stage 3 (stores into every rank's peer-mapped buffer over "
+                                          "NVLink) + barrier kernel"
+                                        + ("" if args.no_graph else "; whole loop replayed as one CUDA graph"))
                                        if dist_on else "none"),
                        "l2": "inputs larger than L2 (%.1f GB streamed per step per GPU)" % (st["stored_bytes"] / 1e9),
                        "assembly_s": round(t_asm, 3), **({"matrix_free": True} if args.matrix_free else {})},
@@ -882,6 +898,7 @@ def run_ours(args):
         if dist_on:
             line["dependent_iteration"] = dependent
             line["x_push_copy_engines"] = x_push
+            line["x_bcast_nccl"] = nccl_loop
             line["comm"] = comm
             line["partition_balance"] = {"max_part_bytes": float(pbytes.item()),
                                          "ideal_part_bytes": st["algorithmic_bytes"] / world,

@@ -39,7 +39,7 @@ __all__ = [
     "cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel", "Plan", "flatten",
     "chebyshevpoints", "HmError", "rmul_", "lmul_", "scale_", "adjoint", "Adjoint",
     "chebyshevbarycentricweights", "EvenBarycentricMatrix", "barycentricmatrix", "Transpose", "transpose",
-    "dist_unique_id",
+    "dist_unique_id", "getrank", "svdtrunc", "lrzeros",
 ]
 
 Matrix = np.ndarray  # the dense leaf type of the reference
@@ -175,6 +175,95 @@ class LowRankMatrix:
 
     def rank(self):
         return self.S.shape[0]
+
+    # ---- low-rank algebra (first step): LowRankMatrix.jl:60-171.  Host side, as in
+    # the reference (LAPACK QR / SVD through numpy); the results are ordinary leaves for the device path.
+    def __getitem__(self, key):
+        """`L[ir, jr]` with 0-based Python slices -- getindex(L, ir::UnitRange, jr::UnitRange), :60-62."""
+        ir, jr = key
+        if isinstance(ir, slice) and isinstance(jr, slice):
+            return LowRankMatrix(self.U[ir, :], self.S, self.V[jr, :])
+        ret = self.dtype.type(0)  # scalar getindex, 1-based, k = r..1 (:50-58)
+        for k in range(self.rank() - 1, -1, -1):
+            ret += self.U[ir - 1, k] * self.S[k] * self.V[jr - 1, k]
+        return ret
+
+    def todense(self):
+        return (self.U * self.S) @ self.V.T
+
+    def _combine(self, other, sign):
+        # (+)/(-)(L1, L2), :95-111: QR of [U1 U2] and [V1 V2], SVD of Ru diag(S1, +-S2) Rv', truncation
+        if not isinstance(other, LowRankMatrix):
+            return NotImplemented
+        if self.shape != other.shape:
+            raise ValueError("DimensionMismatch")
+        Qu, Ru = np.linalg.qr(np.hstack([self.U, other.U]))
+        Qv, Rv = np.linalg.qr(np.hstack([self.V, other.V]))
+        Us, sv, Vt = np.linalg.svd((Ru * np.concatenate([self.S, sign * other.S])) @ Rv.T)
+        r = getrank(sv)
+        return LowRankMatrix((Qu @ Us)[:, :r], sv[:r], (Qv @ Vt.T)[:, :r])
+
+    def __add__(self, other):
+        if isinstance(other, _HierarchicalBase):
+            return other.__radd__(self)
+        if isinstance(other, np.ndarray):  # generic AbstractMatrix + : elementwise, a dense Matrix
+            return self.todense() + other
+        return self._combine(other, 1.0)
+
+    def __sub__(self, other):
+        if isinstance(other, _HierarchicalBase):
+            return other.__rsub__(self)
+        if isinstance(other, np.ndarray):
+            return self.todense() - other
+        return self._combine(other, -1.0)
+
+    def __radd__(self, other):
+        return other + self.todense() if isinstance(other, np.ndarray) else NotImplemented
+
+    def __rsub__(self, other):
+        return other - self.todense() if isinstance(other, np.ndarray) else NotImplemented
+
+    def __mul__(self, other):
+        if isinstance(other, LowRankMatrix):  # :113-118
+            Us, sv, Vt = np.linalg.svd((self.S[:, None] * (self.V.T @ other.U)) * other.S[None, :])
+            r = getrank(sv)
+            return LowRankMatrix((self.U @ Us)[:, :r], sv[:r], (other.V @ Vt.T)[:, :r])
+        if np.isscalar(other):  # :160-161
+            return LowRankMatrix(self.U, self.S * other, self.V)
+        x = np.asarray(other)  # L*x, algebra.jl:88-95
+        return (self.U * self.S) @ (self.V.T @ x)
+
+    def __rmul__(self, other):
+        return LowRankMatrix(self.U, other * self.S, self.V) if np.isscalar(other) else NotImplemented
+
+    def __truediv__(self, other):  # :162
+        return LowRankMatrix(self.U, self.S / other, self.V)
+
+
+def getrank(sigma) -> int:
+    """`getrank(σ)` -- LowRankMatrix.jl:70-80: trailing singular values <= r*eps(σ[1]) are dropped."""
+    sigma = np.asarray(sigma)
+    r = len(sigma)
+    if r == 0:
+        return 0
+    tol = r * np.spacing(sigma[0])
+    while r >= 1:
+        if sigma[r - 1] > tol:
+            return r
+        r -= 1
+    return r
+
+
+def svdtrunc(A) -> "LowRankMatrix":
+    """`svdtrunc(A)` -- LowRankMatrix.jl:82-86 (also `convert(LowRankMatrix, A)`, :68)."""
+    U, sv, Vt = np.linalg.svd(np.asarray(A), full_matrices=False)
+    r = getrank(sv)
+    return LowRankMatrix(U[:, :r], sv[:r], Vt.T[:, :r])
+
+
+def lrzeros(T, m: int, n: int) -> "LowRankMatrix":
+    """`lrzeros(T, m, n)` -- LowRankMatrix.jl:88-93."""
+    return LowRankMatrix(np.zeros((m, 0), dtype=T), np.zeros(0, dtype=T), np.zeros((n, 0), dtype=T))
 
 
 class BarycentricMatrix2D:
@@ -706,6 +795,50 @@ class _HierarchicalBase:
         raise TypeError("x must be a vector or a matrix")
 
     __matmul__ = __mul__
+
+    # ---- H + L, L + H, H - L, L - H  (algebra.jl:394-524): the generated walk adds the matching
+    # window L[pr, qr] to every assigned block -- nested blocks recursively, LowRankMatrix blocks
+    # by recompression (LowRankMatrix.jl:95-111), Matrix blocks elementwise.  Host side; the result
+    # is an ordinary HierarchicalMatrix for the device path.
+    def _add_lowrank(self, L, hsign, lsign, h_first):
+        if not isinstance(L, LowRankMatrix):
+            return NotImplemented
+        if LowRankMatrix not in self._types:
+            raise TypeError("MethodError: +(::%s, ::LowRankMatrix) is defined for HierarchicalMatrix" % self._name)
+        G = type(self)(np.result_type(self.T, L.dtype), self.M, self.N)
+        p = 0
+        for m in range(self.M):
+            q = 0
+            for n in range(self.N):
+                A = self._block(m, n)
+                if A is not None:
+                    rows, cols = self.blocksize(m + 1, n + 1, 1), self.blocksize(m + 1, n + 1, 2)
+                    Lw = L[p:p + rows, q:q + cols]
+                    if isinstance(A, _HierarchicalBase):
+                        B = A._add_lowrank(Lw, hsign, lsign, h_first)
+                    elif isinstance(A, LowRankMatrix):
+                        if h_first:   # H_mn (+-) L
+                            B = A._combine(Lw, lsign)
+                        else:         # L (+-) H_mn
+                            B = Lw._combine(A, hsign)
+                    else:
+                        B = np.asfortranarray(hsign * A + lsign * Lw.todense())
+                    G[Block(m + 1), Block(n + 1)] = B
+                q += self.blocksize(1, n + 1, 2)
+            p += self.blocksize(m + 1, self.N, 1)
+        return G
+
+    def __add__(self, L):
+        return self._add_lowrank(L, 1.0, 1.0, True)
+
+    def __radd__(self, L):
+        return self._add_lowrank(L, 1.0, 1.0, False)
+
+    def __sub__(self, L):
+        return self._add_lowrank(L, 1.0, -1.0, True)
+
+    def __rsub__(self, L):
+        return self._add_lowrank(L, -1.0, 1.0, False)
 
 
 def _type_name(t):

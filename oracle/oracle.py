@@ -355,6 +355,31 @@ def dense_kernel_matvec_ld(kernel, x, y, b) -> np.ndarray:
     return out
 
 
+# ---------------------------------------------------------------- low-rank algebra
+def getrank(sigma) -> int:
+    """LowRankMatrix.jl:70-80: tol = r*eps(first(σ)), trailing values <= tol dropped."""
+    r = len(sigma)
+    if r == 0:
+        return 0
+    tol = r * np.spacing(sigma[0])
+    while r >= 1 and not sigma[r - 1] > tol:
+        r -= 1
+    return r
+
+
+def lowrank_combine(U1, S1, V1, U2, S2, V2, sign=1.0):
+    """(+)(L1, L2) / (-)(L1, L2) -- LowRankMatrix.jl:95-111, step by step:
+    QRU = qr!(hcat(U1, U2)); QRV = qr!(hcat(V1, V2));
+    SVD = svd!(QRU.R * Diagonal(vcat(S1, +-S2)) * QRV.R'); r = getrank(SVD.S);
+    U = (QRU.Q*SVD.U)[:, 1:r], S = SVD.S[1:r], V = (QRV.Q*SVD.V)[:, 1:r]."""
+    QU, RU = np.linalg.qr(np.concatenate([U1, U2], axis=1))
+    QV, RV = np.linalg.qr(np.concatenate([V1, V2], axis=1))
+    core = RU @ np.diag(np.concatenate([S1, sign * np.asarray(S2)])) @ RV.T
+    Us, sv, Vh = np.linalg.svd(core)
+    r = getrank(sv)
+    return (QU @ Us)[:, :r], sv[:r], (QV @ Vh.T)[:, :r]
+
+
 # ---------------------------------------------------------------- synthetic inputs (SURVEY 8d)
 def example_points(N: int, dist: str = "cheb"):
     """Point sets of the benchmark configs: "cheb" = examples/Kernel.jl:61-62,

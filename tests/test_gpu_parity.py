@@ -1010,3 +1010,20 @@ def test_arbitrary_kernel_function_matches_oracle(hm, O, dist, N, kname):
     K0 = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0)
     K1 = hm.KernelMatrix(lambda p, q: 1.0 / (p - q), x, y, a, b, c, d, device=0)
     assert np.array_equal(K0 * v, K1 * v)
+
+
+@pytest.mark.gpu
+def test_hierarchical_plus_lowrank_on_device(hm, O):
+    """SURVEY 8f row f4, first step: G = H +- L (algebra.jl:394-524, recompressed on the host as in the
+    reference) applied on the device against the oracle walk of the same tree and against H*x +- L*x."""
+    rng = np.random.default_rng(9)
+    n = 1500
+    H = random_lowrank_tree(hm, rng, n, leaf=64, r=6)
+    L = hm.LowRankMatrix(rng.standard_normal((n, 4)), np.array([3.0, 2.0, 1.0, 0.5]), rng.standard_normal((n, 4)))
+    v = rng.standard_normal(n)
+    Hx = oracle_tree_from_mirror(O, H).matvec(v)
+    Lx = (L.U * L.S) @ (L.V.T @ v)
+    for G, sign in ((H + L, 1.0), (H - L, -1.0)):
+        out = G * v
+        assert relinf(out, oracle_tree_from_mirror(O, G).matvec(v)) <= TOL
+        assert relinf(out, Hx + sign * Lx) <= 1e-11

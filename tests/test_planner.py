@@ -373,3 +373,61 @@ def test_evenbary_layout_accounting(hm):
         hm.rmul_(H, np.ones(70))       # the reference has no scale! for this leaf type
     with pytest.raises(TypeError):
         hm.mul_(np.zeros(100), H, np.ones(140), 1, 1, 2, 2)   # nor a strided mul!
+
+
+def _dense_of(H):
+    A = np.zeros(H.size())
+    for kind, r0, c0, B in H.leaves():
+        A[r0:r0 + B.shape[0], c0:c0 + B.shape[1]] += B if isinstance(B, np.ndarray) else B.todense()
+    return A
+
+
+def test_lowrank_algebra_host(hm, O):
+    """SURVEY 8f row f4, first step: LowRankMatrix +, -, *, svdtrunc, getrank, lrzeros
+    (LowRankMatrix.jl:60-171) in the host mirror against the oracle restatement and dense arithmetic."""
+    rng = np.random.default_rng(0)
+    L1 = hm.LowRankMatrix(rng.standard_normal((40, 3)), np.array([3.0, 2.0, 1.0]), rng.standard_normal((25, 3)))
+    L2 = hm.LowRankMatrix(rng.standard_normal((40, 2)), np.array([1.5, 0.5]), rng.standard_normal((25, 2)))
+    for sign, G in ((1.0, L1 + L2), (-1.0, L1 - L2)):
+        U, S, V = O.lowrank_combine(L1.U, L1.S, L1.V, L2.U, L2.S, L2.V, sign)
+        assert G.rank() == len(S) == 5 and np.all(np.diff(G.S) <= 0)
+        assert np.allclose(G.S, S, rtol=1e-14) and np.allclose(np.abs(G.U), np.abs(U), atol=1e-12)
+        assert np.allclose(G.todense(), L1.todense() + sign * L2.todense(), atol=1e-13)
+        assert np.allclose(G.U.T @ G.U, np.eye(5), atol=1e-13) and np.allclose(G.V.T @ G.V, np.eye(5), atol=1e-13)
+    # a sum whose exact rank is lower than r1 + r2 is truncated by getrank (tol = r*eps(sigma_1))
+    L3 = hm.LowRankMatrix(L1.U[:, :2], np.array([1.0, 1.0]), L1.V[:, :2])
+    assert (L1 + L3).rank() == 3
+    assert hm.getrank(np.array([1.0, 1e-3, 1e-17])) == 2 and hm.getrank(np.array([])) == 0
+    assert O.getrank(np.array([1.0, 1e-3, 1e-17])) == 2
+    A = rng.standard_normal((30, 4)) @ rng.standard_normal((4, 18))
+    T = hm.svdtrunc(A)
+    assert T.rank() == 4 and np.allclose(T.todense(), A, atol=1e-13)
+    Z = hm.lrzeros(np.float64, 7, 9)
+    assert Z.shape == (7, 9) and Z.rank() == 0 and np.all(Z.todense() == 0)
+    W = hm.LowRankMatrix(rng.standard_normal((25, 2)), np.array([2.0, 1.0]), rng.standard_normal((11, 2)))
+    P = L1 * W                                                   # LowRankMatrix.jl:113-118
+    assert P.shape == (40, 11) and P.rank() == 2 and np.allclose(P.todense(), L1.todense() @ W.todense(), atol=1e-12)
+    assert np.allclose((2.0 * L1).todense(), 2 * L1.todense()) and np.allclose((L1 / 4.0).todense(), L1.todense() / 4)
+    sub = L1[3:20, 5:9]                                          # getindex(L, ir, jr), :60-62
+    assert np.allclose(sub.todense(), L1.todense()[3:20, 5:9])
+    assert L1[2, 3] == L1.U[1, 2] * L1.S[2] * L1.V[2, 2] + L1.U[1, 1] * L1.S[1] * L1.V[2, 1] + L1.U[1, 0] * L1.S[0] * L1.V[2, 0]
+
+
+def test_hierarchical_plus_minus_lowrank_host(hm):
+    """H + L, L + H, H - L, L - H (algebra.jl:394-524): same block structure, LowRankMatrix blocks
+    recompressed, Matrix blocks dense; equal to the dense sum."""
+    from helpers import random_lowrank_tree
+    rng = np.random.default_rng(5)
+    n = 700
+    H = random_lowrank_tree(hm, rng, n, leaf=60, r=5)
+    L = hm.LowRankMatrix(rng.standard_normal((n, 3)), np.array([2.0, 1.0, 0.5]), rng.standard_normal((n, 3)))
+    Hd, Ld = _dense_of(H), L.todense()
+    for G, ref in ((H + L, Hd + Ld), (L + H, Ld + Hd), (H - L, Hd - Ld), (L - H, Ld - Hd)):
+        assert type(G) is type(H) and G.size() == H.size()
+        assert np.array_equal(G.assigned, H.assigned)
+        assert np.allclose(_dense_of(G), ref, atol=1e-12 * np.abs(ref).max())
+        kinds = [k for k, _, _, _ in G.leaves()]
+        assert kinds == [k for k, _, _, _ in H.leaves()]
+        assert max(B.rank() for k, _, _, B in G.leaves() if k == 2) <= 8
+    with pytest.raises(TypeError):
+        hm.KernelMatrix(np.float64, 1, 1) + L

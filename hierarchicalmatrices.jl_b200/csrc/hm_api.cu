@@ -311,6 +311,31 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
         HM_CUDA(dcore_leaf.upload(L.core_leaf, st));
         HM_CUDA(hm_launch_fillcore(P->cores.p, dcore_leaf.p, (int64_t)L.cores.size(), dleaves.p, P->core.p,
                                    P->cheb, P->kernel_id, st));
+        {
+            // Chebyshev form (default; HMB200_FREE_FORM=bary keeps the reference's barycentric arithmetic):
+            // cores become C F C', C = values at the Chebyshev nodes -> Chebyshev coefficients
+            const char *e = getenv("HMB200_FREE_FORM");
+            P->free_cheb = !(e && e[0] == 'b') && P->cheb.r == 20;
+            if (P->free_cheb) {
+                const int R = P->cheb.r;
+                std::vector<double> Cm((size_t)R * R);
+                for (int k = 0; k < R; k++) {
+                    long double tm2 = 1.0L, tm1 = (long double)P->cheb.node[k];
+                    for (int q = 0; q < R; q++) {
+                        long double tq = q == 0 ? 1.0L : q == 1 ? (long double)P->cheb.node[k] : 2.0L * P->cheb.node[k] * tm1 - tm2;
+                        if (q >= 2) {
+                            tm2 = tm1;
+                            tm1 = tq;
+                        }
+                        Cm[(size_t)q + (size_t)k * R] = (double)((q == 0 ? 1.0L : 2.0L) * tq / R);
+                    }
+                }
+                DevBuf<double> dC;
+                HM_CUDA(dC.upload(Cm, st));
+                HM_CUDA(hm_launch_core_cheb(P->cores.p, (int64_t)L.cores.size(), P->core.p, dC.p, st));
+                HM_CUDA(cudaStreamSynchronize(st));
+            }
+        }
         HM_CUDA(cudaStreamSynchronize(st));
     } else {
         // temporary tables for the fill kernels
@@ -987,7 +1012,7 @@ int32_t hm_matvec_device_peers(hm_plan *p, const double *dx, double *dy, int32_t
         }
         if (p->matrix_free)
             HM_CUDA(hm_launch_free1(p->items1.p, (int64_t)L.items1.size(), p->f_ent1.p, p->f_py.p, dx, p->partial.p,
-                                    p->cheb, p->free1_units, st));
+                                    p->cheb, p->free1_units, p->free_cheb, st));
         else
             HM_CUDA(hm_launch_stage1(p->items1.p, (int64_t)L.items1.size(), p->vstream.p, dx, p->partial.p,
                                      p->fuse ? &fz : nullptr, st));
@@ -1004,7 +1029,7 @@ int32_t hm_matvec_device_peers(hm_plan *p, const double *dx, double *dy, int32_t
             if (p->matrix_free)
                 HM_CUDA(hm_launch_free3(p->items3.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p, dx,
                                         p->svec.p, dy, r == 0 ? (accumulate != 0) : 1, p->cheb, p->kernel_id, peers,
-                                        p->free3_zcap, st));
+                                        p->free3_zcap, p->free_cheb, st));
             else
                 HM_CUDA(hm_launch_stage3(p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, dx, p->svec.p, dy,
                                          r == 0 ? (accumulate != 0) : 1, peers, st));
@@ -1062,7 +1087,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
                 const int64_t i0 = L.c1_begin[(size_t)k], i1 = L.c1_begin[(size_t)k + 1];
                 if (p->matrix_free)
                     HM_CUDA(hm_launch_free1(p->items1c.p + i0, i1 - i0, p->f_ent1.p, p->f_py.p, p->dx.p, p->partial.p,
-                                            p->cheb, p->free1_units, st));
+                                            p->cheb, p->free1_units, p->free_cheb, st));
                 else
                     HM_CUDA(hm_launch_stage1(p->items1c.p + i0, i1 - i0, p->vstream.p, p->dx.p, p->partial.p, nullptr, st,
                                              false));
@@ -1077,7 +1102,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
                 if (p->matrix_free)
                     HM_CUDA(hm_launch_free3(p->items3c.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p, p->f_py.p,
                                             p->dx.p, p->svec.p, p->dy.p, accumulate != 0, p->cheb, p->kernel_id,
-                                            nullptr, p->free3_zcap, st));
+                                            nullptr, p->free3_zcap, p->free_cheb, st));
                 else
                     HM_CUDA(hm_launch_stage3(p->items3c.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->dx.p, p->svec.p,
                                              p->dy.p, accumulate != 0, nullptr, st, false));

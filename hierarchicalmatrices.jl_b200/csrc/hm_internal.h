@@ -121,6 +121,7 @@ struct hm_plan {
     DevBuf<HmFreeRun> f_run3;
     DevBuf<double> f_px, f_py;
     int free1_units = 1, free3_zcap = HM_SMAX;
+    bool free_cheb = false; // cores hold C F C' and the apply runs the Chebyshev-series kernels
     // device arrays
     DevBuf<double> vstream, ustream, core, svec, partial;
     DevBuf<HmItem> items1, items3;

@@ -160,7 +160,7 @@ __device__ __noinline__ void core_apply_cta(const HmCoreBlock &cb, const int32_t
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 hm_core_kernel(const HmCoreBlock *__restrict__ blocks, int64_t nblocks,
                const int32_t *__restrict__ plist, const double *__restrict__ partial,
                const double *__restrict__ core, double *__restrict__ svec, int max_r)
@@ -543,6 +543,38 @@ hm_fillcore_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
     }
 }
 
+// Matrix-free plans in Chebyshev form: core <- C F C' per BarycentricMatrix2D leaf, where
+// C[q,k] = (2/R) T_q(cheb_k) (1/R for q = 0) maps values at the R first-kind Chebyshev nodes to
+// Chebyshev coefficients (discrete orthogonality).  With it stage 2 turns the moments mu of stage 1
+// straight into the coefficients c of stage 3:  c = C F C' mu.
+__global__ void __launch_bounds__(128)
+hm_core_cheb_kernel(const HmCoreBlock *__restrict__ blocks, double *__restrict__ core, const double *__restrict__ Cm)
+{
+    constexpr int R = 20;
+    __shared__ double Fs[R * R], Gs[R * R], Cs[R * R];
+    const HmCoreBlock cb = blocks[blockIdx.x];
+    if (cb.kind != HM_LEAF_BARY2D || cb.ru != R || cb.rv != R) return;
+    double *F = core + cb.core;
+    for (int i = threadIdx.x; i < R * R; i += blockDim.x) {
+        Fs[i] = F[i];   // F[m + l*R]
+        Cs[i] = Cm[i];  // C[q + k*R]
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * R; i += blockDim.x) { // G[m][q] = sum_l F[m][l] C[q][l]
+        const int m = i % R, q = i / R;
+        double a = 0.0;
+        for (int l = 0; l < R; l++) a = fma(Fs[m + l * R], Cs[q + l * R], a);
+        Gs[m + q * R] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * R; i += blockDim.x) { // out[p][q] = sum_m C[p][m] G[m][q]
+        const int pp = i % R, q = i / R;
+        double a = 0.0;
+        for (int m = 0; m < R; m++) a = fma(Cs[pp + m * R], Gs[m + q * R], a);
+        F[pp + q * R] = a;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // matrix-free apply ("fused assemble + apply")
 //
@@ -582,8 +614,16 @@ __device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)
 // two-rounding form of BarycentricMatrix.jl:159-167) sit in shared memory, lane pairs stride the
 // columns with private accumulators of r_sk x_s / sigma_s, the warp sum goes through shared
 // memory in lane order, and the chunks of a leaf are combined in chunk order -- deterministic.
-template <int R>
-__global__ void __launch_bounds__(HM_FREE1_THREADS, 8)
+//
+// CHEB = true (the default of matrix-free plans): the same interpolant in the
+// Chebyshev basis.  A barycentric row is the vector of Lagrange cardinal functions l_k(eta) of the
+// R first-kind Chebyshev nodes, l_k(eta) = sum_q C[q,k] T_q(eta), so  t = C' mu  with the moments
+// mu_q = sum_s x_s T_q(eta_s), eta_s = (y_s - mid) / half.  The lane that owns a column runs the
+// three-term recurrence T_{q+1} = 2 eta T_q - T_{q-1} and accumulates x_s T_q: 2 FP64 operations
+// per (column, q) and no reciprocal, against 6 + MUFU for the barycentric entry.  C' (and C for
+// stage 3) are folded into the leaf's core at plan time (hm_core_cheb_kernel), so stage 2 is unchanged.
+template <int R, bool CHEB>
+__global__ void __launch_bounds__(HM_FREE1_THREADS, CHEB ? 6 : 8)
 hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ ents,
                 const double *__restrict__ py, const double *__restrict__ x, double *__restrict__ partial,
                 const HmCheb cheb)
@@ -593,8 +633,8 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ 
     constexpr int T = HM_FREE1_THREADS, H = R / 2;
     static_assert(R % 2 == 0, "rank must be even");
     extern __shared__ double ures[]; // [units][R]
-    __shared__ double2 nodeW[T / 32][R]; // (node_k, lam_k) of the warp's current leaf
-    __shared__ double wred[T / 32][32][H + 1];
+    __shared__ double2 nodeW[CHEB ? 1 : T / 32][CHEB ? 1 : R]; // (node_k, lam_k) of the warp's current leaf
+    __shared__ double wred[T / 32][32][(CHEB ? R : H) + 1];
     const HmItem it = items[blockIdx.x];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int h = lane & 1, cl = lane >> 1;
@@ -603,9 +643,86 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ 
     hm_free1_split(S, it.nrun, nch, CH);
     const int U = it.nrun * nch;
     const double *__restrict__ xs = x + it.zoff;
+    if (CHEB && S <= 256) {
+        // short column segments (the joint slabs of the small leaves: 40-79 columns, a dozen leaves):
+        // eight lanes per leaf, four leaves per warp, so that a lane sums several columns before the
+        // 20 accumulators go through the shared-memory reduction
+        for (int e0 = warp * 4; e0 < it.nrun; e0 += 4 * (T / 32)) {
+            const int sub = lane >> 3, cl = lane & 7;
+            const int e = e0 + sub;
+            double acc[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) acc[k] = 0.0;
+            if (e < it.nrun) {
+                const HmFreeEnt en = ents[it.run0 + e];
+                const double *__restrict__ yc = py + en.yoff;
+                const double ih = __drcp_rn(en.half);
+                for (int s = cl; s < S; s += 8) {
+                    const double eta = (yc[s] - en.mid) * ih, two = eta + eta, xv = xs[s];
+                    double tm2 = 1.0, tm1 = eta;
+                    acc[0] += xv;
+                    acc[1] = fma(xv, eta, acc[1]);
+#pragma unroll
+                    for (int k = 2; k < R; k++) {
+                        const double tk = fma(two, tm1, -tm2);
+                        acc[k] = fma(xv, tk, acc[k]);
+                        tm2 = tm1;
+                        tm1 = tk;
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < R; k++) wred[warp][lane][k] = acc[k];
+            __syncwarp();
+            for (int idx = lane; idx < 4 * R; idx += 32) {
+                const int sb = idx / R, k = idx - sb * R;
+                if (e0 + sb < it.nrun) {
+                    double tsum = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) tsum += wred[warp][sb * 8 + j][k];
+                    partial[it.out + ents[it.run0 + e0 + sb].fofs + k] = tsum;
+                }
+            }
+        }
+        return;
+    }
     for (int u = warp; u < U; u += T / 32) {
         const int e = u / nch, c = u - e * nch;
         const HmFreeEnt en = ents[it.run0 + e];
+        if (CHEB) {
+            const double *__restrict__ yc = py + en.yoff;
+            const double ih = __drcp_rn(en.half);
+            double acc[R];
+#pragma unroll
+            for (int k = 0; k < R; k++) acc[k] = 0.0;
+            const int s1 = min(S, (c + 1) * CH);
+            for (int s = c * CH + lane; s < s1; s += 32) {
+                const double eta = (yc[s] - en.mid) * ih, two = eta + eta, xv = xs[s];
+                double tm2 = 1.0, tm1 = eta;
+                acc[0] += xv;
+                acc[1] = fma(xv, eta, acc[1]);
+#pragma unroll
+                for (int k = 2; k < R; k++) {
+                    const double tk = fma(two, tm1, -tm2);
+                    acc[k] = fma(xv, tk, acc[k]);
+                    tm2 = tm1;
+                    tm1 = tk;
+                }
+            }
+            // warp sum through shared memory, in lane order
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < R; k++) wred[warp][lane][k] = acc[k];
+            __syncwarp();
+            if (lane < R) {
+                double tsum = 0.0;
+#pragma unroll 8
+                for (int j = 0; j < 32; j++) tsum += wred[warp][j][lane];
+                ures[u * R + lane] = tsum;
+            }
+            continue;
+        }
         __syncwarp();
         if (lane < R)
             nodeW[warp][lane] = make_double2(__dadd_rn(en.mid, __dmul_rn(en.half, cheb.node[lane])), cheb.lam[lane]);
@@ -661,8 +778,14 @@ hm_free1_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restrict__ 
 // so that a thread spends one subtraction, one reciprocal and two FMAs per entry and one divide
 // per (row, leaf):  y_i += (sum_k lam_k s_k r_ik) / (sum_k lam_k r_ik).  The group sums are
 // combined in group order -- deterministic.
-template <int R, bool PEERS>
-__global__ void __launch_bounds__(HM_THREADS, 6)
+//
+// CHEB = true: the stage-2 vector holds the Chebyshev coefficients c = C s of every leaf's row
+// interpolant, and a low-rank run is the Clenshaw sum  y_i += sum_q c_q T_q(xi_i),
+// xi_i = (x_i - mid) / half: 2 FP64 operations per (row, q), no reciprocal.  A thread keeps four
+// rows going against one broadcast coefficient (every operand from shared memory would otherwise
+// make the shared-memory port, not the FP64 pipe, the limit).
+template <int R, bool PEERS, bool CHEB>
+__global__ void __launch_bounds__(HM_THREADS, CHEB ? 4 : 6)
 hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                 const HmFreeRun *__restrict__ frun,
                 const double *__restrict__ px, const double *__restrict__ py,
@@ -680,7 +803,8 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
     __shared__ double2 rbox[HM_MAXRUNS]; // (mid, half) of every low-rank run: read once, up front
     __shared__ int64_t rxo[HM_MAXRUNS];
     __shared__ int2 rk[HM_MAXRUNS];
-    __shared__ int nlr_s;
+    __shared__ int nlr_s, ndn_s, samex_s;
+    __shared__ int dnlist[HM_MAXRUNS];
     const HmItem it = items[blockIdx.x];
     const int t = threadIdx.x, lane = t & 31;
     const int S = it.S, F = it.F;
@@ -698,16 +822,27 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
     }
     if (t == 0) rpos[it.nrun] = S;
     __syncthreads();
-    if (t < 32) { // the low-rank runs (src < 0: they read the stage-2 vector), in order
-        int cnt = 0;
+    if (t < 32) { // the low-rank runs (src < 0: they read the stage-2 vector) and the dense ones, in order
+        int cnt = 0, dcnt = 0;
+        bool same = true;
         for (int base = 0; base < it.nrun; base += 32) {
             const int r = base + lane;
-            const bool lrr = r < it.nrun && rsrc[r] < 0;
-            const unsigned m = __ballot_sync(0xffffffffu, lrr);
+            const bool lrr = r < it.nrun && rsrc[r] < 0, dnr = r < it.nrun && rsrc[r] >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, lrr), md = __ballot_sync(0xffffffffu, dnr);
             if (lrr) lrlist[cnt + __popc(m & ((1u << lane) - 1u))] = r;
+            if (dnr) dnlist[dcnt + __popc(md & ((1u << lane) - 1u))] = r;
             cnt += __popc(m);
+            dcnt += __popc(md);
         }
-        if (lane == 0) nlr_s = cnt;
+        __syncwarp();
+        // do all low-rank runs address the same points for the item's rows?
+        for (int i = lane; i < cnt; i += 32) same = same && rxo[lrlist[i]] == rxo[lrlist[0]];
+        same = __all_sync(0xffffffffu, same);
+        if (lane == 0) {
+            nlr_s = cnt;
+            ndn_s = dcnt;
+            samex_s = same && cnt > 0;
+        }
     }
     // z: 32 lanes per run (the low-rank runs are R <= 32 long, the dense ones a few times that)
     for (int idx = t; idx < it.nrun * 32; idx += T) {
@@ -723,8 +858,9 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
     const bool active = g < G;
     double acc = 0.0;
     if (active) {
-        for (int r = 0; r < it.nrun; r++) {
-            if (rsrc[r] < 0) continue;
+        const int ndn = ndn_s;
+        for (int ri = 0; ri < ndn; ri++) {
+            const int r = dnlist[ri];
             const HmFreeRun fr = frun[it.run0 + r];
             const double p = px[fr.xoff + f];
             const double *__restrict__ yc = py + fr.yoff;
@@ -746,7 +882,70 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
             }
         }
     }
-    for (int b0 = 0; b0 < nlr; b0 += B) {
+    // CHEB: row quads.  Thread (g4, fq) owns rows fq, fq + FQ, fq + 2 FQ, fq + 3 FQ of the item
+    const int FQ = (F + 3) >> 2;
+    const int G4 = FQ > 0 ? T / FQ : 1;
+    const int g4 = FQ > 0 ? t / FQ : G4, fq = t - g4 * FQ;
+    double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int BC = 2 * B; // coefficient tables are half the size of the barycentric ones
+    __shared__ double2 tbox[CHEB ? BC : 1];
+    __shared__ int64_t xoffc[CHEB ? BC : 1];
+    // the rows of an item are the same points for every run when rows and points are numbered alike
+    // (always so for KernelMatrix): then a thread loads its four points once
+    const bool same_x = CHEB && samex_s;
+    double p4[4] = {0.0, 0.0, 0.0, 0.0};
+    if (same_x && g4 < G4) {
+        const double *__restrict__ pp = px + rxo[lrlist[0]] + fq;
+#pragma unroll
+        for (int j = 0; j < 4; j++) p4[j] = fq + j * FQ < F ? pp[j * FQ] : 0.0;
+    }
+    for (int b0 = 0; CHEB && b0 < nlr; b0 += BC) {
+        const int nb = min(BC, nlr - b0);
+        __syncthreads(); // the previous batch's tables are no longer read
+        double *tabc = reinterpret_cast<double *>(&tab[0][0]); // [BC][R] coefficients
+        int64_t *xoff = xoffc;
+        for (int idx = t; idx < nb * R; idx += T) {
+            const int b = idx / R, k = idx - b * R;
+            const int r = lrlist[b0 + b];
+            const int2 kr = rk[r];
+            tabc[b * R + k] = (k >= kr.x && k < kr.x + kr.y) ? zs[rpos[r] + k - kr.x] : 0.0;
+            if (k == 0) {
+                const double2 box = rbox[r];
+                tbox[b] = make_double2(box.x, __drcp_rn(box.y));
+                xoff[b] = rxo[r];
+            }
+        }
+        __syncthreads();
+        if (g4 < G4) {
+            for (int b = g4; b < nb; b += G4) {
+                const double2 box = tbox[b];
+                const double *__restrict__ pp = px + xoff[b] + fq;
+                const double *__restrict__ cf = tabc + b * R;
+                double two[4], b1[4], b2[4];
+                const double ih2 = box.y + box.y;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const double p = same_x ? p4[j] : (fq + j * FQ < F ? pp[j * FQ] : box.x);
+                    two[j] = (p - box.x) * ih2; // 2 xi
+                    b1[j] = b2[j] = 0.0;
+                }
+#pragma unroll
+                for (int k = R - 1; k >= 1; k--) {
+                    const double ck = cf[k];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const double nb1 = fma(two[j], b1[j], ck) - b2[j];
+                        b2[j] = b1[j];
+                        b1[j] = nb1;
+                    }
+                }
+                const double c0 = cf[0];
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc4[j] += fma(0.5 * two[j], b1[j], c0) - b2[j];
+            }
+        }
+    }
+    for (int b0 = 0; !CHEB && b0 < nlr; b0 += B) {
         const int nb = min(B, nlr - b0);
         __syncthreads(); // the previous batch's tables are no longer read
         for (int idx = t; idx < nb * R; idx += T) {
@@ -775,10 +974,19 @@ hm_free3_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs
         }
     }
     red[t] = acc;
+    if (CHEB) {
+        __syncthreads(); // z is no longer read: the row-quad sums go through its storage (>= 4 T words)
+#pragma unroll
+        for (int j = 0; j < 4; j++) zs[j * T + t] = acc4[j];
+    }
     __syncthreads();
     if (t < F) {
         double v = red[t];
         for (int gg = 1; gg < G; gg++) v += red[gg * F + t];
+        if (CHEB) {
+            const int j = t / FQ, q = t - j * FQ;
+            for (int gg = 0; gg < G4; gg++) v += zs[j * T + gg * FQ + q];
+        }
         double *o = y + it.out + t;
         const double r = (accumulate ? *o : 0.0) + v;
         if (PEERS) {
@@ -1266,8 +1474,11 @@ cudaError_t hm_launch_stage2(const HmCoreBlock *blocks, int64_t nblocks, const i
     if (smem > 48 * 1024) return cudaErrorInvalidConfiguration;
     int wpb = threads / 32;
     unsigned grid = (unsigned)((nblocks + wpb - 1) / wpb);
-    // (a persistent variant with two leaves in flight per warp was measured in round 2: 0.204 ms vs
-    // 0.108 ms at N = 2^20 -- 16 warps per SM hide less latency than 32 one-leaf warps)
+    // Two restructurings were measured in round 2 and dropped: a persistent kernel with two leaves in
+    // flight per warp (0.204 vs 0.108 ms at N = 2^20: 16 warps per SM hide less latency than 32 one-leaf
+    // warps), and the rank-20 core staged in shared memory by cp.async at 32 registers / 64 warps per SM
+    // (0.110 vs 0.101 ms alone, and 0.76 ms slower per matvec inside a PDL graph: its early-launched CTAs
+    // hold 215 KB of shared memory per SM while they wait for stage 1).
     return launch_k(hm_core_kernel, grid, (unsigned)threads, smem, st, pdl, blocks, nblocks, plist, partial, core,
                     svec, max_r);
 }
@@ -1284,40 +1495,61 @@ cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *r
                     ustream, x, svec, y, accumulate, HmFuse{}, HmPeers{});
 }
 
+cudaError_t hm_launch_core_cheb(const HmCoreBlock *blocks, int64_t nblocks, double *core, const double *Cm,
+                                cudaStream_t st)
+{
+    if (nblocks <= 0) return cudaSuccess;
+    hm_core_cheb_kernel<<<(unsigned)nblocks, 128, 0, st>>>(blocks, core, Cm);
+    return cudaGetLastError();
+}
+
 cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFreeEnt *ents, const double *py,
-                            const double *x, double *partial, const HmCheb &cheb, int max_units,
+                            const double *x, double *partial, const HmCheb &cheb, int max_units, bool cheb_form,
                             cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
     const size_t smem = (size_t)std::max(max_units, 1) * 20 * sizeof(double);
     if (smem > 160 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(hm_free1_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cheb_form ? cudaFuncSetAttribute(hm_free1_kernel<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                              : cudaFuncSetAttribute(hm_free1_kernel<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hm_free1_kernel<20><<<(unsigned)nitems, HM_FREE1_THREADS, smem, st>>>(items, ents, py, x, partial, cheb);
+    if (cheb_form)
+        hm_free1_kernel<20, true><<<(unsigned)nitems, HM_FREE1_THREADS, smem, st>>>(items, ents, py, x, partial, cheb);
+    else
+        hm_free1_kernel<20, false><<<(unsigned)nitems, HM_FREE1_THREADS, smem, st>>>(items, ents, py, x, partial, cheb);
+    return cudaGetLastError();
+}
+
+template <bool PEERS, bool CHEB>
+static cudaError_t launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun,
+                                const double *px, const double *py, const double *x, const double *svec, double *y,
+                                int accumulate, const HmCheb &cheb, int kernel_id, const HmPeers &pe, size_t smem,
+                                cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(hm_free3_kernel<20, PEERS, CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    hm_free3_kernel<20, PEERS, CHEB><<<(unsigned)nitems, HM_THREADS, smem, st>>>(items, runs, frun, px, py, x, svec, y,
+                                                                               accumulate, cheb, kernel_id, pe);
     return cudaGetLastError();
 }
 
 cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun,
                             const double *px, const double *py, const double *x,
                             const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
-                            const HmPeers *peers, int zcap, cudaStream_t st)
+                            const HmPeers *peers, int zcap, bool cheb_form, cudaStream_t st)
 {
     if (nitems <= 0) return cudaSuccess;
     if (zcap < 2 || zcap > HM_SMAX) zcap = HM_SMAX;
+    if (cheb_form) zcap = std::max(zcap, 4 * HM_THREADS); // the row-quad sums are combined through z's storage
     const size_t smem = (size_t)zcap * sizeof(double);
-    {
-        cudaError_t e = cudaFuncSetAttribute(hm_free3_kernel<20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(hm_free3_kernel<20, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    if (peers && peers->n > 0)
-        hm_free3_kernel<20, true><<<(unsigned)nitems, HM_THREADS, smem, st>>>(items, runs, frun, px, py, x, svec,
-                                                                        y, accumulate, cheb, kernel_id, *peers);
-    else
-        hm_free3_kernel<20, false><<<(unsigned)nitems, HM_THREADS, smem, st>>>(items, runs, frun, px, py, x, svec,
-                                                                         y, accumulate, cheb, kernel_id, HmPeers{});
-    return cudaGetLastError();
+    const bool pe = peers && peers->n > 0;
+    const HmPeers none{};
+    if (cheb_form)
+        return pe ? launch_free3<true, true>(items, nitems, runs, frun, px, py, x, svec, y, accumulate, cheb, kernel_id, *peers, smem, st)
+                  : launch_free3<false, true>(items, nitems, runs, frun, px, py, x, svec, y, accumulate, cheb, kernel_id, none, smem, st);
+    return pe ? launch_free3<true, false>(items, nitems, runs, frun, px, py, x, svec, y, accumulate, cheb, kernel_id, *peers, smem, st)
+              : launch_free3<false, false>(items, nitems, runs, frun, px, py, x, svec, y, accumulate, cheb, kernel_id, none, smem, st);
 }
 
 cudaError_t hm_launch_fill3(const HmFill *fills, int64_t nfills, const HmLeaf *leaves, double *ustream,

@@ -105,13 +105,16 @@ __host__ __device__ inline void hm_free1_split(int S, int nrun, int &nch, int &C
     if (CH < 32) CH = 32;
     nch = S > 0 ? (S + CH - 1) / CH : 1;
 }
+// cheb_form: the plan's cores were transformed by hm_launch_core_cheb (Chebyshev-series kernels)
+cudaError_t hm_launch_core_cheb(const HmCoreBlock *blocks, int64_t nblocks, double *core, const double *Cm,
+                                cudaStream_t st);
 cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFreeEnt *ents, const double *py,
-                            const double *x, double *partial, const HmCheb &cheb, int max_units,
+                            const double *x, double *partial, const HmCheb &cheb, int max_units, bool cheb_form,
                             cudaStream_t st);
 cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun,
                             const double *px, const double *py, const double *x,
                             const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
-                            const HmPeers *peers, int zcap, cudaStream_t st);
+                            const HmPeers *peers, int zcap, bool cheb_form, cudaStream_t st);
 
 // many right-hand sides (hm_panel.cu): panels are row-major with pitch CS = hm_panel_width(nrhs)
 int hm_panel_width(int nrhs);

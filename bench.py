@@ -819,21 +819,23 @@ def run_ours(args):
         ms_f = f0.elapsed_time(f1) / nmf
         fst, fn = pf.timing_end()
         dev_rel = float((yf - y_dev).abs().max() / y_dev.abs().max())
-        # FP64 work of one matrix-free matvec: per stored U / V / dense word one subtraction, one
-        # reciprocal (rcp.approx + 3 DFMA refinement) and two FMAs -- counted as 6 FP64-pipe issues;
-        # peak = the DFMA issue rate measured by profiles/microbench/fp64_pipes.cu (34.2 TFLOP/s = 17.1e12 issues/s)
-        words = st["dense_words"] + st["lowrank_words"] - st["core_words"]
-        issues = 6.0 * words
+        # FP64 work of one matrix-free matvec in the Chebyshev form: per (column,
+        # leaf) of stage 1 one mapping + 18 recurrence DFMA + 20 accumulations = 39 FP64-pipe
+        # instructions, per (row, leaf) of stage 3 a 20-term Clenshaw sum = 41, per dense entry 5 (sub,
+        # 3 refinement DFMA of the reciprocal, 1 accumulate; the rcp.approx itself runs on the XU pipe).
+        # peak = the DFMA issue rate measured by profiles/microbench/fp64_pipes.cu (34.2 TFLOP/s / 2)
+        issues = 39.0 * st["part_v_words"] / 20 + 41.0 * st["part_u_words"] / 20 + 5.0 * st["part_dense_words"]
         mfree = {"value": 1e3 / ms_f, "unit": "matvecs/s", "ms_per_step": ms_f, "steps": nmf,
                  "resident_bytes": pf.stats()["stored_bytes"], "setup_s": round(t_setup, 3),
                  "relinf_vs_stored": dev_rel, "api": "hm_assemble_kernel_free + hm_matvec_device",
+                 "form": "Chebyshev series (moments + Clenshaw), cores C F C' with the node correction",
                  "ms_per_launch": {"stage1": fst[0] / max(fn, 1), "stage2": fst[1] / max(fn, 1), "stage3": fst[2] / max(fn, 1)},
                  "roofline": {"bound": "fp64", "kernel": "hm_free1_kernel + hm_free3_kernel",
                               "achieved": issues / (ms_f / 1e3) / 1e12, "peak": 17.1,
                               "unit": "10^12 FP64-pipe instructions/s (lane-level)",
                               "frac": issues / (ms_f / 1e3) / 1e12 / 17.1,
-                              "how": "6 FP64-pipe issues per evaluated entry (sub, rcp.approx, 3 refinement DFMA "
-                                     "incl. the use, 1 accumulate DFMA); peak = DFMA rate of "
+                              "how": "algorithmic FP64-pipe instructions of the Chebyshev form (39 per column and leaf, "
+                                     "41 per row and leaf, 5 per dense entry) / time; peak = DFMA rate of "
                                      "profiles/microbench/fp64_pipes.cu (34.2 TFLOP/s / 2)"}}
         if not args.no_e2e:
             for _ in range(3):

@@ -330,9 +330,25 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
                         Cm[(size_t)q + (size_t)k * R] = (double)((q == 0 ? 1.0L : 2.0L) * tq / R);
                     }
                 }
-                DevBuf<double> dC;
+                // Chebyshev differentiation matrix of the first-kind points (barycentric form):
+                // D[i][j] = (w_j / w_i) / (x_i - x_j), D[i][i] = -sum_{j != i} D[i][j]
+                std::vector<double> Dm((size_t)R * R);
+                for (int i = 0; i < R; i++) {
+                    long double diag = 0.0L;
+                    for (int j = 0; j < R; j++) {
+                        if (j == i) continue;
+                        const long double dij = ((long double)P->cheb.lam[j] / (long double)P->cheb.lam[i]) /
+                                                ((long double)P->cheb.node[i] - (long double)P->cheb.node[j]);
+                        Dm[(size_t)i + (size_t)j * R] = (double)dij;
+                        diag -= dij;
+                    }
+                    Dm[(size_t)i + (size_t)i * R] = (double)diag;
+                }
+                DevBuf<double> dC, dD;
                 HM_CUDA(dC.upload(Cm, st));
-                HM_CUDA(hm_launch_core_cheb(P->cores.p, (int64_t)L.cores.size(), P->core.p, dC.p, st));
+                HM_CUDA(dD.upload(Dm, st));
+                HM_CUDA(hm_launch_core_cheb(P->cores.p, dcore_leaf.p, (int64_t)L.cores.size(), dleaves.p, P->core.p, dC.p,
+                                            dD.p, P->cheb, st));
                 HM_CUDA(cudaStreamSynchronize(st));
             }
         }

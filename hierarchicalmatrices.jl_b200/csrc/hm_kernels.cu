@@ -543,31 +543,66 @@ hm_fillcore_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__rest
     }
 }
 
-// Matrix-free plans in Chebyshev form: core <- C F C' per BarycentricMatrix2D leaf, where
+// Matrix-free plans in Chebyshev form: core <- C F~ C' per BarycentricMatrix2D leaf, where
 // C[q,k] = (2/R) T_q(cheb_k) (1/R for q = 0) maps values at the R first-kind Chebyshev nodes to
 // Chebyshev coefficients (discrete orthogonality).  With it stage 2 turns the moments mu of stage 1
-// straight into the coefficients c of stage 3:  c = C F C' mu.
+// straight into the coefficients c of stage 3:  c = C F~ C' mu.
+//
+// F~ is F moved from the nodes the reference really uses to the exact Chebyshev nodes.  The reference
+// evaluates f at the *rounded* nodes n_k = fl(mid + fl(half cheb_k)) (BarycentricMatrix.jl:159-167);
+// in the box variable that is xi_k = cheb_k + eps_k with eps_k up to ulp(mid) / half -- 1e-6 for the
+// tiny boxes of clustered point sets.  Treating those values as values at cheb_k would cost that
+// much relative accuracy on the block; one Newton-like step with the Chebyshev differentiation
+// matrix D removes it to second order:  g(cheb) = f - diag(eps) D f, for rows and for columns.
 __global__ void __launch_bounds__(128)
-hm_core_cheb_kernel(const HmCoreBlock *__restrict__ blocks, double *__restrict__ core, const double *__restrict__ Cm)
+hm_core_cheb_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__restrict__ core_leaf,
+                    const HmLeaf *__restrict__ leaves, double *__restrict__ core, const double *__restrict__ Cm,
+                    const double *__restrict__ Dm, const HmCheb cheb)
 {
     constexpr int R = 20;
-    __shared__ double Fs[R * R], Gs[R * R], Cs[R * R];
+    __shared__ double Fs[R * R], Gs[R * R], Cs[R * R], Ds[R * R], ex[R], ey[R];
     const HmCoreBlock cb = blocks[blockIdx.x];
     if (cb.kind != HM_LEAF_BARY2D || cb.ru != R || cb.rv != R) return;
+    const HmLeaf *l = leaves + core_leaf[blockIdx.x];
     double *F = core + cb.core;
-    for (int i = threadIdx.x; i < R * R; i += blockDim.x) {
+    const int t = threadIdx.x, T = blockDim.x;
+    for (int i = t; i < R * R; i += T) {
         Fs[i] = F[i];   // F[m + l*R]
         Cs[i] = Cm[i];  // C[q + k*R]
+        Ds[i] = Dm[i];  // D[i + j*R]
+    }
+    if (t < 2 * R) {
+        const bool xs = t < R;
+        const int k = xs ? t : t - R;
+        const double lo = xs ? l->a : l->c, hi = xs ? l->b : l->d;
+        const double mid = __dmul_rn(0.5, __dadd_rn(lo, hi)), half = __dmul_rn(0.5, __dsub_rn(hi, lo));
+        const double node = __dadd_rn(mid, __dmul_rn(half, cheb.node[k])); // the node the reference uses
+        const double e = __ddiv_rn(__dsub_rn(node, mid), half) - cheb.node[k];
+        (xs ? ex : ey)[k] = e;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < R * R; i += blockDim.x) { // G[m][q] = sum_l F[m][l] C[q][l]
+    for (int i = t; i < R * R; i += T) { // rows: G = F - diag(ex) D F
+        const int m = i % R, c = i / R;
+        double a = 0.0;
+        for (int j = 0; j < R; j++) a = fma(Ds[m + j * R], Fs[j + c * R], a);
+        Gs[i] = Fs[i] - ex[m] * a;
+    }
+    __syncthreads();
+    for (int i = t; i < R * R; i += T) { // columns: F~ = G - (D G')' diag(ey)
+        const int m = i % R, c = i / R;
+        double a = 0.0;
+        for (int j = 0; j < R; j++) a = fma(Ds[c + j * R], Gs[m + j * R], a);
+        Fs[i] = Gs[i] - ey[c] * a;
+    }
+    __syncthreads();
+    for (int i = t; i < R * R; i += T) { // G[m][q] = sum_l F~[m][l] C[q][l]
         const int m = i % R, q = i / R;
         double a = 0.0;
-        for (int l = 0; l < R; l++) a = fma(Fs[m + l * R], Cs[q + l * R], a);
+        for (int c = 0; c < R; c++) a = fma(Fs[m + c * R], Cs[q + c * R], a);
         Gs[m + q * R] = a;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < R * R; i += blockDim.x) { // out[p][q] = sum_m C[p][m] G[m][q]
+    for (int i = t; i < R * R; i += T) { // out[p][q] = sum_m C[p][m] G[m][q]
         const int pp = i % R, q = i / R;
         double a = 0.0;
         for (int m = 0; m < R; m++) a = fma(Cs[pp + m * R], Gs[m + q * R], a);
@@ -1495,11 +1530,12 @@ cudaError_t hm_launch_stage3(const HmItem *items, int64_t nitems, const HmRun *r
                     ustream, x, svec, y, accumulate, HmFuse{}, HmPeers{});
 }
 
-cudaError_t hm_launch_core_cheb(const HmCoreBlock *blocks, int64_t nblocks, double *core, const double *Cm,
-                                cudaStream_t st)
+cudaError_t hm_launch_core_cheb(const HmCoreBlock *blocks, const int32_t *core_leaf, int64_t nblocks,
+                                const HmLeaf *leaves, double *core, const double *Cm, const double *Dm,
+                                const HmCheb &cheb, cudaStream_t st)
 {
     if (nblocks <= 0) return cudaSuccess;
-    hm_core_cheb_kernel<<<(unsigned)nblocks, 128, 0, st>>>(blocks, core, Cm);
+    hm_core_cheb_kernel<<<(unsigned)nblocks, 128, 0, st>>>(blocks, core_leaf, leaves, core, Cm, Dm, cheb);
     return cudaGetLastError();
 }
 

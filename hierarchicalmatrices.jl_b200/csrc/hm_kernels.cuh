@@ -106,8 +106,9 @@ __host__ __device__ inline void hm_free1_split(int S, int nrun, int &nch, int &C
     nch = S > 0 ? (S + CH - 1) / CH : 1;
 }
 // cheb_form: the plan's cores were transformed by hm_launch_core_cheb (Chebyshev-series kernels)
-cudaError_t hm_launch_core_cheb(const HmCoreBlock *blocks, int64_t nblocks, double *core, const double *Cm,
-                                cudaStream_t st);
+cudaError_t hm_launch_core_cheb(const HmCoreBlock *blocks, const int32_t *core_leaf, int64_t nblocks,
+                                const HmLeaf *leaves, double *core, const double *Cm, const double *Dm,
+                                const HmCheb &cheb, cudaStream_t st);
 cudaError_t hm_launch_free1(const HmItem *items, int64_t nitems, const HmFreeEnt *ents, const double *py,
                             const double *x, double *partial, const HmCheb &cheb, int max_units, bool cheb_form,
                             cudaStream_t st);

@@ -39,7 +39,7 @@ __all__ = [
     "cauchykernel", "coulombkernel", "coulombprimekernel", "logkernel", "Plan", "flatten",
     "chebyshevpoints", "HmError", "rmul_", "lmul_", "scale_", "adjoint", "Adjoint",
     "chebyshevbarycentricweights", "EvenBarycentricMatrix", "barycentricmatrix", "Transpose", "transpose",
-    "dist_unique_id", "getrank", "svdtrunc", "lrzeros",
+    "dist_unique_id", "getrank", "svdtrunc", "lrzeros", "hierarchicalcholesky", "solvetransposed",
 ]
 
 Matrix = np.ndarray  # the dense leaf type of the reference
@@ -235,6 +235,15 @@ class LowRankMatrix:
 
     def __rmul__(self, other):
         return LowRankMatrix(self.U, other * self.S, self.V) if np.isscalar(other) else NotImplemented
+
+    def adjoint_mul(self, other):
+        """`L1' * L2` (LowRankMatrix.jl:120-126; the step R12'R12 of cholesky.jl:24) and `L' * x`
+        (algebra.jl:97-104, real element type)."""
+        if isinstance(other, LowRankMatrix):
+            Us, sv, Vt = np.linalg.svd((self.S[:, None] * (self.U.T @ other.U)) * other.S[None, :])
+            r = getrank(sv)
+            return LowRankMatrix((self.V @ Us)[:, :r], sv[:r], (other.V @ Vt.T)[:, :r])
+        return (self.V * self.S) @ (self.U.T @ np.asarray(other))
 
     def __truediv__(self, other):  # :162
         return LowRankMatrix(self.U, self.S / other, self.V)
@@ -828,16 +837,33 @@ class _HierarchicalBase:
             p += self.blocksize(m + 1, self.N, 1)
         return G
 
+    def todense(self) -> np.ndarray:
+        """`Matrix(H)`: every assigned block written out (what the generic AbstractMatrix fallbacks of
+        the reference compute through getindex, hierarchical.jl:120-147)."""
+        D = np.zeros(self.size(), dtype=self.T, order="F")
+        for kind, i0, j0, A in self.leaves():
+            blk = A if isinstance(A, np.ndarray) else A.todense()
+            D[i0:i0 + blk.shape[0], j0:j0 + blk.shape[1]] += blk
+        return D
+
     def __add__(self, L):
+        if isinstance(L, np.ndarray):  # generic AbstractMatrix arithmetic: a dense Matrix
+            return self.todense() + L
         return self._add_lowrank(L, 1.0, 1.0, True)
 
     def __radd__(self, L):
+        if isinstance(L, np.ndarray):
+            return L + self.todense()
         return self._add_lowrank(L, 1.0, 1.0, False)
 
     def __sub__(self, L):
+        if isinstance(L, np.ndarray):
+            return self.todense() - L
         return self._add_lowrank(L, 1.0, -1.0, True)
 
     def __rsub__(self, L):
+        if isinstance(L, np.ndarray):
+            return L - self.todense()
         return self._add_lowrank(L, -1.0, 1.0, False)
 
 
@@ -856,6 +882,84 @@ def hierarchical(name: str, *types):
 
 HierarchicalMatrix = hierarchical("HierarchicalMatrix", LowRankMatrix, Matrix)
 _KernelMatrixBlocks = hierarchical("KernelMatrix", BarycentricMatrix2D, Matrix)
+
+
+# ---- hierarchicalcholesky / solvetransposed (/root/reference/src/cholesky.jl:12-228).
+# The reference spells the recursion out as eight Val-dispatched methods per function, one per
+# combination of the `assigned` codes of the (1,1), (1,2), (2,2) blocks; here the codes select the
+# blocks and one body serves all eight.  Host side: dense leaves go through LAPACK exactly where the
+# reference calls it (cholesky(Symmetric(A)).U, UpperTriangular(R)'\b), the low-rank algebra is the
+# mirror above.  The factor is an ordinary HierarchicalMatrix: R*x and R'*x run on the device.
+def _chol_blocks(A, what):
+    if not isinstance(A, HierarchicalMatrix):
+        raise TypeError(f"MethodError: {what}(::{type(A).__name__})")
+    if A.blocksize() != (2, 2):
+        raise AssertionError("blocksize(A) == (2, 2)")           # cholesky.jl:13, :158
+    c11, c12, c22 = (int(A.assigned[0, 0]), int(A.assigned[0, 1]), int(A.assigned[1, 1]))
+    if c11 not in (1, 3) or c22 not in (1, 3) or c12 not in (2, 3):
+        # no method for Val{c11}, Val{c12}, Val{c22}: low-rank diagonal blocks and nested or
+        # unassigned off-diagonal blocks are outside the eight cases (cholesky.jl:5-9)
+        raise TypeError(f"MethodError: {what}(::HierarchicalMatrix, Val({c11}), Val({c12}), Val({c22}))")
+    return A._block(0, 0), A._block(0, 1), A._block(1, 1)
+
+
+def hierarchicalcholesky(A):
+    """Upper Cholesky factor R (A = R'R) of a symmetric positive definite HierarchicalMatrix, of which
+    only the upper blocks are read -- cholesky.jl:12-94.  `hierarchicalcholesky(A::Matrix)` is the
+    dense factor (:18-20)."""
+    if isinstance(A, np.ndarray):
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("DimensionMismatch: matrix is not square")
+        # Symmetric(A) reads the upper triangle; LAPACK potrf
+        Au = np.triu(A)
+        return np.asfortranarray(np.linalg.cholesky(Au + np.triu(A, 1).T).T)
+    A11, A12, A22 = _chol_blocks(A, "hierarchicalcholesky")
+    R = HierarchicalMatrix(A.T, 2, 2)
+    R11 = hierarchicalcholesky(A11)
+    R[Block(1), Block(1)] = R11
+    R12 = solvetransposed(R11, A12)
+    R[Block(1), Block(2)] = R12
+    if isinstance(R12, LowRankMatrix):
+        LL = R12.adjoint_mul(R12)                 # R12'R12, LowRankMatrix.jl:120-126
+        # H - L (algebra.jl:460-491) or Matrix - L (generic elementwise, a dense Matrix)
+        S = A22 - LL.todense() if isinstance(A22, np.ndarray) else A22 - LL
+    else:
+        S = A22 - R12.T @ R12                     # generic AbstractMatrix arithmetic: dense
+    if isinstance(S, np.ndarray):
+        S = np.asfortranarray(S)
+    R[Block(2), Block(2)] = hierarchicalcholesky(S)
+    return R
+
+
+def solvetransposed(R, B):
+    """`R' \\ B` for the upper factor R: B a vector (cholesky.jl:154-228), a Matrix (column by column,
+    :109-116, :128-135) or a LowRankMatrix (its U factor column by column, :99-107, :118-126)."""
+    if isinstance(B, LowRankMatrix):
+        Uh = np.zeros_like(B.U)
+        for j in range(B.U.shape[1]):
+            Uh[:, j] = solvetransposed(R, np.ascontiguousarray(B.U[:, j]))
+        return LowRankMatrix(Uh, B.S, B.V)
+    B = np.asarray(B)
+    if B.ndim == 2:
+        Mh = np.zeros_like(B, order="F")
+        for j in range(B.shape[1]):
+            Mh[:, j] = solvetransposed(R, np.ascontiguousarray(B[:, j]))
+        return Mh
+    if B.ndim != 1:
+        raise TypeError("MethodError: solvetransposed")
+    if isinstance(R, np.ndarray):                 # UpperTriangular(R)' \ b, :150-152
+        import scipy.linalg
+        if R.shape[0] != B.shape[0]:
+            raise ValueError("DimensionMismatch")
+        return scipy.linalg.solve_triangular(R, B, trans="T", lower=False, check_finite=False)
+    R11, R12, R22 = _chol_blocks(R, "solvetransposed")
+    n = R.size(2)
+    s = R11.shape[1] if isinstance(R11, np.ndarray) else R11.size(2)
+    b1, b2 = B[:s], B[s:n]
+    x1 = solvetransposed(R11, b1)
+    r12x = R12.adjoint_mul(x1) if isinstance(R12, LowRankMatrix) else R12.T @ x1
+    x2 = solvetransposed(R22, b2 - r12x)
+    return np.concatenate([x1, x2])
 
 
 class KernelMatrix(_KernelMatrixBlocks):

@@ -1281,7 +1281,6 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
 {
     return guarded([&]() -> int32_t {
         if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-        if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
         if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
         if (nrhs == 0) return HM_OK;
         const HmLayout &L = p->L;
@@ -1289,7 +1288,9 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
             return fail(HM_ERR_SHAPE, "leading dimension smaller than the vector length");
         if ((!dX && L.ncols > 0) || (!dY && L.nrows > 0)) return fail(HM_ERR_NULL, "panel pointer is NULL");
         if (nrhs == 1) return hm_matvec_device(p, dX, dY, accumulate, stream);
-        if (!hm_panel_supports_rank(L.max_r, (int)std::min<int64_t>(nrhs, 64))) {
+        // a matrix-free plan has panel kernels for its Chebyshev form (hm_free_panel.cu); the barycentric
+        // form (HMB200_FREE_FORM=bary) goes column by column
+        if (!hm_panel_supports_rank(L.max_r, (int)std::min<int64_t>(nrhs, 64)) || (p->matrix_free && !p->free_cheb)) {
             // ranks beyond the panel kernels' shared-memory staging: column by column
             for (int64_t c = 0; c < nrhs; c++)
                 if (int32_t rc = hm_matvec_device(p, dX + c * ldx, dY + c * ldy, accumulate, stream)) return rc;
@@ -1319,16 +1320,25 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
             cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
             if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
             HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st));
-            HM_CUDA(hm_launch_panel_stage1(CS, p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->wXt.p,
-                                           p->wPp.p, st));
+            if (p->matrix_free)
+                HM_CUDA(hm_launch_free1_panel(CS, p->items1.p, (int64_t)L.items1.size(), p->f_ent1.p, p->f_py.p,
+                                              p->wXt.p, p->wPp.p, st));
+            else
+                HM_CUDA(hm_launch_panel_stage1(CS, p->items1.p, (int64_t)L.items1.size(), p->vstream.p, p->wXt.p,
+                                               p->wPp.p, st));
             if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
             HM_CUDA(hm_launch_panel_stage2(CS, p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->wPp.p, p->core.p,
                                            p->wSp, std::max(L.max_r, 1), st));
             if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
             for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
                 int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];
-                HM_CUDA(hm_launch_panel_stage3(CS, p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->wXt.p,
-                                               p->wSp, p->wYt.p, r == 0 ? 0 : 1, p->panel_zcap, st));
+                if (p->matrix_free)
+                    HM_CUDA(hm_launch_free3_panel(CS, p->items3.p + i0, i1 - i0, p->runs.p, p->f_run3.p, p->f_px.p,
+                                                  p->f_py.p, p->wXt.p, p->wSp, p->wYt.p, r == 0 ? 0 : 1,
+                                                  p->kernel_id, st));
+                else
+                    HM_CUDA(hm_launch_panel_stage3(CS, p->items3.p + i0, i1 - i0, p->runs.p, p->ustream.p, p->wXt.p,
+                                                   p->wSp, p->wYt.p, r == 0 ? 0 : 1, p->panel_zcap, st));
             }
             HM_CUDA(hm_launch_panel_out(p->wYt.p, CS, L.row_begin, L.row_end, nc, dY + c0 * ldy, ldy,
                                         accumulate != 0, st));
@@ -1346,7 +1356,6 @@ int32_t hm_matmat(hm_plan *p, const double *X, int64_t ldx, double *Y, int64_t l
 {
     return guarded([&]() -> int32_t {
         if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-        if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
         if (nrhs < 0) return fail(HM_ERR_SHAPE, "negative nrhs");
         if (nrhs == 0) return HM_OK;
         const HmLayout &L = p->L;

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "hm_device.cuh"
 #include "hm_kernels.cuh"
 
 namespace {
@@ -621,28 +622,6 @@ hm_core_cheb_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__res
 // one per entry.  The bound moves from HBM to the FP64 pipe (one reciprocal per entry); the
 // operator occupies no memory beyond its tables and the r x r cores, so N = 2^24 fits one GPU.
 // ---------------------------------------------------------------------------
-// 1/d to about one ulp: the hardware's 2^-23 approximation r0 and one cubic (Halley) step,
-// 1/d = r0 (1 + e + e^2 + ...), e = 1 - d r0, truncated after e^2 (error e^3 ~ 2^-69): 3 DFMA,
-// against the ~3x longer correctly rounded __drcp_rn.  The matrix-free kernels spend their time here.
-__device__ __forceinline__ double frcp(double d)
-{
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-    const double e = fma(-d, r, 1.0);
-    return fma(r, fma(e, e, e), r);
-}
-
-__device__ __forceinline__ double kernel_eval_fast(int id, double x, double y)
-{
-    const double d = __dsub_rn(x, y);
-    switch (id) {
-    case 0: return frcp(d);
-    case 1: return frcp(__dmul_rn(d, d));
-    case 2: return frcp(__dmul_rn(__dmul_rn(d, d), d));
-    default: return log(fabs(d));
-    }
-}
-
 // stage 1: partial[item.out + (leaf, k)] = sum_s V_leaf[s, k] x[zoff + s] with V evaluated on the
 // fly: V[s,k] = lam_k r_sk / sigma_s, r_sk = 1/(y_s - node_k), sigma_s = sum_k lam_k r_sk.  A warp
 // owns a unit = (leaf of the item, chunk of its columns); the leaf's mapped nodes (exact

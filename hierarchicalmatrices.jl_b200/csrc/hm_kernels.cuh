@@ -117,6 +117,14 @@ cudaError_t hm_launch_free3(const HmItem *items, int64_t nitems, const HmRun *ru
                             const double *svec, double *y, int accumulate, const HmCheb &cheb, int kernel_id,
                             const HmPeers *peers, int zcap, bool cheb_form, cudaStream_t st);
 
+// many right-hand sides on a matrix-free plan in Chebyshev form (hm_free_panel.cu): stage 1 and stage 3
+// with the operator generated in MMA fragment layout; stage 2 is hm_launch_panel_stage2
+cudaError_t hm_launch_free1_panel(int CS, const HmItem *items, int64_t nitems, const HmFreeEnt *ents, const double *py,
+                                  const double *Xt, double *Pp, cudaStream_t st);
+cudaError_t hm_launch_free3_panel(int CS, const HmItem *items, int64_t nitems, const HmRun *runs,
+                                  const HmFreeRun *frun, const double *px, const double *py, const double *Xt,
+                                  const double *Sp, double *Yt, int accumulate, int kernel_id, cudaStream_t st);
+
 // many right-hand sides (hm_panel.cu): panels are row-major with pitch CS = hm_panel_width(nrhs)
 int hm_panel_width(int nrhs);
 bool hm_panel_supports_rank(int max_r, int nrhs);

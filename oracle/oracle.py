@@ -380,6 +380,32 @@ def lowrank_combine(U1, S1, V1, U2, S2, V2, sign=1.0):
     return (QU @ Us)[:, :r], sv[:r], (QV @ Vh.T)[:, :r]
 
 
+def lowrank_adjoint_times(U1, S1, V1, U2, S2, V2):
+    """(*)(L1', L2) -- LowRankMatrix.jl:120-126: SVD = svd!(S1 * U1'U2 * S2); r = getrank(SVD.S);
+    LowRankMatrix((V1*SVD.U)[:, 1:r], SVD.S[1:r], (V2*SVD.V)[:, 1:r])."""
+    Us, sv, Vh = np.linalg.svd(np.diag(S1) @ (U1.T @ U2) @ np.diag(S2))
+    r = getrank(sv)
+    return (V1 @ Us)[:, :r], sv[:r], (V2 @ Vh.T)[:, :r]
+
+
+def block_cholesky_dense(A11, A12, A22):
+    """cholesky.jl:18-94 with every block dense (the Val{3}, Val{3}, Val{3} method, :86-94):
+    R11 = chol(A11); R12 = R11' \\ A12 column by column (:128-135, :150-152); R22 = chol(A22 - R12'R12).
+    For a symmetric positive definite A the upper factor is unique, so the hierarchical factor of the
+    same A -- whatever its block structure -- has to agree with this one up to its truncation error."""
+    import scipy.linalg
+    R11 = np.linalg.cholesky(np.triu(A11) + np.triu(A11, 1).T).T
+    R12 = np.zeros_like(A12)
+    for j in range(A12.shape[1]):
+        R12[:, j] = scipy.linalg.solve_triangular(R11, A12[:, j], trans="T", lower=False)
+    S = A22 - R12.T @ R12
+    R22 = np.linalg.cholesky(np.triu(S) + np.triu(S, 1).T).T
+    n1 = A11.shape[0]
+    R = np.zeros((n1 + A22.shape[0],) * 2)
+    R[:n1, :n1], R[:n1, n1:], R[n1:, n1:] = R11, R12, R22
+    return R
+
+
 # ---------------------------------------------------------------- synthetic inputs (SURVEY 8d)
 def example_points(N: int, dist: str = "cheb"):
     """Point sets of the benchmark configs: "cheb" = examples/Kernel.jl:61-62,

@@ -960,11 +960,56 @@ def test_matrix_free_parts_determinism_and_unsupported(hm, O):
     with pytest.raises(hm.HmError):
         P.rmatvec(v, np.zeros(N))
     with pytest.raises(hm.HmError):
-        P.matmat(np.asfortranarray(np.ones((N, 2))), np.zeros((N, 2), order="F"))
-    with pytest.raises(hm.HmError):
         P.scale(np.ones(N), 0)
     with pytest.raises(hm.HmError):
         P.read_leaf(0, 3 if P.leaf_info(0)["kind"] == 3 else 0)
+
+
+@pytest.mark.parametrize("nrhs", [2, 16, 17, 33, 64, 70])
+@pytest.mark.parametrize("kernel,dist,N", [("cauchykernel", "cheb", 4096), ("cauchykernel", "unif", 3000),
+                                           ("coulombkernel", "quad", 1000), ("logkernel", "cheb", 77 * 2),
+                                           ("coulombprimekernel", "unif", 20011)])
+def test_matrix_free_matmat_matches_oracle(hm, O, kernel, dist, N, nrhs):
+    """H*X on a matrix-free plan (hm_free_panel.cu): U, V and dense entries are generated in MMA
+    fragment layout and consumed by FP64 tensor-core MMAs, for every panel width (16 / 32 / 64 and
+    ragged last panels).  Same columns as the oracle's mul! (src/KernelMatrix.jl:9-12 per column)."""
+    x, y, (a, b, c, d) = O.example_points(N, dist)
+    f = getattr(hm, kernel)
+    Kf = hm.KernelMatrix(f, x, y, a, b, c, d, device=0, matrix_free=True)
+    Kref = O.kernelmatrix(getattr(O, kernel[:-6].upper()), x, y, a, b, c, d)
+    rng = np.random.default_rng(100 + nrhs)
+    X = np.asfortranarray(rng.standard_normal((N, nrhs)))
+    Y = Kf * X
+    assert Y.shape == (N, nrhs)
+    for c_ in sorted({0, 1, nrhs // 2, nrhs - 1}):
+        assert relinf(Y[:, c_], Kref.matvec(np.ascontiguousarray(X[:, c_]))) <= TOL
+    # every column agrees with the plan's own single-vector path to rounding, and the product is deterministic
+    for c_ in sorted({0, nrhs - 1}):
+        assert relinf(Y[:, c_], Kf * np.ascontiguousarray(X[:, c_])) <= 1e-13
+    assert np.array_equal(Y, Kf * X)
+    # accumulate form with leading dimensions larger than the extents
+    Xb = np.zeros((N + 5, nrhs), order="F")
+    Xb[:N] = X
+    Y0 = np.asfortranarray(rng.standard_normal((N + 3, nrhs)))
+    Yb = Y0.copy(order="F")
+    dp = C.POINTER(C.c_double)
+    hm._lib.check(hm.lib().hm_matmat(Kf.plan().handle, Xb.ctypes.data_as(dp), N + 5, Yb.ctypes.data_as(dp), N + 3,
+                                     nrhs, 1))
+    assert relinf(Yb[:N], Y0[:N] + Y) <= TOL
+    assert np.array_equal(Yb[N:], Y0[N:])
+
+
+def test_matrix_free_matmat_row_parts(hm, O):
+    """Row parts of a matrix-free plan tile the panel product."""
+    N, nrhs = 6000, 24
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    X = np.asfortranarray(np.random.default_rng(3).standard_normal((N, nrhs)))
+    whole = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, matrix_free=True) * X
+    res = np.full((N, nrhs), np.nan, order="F")
+    for p in range(3):
+        part = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, part=p, nparts=3, matrix_free=True)
+        part.plan().matmat(X, res, accumulate=False)
+    assert relinf(res, whole) <= 1e-13
 
 
 @pytest.mark.gpu
@@ -1027,3 +1072,37 @@ def test_hierarchical_plus_lowrank_on_device(hm, O):
         out = G * v
         assert relinf(out, oracle_tree_from_mirror(O, G).matvec(v)) <= TOL
         assert relinf(out, Hx + sign * Lx) <= 1e-11
+
+
+def test_hierarchicalcholesky_factor_on_device(hm, O):
+    """R = hierarchicalcholesky(A) (cholesky.jl:12-94, host recursion as in the
+    reference) is an ordinary upper-stored HierarchicalMatrix; R*x and R'*y run on the device and
+    R'(R x) reproduces A x; the oracle walk of the same factor agrees with the device product."""
+    rng = np.random.default_rng(21)
+    n = 1600
+    x = np.sort(rng.uniform(0.0, 80.0, n))
+
+    def hodlr(p):
+        m = len(p)
+        if m <= 100:
+            return np.asfortranarray(np.exp(-np.abs(p[:, None] - p[None, :])) + 0.5 * np.eye(m))
+        h = m // 2
+        H = hm.HierarchicalMatrix(2, 2)
+        H[hm.Block(1), hm.Block(1)] = hodlr(p[:h])
+        H[hm.Block(1), hm.Block(2)] = hm.svdtrunc(np.exp(-np.abs(p[:h, None] - p[None, h:])))
+        H[hm.Block(2), hm.Block(2)] = hodlr(p[h:])
+        return H
+
+    A = hodlr(x)
+    Ad = np.exp(-np.abs(x[:, None] - x[None, :])) + 0.5 * np.eye(n)
+    R = hm.hierarchicalcholesky(A)
+    v = rng.standard_normal(n)
+    Rv = R * v                                                     # device, forward streams
+    assert relinf(Rv, oracle_tree_from_mirror(O, R).matvec(v)) <= TOL
+    RtRv = hm.adjoint(R) * Rv                                      # device, adjoint apply
+    assert relinf(RtRv, Ad @ v) <= 1e-11
+    # a solve through the factor: z = R \ (R' \ b) with the host triangular solves of cholesky.jl:150-228
+    import scipy.linalg
+    w = hm.solvetransposed(R, v)
+    z = scipy.linalg.solve_triangular(R.todense(), w, lower=False)
+    assert relinf(Ad @ z, v) <= 1e-9

@@ -431,3 +431,112 @@ def test_hierarchical_plus_minus_lowrank_host(hm):
         assert max(B.rank() for k, _, _, B in G.leaves() if k == 2) <= 8
     with pytest.raises(TypeError):
         hm.KernelMatrix(np.float64, 1, 1) + L
+
+
+# ---------------------------------------------------------------- hierarchicalcholesky
+def _spd_hodlr(hm, x, leaf, shift=0.5):
+    """Upper-stored HODLR form of the SPD kernel matrix exp(-|x_i - x_j|) + shift*I on sorted points
+    (off-diagonal blocks are numerically low rank): the input cholesky.jl:1-10 describes."""
+    n = len(x)
+    if n <= leaf:
+        return np.asfortranarray(np.exp(-np.abs(x[:, None] - x[None, :])) + shift * np.eye(n))
+    h = n // 2
+    H = hm.HierarchicalMatrix(2, 2)
+    H[hm.Block(1), hm.Block(1)] = _spd_hodlr(hm, x[:h], leaf, shift)
+    H[hm.Block(1), hm.Block(2)] = hm.svdtrunc(np.exp(-np.abs(x[:h, None] - x[None, h:])))
+    H[hm.Block(2), hm.Block(2)] = _spd_hodlr(hm, x[h:], leaf, shift)
+    return H
+
+
+def _upper_dense(R):
+    return R if isinstance(R, np.ndarray) else R.todense()
+
+
+def test_hierarchicalcholesky_host(hm, O):
+    """hierarchicalcholesky / solvetransposed (cholesky.jl:12-228) in the host mirror: R'R = A, the factor
+    keeps A's block structure with the (2,1) blocks unassigned, agrees with the unique dense upper factor
+    (oracle restatement of the all-dense method), and solvetransposed(R, b) = R' \\ b for vectors,
+    matrices and LowRankMatrix right-hand sides."""
+    import scipy.linalg
+    rng = np.random.default_rng(7)
+    n = 600
+    x = np.sort(rng.uniform(0.0, 40.0, n))
+    A = _spd_hodlr(hm, x, leaf=80)
+    Ad = np.exp(-np.abs(x[:, None] - x[None, :])) + 0.5 * np.eye(n)
+    assert np.allclose(np.triu(A.todense()), np.triu(Ad), atol=1e-13)   # only the upper blocks are stored
+    assert np.all(A.todense()[n // 2:, :n // 2] == 0)
+    R = hm.hierarchicalcholesky(A)
+    assert type(R) is hm.HierarchicalMatrix and R.size() == (n, n)
+    assert R.assigned.tolist() == [[1, 2], [0, 1]]       # nested, LowRankMatrix, unassigned, nested
+    Rd = R.todense()
+    assert np.allclose(np.tril(Rd, -1), 0.0)
+    assert np.max(np.abs(Rd.T @ Rd - Ad)) <= 1e-12 * np.abs(Ad).max() * n
+    # the upper factor of an SPD matrix is unique: compare with the dense block restatement
+    h = n // 2
+    Rref = O.block_cholesky_dense(Ad[:h, :h], Ad[:h, h:], Ad[h:, h:])
+    assert np.max(np.abs(Rd - Rref)) <= 1e-11
+    # solvetransposed
+    b = rng.standard_normal(n)
+    xs = hm.solvetransposed(R, b)
+    assert np.max(np.abs(xs - scipy.linalg.solve_triangular(Rref, b, trans="T"))) <= 1e-10 * np.abs(xs).max()
+    B = np.asfortranarray(rng.standard_normal((n, 3)))
+    XB = hm.solvetransposed(R, B)
+    assert XB.shape == (n, 3) and np.max(np.abs(Rd.T @ XB - B)) <= 1e-10
+    L = hm.LowRankMatrix(rng.standard_normal((n, 2)), np.array([2.0, 1.0]), rng.standard_normal((17, 2)))
+    XL = hm.solvetransposed(R, L)
+    assert isinstance(XL, hm.LowRankMatrix) and XL.shape == (n, 17) and XL.V is L.V
+    assert np.max(np.abs(Rd.T @ XL.todense() - L.todense())) <= 1e-9
+    # a full solve A z = b through the factor: z = R \ (R' \ b)
+    z = scipy.linalg.solve_triangular(Rd, xs, lower=False)
+    assert np.max(np.abs(Ad @ z - b)) <= 1e-9 * np.abs(b).max()
+    # L' * L2 (LowRankMatrix.jl:120-126) against the oracle restatement and dense arithmetic
+    L2 = hm.LowRankMatrix(rng.standard_normal((n, 3)), np.array([3.0, 1.0, 0.5]), rng.standard_normal((9, 3)))
+    P = L.adjoint_mul(L2)
+    U, S, V = O.lowrank_adjoint_times(L.U, L.S, L.V, L2.U, L2.S, L2.V)
+    assert P.shape == (17, 9) and np.allclose(P.S, S, rtol=1e-13)
+    assert np.allclose(P.todense(), L.todense().T @ L2.todense(), atol=1e-10)
+    assert np.allclose(L.adjoint_mul(b), L.todense().T @ b, atol=1e-10)
+
+
+@pytest.mark.parametrize("c11,c12,c22", [(1, 2, 1), (1, 2, 3), (1, 3, 1), (1, 3, 3), (3, 2, 1), (3, 2, 3), (3, 3, 1), (3, 3, 3)])
+def test_hierarchicalcholesky_eight_cases(hm, c11, c12, c22):
+    """The eight Val{M11}, Val{M12}, Val{M22} methods of cholesky.jl:22-94 and :163-228: nested or dense
+    diagonal blocks, LowRankMatrix or dense (1,2) block."""
+    rng = np.random.default_rng(c11 * 100 + c12 * 10 + c22)
+    n = 240
+    x = np.sort(rng.uniform(0.0, 20.0, n))
+    Ad = np.exp(-np.abs(x[:, None] - x[None, :])) + 0.5 * np.eye(n)
+    h = n // 2
+    A = hm.HierarchicalMatrix(2, 2)
+    A[hm.Block(1), hm.Block(1)] = _spd_hodlr(hm, x[:h], leaf=40 if c11 == 1 else n)
+    A[hm.Block(2), hm.Block(2)] = _spd_hodlr(hm, x[h:], leaf=40 if c22 == 1 else n)
+    off = np.asfortranarray(Ad[:h, h:])
+    A[hm.Block(1), hm.Block(2)] = hm.svdtrunc(off) if c12 == 2 else off
+    assert (A.assigned[0, 0], A.assigned[0, 1], A.assigned[1, 1]) == (c11, c12, c22)
+    R = hm.hierarchicalcholesky(A)
+    Rd = R.todense()
+    assert np.allclose(np.tril(Rd, -1), 0.0)
+    assert np.max(np.abs(Rd.T @ Rd - Ad)) <= 1e-11
+    assert R.assigned[0, 1] == c12 and R.assigned[1, 0] == 0 and R.assigned[0, 0] == c11
+    # a dense R12 makes A22 - R12'R12 dense (generic AbstractMatrix arithmetic), as in the reference
+    assert R.assigned[1, 1] == (3 if c12 == 3 else c22)
+    b = rng.standard_normal(n)
+    assert np.max(np.abs(Rd.T @ hm.solvetransposed(R, b) - b)) <= 1e-10
+
+
+def test_hierarchicalcholesky_rejects_what_the_reference_rejects(hm):
+    rng = np.random.default_rng(1)
+    D = np.asfortranarray(np.eye(6) * 2.0)
+    A = hm.HierarchicalMatrix(2, 2)
+    A[hm.Block(1), hm.Block(1)] = hm.svdtrunc(D)          # low-rank diagonal block: no method (cholesky.jl:5-9)
+    A[hm.Block(1), hm.Block(2)] = D
+    A[hm.Block(2), hm.Block(2)] = D
+    with pytest.raises(TypeError):
+        hm.hierarchicalcholesky(A)
+    B = hm.HierarchicalMatrix(3, 3)                        # @assert blocksize(A) == (2, 2)
+    with pytest.raises(AssertionError):
+        hm.hierarchicalcholesky(B)
+    with pytest.raises(np.linalg.LinAlgError):             # PosDefException
+        hm.hierarchicalcholesky(np.asfortranarray(-np.eye(4)))
+    with pytest.raises(TypeError):
+        hm.hierarchicalcholesky(hm.svdtrunc(D))

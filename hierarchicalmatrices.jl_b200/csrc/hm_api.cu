@@ -1310,8 +1310,9 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
                 HM_CUDA(cudaStreamSynchronize(st));
                 // Xt and Sp share one allocation (Sp right behind Xt): the stage-3 kernel addresses the z
                 // rows of both through one base pointer and a 32-bit row index
-                const size_t xt_rows = (size_t)std::max<int64_t>(L.ncols, 1);
-                HM_CUDA(p->wXt.alloc((xt_rows + (size_t)std::max<int64_t>(L.s_words, 1)) * CS));
+                // (rows rounded up to the 4-row tiles of the blocked layout of matrix-free plans)
+                const size_t xt_rows = ((size_t)std::max<int64_t>(L.ncols, 1) + 3) & ~(size_t)3;
+                HM_CUDA(p->wXt.alloc((xt_rows + (((size_t)std::max<int64_t>(L.s_words, 1) + 3) & ~(size_t)3)) * CS));
                 p->wSp = p->wXt.p + xt_rows * CS;
                 HM_CUDA(p->wPp.alloc((size_t)std::max<int64_t>(L.partial_words, 1) * CS));
                 HM_CUDA(p->wYt.alloc((size_t)std::max<int64_t>(L.nrows, 1) * CS));
@@ -1319,7 +1320,7 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
             }
             cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
             if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
-            HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st));
+            HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st, p->matrix_free));
             if (p->matrix_free)
                 HM_CUDA(hm_launch_free1_panel(CS, p->items1.p, (int64_t)L.items1.size(), p->f_ent1.p, p->f_py.p,
                                               p->wXt.p, p->wPp.p, st));
@@ -1328,7 +1329,7 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
                                                p->wPp.p, st));
             if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
             HM_CUDA(hm_launch_panel_stage2(CS, p->cores.p, (int64_t)L.cores.size(), p->plist.p, p->wPp.p, p->core.p,
-                                           p->wSp, std::max(L.max_r, 1), st));
+                                           p->wSp, std::max(L.max_r, 1), st, p->matrix_free));
             if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
             for (size_t r = 0; r + 1 < L.round_begin.size(); r++) {
                 int64_t i0 = L.round_begin[r], i1 = L.round_begin[r + 1];

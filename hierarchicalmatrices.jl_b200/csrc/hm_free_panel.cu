@@ -18,8 +18,9 @@
 //            recurrence T_{n+4} = 2 T_4 T_n - T_{|n-4|} seeded with (T_t, T_{4-t}) gives them with one
 //            FMA each and no shared memory; dense entries are one reciprocal per lane and k-step.
 //
-// B fragments (rows of Xt / Sp, the panels are row-major with pitch CS) come through L1: the warps
-// of a CTA read the same rows.  Per MMA the kernels execute about two instructions (the stored
+// B fragments (rows of Xt / Sp) come through L1: the warps of a CTA read the same rows.  Both panels
+// are kept fragment-major (hm_panel_blocked_index: 4 x 8 tiles in lane order), so a warp's fragment
+// load is one contiguous 256-byte piece; Pp and Yt stay row-major with pitch CS.  Per MMA the kernels execute about two instructions (the stored
 // panel kernels: 8-12), so the FP64 pipe, not instruction issue, is what bounds them.
 // Deterministic: fixed k order per accumulator, k-groups combined in group order.
 #include <cuda_runtime.h>
@@ -82,7 +83,9 @@ hm_free1_panel_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restr
         const HmFreeEnt en = ents[it.run0 + e];
         const double ih = __drcp_rn(en.half);
         const double *__restrict__ yc = py + en.yoff;
-        const double *__restrict__ xb = Xt + (size_t)it.zoff * CS + ch * (NBW * 8) + gid;
+        // Xt is fragment-major (hm_panel_blocked_index): the lane's element of k-step j, column block n
+        // of its chunk is xb[(row0 >> 2 + j) tiles rows + n tiles], one contiguous 256-byte piece per warp
+        const int row00 = it.zoff + tig;
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
@@ -107,13 +110,15 @@ hm_free1_panel_kernel(const HmItem *__restrict__ items, const HmFreeEnt *__restr
             }
             __syncwarp();
             const bool full = s0 + 32 <= S;
+            const int row0 = row00 + s0;
+            const double *__restrict__ xb = Xt + ((size_t)(row0 >> 2) * NB + ch * NBW) * 32 + gid * 4 + (row0 & 3);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const int s = s0 + 4 * j + tig;
                 const bool v = full || s < S;
                 double b[NBW];
 #pragma unroll
-                for (int n = 0; n < NBW; n++) b[n] = v ? __ldg(xb + (size_t)s * CS + n * 8) : 0.0;
+                for (int n = 0; n < NBW; n++) b[n] = v ? __ldg(xb + (j * NB + n) * 32) : 0.0;
                 const double a0 = Tw[gid * TPITCH + 4 * j + tig];
                 const double a1 = Tw[(8 + gid) * TPITCH + 4 * j + tig];
                 const double a2 = Tw[(16 + gid) * TPITCH + 4 * j + tig];
@@ -241,7 +246,7 @@ hm_free3_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict_
         const int ft = u / NCH, ch = u - ft * NCH;
         const bool two_blocks = 2 * ft + 1 < nfb;
         const int i0 = min(ft * 16 + gid, F - 1), i1 = min(ft * 16 + 8 + gid, F - 1); // pad rows repeat the last one
-        const int cofs = ch * (NBW * 8) + gid;
+        const int cb0 = ch * NBW; // first column block of the unit
         double p0 = 0.0, p1 = 0.0;
         if (same_x) {
             p0 = px[xo0 + i0];
@@ -262,20 +267,22 @@ hm_free3_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict_
             }
             if (src < 0) {
                 // low-rank run: rows [k0, k0 + kn) of the leaf's 20 coefficients are rows of Sp
-                const double *__restrict__ bp = Sp + ((int64_t)(~src) - k0) * CS + cofs + tig * CS;
+                // (Sp and Xt are fragment-major: hm_panel_blocked_index)
+                const int64_t row0 = (int64_t)(~src) - k0 + tig; // row of rank k = tig
+                const double *__restrict__ bp = Sp + ((row0 >> 2) * NB + cb0) * 32 + gid * 4 + (row0 & 3);
                 double b[5][NBW];
                 if (k0 == 0 && kn == R) {
 #pragma unroll
                     for (int j = 0; j < 5; j++)
 #pragma unroll
-                        for (int n = 0; n < NBW; n++) b[j][n] = __ldg(bp + j * 4 * CS + n * 8);
+                        for (int n = 0; n < NBW; n++) b[j][n] = __ldg(bp + (j * NB + n) * 32);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 5; j++) {
                         const int k = 4 * j + tig;
                         const bool v = k >= k0 && k < k0 + kn;
 #pragma unroll
-                        for (int n = 0; n < NBW; n++) b[j][n] = v ? __ldg(bp + j * 4 * CS + n * 8) : 0.0;
+                        for (int n = 0; n < NBW; n++) b[j][n] = v ? __ldg(bp + (j * NB + n) * 32) : 0.0;
                     }
                 }
                 const double2 box = rbox[r];
@@ -307,14 +314,15 @@ hm_free3_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict_
                 }
             } else {
                 // dense run: kn columns, entries K(x_i, y_j) evaluated by the lane that holds them
-                const double *__restrict__ bp = Xt + (int64_t)src * CS + cofs + tig * CS;
+                const int64_t row0 = (int64_t)src + tig;
+                const double *__restrict__ bp = Xt + ((row0 >> 2) * NB + cb0) * 32 + gid * 4 + (row0 & 3);
                 const double *__restrict__ yc = py + ryo[r] + tig;
                 int j0 = 0;
                 for (; j0 + 4 <= kn; j0 += 4) {
                     const double yv = yc[j0];
                     double b[NBW];
 #pragma unroll
-                    for (int n = 0; n < NBW; n++) b[n] = __ldg(bp + (int64_t)j0 * CS + n * 8);
+                    for (int n = 0; n < NBW; n++) b[n] = __ldg(bp + ((j0 >> 2) * NB + n) * 32);
                     const double a0 = kernel_eval_fast(KID, p0, yv);
                     const double a1 = kernel_eval_fast(KID, p1, yv);
 #pragma unroll
@@ -328,7 +336,7 @@ hm_free3_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict_
                     const double yv = v ? yc[j0] : 0.0;
                     double b[NBW];
 #pragma unroll
-                    for (int n = 0; n < NBW; n++) b[n] = v ? __ldg(bp + (int64_t)j0 * CS + n * 8) : 0.0;
+                    for (int n = 0; n < NBW; n++) b[n] = v ? __ldg(bp + ((j0 >> 2) * NB + n) * 32) : 0.0;
                     const double a0 = selp(kernel_eval_fast(KID, p0, yv), 0.0, v);
                     const double a1 = selp(kernel_eval_fast(KID, p1, yv), 0.0, v);
 #pragma unroll

@@ -126,16 +126,24 @@ cudaError_t hm_launch_free3_panel(int CS, const HmItem *items, int64_t nitems, c
                                   const double *Sp, double *Yt, int accumulate, int kernel_id, cudaStream_t st);
 
 // many right-hand sides (hm_panel.cu): panels are row-major with pitch CS = hm_panel_width(nrhs)
+// blocked = true (matrix-free plans): Xt and Sp are kept "fragment-major" instead -- tiles of 4 rows x
+// 8 columns (256 bytes) in the lane order of an m8n8k4 B fragment, tile rows first -- so that a warp's
+// fragment load is one contiguous 256-byte piece (two L1 wavefronts instead of one per row and more)
+__host__ __device__ inline size_t hm_panel_blocked_index(int64_t k, int c, int NB)
+{
+    return ((size_t)(k >> 2) * NB + (c >> 3)) * 32 + (size_t)((c & 7) * 4) + (size_t)(k & 3);
+}
 int hm_panel_width(int nrhs);
 bool hm_panel_supports_rank(int max_r, int nrhs);
 cudaError_t hm_launch_panel_in(const double *X, int64_t ldx, int64_t n, int nrhs, int CS, double *Xt,
-                               cudaStream_t st);
+                               cudaStream_t st, bool blocked = false);
 cudaError_t hm_launch_panel_out(const double *Yt, int CS, int64_t r0, int64_t r1, int nrhs, double *Y,
                                 int64_t ldy, int accumulate, cudaStream_t st);
 cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, const double *vstream,
                                    const double *Xt, double *Pp, cudaStream_t st);
 cudaError_t hm_launch_panel_stage2(int CS, const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
-                                   const double *Pp, const double *core, double *Sp, int max_r, cudaStream_t st);
+                                   const double *Pp, const double *core, double *Sp, int max_r, cudaStream_t st,
+                                   bool blocked = false);
 // zcap: largest S of the items (sizes the z row table of the pipelined kernel)
 cudaError_t hm_launch_panel_stage3(int CS, const HmItem *items, int64_t nitems, const HmRun *runs,
                                    const double *ustream, const double *Xt, const double *Sp, double *Yt,

@@ -695,7 +695,7 @@ template <int NB>
 __global__ void __launch_bounds__(128)
 hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__restrict__ plist,
                      const double *__restrict__ Pp, const double *__restrict__ core,
-                     double *__restrict__ Sp, int max_r)
+                     double *__restrict__ Sp, int max_r, int blocked)
 {
     constexpr int CS = NB * 8, TP = CS + 4; // TP = 4 (mod 16): conflict-free B-fragment reads
     extern __shared__ double sm[];
@@ -728,7 +728,11 @@ hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__re
     if (cb.kind == HM_LEAF_LOWRANK) {
         for (int e = t; e < cb.ru * CS; e += T) {
             const int k = e / CS, c = e - k * CS;
-            o[e] = Tsm[k * TP + c] * __ldg(Fg + k);
+            const double v = Tsm[k * TP + c] * __ldg(Fg + k);
+            if (blocked)
+                Sp[hm_panel_blocked_index(cb.soff + k, c, NB)] = v;
+            else
+                o[e] = v;
         }
     } else {
         // S = F T on the FP64 tensor cores: a warp owns 8-column blocks of the panel; A fragments
@@ -746,8 +750,15 @@ hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__re
                     const double a = (row < cb.ru && kk < cb.rv) ? __ldg(Fg + row + (size_t)kk * cb.ru) : 0.0;
                     dmma884(d0, d1, a, Tsm[kk * TP + n * 8 + gid]);
                 }
-                if (row < cb.ru)
-                    *reinterpret_cast<double2 *>(o + (size_t)row * CS + n * 8 + 2 * tig) = make_double2(d0, d1);
+                if (row < cb.ru) {
+                    if (blocked) {
+                        double *ob = Sp + hm_panel_blocked_index(cb.soff + row, n * 8 + 2 * tig, NB);
+                        ob[0] = d0;
+                        ob[4] = d1; // the next column of the 4 x 8 tile
+                    } else {
+                        *reinterpret_cast<double2 *>(o + (size_t)row * CS + n * 8 + 2 * tig) = make_double2(d0, d1);
+                    }
+                }
             }
         }
     }
@@ -759,7 +770,7 @@ hm_core_panel_kernel(const HmCoreBlock *__restrict__ blocks, const int32_t *__re
 //   out: Y[i + c*ldy] = (accumulate ? Y : 0) + Yt[i][c],  rows [r0, r1)
 // ---------------------------------------------------------------------------
 __global__ void hm_panel_in_kernel(const double *__restrict__ X, int64_t ldx, int64_t n, int nrhs, int CS,
-                                   double *__restrict__ Xt)
+                                   double *__restrict__ Xt, int blocked)
 {
     __shared__ double tile[32][33];
     const int64_t j0 = (int64_t)blockIdx.x * 32;
@@ -773,7 +784,7 @@ __global__ void hm_panel_in_kernel(const double *__restrict__ X, int64_t ldx, in
     for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
         int64_t j = j0 + jj;
         int c = c0 + threadIdx.x;
-        if (j < n && c < CS) Xt[j * CS + c] = tile[threadIdx.x][jj];
+        if (j < n && c < CS) Xt[blocked ? hm_panel_blocked_index(j, c, CS >> 3) : (size_t)(j * CS + c)] = tile[threadIdx.x][jj];
     }
 }
 
@@ -820,7 +831,7 @@ inline size_t core_panel_smem(int max_r, int NB) { return (size_t)(max_r + 3) * 
 
 template <int NB>
 cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist, const double *Pp,
-                              const double *core, double *Sp, int max_r, cudaStream_t st)
+                              const double *core, double *Sp, int max_r, cudaStream_t st, bool blocked)
 {
     if (nblocks <= 0) return cudaSuccess;
     const size_t smem = core_panel_smem(max_r, NB);
@@ -831,7 +842,8 @@ cudaError_t launch_core_panel(const HmCoreBlock *blocks, int64_t nblocks, const 
         if (e != cudaSuccess) return e;
     }
     // small CTAs: the kernel is latency-bound, more leaves in flight per SM
-    hm_core_panel_kernel<NB><<<(unsigned)nblocks, NB >= 8 ? 128 : 64, smem, st>>>(blocks, plist, Pp, core, Sp, max_r);
+    hm_core_panel_kernel<NB><<<(unsigned)nblocks, NB >= 8 ? 128 : 64, smem, st>>>(blocks, plist, Pp, core, Sp, max_r,
+                                                                                  blocked ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -847,11 +859,11 @@ bool hm_panel_supports_rank(int max_r, int nrhs)
 }
 
 cudaError_t hm_launch_panel_in(const double *X, int64_t ldx, int64_t n, int nrhs, int CS, double *Xt,
-                               cudaStream_t st)
+                               cudaStream_t st, bool blocked)
 {
     if (n <= 0) return cudaSuccess;
     dim3 grid((unsigned)((n + 31) / 32), (unsigned)((CS + 31) / 32)), block(32, 8);
-    hm_panel_in_kernel<<<grid, block, 0, st>>>(X, ldx, n, nrhs, CS, Xt);
+    hm_panel_in_kernel<<<grid, block, 0, st>>>(X, ldx, n, nrhs, CS, Xt, blocked ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -920,12 +932,13 @@ cudaError_t hm_launch_panel_stage1(int CS, const HmItem *items, int64_t nitems, 
 }
 
 cudaError_t hm_launch_panel_stage2(int CS, const HmCoreBlock *blocks, int64_t nblocks, const int32_t *plist,
-                                   const double *Pp, const double *core, double *Sp, int max_r, cudaStream_t st)
+                                   const double *Pp, const double *core, double *Sp, int max_r, cudaStream_t st,
+                                   bool blocked)
 {
     switch (CS) {
-    case 16: return launch_core_panel<2>(blocks, nblocks, plist, Pp, core, Sp, max_r, st);
-    case 32: return launch_core_panel<4>(blocks, nblocks, plist, Pp, core, Sp, max_r, st);
-    case 64: return launch_core_panel<8>(blocks, nblocks, plist, Pp, core, Sp, max_r, st);
+    case 16: return launch_core_panel<2>(blocks, nblocks, plist, Pp, core, Sp, max_r, st, blocked);
+    case 32: return launch_core_panel<4>(blocks, nblocks, plist, Pp, core, Sp, max_r, st, blocked);
+    case 64: return launch_core_panel<8>(blocks, nblocks, plist, Pp, core, Sp, max_r, st, blocked);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -74,6 +74,7 @@ SIGNATURES = {
                                   _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "hm_assemble_kernel_fn": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                      KERNEL_FN, _vp, _i32, _i32, _i32, C.POINTER(_vp)]),
+    "hm_plan_form": (_i32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "hm_assemble_kernel_free": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double, C.c_double,
                                        _i32, _i32, _i32, _i32, C.POINTER(_vp)]),
     "hm_assemble_kernel_stats": (_i32, [_dp, _i64, _dp, _i64, C.c_double, C.c_double, C.c_double,

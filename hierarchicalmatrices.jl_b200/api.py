@@ -334,6 +334,13 @@ class Plan:
         return (s["nrows"], s["ncols"])
 
     @property
+    def form(self) -> int:
+        """0 stored streams, 1 matrix-free (barycentric), 2 matrix-free (Chebyshev), 3 matrix-free nested-basis."""
+        f = C.c_int32()
+        _lib.check(_lib.lib().hm_plan_form(self._h, C.byref(f)))
+        return f.value
+
+    @property
     def launches_per_matvec(self) -> int:
         return int(_lib.lib().hm_plan_launches_per_matvec(self._h))
 

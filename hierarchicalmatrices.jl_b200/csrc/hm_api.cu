@@ -724,6 +724,14 @@ int32_t hm_plan_launches_per_matvec(const hm_plan *p)
 {
     if (!p) return 0;
     int n = 0;
+    if (p->nested) { // up (subtrees, top), cores, down (top, subtrees), dense rounds
+        n = (p->n_rows.nnodes > 0) + (p->n_cols.nbase > 0);
+        for (const HmNestDev *T : {&p->n_cols, &p->n_rows})
+            for (int k = 0; k < T->ntiers; k++) n += T->tier_sub0[k + 1] > T->tier_sub0[k];
+        for (size_t r = 0; r + 1 < p->n_round_begin.size(); r++)
+            if (p->n_round_begin[r + 1] > p->n_round_begin[r]) n++;
+        return n;
+    }
     if (!p->L.items1.empty()) n++;
     if (!p->fuse && !p->L.cores.empty()) n++;
     if (!p->fuse && p->nbig > 0) n++;
@@ -895,6 +903,79 @@ static int32_t host_fill(hm_plan *P, const double *x, const double *y, hm_kernel
     return HM_OK;
 }
 
+// Nested-basis form of a matrix-free plan (hm_nest.h): the default when the operator has the dyadic
+// structure of KernelMatrix(f, x, y, a, b, c, d) with descending points; HMB200_FREE_FORM=cheb keeps the
+// per-leaf Chebyshev form.  A structure the builder declines is not an error: the plan stays as it is.
+static int32_t build_nested(hm_plan *P, const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
+                            double c, double d)
+{
+    const char *e = getenv("HMB200_FREE_FORM");
+    if (e && e[0] == 'c') return HM_OK;
+    const HmLayout &L = P->L;
+    std::vector<HmFreeRun> run3(L.fill3.size());
+    for (size_t i = 0; i < L.fill3.size(); i++) {
+        const HmFill &f = L.fill3[i];
+        const HmLeaf &l = L.leaves[(size_t)f.leaf];
+        run3[i] = HmFreeRun{0.5 * (l.a + l.b), 0.5 * (l.b - l.a), l.xi0 + f.off, l.yj0 + f.k0, f.k0, f.kn};
+    }
+    HmNest N;
+    const std::string why = hm_nest_build(L, x, nx, y, ny, a, b, c, d, P->kernel_id, run3, N);
+    if (!why.empty()) return HM_OK;
+    if ((int)N.rows.tier_sub0.size() - 1 > HM_NEST_MAXTIERS || (int)N.cols.tier_sub0.size() - 1 > HM_NEST_MAXTIERS) return HM_OK;
+    for (const HmItem &it : N.items3)
+        if (it.F > 128) return HM_OK; // hm_nest_dense_kernel: four rows per lane
+    cudaStream_t st = P->stream;
+    HM_CUDA(P->nr_nodes.upload(N.rows.nodes, st));
+    HM_CUDA(P->nr_order.upload(N.rows.order, st));
+    HM_CUDA(P->nr_grp.upload(N.rows.grp, st));
+    HM_CUDA(P->nr_sub.upload(N.rows.sub_g0, st));
+    HM_CUDA(P->nc_nodes.upload(N.cols.nodes, st));
+    HM_CUDA(P->nc_order.upload(N.cols.order, st));
+    HM_CUDA(P->nc_grp.upload(N.cols.grp, st));
+    HM_CUDA(P->nc_sub.upload(N.cols.sub_g0, st));
+    HM_CUDA(P->nr_base.upload(N.rows.base, st));
+    HM_CUDA(P->nc_base.upload(N.cols.base, st));
+    HM_CUDA(P->n_item_box.upload(N.item_box, st));
+    HM_CUDA(P->n_fin.upload(N.fin, st));
+    HM_CUDA(P->n_items3p.upload(N.items3p, st));
+    HM_CUDA(P->n_runsp.upload(N.runsp, st));
+    HM_CUDA(P->n_frunp.upload(N.frunp, st));
+    P->n_fin_rows = (int64_t)N.rows.base.size() * HM_NEST_R;
+    HM_CUDA(hm_nest_panel_init(N.M.data()));
+    P->n_fused_eval = N.fused_eval;
+    HM_CUDA(P->n_rleaf_begin.upload(N.rleaf_begin, st));
+    HM_CUDA(P->n_rleaf.upload(N.rleaf, st));
+    HM_CUDA(P->n_cores.upload(N.cores, st));
+    HM_CUDA(P->n_M.upload(N.M, st));
+    HM_CUDA(P->n_MU.alloc(N.cols.nodes.size() * HM_NEST_R));
+    HM_CUDA(P->n_LAM.alloc(N.rows.nodes.size() * HM_NEST_R));
+    HM_CUDA(P->n_items3.upload(N.items3, st));
+    HM_CUDA(P->n_runs.upload(N.runs, st));
+    HM_CUDA(P->n_frun.upload(N.frun, st));
+    HM_CUDA(cudaStreamSynchronize(st));
+    auto dev = [](const HmNestTree &T, const DevBuf<HmNestNode> &nodes, const DevBuf<int32_t> &order,
+                  const DevBuf<int32_t> &grp, const DevBuf<int32_t> &sub, const DevBuf<int32_t> &base) {
+        HmNestDev D;
+        D.base = base.p;
+        D.nbase = (int)T.base.size();
+        D.nodes = nodes.p;
+        D.order = order.p;
+        D.grp = grp.p;
+        D.sub_g0 = sub.p;
+        D.ntiers = (int)T.tier_sub0.size() - 1;
+        for (int k = 0; k <= D.ntiers; k++) D.tier_sub0[k] = T.tier_sub0[(size_t)k];
+        D.nnodes = (int)T.nodes.size();
+        return D;
+    };
+    P->n_rows = dev(N.rows, P->nr_nodes, P->nr_order, P->nr_grp, P->nr_sub, P->nr_base);
+    P->n_cols = dev(N.cols, P->nc_nodes, P->nc_order, P->nc_grp, P->nc_sub, P->nc_base);
+    P->n_round_begin = N.round_begin;
+    P->n_zcap = (N.zcap + 1) & ~1;
+    P->n_distinct_cores = (int64_t)(N.cores.size() / (HM_NEST_R * HM_NEST_R));
+    P->nested = true;
+    return HM_OK;
+}
+
 static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                                     double c, double d, int32_t kernel_id, int32_t device, int32_t part,
                                     int32_t nparts, bool matrix_free, hm_plan **out, hm_kernel_fn fn = nullptr,
@@ -932,6 +1013,13 @@ static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y
             delete P;
             return st;
         }
+        if (matrix_free && P->free_cheb) {
+            st = build_nested(P, x, nx, y, ny, a, b, c, d);
+            if (st != HM_OK) {
+                delete P;
+                return st;
+            }
+        }
         if (fn) {
             st = host_fill(P, x, y, fn, user);
             if (st != HM_OK) {
@@ -965,6 +1053,15 @@ int32_t hm_assemble_kernel_fn(const double *x, int64_t nx, const double *y, int6
         if (!f) return fail(HM_ERR_NULL, "kernel function is NULL");
         return assemble_kernel_impl(x, nx, y, ny, a, b, c, d, HM_KERNEL_HOST_FN, device, part, nparts, false, out, f,
                                     user);
+    });
+}
+
+int32_t hm_plan_form(const hm_plan *p, int32_t *form)
+{
+    return guarded([&]() -> int32_t {
+        if (!p || !form) return fail(HM_ERR_NULL, "NULL argument");
+        *form = !p->matrix_free ? 0 : p->nested ? 3 : p->free_cheb ? 2 : 1;
+        return HM_OK;
     });
 }
 
@@ -1026,6 +1123,30 @@ int32_t hm_matvec_device_peers(hm_plan *p, const double *dx, double *dy, int32_t
             fz.svec = p->svec.p;
             fz.max_r = std::max(L.max_r, 1);
         }
+        if (p->nested) {
+            // nested-basis form: moments up the column boxes, cores, coefficients down the row boxes and
+            // their evaluation (writes every owned row), then the dense leaves on top
+            const double *M = p->n_M.p, *Mt = p->n_M.p + 2 * HM_NEST_R * HM_NEST_R;
+            HM_CUDA(hm_launch_nest_up(p->n_cols, p->f_py.p, dx, Mt, p->n_MU.p, st));
+            if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
+            HM_CUDA(hm_launch_nest_core(p->n_rows.nnodes, p->n_rleaf_begin.p, p->n_rleaf.p, p->n_cores.p, p->n_MU.p,
+                                        p->n_LAM.p, st));
+            if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
+            const bool fused = p->n_fused_eval; // the dense pass evaluates the low-rank part of its rows too
+            HM_CUDA(hm_launch_nest_down(p->n_rows, p->f_px.p, M, p->n_LAM.p, dy, accumulate != 0, L.row_begin, L.row_end,
+                                        !fused, st));
+            for (size_t r = 0; r + 1 < p->n_round_begin.size(); r++) {
+                const int64_t i0 = p->n_round_begin[r], i1 = p->n_round_begin[r + 1];
+                HM_CUDA(hm_launch_nest_dense(p->n_items3.p + i0, i1 - i0, p->n_runs.p, p->n_frun.p, p->f_px.p, p->f_py.p,
+                                             dx, dy, fused ? (accumulate != 0) : 1, p->kernel_id,
+                                             fused ? p->n_item_box.p : nullptr, p->nr_nodes.p, p->n_LAM.p, peers, st));
+            }
+            if (ev) {
+                HM_CUDA(cudaEventRecord(ev[3], st));
+                p->tcount++;
+            }
+            return HM_OK;
+        }
         if (p->matrix_free)
             HM_CUDA(hm_launch_free1(p->items1.p, (int64_t)L.items1.size(), p->f_ent1.p, p->f_py.p, dx, p->partial.p,
                                     p->cheb, p->free1_units, p->free_cheb, st));
@@ -1077,7 +1198,7 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
         // Below ~2 MB of vector data the extra launches and events cost more than the overlap gains
         // (measured: N = 4096 48 vs 100 us, N = 65 536 175 vs 230 us, N = 262 144 600 vs 577 us).
         if (incx == 1 && incy == 1 && nc > 0 && nr > 0 && nc + nr >= 400000 && L.round_begin.size() == 2 &&
-            !L.items3c.empty() && p->tcap == 0 && !getenv("HMB200_NO_COPY_PIPELINE")) {
+            !L.items3c.empty() && p->tcap == 0 && !p->nested && !getenv("HMB200_NO_COPY_PIPELINE")) {
             if (!p->chunk_ready) {
                 HM_CUDA(p->items1c.upload(L.items1c, st));
                 HM_CUDA(p->items3c.upload(L.items3c, st));
@@ -1274,6 +1395,46 @@ int32_t hm_matvec_adjoint(hm_plan *p, const double *x, int64_t incx, double *y, 
     });
 }
 
+// Multi-RHS on the nested-basis form (hm_nest_panel.cu): moments up, cores, coefficients down, then the dense
+// leaves together with the evaluation of every row's coefficients (hm_free3_panel_kernel).
+static int32_t matmat_nested(hm_plan *p, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t nrhs,
+                             int32_t accumulate, cudaStream_t st)
+{
+    const HmLayout &L = p->L;
+    for (int64_t c0 = 0; c0 < nrhs; c0 += 64) {
+        const int nc = (int)std::min<int64_t>(64, nrhs - c0);
+        const int CS = hm_panel_width(nc);
+        if (CS > p->n_ws_cs) {
+            HM_CUDA(cudaStreamSynchronize(st));
+            const size_t xt_rows = ((size_t)std::max<int64_t>(L.ncols, 1) + 3) & ~(size_t)3;
+            HM_CUDA(p->wXt.alloc(xt_rows * CS));
+            HM_CUDA(p->wYt.alloc((size_t)std::max<int64_t>(L.nrows, 1) * CS));
+            HM_CUDA(p->n_MUp.alloc((size_t)std::max(p->n_cols.nnodes, 1) * HM_NEST_R * CS));
+            HM_CUDA(p->n_LAMp.alloc((size_t)std::max(p->n_rows.nnodes, 1) * HM_NEST_R * CS));
+            HM_CUDA(p->n_Sp.alloc((((size_t)std::max<int64_t>(p->n_fin_rows, 1) + 3) & ~(size_t)3) * CS));
+            p->n_ws_cs = CS;
+            p->ws_cs = 0; // the plain panel path re-allocates its own workspace if it is ever taken
+        }
+        cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
+        if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
+        HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st, true));
+        HM_CUDA(hm_launch_nest_up_panel(CS, p->n_cols, p->f_py.p, p->wXt.p, p->n_MUp.p, st));
+        if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
+        HM_CUDA(hm_launch_nest_core_panel(CS, p->n_rows.nnodes, p->n_rleaf_begin.p, p->n_rleaf.p, p->n_cores.p,
+                                          p->n_MUp.p, p->n_LAMp.p, st));
+        if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
+        HM_CUDA(hm_launch_nest_down_panel(CS, p->n_rows, p->n_fin.p, p->n_LAMp.p, p->n_Sp.p, st));
+        HM_CUDA(hm_launch_free3_panel(CS, p->n_items3p.p, (int64_t)p->n_items3p.n, p->n_runsp.p, p->n_frunp.p, p->f_px.p,
+                                      p->f_py.p, p->wXt.p, p->n_Sp.p, p->wYt.p, 0, p->kernel_id, st));
+        HM_CUDA(hm_launch_panel_out(p->wYt.p, CS, L.row_begin, L.row_end, nc, dY + c0 * ldy, ldy, accumulate != 0, st));
+        if (ev) {
+            HM_CUDA(cudaEventRecord(ev[3], st));
+            p->tcount++;
+        }
+    }
+    return HM_OK;
+}
+
 // Multi-RHS: Y[:, c] (+)= H X[:, c].  Columns are processed in panels of up to 64 with the
 // FP64 tensor-core kernels of hm_panel.cu; a single column takes the matvec path.
 int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, int64_t ldy, int64_t nrhs,
@@ -1298,6 +1459,7 @@ int32_t hm_matmat_device(hm_plan *p, const double *dX, int64_t ldx, double *dY, 
         }
         HM_DEVICE(p->device);
         cudaStream_t st = (cudaStream_t)stream;
+        if (p->nested && p->n_fused_eval) return matmat_nested(p, dX, ldx, dY, ldy, nrhs, accumulate, st);
         if (p->panel_zcap == 0) {
             int zc = 4;
             for (const HmItem &it : L.items3) zc = std::max(zc, (int)it.S);

@@ -14,6 +14,7 @@
 #include "../../include/hmb200.h"
 #include "hm_kernels.cuh"
 #include "hm_layout.h"
+#include "hm_nest.h"
 
 // ---------------------------------------------------------------------------
 // error plumbing
@@ -122,6 +123,28 @@ struct hm_plan {
     DevBuf<double> f_px, f_py;
     int free1_units = 1, free3_zcap = HM_SMAX;
     bool free_cheb = false; // cores hold C F C' and the apply runs the Chebyshev-series kernels
+    // nested-basis form of a matrix-free plan (hm_nest.h): box trees, transfer maps, shared cores
+    bool nested = false;
+    DevBuf<HmNestNode> nr_nodes, nc_nodes;
+    DevBuf<int32_t> nr_order, nr_grp, nr_sub, nc_order, nc_grp, nc_sub, n_rleaf_begin, nr_base, nc_base, n_item_box;
+    bool n_fused_eval = false;
+    // many right-hand sides in nested form: items with the coefficient run, per-box panels
+    DevBuf<int32_t> n_fin;
+    DevBuf<HmItem> n_items3p;
+    DevBuf<HmRun> n_runsp;
+    DevBuf<HmFreeRun> n_frunp;
+    DevBuf<double> n_MUp, n_LAMp, n_Sp;
+    int n_ws_cs = 0;
+    int64_t n_fin_rows = 0;
+    DevBuf<HmNestLeaf> n_rleaf;
+    DevBuf<double> n_cores, n_M, n_MU, n_LAM;
+    DevBuf<HmItem> n_items3; // the stage-3 items with their dense runs only
+    DevBuf<HmRun> n_runs;
+    DevBuf<HmFreeRun> n_frun;
+    std::vector<int64_t> n_round_begin;
+    int n_zcap = 2;
+    HmNestDev n_rows, n_cols;
+    int64_t n_distinct_cores = 0;
     // device arrays
     DevBuf<double> vstream, ustream, core, svec, partial;
     DevBuf<HmItem> items1, items3;

@@ -1,0 +1,391 @@
+// hm_nest.cu -- kernels of the nested-basis form of a matrix-free plan (hm_nest.h): the low-rank
+// part of y (+)= K x as one upward pass (moments), one pass over the leaves (cores) and one
+// downward pass (coefficients, evaluation); the dense leaves are applied by hm_free3_kernel /
+// hm_free3_panel_kernel on the item list without low-rank runs.
+//
+// A CTA owns a subtree of the box tree and walks it depth by depth (a warp per box, __syncthreads
+// between depths).  Subtrees are cut by point count into tiers (hm_nest_host.cpp), one launch per tier:
+// three launches per pass at N = 2^20.  Every box value has one writer and a fixed summation order:
+// deterministic.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "hm_device.cuh"
+#include "hm_kernels.cuh"
+#include "hm_nest.h"
+
+namespace {
+
+constexpr int R = HM_NEST_R;
+constexpr int NT = 256; // threads of a subtree CTA
+
+// ---------------------------------------------------------------------------
+// upward pass: MU[box][q] = sum over the box's columns of T_q(eta_s) x_s
+//   finest boxes from the points (flat kernel, a warp per box), the others from their two halves
+//   (M0, M1), subtree by subtree
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+hm_nest_base_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ base, int nbase,
+                    const double *__restrict__ pts, const double *__restrict__ x, double *__restrict__ MU)
+{
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (b >= nbase) return;
+    const int id = base[b];
+    const HmNestNode nd = nodes[id];
+    double acc[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) acc[k] = 0.0;
+    const double *__restrict__ pp = pts + nd.p0;
+    const double *__restrict__ xs = x + nd.p0;
+    for (int s = lane; s < nd.np; s += 32) {
+        const double eta = (pp[s] - nd.mid) * nd.ih, two = eta + eta, xv = xs[s];
+        double tm2 = 1.0, tm1 = eta;
+        acc[0] += xv;
+        acc[1] = fma(xv, eta, acc[1]);
+#pragma unroll
+        for (int k = 2; k < R; k++) {
+            const double tk = fma(two, tm1, -tm2);
+            acc[k] = fma(xv, tk, acc[k]);
+            tm2 = tm1;
+            tm1 = tk;
+        }
+    }
+    // lane sums in a fixed (butterfly) order; lane k keeps moment k
+    double mine = 0.0;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        if (lane == k) mine = acc[k];
+    }
+    if (lane < R) MU[(size_t)id * R + lane] = mine;
+}
+
+__global__ void __launch_bounds__(NT)
+hm_nest_up_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
+                  const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
+                  const double *__restrict__ Mt, double *MU)
+{
+    __shared__ double sMt[2][R * R]; // transposed maps: [p][q]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    for (int i = t; i < 2 * R * R; i += blockDim.x) sMt[0][i] = Mt[i];
+    __syncthreads();
+    const int sub = sub0 + blockIdx.x;
+    for (int g = sub_g0[sub]; g < sub_g0[sub + 1]; g++) {
+        const int e0 = grp[g], e1 = grp[g + 1];
+        for (int e = e0 + warp; e < e1; e += nw) {
+            const int id = order[e];
+            const int c0 = nodes[id].child0;
+            if (c0 >= 0 && lane < R) {
+                const double *m0 = MU + (size_t)c0 * R, *m1 = m0 + R;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0; // four short chains instead of one of 40
+#pragma unroll
+                for (int p = 0; p < R; p += 2) {
+                    s0 = fma(sMt[0][p * R + lane], m0[p], s0);
+                    s1 = fma(sMt[0][(p + 1) * R + lane], m0[p + 1], s1);
+                    s2 = fma(sMt[1][p * R + lane], m1[p], s2);
+                    s3 = fma(sMt[1][(p + 1) * R + lane], m1[p + 1], s3);
+                }
+                MU[(size_t)id * R + lane] = (s0 + s1) + (s2 + s3);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// the leaves: LAM[row box][q] = sum over the box's leaves of G_leaf[q][:] . MU[column box of the leaf]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+hm_nest_core_kernel(int nboxes, const int32_t *__restrict__ rleaf_begin, const HmNestLeaf *__restrict__ rleaf,
+                    const double *__restrict__ cores, const double *__restrict__ MU, double *__restrict__ LAM)
+{
+    const int lane = threadIdx.x & 31;
+    const int box = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (box >= nboxes || lane >= R) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int l = rleaf_begin[box]; l < rleaf_begin[box + 1]; l++) {
+        const HmNestLeaf lf = rleaf[l];
+        const double *__restrict__ G = cores + (size_t)lf.core * (R * R) + lane;
+        const double *__restrict__ mu = MU + (size_t)lf.cnode * R;
+#pragma unroll
+        for (int p = 0; p < R; p += 4) {
+            s0 = fma(__ldg(G + p * R), mu[p], s0);
+            s1 = fma(__ldg(G + (p + 1) * R), mu[p + 1], s1);
+            s2 = fma(__ldg(G + (p + 2) * R), mu[p + 2], s2);
+            s3 = fma(__ldg(G + (p + 3) * R), mu[p + 3], s3);
+        }
+    }
+    LAM[(size_t)box * R + lane] = (s0 + s1) + (s2 + s3);
+}
+
+// ---------------------------------------------------------------------------
+// downward pass: LAM[box] += M_which' LAM[parent]; at a finest box the series is evaluated at its
+// rows (Clenshaw):  y_i = (accumulate ? y_i : 0) + sum_q LAM[box][q] T_q(xi_i)
+// ---------------------------------------------------------------------------
+template <bool EVAL>
+__global__ void __launch_bounds__(NT)
+hm_nest_down_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
+                    const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
+                    const double *__restrict__ pts, const double *__restrict__ M, double *LAM, double *y,
+                    int accumulate, int row_begin, int row_end)
+{
+    __shared__ double sM[2][R * R]; // maps: [q][p]
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    for (int i = t; i < 2 * R * R; i += blockDim.x) sM[0][i] = M[i];
+    __syncthreads();
+    const int sub = sub0 + blockIdx.x;
+    for (int g = sub_g0[sub + 1] - 1; g >= sub_g0[sub]; g--) { // shallowest depth first
+        const int e0 = grp[g], e1 = grp[g + 1];
+        for (int e = e0 + warp; e < e1; e += nw) {
+            const int id = order[e];
+            const HmNestNode nd = nodes[id];
+            double *lam = LAM + (size_t)id * R;
+            if (nd.parent >= 0 && lane < R) {
+                const double *lp = LAM + (size_t)nd.parent * R;
+                const double *m = sM[nd.which];
+                double s0 = lam[lane], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+                for (int q = 0; q < R; q += 4) {
+                    s0 = fma(m[q * R + lane], lp[q], s0);
+                    s1 = fma(m[(q + 1) * R + lane], lp[q + 1], s1);
+                    s2 = fma(m[(q + 2) * R + lane], lp[q + 2], s2);
+                    s3 = fma(m[(q + 3) * R + lane], lp[q + 3], s3);
+                }
+                lam[lane] = (s0 + s1) + (s2 + s3);
+            }
+            if (EVAL && nd.child0 < 0) {
+                __syncwarp();
+                double cf[R];
+#pragma unroll
+                for (int k = 0; k < R; k++) cf[k] = lam[k];
+                const double *__restrict__ pp = pts + nd.p0;
+                for (int i = lane; i < nd.np; i += 32) {
+                    const int row = nd.p0 + i;
+                    if (row < row_begin || row >= row_end) continue;
+                    const double xi = (pp[i] - nd.mid) * nd.ih, two = xi + xi;
+                    double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+                    for (int k = R - 1; k >= 1; k--) {
+                        const double nb = fma(two, b1, cf[k]) - b2;
+                        b2 = b1;
+                        b1 = nb;
+                    }
+                    const double v = fma(xi, b1, cf[0]) - b2;
+                    y[row] = (accumulate ? y[row] : 0.0) + v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// dense leaves: y[rows of the item] += sum over its dense runs of K(x_i, y_j) v_j, entries evaluated on
+// the fly (src/KernelMatrix.jl:57-60, src/algebra.jl:37-48).  A warp owns an item (a row segment of at
+// most 128 rows, up to four rows per lane) and walks the columns of its runs; the column point and the
+// vector entry are warp-uniform loads.  No shared memory, no block barrier: eight independent items
+// per CTA keep their short dependent chains (item -> runs -> points) in flight together.
+// ---------------------------------------------------------------------------
+// ibox != nullptr: the low-rank part is evaluated here too -- the rows of item i lie in the finest row box
+// ibox[i], whose coefficients LAM the downward pass has completed: y_i = (accumulate ? y_i : 0) +
+// sum_q LAM[box][q] T_q(xi_i) + dense part, one pass over y.
+template <int KID, int NRL> // NRL rows per lane
+__device__ __forceinline__ void nest_dense_rows(const HmItem &it, int lane, const HmRun *__restrict__ runs,
+                                                const HmFreeRun *__restrict__ frun, const double *__restrict__ px,
+                                                const double *__restrict__ py, const double *__restrict__ x,
+                                                const int32_t *__restrict__ ibox, int idx,
+                                                const HmNestNode *__restrict__ nodes, const double *__restrict__ LAM,
+                                                double (&out)[4])
+{
+    const int F = it.F;
+    double acc[NRL][2];
+#pragma unroll
+    for (int k = 0; k < NRL; k++) acc[k][0] = acc[k][1] = 0.0;
+    if (ibox) {
+        const int box = ibox[idx];
+        const HmNestNode nd = nodes[box];
+        const double *__restrict__ lam = LAM + (size_t)box * R;
+        double cf[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) cf[k] = lam[k];
+        const double *__restrict__ pp = px + it.out; // rows are numbered like the points
+#pragma unroll
+        for (int k = 0; k < NRL; k++) {
+            const double xi = (pp[min(lane + 32 * k, F - 1)] - nd.mid) * nd.ih, two = xi + xi;
+            double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+            for (int q = R - 1; q >= 1; q--) {
+                const double nb = fma(two, b1, cf[q]) - b2;
+                b2 = b1;
+                b1 = nb;
+            }
+            acc[k][0] = fma(xi, b1, cf[0]) - b2;
+        }
+    }
+    int64_t xo_prev = -1;
+    double p[NRL];
+#pragma unroll
+    for (int k = 0; k < NRL; k++) p[k] = 0.0;
+    for (int r = 0; r < it.nrun; r++) {
+        const HmRun rr = runs[it.run0 + r];
+        const HmFreeRun fr = frun[it.run0 + r];
+        if (fr.xoff != xo_prev) { // the rows' points (the same for every run of a KernelMatrix item)
+            xo_prev = fr.xoff;
+#pragma unroll
+            for (int k = 0; k < NRL; k++) p[k] = px[fr.xoff + min(lane + 32 * k, F - 1)];
+        }
+        const double *__restrict__ yc = py + fr.yoff;
+        const double *__restrict__ xs = x + rr.src;
+        const int kn = fr.kn;
+        // two columns per step, the next two already in flight (warp-uniform loads)
+        double y0 = 0.0, y1 = 0.0, v0 = 0.0, v1 = 0.0;
+        if (kn > 0) {
+            y0 = yc[0];
+            v0 = xs[0];
+        }
+        if (kn > 1) {
+            y1 = yc[1];
+            v1 = xs[1];
+        }
+        int j = 0;
+        for (; j + 1 < kn; j += 2) {
+            const int jn0 = min(j + 2, kn - 1), jn1 = min(j + 3, kn - 1);
+            const double ny0 = yc[jn0], nv0 = xs[jn0], ny1 = yc[jn1], nv1 = xs[jn1];
+#pragma unroll
+            for (int k = 0; k < NRL; k++) {
+                acc[k][0] = fma(kernel_eval_fast(KID, p[k], y0), v0, acc[k][0]);
+                acc[k][1] = fma(kernel_eval_fast(KID, p[k], y1), v1, acc[k][1]);
+            }
+            y0 = ny0;
+            v0 = nv0;
+            y1 = ny1;
+            v1 = nv1;
+        }
+        if (j < kn) {
+#pragma unroll
+            for (int k = 0; k < NRL; k++) acc[k][0] = fma(kernel_eval_fast(KID, p[k], y0), v0, acc[k][0]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NRL; k++) out[k] = acc[k][0] + acc[k][1];
+}
+
+template <int KID, bool PEERS>
+__global__ void __launch_bounds__(NT)
+hm_nest_dense_kernel(const HmItem *__restrict__ items, int nitems, const HmRun *__restrict__ runs,
+                     const HmFreeRun *__restrict__ frun, const double *__restrict__ px,
+                     const double *__restrict__ py, const double *__restrict__ x, double *y, int accumulate,
+                     const int32_t *__restrict__ ibox, const HmNestNode *__restrict__ nodes,
+                     const double *__restrict__ LAM, HmPeers pe)
+{
+    const int lane = threadIdx.x & 31;
+    const int idx = __shfl_sync(0xffffffffu, blockIdx.x * (NT / 32) + (threadIdx.x >> 5), 0);
+    if (idx >= nitems) return;
+    const HmItem it = items[idx];
+    const int F = it.F;
+    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    const int nrl = __shfl_sync(0xffffffffu, (F + 31) >> 5, 0); // warp-uniform, and the compiler knows it
+    switch (nrl) {
+    case 1: nest_dense_rows<KID, 1>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
+    case 2: nest_dense_rows<KID, 2>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
+    case 3: nest_dense_rows<KID, 3>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
+    default: nest_dense_rows<KID, 4>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int f = lane + 32 * k;
+        if (f < F) {
+            double *o = y + it.out + f;
+            const double v = (accumulate ? *o : 0.0) + out[k];
+            if (PEERS) {
+                for (int q = 0; q < pe.n; q++) pe.y[q][it.out + f] = v;
+            } else {
+                *o = v;
+            }
+        }
+    }
+}
+
+template <int KID>
+cudaError_t launch_dense(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun, const double *px,
+                         const double *py, const double *x, double *y, int accumulate, const int32_t *ibox,
+                         const HmNestNode *nodes, const double *LAM, const HmPeers *peers, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((nitems + NT / 32 - 1) / (NT / 32));
+    const HmPeers none{};
+    if (peers && peers->n > 0)
+        hm_nest_dense_kernel<KID, true><<<grid, NT, 0, st>>>(items, (int)nitems, runs, frun, px, py, x, y, accumulate, ibox,
+                                                             nodes, LAM, *peers);
+    else
+        hm_nest_dense_kernel<KID, false><<<grid, NT, 0, st>>>(items, (int)nitems, runs, frun, px, py, x, y, accumulate, ibox,
+                                                              nodes, LAM, none);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t hm_launch_nest_dense(const HmItem *items, int64_t nitems, const HmRun *runs, const HmFreeRun *frun,
+                                 const double *px, const double *py, const double *x, double *y, int accumulate,
+                                 int kernel_id, const int32_t *ibox, const HmNestNode *nodes, const double *LAM,
+                                 const HmPeers *peers, cudaStream_t st)
+{
+    if (nitems <= 0) return cudaSuccess;
+    switch (kernel_id) {
+    case 0: return launch_dense<0>(items, nitems, runs, frun, px, py, x, y, accumulate, ibox, nodes, LAM, peers, st);
+    case 1: return launch_dense<1>(items, nitems, runs, frun, px, py, x, y, accumulate, ibox, nodes, LAM, peers, st);
+    case 2: return launch_dense<2>(items, nitems, runs, frun, px, py, x, y, accumulate, ibox, nodes, LAM, peers, st);
+    case 3: return launch_dense<3>(items, nitems, runs, frun, px, py, x, y, accumulate, ibox, nodes, LAM, peers, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t hm_launch_nest_up(const HmNestDev &T, const double *pts, const double *x, const double *Mt, double *MU,
+                              cudaStream_t st)
+{
+    if (T.nbase > 0) {
+        hm_nest_base_kernel<<<(unsigned)((T.nbase + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(T.nodes, T.base, T.nbase, pts, x,
+                                                                                         MU);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    for (int k = 0; k < T.ntiers; k++) { // finest tier first
+        const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
+        if (n <= 0) continue;
+        hm_nest_up_kernel<<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], Mt, MU);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t hm_launch_nest_core(int nboxes, const int32_t *rleaf_begin, const HmNestLeaf *rleaf, const double *cores,
+                                const double *MU, double *LAM, cudaStream_t st)
+{
+    if (nboxes <= 0) return cudaSuccess;
+    hm_nest_core_kernel<<<(unsigned)((nboxes + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(nboxes, rleaf_begin, rleaf, cores,
+                                                                                   MU, LAM);
+    return cudaGetLastError();
+}
+
+// eval: the finest boxes also evaluate their series into y (otherwise hm_launch_nest_dense does, fused
+// with the dense leaves)
+cudaError_t hm_launch_nest_down(const HmNestDev &T, const double *pts, const double *M, double *LAM, double *y,
+                                int accumulate, int64_t row_begin, int64_t row_end, bool eval, cudaStream_t st)
+{
+    for (int k = T.ntiers - 1; k >= 0; k--) { // coarsest tier first
+        const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
+        if (n <= 0) continue;
+        if (eval)
+            hm_nest_down_kernel<true><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], pts, M,
+                                                                 LAM, y, accumulate, (int)row_begin, (int)row_end);
+        else
+            hm_nest_down_kernel<false><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], pts, M,
+                                                                  LAM, y, accumulate, (int)row_begin, (int)row_end);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}

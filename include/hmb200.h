@@ -172,10 +172,22 @@ HM_API int32_t hm_assemble_kernel_fn(const double *x, int64_t nx, const double *
  * applying it (the arithmetic of src/BarycentricMatrix.jl:248-297 and src/KernelMatrix.jl:57-60).
  * The plan holds the r x r cores and the planner tables only, so an operator whose packed form
  * exceeds the GPU memory still fits; the apply is bound by the FP64 pipe instead of HBM.
- * hm_matmat, hm_matvec_adjoint, hm_plan_scale and hm_plan_read_leaf return HM_ERR_UNSUPPORTED. */
+ * hm_matmat works (panel kernels that generate the entries in tensor-core fragment layout);
+ * hm_matvec_adjoint, hm_plan_scale and hm_plan_read_leaf return HM_ERR_UNSUPPORTED.
+ * When the points are in descending order (as KernelMatrix's indsplit assumes) the plan takes its
+ * nested-basis form: all leaves interpolate on dyadic halves of the root boxes with the same 20 nodes,
+ * so column moments are formed once at the finest boxes and translated up the box tree, coefficients are
+ * translated down and evaluated once per row, and the few hundred distinct r x r cores of the
+ * translation-invariant kernels are shared -- O(N r) work for the low-rank part instead of O(N r depth).
+ * Same operator within rounding (<= 1e-12 from the reference's mul!). */
 HM_API int32_t hm_assemble_kernel_free(const double *x, int64_t nx, const double *y, int64_t ny, double a,
                                 double b, double c, double d, int32_t kernel_id, int32_t device,
                                 int32_t part, int32_t nparts, hm_plan **out);
+
+/* How the plan applies its operator: 0 = stored streams, 1 = matrix-free with the reference's barycentric
+ * arithmetic, 2 = matrix-free in Chebyshev form leaf by leaf, 3 = matrix-free in nested-basis form.
+ * HMB200_FREE_FORM=bary|cheb at plan time selects 1 or 2 instead of the default. */
+HM_API int32_t hm_plan_form(const hm_plan *plan, int32_t *form);
 
 /* One leaf of the assembled tree, as the planner sees it (device-free). */
 typedef struct hm_tree_leaf {

@@ -941,7 +941,6 @@ static int32_t build_nested(hm_plan *P, const double *x, int64_t nx, const doubl
     HM_CUDA(P->n_runsp.upload(N.runsp, st));
     HM_CUDA(P->n_frunp.upload(N.frunp, st));
     P->n_fin_rows = (int64_t)N.rows.base.size() * HM_NEST_R;
-    HM_CUDA(hm_nest_panel_init(N.M.data()));
     P->n_fused_eval = N.fused_eval;
     HM_CUDA(P->n_rleaf_begin.upload(N.rleaf_begin, st));
     HM_CUDA(P->n_rleaf.upload(N.rleaf, st));
@@ -1418,12 +1417,12 @@ static int32_t matmat_nested(hm_plan *p, const double *dX, int64_t ldx, double *
         cudaEvent_t *ev = p->tcount < p->tcap ? &p->tev[(size_t)p->tcount * 4] : nullptr;
         if (ev) HM_CUDA(cudaEventRecord(ev[0], st));
         HM_CUDA(hm_launch_panel_in(dX + c0 * ldx, ldx, L.ncols, nc, CS, p->wXt.p, st, true));
-        HM_CUDA(hm_launch_nest_up_panel(CS, p->n_cols, p->f_py.p, p->wXt.p, p->n_MUp.p, st));
+        HM_CUDA(hm_launch_nest_up_panel(CS, p->n_cols, p->f_py.p, p->wXt.p, p->n_M.p, p->n_MUp.p, st));
         if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
         HM_CUDA(hm_launch_nest_core_panel(CS, p->n_rows.nnodes, p->n_rleaf_begin.p, p->n_rleaf.p, p->n_cores.p,
                                           p->n_MUp.p, p->n_LAMp.p, st));
         if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
-        HM_CUDA(hm_launch_nest_down_panel(CS, p->n_rows, p->n_fin.p, p->n_LAMp.p, p->n_Sp.p, st));
+        HM_CUDA(hm_launch_nest_down_panel(CS, p->n_rows, p->n_fin.p, p->n_M.p, p->n_LAMp.p, p->n_Sp.p, st));
         HM_CUDA(hm_launch_free3_panel(CS, p->n_items3p.p, (int64_t)p->n_items3p.n, p->n_runsp.p, p->n_frunp.p, p->f_px.p,
                                       p->f_py.p, p->wXt.p, p->n_Sp.p, p->wYt.p, 0, p->kernel_id, st));
         HM_CUDA(hm_launch_panel_out(p->wYt.p, CS, L.row_begin, L.row_end, nc, dY + c0 * ldy, ldy, accumulate != 0, st));

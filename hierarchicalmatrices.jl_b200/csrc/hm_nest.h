@@ -117,10 +117,9 @@ cudaError_t hm_launch_nest_dense(const HmItem *items, int64_t nitems, const HmRu
                                  const HmPeers *peers, cudaStream_t st);
 
 // many right-hand sides (hm_nest_panel.cu); MUp / LAMp: 20 x CS words per box, row-major; Xt, Sp fragment-major
-cudaError_t hm_nest_panel_init(const double *M_host); // the two maps [q][p] into constant memory (per device)
-cudaError_t hm_launch_nest_up_panel(int CS, const HmNestDev &T, const double *pts, const double *Xt, double *MUp,
-                                    cudaStream_t st);
+cudaError_t hm_launch_nest_up_panel(int CS, const HmNestDev &T, const double *pts, const double *Xt, const double *M,
+                                    double *MUp, cudaStream_t st);
 cudaError_t hm_launch_nest_core_panel(int CS, int nboxes, const int32_t *rleaf_begin, const HmNestLeaf *rleaf,
                                       const double *cores, const double *MUp, double *LAMp, cudaStream_t st);
-cudaError_t hm_launch_nest_down_panel(int CS, const HmNestDev &T, const int32_t *fin, double *LAMp, double *Sp,
-                                      cudaStream_t st);
+cudaError_t hm_launch_nest_down_panel(int CS, const HmNestDev &T, const int32_t *fin, const double *M, double *LAMp,
+                                      double *Sp, cudaStream_t st);

@@ -1,6 +1,8 @@
 // hm_nest_host.cpp -- host builder of the nested-basis form (hm_nest.h).  Pure C++.
 #include "hm_nest.h"
 
+#include "hm_kernels.cuh"
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -374,15 +376,31 @@ std::string hm_nest_build(const HmLayout &L, const double *x, int64_t nx, const 
             const int32_t box = out.item_box[i];
             const int32_t r0 = it.run0;
             it.run0 = (int32_t)out.runsp.size();
+            // (the merged dense run is cut into pieces of at most 32 columns again: the panel kernel deals
+            // whole runs out to its warp groups)
             for (int32_t k = r0; k < r0 + it.nrun; k++) {
-                out.runsp.push_back(out.runs[(size_t)k]);
-                out.frunp.push_back(out.frun[(size_t)k]);
+                const HmRun &rr = out.runs[(size_t)k];
+                const HmFreeRun &fr = out.frun[(size_t)k];
+                for (int32_t o = 0; o < rr.len; o += 32) {
+                    const int32_t len = std::min<int32_t>(32, rr.len - o);
+                    out.runsp.push_back(HmRun{rr.src + o, len, rr.pos + o});
+                    out.frunp.push_back(HmFreeRun{fr.mid, fr.half, fr.xoff, fr.yoff + o, 0, len});
+                }
             }
+            it.nrun = (int32_t)out.runsp.size() - it.run0;
             out.runsp.push_back(HmRun{~(int32_t)(R * out.fin[(size_t)box]), R, it.S});
             out.frunp.push_back(HmFreeRun{0.5 * (TR.ba[(size_t)box] + TR.bb[(size_t)box]),
                                           0.5 * (TR.bb[(size_t)box] - TR.ba[(size_t)box]), it.out, 0, 0, R});
             it.nrun += 1;
             it.S += R;
+            if (it.nrun > HM_MAXRUNS) { // outside the panel kernel's run table: no panel form
+                out.items3p.clear();
+                out.runsp.clear();
+                out.frunp.clear();
+                out.fused_eval = false;
+                out.item_box.clear();
+                break;
+            }
             out.items3p.push_back(it);
         }
     }

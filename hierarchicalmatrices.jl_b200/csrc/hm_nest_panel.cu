@@ -5,9 +5,8 @@
 //   base   MUp[finest column box] = T(eta)' Xt[columns of the box]      FP64 tensor cores (DMMA), the 20 x 32
 //          Chebyshev tile generated per chunk of 32 points into a warp-private shared-memory tile
 //   up     MUp[box] = M0 MUp[half 0] + M1 MUp[half 1]                   lane = column; the maps are lower
-//   down   LAMp[box] += M_which' LAMp[parent]                           triangular constants, read as constant-
-//          bank operands of the DFMAs: no load instructions for them at all
-//   cores  LAMp[row box] = sum over its leaves of G_leaf MUp[column box of the leaf]
+//   down   LAMp[box] += M_which' LAMp[parent]                           triangular, broadcast from shared memory
+//   cores  LAMp[row box] = sum over its leaves of G_leaf MUp[column box of the leaf]           DMMA
 //   the finest row boxes leave their coefficients fragment-major in Sp, where the panel kernel of the dense
 //   leaves (hm_free3_panel_kernel, hm_free_panel.cu) picks them up as one 20-term "low-rank run" per item
 //   and evaluates them together with the dense entries.
@@ -24,8 +23,6 @@ constexpr int R = HM_NEST_R;
 constexpr int NT = 256;
 constexpr int TPITCH = 36; // tile pitch of the base kernel: 4 (mod 16) words -> conflict-free A fragments
 constexpr int TROWS = 24;  // 20 moments padded to three 8-row MMA blocks
-
-__constant__ double cM[2][R * R]; // the two transfer maps, [w][q * R + p], zero above the diagonal
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
@@ -108,18 +105,25 @@ hm_nest_base_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *_
     }
 }
 
-// out[q] += sum_{p <= q} M_w[q][p] in[p] (W = 0, 1) or, transposed, out[p] += sum_{q >= p} M_w[q][p] in[q]
-template <int W, bool TRANSPOSED>
-__device__ __forceinline__ void apply_map(double (&out)[R], const double (&in)[R])
+// out[q] += sum_{p <= q} M[q][p] in[p] or, transposed, out[p] += sum_{q >= p} M[q][p] in[q].  M (row-major
+// [q][p], zero above the diagonal) sits in shared memory and is read two entries at a time with
+// warp-uniform (broadcast) 128-bit loads.  (As constant-bank operands of the DFMAs the 840 distinct
+// words of the two maps overflow the immediate-constant cache and every FMA waits for a refill.)
+template <bool TRANSPOSED>
+__device__ __forceinline__ void apply_map(double (&out)[R], const double (&in)[R], const double *__restrict__ M)
 {
 #pragma unroll
     for (int q = 0; q < R; q++)
 #pragma unroll
-        for (int p = 0; p <= q; p++) {
-            if (TRANSPOSED)
-                out[p] = fma(cM[W][q * R + p], in[q], out[p]);
-            else
-                out[q] = fma(cM[W][q * R + p], in[p], out[q]);
+        for (int p = 0; p <= q; p += 2) {
+            const double2 m = *reinterpret_cast<const double2 *>(M + q * R + p); // (M[q][p], M[q][p + 1]); R is even
+            if (TRANSPOSED) {
+                out[p] = fma(m.x, in[q], out[p]);
+                if (p + 1 <= q) out[p + 1] = fma(m.y, in[q], out[p + 1]);
+            } else {
+                out[q] = fma(m.x, in[p], out[q]);
+                if (p + 1 <= q) out[q] = fma(m.y, in[p + 1], out[q]);
+            }
         }
 }
 
@@ -127,12 +131,16 @@ __device__ __forceinline__ void apply_map(double (&out)[R], const double (&in)[R
 // up / down over the subtree schedule of hm_nest_host.cpp; a warp owns (box, 32 columns), lane = column
 // ---------------------------------------------------------------------------
 template <int CS>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 hm_nest_up_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
-                        const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0, double *MUp)
+                        const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
+                        const double *__restrict__ M, double *MUp)
 {
     constexpr int CG = CS > 32 ? CS / 32 : 1;
+    __shared__ __align__(16) double sM[2][R * R];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    for (int i = t; i < 2 * R * R; i += blockDim.x) sM[0][i] = M[i];
+    __syncthreads();
     const int sub = sub0 + blockIdx.x;
     for (int g = sub_g0[sub]; g < sub_g0[sub + 1]; g++) {
         const int e0 = grp[g], nu = (grp[g + 1] - e0) * CG;
@@ -146,10 +154,10 @@ hm_nest_up_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__r
             const double *m0 = MUp + (size_t)c0 * R * CS + c;
 #pragma unroll
             for (int p = 0; p < R; p++) in[p] = m0[(size_t)p * CS];
-            apply_map<0, false>(out, in);
+            apply_map<false>(out, in, sM[0]);
 #pragma unroll
             for (int p = 0; p < R; p++) in[p] = m0[(size_t)(R + p) * CS];
-            apply_map<1, false>(out, in);
+            apply_map<false>(out, in, sM[1]);
             double *o = MUp + (size_t)id * R * CS + c;
 #pragma unroll
             for (int q = 0; q < R; q++) o[(size_t)q * CS] = out[q];
@@ -160,13 +168,17 @@ hm_nest_up_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__r
 
 // fin[box] >= 0: a finest box; its completed coefficients go fragment-major into Sp at rows 20 fin[box] ..
 template <int CS>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 2)
 hm_nest_down_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
                           const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
-                          const int32_t *__restrict__ fin, double *LAMp, double *__restrict__ Sp)
+                          const int32_t *__restrict__ fin, const double *__restrict__ M, double *LAMp,
+                          double *__restrict__ Sp)
 {
     constexpr int CG = CS > 32 ? CS / 32 : 1, NB = CS / 8;
+    __shared__ __align__(16) double sM[2][R * R];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    for (int i = t; i < 2 * R * R; i += blockDim.x) sM[0][i] = M[i];
+    __syncthreads();
     const int sub = sub0 + blockIdx.x;
     for (int g = sub_g0[sub + 1] - 1; g >= sub_g0[sub]; g--) { // shallowest depth first
         const int e0 = grp[g], nu = (grp[g + 1] - e0) * CG;
@@ -174,18 +186,24 @@ hm_nest_down_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *_
             const int id = order[e0 + u / CG], c = (u % CG) * 32 + lane;
             if (c >= CS) continue;
             const HmNestNode nd = nodes[id];
-            double out[R], in[R];
+            double out[R];
             double *o = LAMp + (size_t)id * R * CS + c;
 #pragma unroll
             for (int p = 0; p < R; p++) out[p] = o[(size_t)p * CS];
             if (nd.parent >= 0) {
+                // out[p] += sum_{q >= p} M[q][p] in[q]: one parent coefficient at a time (few live registers)
                 const double *lp = LAMp + (size_t)nd.parent * R * CS + c;
+                const double *__restrict__ Mw = sM[nd.which];
 #pragma unroll
-                for (int q = 0; q < R; q++) in[q] = lp[(size_t)q * CS];
-                if (nd.which == 0)
-                    apply_map<0, true>(out, in);
-                else
-                    apply_map<1, true>(out, in);
+                for (int q = 0; q < R; q++) {
+                    const double inq = lp[(size_t)q * CS];
+#pragma unroll
+                    for (int p = 0; p <= q; p += 2) {
+                        const double2 m = *reinterpret_cast<const double2 *>(Mw + q * R + p);
+                        out[p] = fma(m.x, inq, out[p]);
+                        if (p + 1 <= q) out[p + 1] = fma(m.y, inq, out[p + 1]);
+                    }
+                }
             }
             const int f = fin[id];
             if (f >= 0) {
@@ -201,44 +219,60 @@ hm_nest_down_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *_
 }
 
 // ---------------------------------------------------------------------------
-// cores: a warp owns (row box, 32 columns); G is read with warp-uniform 128-bit loads
+// cores: LAMp[row box] = sum over its leaves of G_leaf (20 x 20) MUp[column box] (20 x CS), on the FP64
+// tensor cores.  A warp owns (row box, half of the columns when CS = 64); A fragments (G, column-major,
+// one of a few hundred distinct cores: L1-resident) and B fragments (rows of MUp) through L1.
 // ---------------------------------------------------------------------------
-template <int CS>
+template <int NB>
 __global__ void __launch_bounds__(NT)
 hm_nest_core_panel_kernel(int nboxes, const int32_t *__restrict__ rleaf_begin, const HmNestLeaf *__restrict__ rleaf,
                           const double *__restrict__ cores, const double *__restrict__ MUp, double *__restrict__ LAMp)
 {
-    constexpr int CG = CS > 32 ? CS / 32 : 1;
+    constexpr int CS = NB * 8, NBW = NB > 4 ? 4 : NB, NCH = NB / NBW;
     const int lane = threadIdx.x & 31;
-    const int u = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-    if (u >= nboxes * CG) return;
-    const int box = u / CG, c = (u % CG) * 32 + lane;
-    if (c >= CS) return;
-    double out[R];
+    const int gid = lane >> 2, tig = lane & 3;
+    const int u = __shfl_sync(0xffffffffu, blockIdx.x * (NT / 32) + (threadIdx.x >> 5), 0);
+    if (u >= nboxes * NCH) return;
+    const int box = u / NCH, ch = u - box * NCH;
+    double acc[3][NBW][2];
 #pragma unroll
-    for (int q = 0; q < R; q++) out[q] = 0.0;
-    for (int l = rleaf_begin[box]; l < rleaf_begin[box + 1]; l++) {
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int n = 0; n < NBW; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
+    const int l0 = __shfl_sync(0xffffffffu, rleaf_begin[box], 0), l1 = __shfl_sync(0xffffffffu, rleaf_begin[box + 1], 0);
+    const int q2 = min(16 + gid, R - 1); // rows 20 .. 23 of the third block repeat row 19 and are dropped
+    for (int l = l0; l < l1; l++) {
         const HmNestLeaf lf = rleaf[l];
-        const double2 *__restrict__ G = reinterpret_cast<const double2 *>(cores + (size_t)lf.core * (R * R));
-        const double *__restrict__ mu = MUp + (size_t)lf.cnode * R * CS + c;
-#pragma unroll 4
-        for (int p = 0; p < R; p++) {
-            const double m = mu[(size_t)p * CS];
+        const double *__restrict__ G = cores + (size_t)lf.core * (R * R) + (size_t)tig * R; // G[q + p R], p = 4 j + tig
+        const double *__restrict__ mu = MUp + ((size_t)lf.cnode * R + tig) * CS + ch * (NBW * 8) + gid;
 #pragma unroll
-            for (int q2 = 0; q2 < R / 2; q2++) {
-                const double2 gg = __ldg(G + p * (R / 2) + q2); // G[2 q2 + p * R], G[2 q2 + 1 + p * R]
-                out[2 * q2] = fma(gg.x, m, out[2 * q2]);
-                out[2 * q2 + 1] = fma(gg.y, m, out[2 * q2 + 1]);
+        for (int j = 0; j < R / 4; j++) {
+            double bf[NBW];
+#pragma unroll
+            for (int n = 0; n < NBW; n++) bf[n] = mu[(size_t)(4 * j) * CS + n * 8];
+            const double a0 = __ldg(G + 4 * j * R + gid), a1 = __ldg(G + 4 * j * R + 8 + gid), a2 = __ldg(G + 4 * j * R + q2);
+#pragma unroll
+            for (int n = 0; n < NBW; n++) {
+                dmma884(acc[0][n][0], acc[0][n][1], a0, bf[n]);
+                dmma884(acc[1][n][0], acc[1][n][1], a1, bf[n]);
+                dmma884(acc[2][n][0], acc[2][n][1], a2, bf[n]);
             }
         }
     }
-    double *o = LAMp + (size_t)box * R * CS + c;
+    double *o = LAMp + (size_t)box * R * CS + ch * (NBW * 8) + 2 * tig;
 #pragma unroll
-    for (int q = 0; q < R; q++) o[(size_t)q * CS] = out[q];
+    for (int a = 0; a < 3; a++) {
+        const int q = 8 * a + gid;
+        if (q < R) {
+#pragma unroll
+            for (int n = 0; n < NBW; n++)
+                *reinterpret_cast<double2 *>(o + (size_t)q * CS + n * 8) = make_double2(acc[a][n][0], acc[a][n][1]);
+        }
+    }
 }
 
 template <int NB>
-cudaError_t run_up(const HmNestDev &T, const double *pts, const double *Xt, double *MUp, cudaStream_t st)
+cudaError_t run_up(const HmNestDev &T, const double *pts, const double *Xt, const double *M, double *MUp, cudaStream_t st)
 {
     constexpr int NCH = NB > 4 ? 2 : 1;
     if (T.nbase > 0) {
@@ -251,7 +285,8 @@ cudaError_t run_up(const HmNestDev &T, const double *pts, const double *Xt, doub
     for (int k = 0; k < T.ntiers; k++) {
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
         if (n <= 0) continue;
-        hm_nest_up_panel_kernel<NB * 8><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], MUp);
+        hm_nest_up_panel_kernel<NB * 8><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], M,
+                                                                    MUp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -259,45 +294,40 @@ cudaError_t run_up(const HmNestDev &T, const double *pts, const double *Xt, doub
 }
 
 template <int CS>
-cudaError_t run_down(const HmNestDev &T, const int32_t *fin, double *LAMp, double *Sp, cudaStream_t st)
+cudaError_t run_down(const HmNestDev &T, const int32_t *fin, const double *M, double *LAMp, double *Sp, cudaStream_t st)
 {
     for (int k = T.ntiers - 1; k >= 0; k--) {
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
         if (n <= 0) continue;
-        hm_nest_down_panel_kernel<CS><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], fin, LAMp,
-                                                                 Sp);
+        hm_nest_down_panel_kernel<CS><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], fin, M,
+                                                                 LAMp, Sp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-template <int CS>
+template <int NB>
 cudaError_t run_core(int nboxes, const int32_t *rleaf_begin, const HmNestLeaf *rleaf, const double *cores,
                      const double *MUp, double *LAMp, cudaStream_t st)
 {
-    constexpr int CG = CS > 32 ? CS / 32 : 1;
-    const int units = nboxes * CG;
+    constexpr int NCH = NB > 4 ? 2 : 1;
+    const int units = nboxes * NCH;
     if (units <= 0) return cudaSuccess;
-    hm_nest_core_panel_kernel<CS><<<(unsigned)((units + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(nboxes, rleaf_begin, rleaf,
+    hm_nest_core_panel_kernel<NB><<<(unsigned)((units + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(nboxes, rleaf_begin, rleaf,
                                                                                             cores, MUp, LAMp);
     return cudaGetLastError();
 }
 
 } // namespace
 
-cudaError_t hm_nest_panel_init(const double *M_host)
-{
-    return cudaMemcpyToSymbol(cM, M_host, sizeof(double) * 2 * R * R);
-}
-
-cudaError_t hm_launch_nest_up_panel(int CS, const HmNestDev &T, const double *pts, const double *Xt, double *MUp,
-                                    cudaStream_t st)
+cudaError_t hm_launch_nest_up_panel(int CS, const HmNestDev &T, const double *pts, const double *Xt, const double *M,
+                                    double *MUp, cudaStream_t st)
 {
     switch (CS) {
-    case 16: return run_up<2>(T, pts, Xt, MUp, st);
-    case 32: return run_up<4>(T, pts, Xt, MUp, st);
-    case 64: return run_up<8>(T, pts, Xt, MUp, st);
+    case 16: return run_up<2>(T, pts, Xt, M, MUp, st);
+    case 32: return run_up<4>(T, pts, Xt, M, MUp, st);
+    case 64: return run_up<8>(T, pts, Xt, M, MUp, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -306,20 +336,20 @@ cudaError_t hm_launch_nest_core_panel(int CS, int nboxes, const int32_t *rleaf_b
                                       const double *cores, const double *MUp, double *LAMp, cudaStream_t st)
 {
     switch (CS) {
-    case 16: return run_core<16>(nboxes, rleaf_begin, rleaf, cores, MUp, LAMp, st);
-    case 32: return run_core<32>(nboxes, rleaf_begin, rleaf, cores, MUp, LAMp, st);
-    case 64: return run_core<64>(nboxes, rleaf_begin, rleaf, cores, MUp, LAMp, st);
+    case 16: return run_core<2>(nboxes, rleaf_begin, rleaf, cores, MUp, LAMp, st);
+    case 32: return run_core<4>(nboxes, rleaf_begin, rleaf, cores, MUp, LAMp, st);
+    case 64: return run_core<8>(nboxes, rleaf_begin, rleaf, cores, MUp, LAMp, st);
     default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t hm_launch_nest_down_panel(int CS, const HmNestDev &T, const int32_t *fin, double *LAMp, double *Sp,
-                                      cudaStream_t st)
+cudaError_t hm_launch_nest_down_panel(int CS, const HmNestDev &T, const int32_t *fin, const double *M, double *LAMp,
+                                      double *Sp, cudaStream_t st)
 {
     switch (CS) {
-    case 16: return run_down<16>(T, fin, LAMp, Sp, st);
-    case 32: return run_down<32>(T, fin, LAMp, Sp, st);
-    case 64: return run_down<64>(T, fin, LAMp, Sp, st);
+    case 16: return run_down<16>(T, fin, M, LAMp, Sp, st);
+    case 32: return run_down<32>(T, fin, M, LAMp, Sp, st);
+    case 64: return run_down<64>(T, fin, M, LAMp, Sp, st);
     default: return cudaErrorInvalidValue;
     }
 }

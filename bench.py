@@ -316,8 +316,21 @@ def measure_matmat(torch, plan, st, px, py, dev, nrhs, steps, warmup):
     clocks = sampler.stop(t_wall0)
     dgemm_tflops = dgemm_peak(torch, dev)
     words = st["dense_words"] + st["lowrank_words"]
-    flops = 2.0 * words * nrhs
-    bytes_alg = 8 * words + 8 * (st["ncols"] + st["nrows"]) * nrhs
+    form = plan.form
+    flops_stored = 2.0 * words * nrhs
+    if form == 3:
+        # nested-basis form (hm_nest*): the work is that of the dense leaves, one 20-term moment / series
+        # per point and side, and one 20 x 20 core per leaf; the box-to-box translations (~3 % more) are
+        # not counted.  No operator bytes are read: the bound is the FP64 pipe.
+        flops = 2.0 * nrhs * (st["dense_words"] + 20.0 * (st["ncols"] + st["nrows"]) + 400.0 * st["n_bary2d"])
+        bytes_alg = 8 * (st["ncols"] + st["nrows"]) * nrhs
+        kern = ("hm_nest_*_panel_kernel + hm_free3_panel_kernel (nested-basis form; FP64 DMMA m8n8k4, entries of the "
+                "dense leaves evaluated into MMA fragments)")
+    else:
+        flops = flops_stored
+        bytes_alg = (8 * words if form == 0 else 0) + 8 * (st["ncols"] + st["nrows"]) * nrhs
+        kern = ("hm_panel kernels (FP64 DMMA m8n8k4; stage 1 + stage 2 + stage 3)" if form == 0 else
+                "hm_free1/3_panel_kernel (U, V and dense entries evaluated into MMA fragments)")
     peak, peak_src = measured_peak()
     # spot check of two columns against dense kernel rows in long double
     Yh = Y.cpu().numpy()
@@ -329,9 +342,12 @@ def measure_matmat(torch, plan, st, px, py, dev, nrhs, steps, warmup):
     out = {
         "value": nrhs / (ms / 1e3), "unit": "columns/s", "ms_per_step": ms, "steps": steps, "nrhs": nrhs,
         "panel_width": 16 if nrhs <= 16 else 32 if nrhs <= 32 else 64,
+        "form": ["stored", "matrix-free (barycentric)", "matrix-free (Chebyshev, leaf by leaf)",
+                 "matrix-free nested-basis"][form],
         "tflops": tf, "effective_gbs": gbs, "algorithmic_flops": flops, "algorithmic_bytes": bytes_alg,
+        "stored_form_flops": flops_stored, "stored_form_equivalent_tflops": flops_stored / (ms / 1e3) / 1e12,
         "roofline": {"bound": bound,
-                     "kernel": "hm_panel kernels (FP64 DMMA m8n8k4; stage 1 + stage 2 + stage 3)",
+                     "kernel": kern,
                      "achieved": tf if bound == "tensor" else gbs,
                      "peak": dgemm_tflops if bound == "tensor" else peak,
                      "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
@@ -408,7 +424,31 @@ def measure_cfg5(hm, torch, dev, local, dist_name, steps):
                    "effective_gbs": st["algorithmic_bytes"] / ms1 / 1e6,
                    "frac_hbm": st["algorithmic_bytes"] / ms1 / 1e6 / peak,
                    "check_sampled_dense_rows_relerr": sampled_rows_check(px, py, x1.cpu().numpy(), y1.cpu().numpy(), 12)}
-    del K, plan, x1, y1
+    del K, plan
+    torch.cuda.empty_cache()
+    # the same configuration on a matrix-free plan: nothing to assemble but the cores and the box tree
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Kf = hm.KernelMatrix(hm.cauchykernel, px, py, 1.0, -1.0, 1.0, -1.0, device=local, matrix_free=True)
+    pf = Kf.plan()
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    of = measure_matmat(torch, pf, pf.stats(), px, py, dev, 16, steps, 3)
+    of["setup_s"] = round(t_setup, 3)
+    of["resident_bytes"] = pf.stats()["stored_bytes"]
+    for _ in range(3):
+        pf.matvec_device(x1.data_ptr(), y1.data_ptr(), False, sm.cuda_stream)
+    torch.cuda.synchronize()
+    e0.record(sm)
+    for _ in range(steps):
+        pf.matvec_device(x1.data_ptr(), y1.data_ptr(), False, sm.cuda_stream)
+    e1.record(sm)
+    torch.cuda.synchronize()
+    msf = e0.elapsed_time(e1) / steps
+    of["matvec"] = {"ms_per_step": msf, "value": 1e3 / msf, "unit": "matvecs/s",
+                    "check_sampled_dense_rows_relerr": sampled_rows_check(px, py, x1.cpu().numpy(), y1.cpu().numpy(), 12)}
+    o["matrix_free"] = of
+    del Kf, pf, x1, y1
     torch.cuda.empty_cache()
     return o
 
@@ -819,24 +859,38 @@ def run_ours(args):
         ms_f = f0.elapsed_time(f1) / nmf
         fst, fn = pf.timing_end()
         dev_rel = float((yf - y_dev).abs().max() / y_dev.abs().max())
-        # FP64 work of one matrix-free matvec in the Chebyshev form: per (column,
-        # leaf) of stage 1 one mapping + 18 recurrence DFMA + 20 accumulations = 39 FP64-pipe
-        # instructions, per (row, leaf) of stage 3 a 20-term Clenshaw sum = 41, per dense entry 5 (sub,
+        # FP64 work of one matrix-free matvec, in lane-level FP64-pipe instructions.
+        # Chebyshev form leaf by leaf: per (column, leaf) of stage 1 one mapping + 18 recurrence DFMA + 20
+        # accumulations = 39, per (row, leaf) of stage 3 a 20-term Clenshaw sum = 41, per dense entry 5 (sub,
         # 3 refinement DFMA of the reciprocal, 1 accumulate; the rcp.approx itself runs on the XU pipe).
+        # Nested-basis form: the same 39 / 41 once per column / row (not per leaf), 400 per leaf for its
+        # core, 5 per dense entry; the box-to-box translations (~3 % more) are not counted.
         # peak = the DFMA issue rate measured by profiles/microbench/fp64_pipes.cu (34.2 TFLOP/s / 2)
-        issues = 39.0 * st["part_v_words"] / 20 + 41.0 * st["part_u_words"] / 20 + 5.0 * st["part_dense_words"]
+        fform = pf.form
+        if fform == 3:
+            issues = 39.0 * st["ncols"] + 41.0 * st["nrows"] + 400.0 * st["n_bary2d"] + 5.0 * st["part_dense_words"]
+            fkern = "hm_nest_base/up/core/down kernels + hm_nest_dense_kernel (dominant: the dense leaves)"
+            fhow = ("algorithmic FP64-pipe instructions of the nested-basis form (39 per column, 41 per row, 400 per "
+                    "leaf core, 5 per dense entry) / time")
+            fname = ("nested basis: moments at the finest column boxes, translated up the dyadic box tree; shared "
+                     "cores; coefficients translated down and evaluated once per row; dense leaves evaluated on the fly")
+        else:
+            issues = 39.0 * st["part_v_words"] / 20 + 41.0 * st["part_u_words"] / 20 + 5.0 * st["part_dense_words"]
+            fkern = "hm_free1_kernel + hm_free3_kernel"
+            fhow = ("algorithmic FP64-pipe instructions of the Chebyshev form (39 per column and leaf, 41 per row and "
+                    "leaf, 5 per dense entry) / time")
+            fname = "Chebyshev series (moments + Clenshaw), cores C F C' with the node correction"
         mfree = {"value": 1e3 / ms_f, "unit": "matvecs/s", "ms_per_step": ms_f, "steps": nmf,
                  "resident_bytes": pf.stats()["stored_bytes"], "setup_s": round(t_setup, 3),
                  "relinf_vs_stored": dev_rel, "api": "hm_assemble_kernel_free + hm_matvec_device",
-                 "form": "Chebyshev series (moments + Clenshaw), cores C F C' with the node correction",
+                 "form": fname, "launches_per_matvec": pf.launches_per_matvec,
                  "ms_per_launch": {"stage1": fst[0] / max(fn, 1), "stage2": fst[1] / max(fn, 1), "stage3": fst[2] / max(fn, 1)},
-                 "roofline": {"bound": "fp64", "kernel": "hm_free1_kernel + hm_free3_kernel",
+                 "stored_form_equivalent_gbs": st["algorithmic_bytes"] / ms_f / 1e6,
+                 "roofline": {"bound": "fp64", "kernel": fkern,
                               "achieved": issues / (ms_f / 1e3) / 1e12, "peak": 17.1,
                               "unit": "10^12 FP64-pipe instructions/s (lane-level)",
                               "frac": issues / (ms_f / 1e3) / 1e12 / 17.1,
-                              "how": "algorithmic FP64-pipe instructions of the Chebyshev form (39 per column and leaf, "
-                                     "41 per row and leaf, 5 per dense entry) / time; peak = DFMA rate of "
-                                     "profiles/microbench/fp64_pipes.cu (34.2 TFLOP/s / 2)"}}
+                              "how": fhow + "; peak = DFMA rate of profiles/microbench/fp64_pipes.cu (34.2 TFLOP/s / 2)"}}
         if not args.no_e2e:
             for _ in range(3):
                 pf.matvec(xn, yn, accumulate=False)
@@ -846,6 +900,12 @@ def run_ours(args):
             torch.cuda.synchronize()
             mfree["e2e"] = {"value": nmf / (time.perf_counter() - t0), "unit": "matvecs/s",
                             "api": "hm_matvec (C ABI, host pointers)"}
+        if not args.no_secondary:
+            # BASELINE configs[2] on the matrix-free plan
+            mm = measure_matmat(torch, pf, pf.stats(), px, py, dev, 64, 10, 3)
+            mm["workload"] = workload_name(n, args.dist).replace("single-vector mul!", "64 right-hand sides") + \
+                " (BASELINE configs[2]), matrix-free plan"
+            mfree["matmat64"] = mm
         del Kf, pf, yf
     if world == 1 and not args.matrix_free and not args.no_secondary:
         # BASELINE configs[2]: the same operator applied to 64 right-hand sides

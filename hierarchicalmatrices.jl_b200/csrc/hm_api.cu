@@ -740,16 +740,30 @@ int32_t hm_plan_launches_per_matvec(const hm_plan *p)
     return n;
 }
 
+// transposed: (x, a, b) are the COLUMN points and box of the reference's tree, (y, c, d) its row points and
+// box -- the leaves of KernelMatrix(f, y, x, c, d, a, b) with rows and columns exchanged, i.e. the block
+// structure of the adjoint operator (whose rows are the points x)
 static int32_t kernel_tree_layout(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
-                                  double c, double d, int32_t part, int32_t nparts, HmLayout &L)
+                                  double c, double d, int32_t part, int32_t nparts, HmLayout &L,
+                                  bool transposed = false)
 {
     return guarded([&]() -> int32_t {
         if (!x || !y) return fail(HM_ERR_NULL, "point set is NULL");
         if (nx < 0 || ny < 0) return fail(HM_ERR_SHAPE, "negative point count");
         std::vector<HmLeaf> leaves;
         int64_t nrows = 0, ncols = 0;
-        std::string err = hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
+        std::string err = transposed ? hm_kernel_tree(y, ny, x, nx, c, d, a, b, leaves, ncols, nrows)
+                                     : hm_kernel_tree(x, nx, y, ny, a, b, c, d, leaves, nrows, ncols);
         if (!err.empty()) return fail(HM_ERR_REFERENCE, "%s", err.c_str());
+        if (transposed)
+            for (HmLeaf &l : leaves) {
+                std::swap(l.row0, l.col0);
+                std::swap(l.m, l.n);
+                std::swap(l.ru, l.rv);
+                std::swap(l.xi0, l.yj0);
+                std::swap(l.a, l.c);
+                std::swap(l.b, l.d);
+            }
         err = hm_build_layout(leaves, nrows, ncols, part, nparts, layout_params(), L);
         if (!err.empty()) return fail(HM_ERR_INVALID, "%s", err.c_str());
         return HM_OK;
@@ -978,7 +992,7 @@ static int32_t build_nested(hm_plan *P, const double *x, int64_t nx, const doubl
 static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y, int64_t ny, double a, double b,
                                     double c, double d, int32_t kernel_id, int32_t device, int32_t part,
                                     int32_t nparts, bool matrix_free, hm_plan **out, hm_kernel_fn fn = nullptr,
-                                    void *user = nullptr)
+                                    void *user = nullptr, bool transposed = false)
 {
     return guarded([&]() -> int32_t {
         if (!out) return fail(HM_ERR_NULL, "out is NULL");
@@ -992,7 +1006,11 @@ static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y
         P->device = device;
         P->kernel_id = kernel_id;
         P->matrix_free = matrix_free;
-        if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, P->L)) {
+        P->box[0] = a;
+        P->box[1] = b;
+        P->box[2] = c;
+        P->box[3] = d;
+        if (int32_t st = kernel_tree_layout(x, nx, y, ny, a, b, c, d, part, nparts, P->L, transposed)) {
             delete P;
             return st;
         }
@@ -1293,14 +1311,51 @@ int32_t hm_matvec(hm_plan *p, const double *x, int64_t incx, double *y, int64_t 
     });
 }
 
+// Adjoint of a matrix-free plan.  K' is again a kernel operator: its rows are the points y, its columns the
+// points x, its leaves the transposed leaves (same boxes, roles exchanged) and its entries f(x_i, y_j) =
+// phi(x_i - y_j) = s phi(y_j - x_i) with s = -1 for the odd kernels (cauchy, coulomb') and +1 for the even ones
+// (coulomb, log): K' w = s K~ w = K~ (s w) with K~ the matrix-free plan of (f, y, x) on the transposed
+// leaves -- in nested-basis form whenever the forward plan is.  Built on first use, whole operators only.
+static int32_t adjoint_matrix_free(hm_plan *p, const double *dx, double *dy, int32_t accumulate, cudaStream_t st)
+{
+    const HmLayout &L = p->L;
+    if (L.nparts != 1) return fail(HM_ERR_UNSUPPORTED, "adjoint of a matrix-free plan: whole operators only (nparts = 1)");
+    if (p->kernel_id < 0 || p->kernel_id > 3) return fail(HM_ERR_UNSUPPORTED, "adjoint of a matrix-free plan: built-in kernels only");
+    if (!p->adj) {
+        HM_CUDA(cudaStreamSynchronize(st));
+        std::vector<double> hx((size_t)std::max<int64_t>(L.nrows, 1)), hy((size_t)std::max<int64_t>(L.ncols, 1));
+        if (L.nrows) HM_CUDA(cudaMemcpy(hx.data(), p->f_px.p, (size_t)L.nrows * 8, cudaMemcpyDeviceToHost));
+        if (L.ncols) HM_CUDA(cudaMemcpy(hy.data(), p->f_py.p, (size_t)L.ncols * 8, cudaMemcpyDeviceToHost));
+        hm_plan *q = nullptr;
+        if (int32_t rc = assemble_kernel_impl(hy.data(), L.ncols, hx.data(), L.nrows, p->box[2], p->box[3], p->box[0],
+                                              p->box[1], p->kernel_id, p->device, 0, 1, true, &q, nullptr, nullptr, true))
+            return rc;
+        p->adj = q;
+    }
+    const bool odd = p->kernel_id == 0 || p->kernel_id == 2;
+    const double *xin = dx;
+    if (odd && L.nrows > 0) {
+        if (!p->adj_x.p) {
+            HM_CUDA(cudaStreamSynchronize(st));
+            HM_CUDA(p->adj_x.alloc((size_t)L.nrows));
+        }
+        HM_CUDA(hm_launch_negate(dx, p->adj_x.p, L.nrows, st));
+        xin = p->adj_x.p;
+    }
+    return hm_matvec_device(p->adj, xin, dy, accumulate, (void *)st);
+}
+
 // Adjoint apply y (+)= H' x.
 int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate, void *stream)
 {
     return guarded([&]() -> int32_t {
         if (!p) return fail(HM_ERR_NULL, "plan is NULL");
-        if (p->matrix_free) return fail(HM_ERR_UNSUPPORTED, "not available on a matrix-free plan (hm_assemble_kernel_free)");
         const HmLayout &L = p->L;
         if ((!dx && L.nrows > 0) || (!dy && L.ncols > 0)) return fail(HM_ERR_NULL, "vector pointer is NULL");
+        if (p->matrix_free) {
+            HM_DEVICE(p->device);
+            return adjoint_matrix_free(p, dx, dy, accumulate, (cudaStream_t)stream);
+        }
         if (L.adj_max_f > HM_SMAX) return fail(HM_ERR_UNSUPPORTED, "adjoint: a column segment is covered by too many ranks");
         HM_DEVICE(p->device);
         cudaStream_t st = (cudaStream_t)stream;

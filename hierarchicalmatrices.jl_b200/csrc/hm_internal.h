@@ -190,8 +190,14 @@ struct hm_plan {
     bool indexed = false;
     // multi-GPU exchange (hm_dist_init)
     HmDist *dist = nullptr;
+    // adjoint of a matrix-free plan: a second matrix-free plan over the transposed leaves with the two
+    // point sets exchanged (built on the first hm_matvec_adjoint*), and the buffer for -x of the odd kernels
+    double box[4] = {0, 0, 0, 0}; // a, b, c, d of hm_assemble_kernel*
+    hm_plan *adj = nullptr;
+    DevBuf<double> adj_x;
     ~hm_plan()
     {
+        delete adj;
         hm_dist_release(dist);
         for (cudaEvent_t e : tev) cudaEventDestroy(e);
         for (int k = 0; k < HM_NCHUNK; k++) {

@@ -1370,6 +1370,21 @@ hm_colsum_kernel(const HmColSeg *__restrict__ segs, const int64_t *__restrict__ 
 
 } // namespace
 
+namespace {
+__global__ void hm_negate_kernel(const double *__restrict__ in, double *__restrict__ out, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = -in[i];
+}
+} // namespace
+
+cudaError_t hm_launch_negate(const double *in, double *out, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return cudaSuccess;
+    hm_negate_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(in, out, n);
+    return cudaGetLastError();
+}
+
 cudaError_t hm_launch_adjoint(const HmAdjoint &A, const double *x, double *y, int accumulate, cudaStream_t st)
 {
     if (A.n3 > 0)

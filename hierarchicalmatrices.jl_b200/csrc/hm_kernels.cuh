@@ -73,6 +73,8 @@ struct HmAdjoint {
     int max_r = 1;
 };
 cudaError_t hm_launch_adjoint(const HmAdjoint &A, const double *x, double *y, int accumulate, cudaStream_t st);
+// out = -in (the adjoint of a matrix-free plan with an odd kernel applies K~(-x))
+cudaError_t hm_launch_negate(const double *in, double *out, int64_t n, cudaStream_t st);
 
 // operator updates in place: H <- Diagonal(b) H (rows) and H <- H Diagonal(b) (columns)
 cudaError_t hm_launch_scale_rows(const HmItem *items3, int64_t n3, double *ustream, const double *b,

@@ -4,8 +4,8 @@
 //   MUp[box][q][c], LAMp[box][q][c]   row-major panels of 20 x CS words per box
 //   base   MUp[finest column box] = T(eta)' Xt[columns of the box]      FP64 tensor cores (DMMA), the 20 x 32
 //          Chebyshev tile generated per chunk of 32 points into a warp-private shared-memory tile
-//   up     MUp[box] = M0 MUp[half 0] + M1 MUp[half 1]                   lane = column; the maps are lower
-//   down   LAMp[box] += M_which' LAMp[parent]                           triangular, broadcast from shared memory
+//   up     MUp[box] = [M0 M1] [MUp[half 0]; MUp[half 1]]                DMMA; the maps are triangular, their
+//   down   LAMp[box] += M_which' LAMp[parent]                           zero k-steps skipped
 //   cores  LAMp[row box] = sum over its leaves of G_leaf MUp[column box of the leaf]           DMMA
 //   the finest row boxes leave their coefficients fragment-major in Sp, where the panel kernel of the dense
 //   leaves (hm_free3_panel_kernel, hm_free_panel.cu) picks them up as one 20-term "low-rank run" per item
@@ -105,113 +105,162 @@ hm_nest_base_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *_
     }
 }
 
-// out[q] += sum_{p <= q} M[q][p] in[p] or, transposed, out[p] += sum_{q >= p} M[q][p] in[q].  M (row-major
-// [q][p], zero above the diagonal) sits in shared memory and is read two entries at a time with
-// warp-uniform (broadcast) 128-bit loads.  (As constant-bank operands of the DFMAs the 840 distinct
-// words of the two maps overflow the immediate-constant cache and every FMA waits for a refill.)
-template <bool TRANSPOSED>
-__device__ __forceinline__ void apply_map(double (&out)[R], const double (&in)[R], const double *__restrict__ M)
-{
-#pragma unroll
-    for (int q = 0; q < R; q++)
-#pragma unroll
-        for (int p = 0; p <= q; p += 2) {
-            const double2 m = *reinterpret_cast<const double2 *>(M + q * R + p); // (M[q][p], M[q][p + 1]); R is even
-            if (TRANSPOSED) {
-                out[p] = fma(m.x, in[q], out[p]);
-                if (p + 1 <= q) out[p + 1] = fma(m.y, in[q], out[p + 1]);
-            } else {
-                out[q] = fma(m.x, in[p], out[q]);
-                if (p + 1 <= q) out[q] = fma(m.y, in[p + 1], out[q]);
-            }
-        }
-}
+// ---------------------------------------------------------------------------
+// up / down over the subtree schedule of hm_nest_host.cpp, on the FP64 tensor cores: a warp owns
+// (box, 32 columns).  The transfer maps are the A operands, staged once per CTA in shared memory with
+// pitches of 4 (mod 16) words (conflict-free m8n8k4 fragment reads); they are triangular, so the 4-wide
+// k-steps that lie entirely in the zero part are skipped at compile time (22 of 30 remain going up,
+// 9 of 15 going down).  B fragments are rows of the children's / the parent's panel through L1 (written
+// by this CTA or by an earlier launch).  The first version kept lane = column with 20 + 20 FMA
+// registers and broadcast the maps from shared memory: one LDS.128 per two DFMAs, 128 registers with
+// spills, 0.58 ms per 64-column pass over the column tree at N = 2^20.
+// ---------------------------------------------------------------------------
+constexpr int UPITCH = 44; // [q][20 w + p], 40 + 4
 
-// ---------------------------------------------------------------------------
-// up / down over the subtree schedule of hm_nest_host.cpp; a warp owns (box, 32 columns), lane = column
-// ---------------------------------------------------------------------------
-template <int CS>
-__global__ void __launch_bounds__(NT, 2)
+template <int NB>
+__global__ void __launch_bounds__(NT)
 hm_nest_up_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
                         const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
                         const double *__restrict__ M, double *MUp)
 {
-    constexpr int CG = CS > 32 ? CS / 32 : 1;
-    __shared__ __align__(16) double sM[2][R * R];
+    constexpr int CS = NB * 8, NBW = NB > 4 ? 4 : NB, NCH = NB / NBW;
+    __shared__ double sA[TROWS][UPITCH]; // MUp[box][q] = sum_w sum_p M_w[q][p] MUp[half w][p]
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
-    for (int i = t; i < 2 * R * R; i += blockDim.x) sM[0][i] = M[i];
+    const int gid = lane >> 2, tig = lane & 3;
+    for (int i = t; i < TROWS * UPITCH; i += blockDim.x) {
+        const int q = i / UPITCH, k = i - q * UPITCH;
+        sA[q][k] = (q < R && k < 2 * R) ? M[(k / R) * (R * R) + q * R + (k % R)] : 0.0;
+    }
     __syncthreads();
     const int sub = sub0 + blockIdx.x;
     for (int g = sub_g0[sub]; g < sub_g0[sub + 1]; g++) {
-        const int e0 = grp[g], nu = (grp[g + 1] - e0) * CG;
+        const int e0 = grp[g], nu = (grp[g + 1] - e0) * NCH;
         for (int u = warp; u < nu; u += nw) {
-            const int id = order[e0 + u / CG], c = (u % CG) * 32 + lane;
+            const int id = order[e0 + u / NCH], ch = u % NCH;
             const int c0 = nodes[id].child0;
-            if (c0 < 0 || c >= CS) continue;
-            double out[R], in[R];
+            if (c0 < 0) continue; // (warp-uniform)
+            double acc[3][NBW][2];
 #pragma unroll
-            for (int q = 0; q < R; q++) out[q] = 0.0;
-            const double *m0 = MUp + (size_t)c0 * R * CS + c;
+            for (int a = 0; a < 3; a++)
 #pragma unroll
-            for (int p = 0; p < R; p++) in[p] = m0[(size_t)p * CS];
-            apply_map<false>(out, in, sM[0]);
+                for (int n = 0; n < NBW; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
+            const double *B = MUp + ((size_t)c0 * R + tig) * CS + ch * (NBW * 8) + gid; // 40 rows: both halves
 #pragma unroll
-            for (int p = 0; p < R; p++) in[p] = m0[(size_t)(R + p) * CS];
-            apply_map<false>(out, in, sM[1]);
-            double *o = MUp + (size_t)id * R * CS + c;
+            for (int j = 0; j < 2 * R / 4; j++) {
+                const int jj = j % (R / 4); // k-step inside its map: columns p = 4 jj .. 4 jj + 3
+                double bf[NBW];
 #pragma unroll
-            for (int q = 0; q < R; q++) o[(size_t)q * CS] = out[q];
+                for (int n = 0; n < NBW; n++) bf[n] = B[(size_t)(4 * j) * CS + n * 8];
+                // row block a (q = 8 a ..) meets columns p <= q: active iff 4 jj <= 8 a + 7
+                if (jj <= 1) {
+                    const double a0 = sA[gid][4 * j + tig];
+#pragma unroll
+                    for (int n = 0; n < NBW; n++) dmma884(acc[0][n][0], acc[0][n][1], a0, bf[n]);
+                }
+                if (jj <= 3) {
+                    const double a1 = sA[8 + gid][4 * j + tig];
+#pragma unroll
+                    for (int n = 0; n < NBW; n++) dmma884(acc[1][n][0], acc[1][n][1], a1, bf[n]);
+                }
+                {
+                    const double a2 = sA[16 + gid][4 * j + tig];
+#pragma unroll
+                    for (int n = 0; n < NBW; n++) dmma884(acc[2][n][0], acc[2][n][1], a2, bf[n]);
+                }
+            }
+            double *o = MUp + (size_t)id * R * CS + ch * (NBW * 8) + 2 * tig;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const int q = 8 * a + gid;
+                if (q < R) {
+#pragma unroll
+                    for (int n = 0; n < NBW; n++)
+                        *reinterpret_cast<double2 *>(o + (size_t)q * CS + n * 8) = make_double2(acc[a][n][0], acc[a][n][1]);
+                }
+            }
         }
         __syncthreads();
     }
 }
 
 // fin[box] >= 0: a finest box; its completed coefficients go fragment-major into Sp at rows 20 fin[box] ..
-template <int CS>
-__global__ void __launch_bounds__(NT, 2)
+template <int NB>
+__global__ void __launch_bounds__(NT)
 hm_nest_down_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
                           const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
                           const int32_t *__restrict__ fin, const double *__restrict__ M, double *LAMp,
                           double *__restrict__ Sp)
 {
-    constexpr int CG = CS > 32 ? CS / 32 : 1, NB = CS / 8;
-    __shared__ __align__(16) double sM[2][R * R];
+    constexpr int CS = NB * 8, NBW = NB > 4 ? 4 : NB, NCH = NB / NBW;
+    __shared__ double sA[2][TROWS][R]; // LAMp[box][p] += sum_q M_which[q][p] LAMp[parent][q]: A = M_which'
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
-    for (int i = t; i < 2 * R * R; i += blockDim.x) sM[0][i] = M[i];
+    const int gid = lane >> 2, tig = lane & 3;
+    for (int i = t; i < 2 * TROWS * R; i += blockDim.x) {
+        const int w = i / (TROWS * R), pq = i - w * (TROWS * R), pr = pq / R, q = pq - pr * R;
+        sA[w][pr][q] = pr < R ? M[w * (R * R) + q * R + pr] : 0.0;
+    }
     __syncthreads();
     const int sub = sub0 + blockIdx.x;
     for (int g = sub_g0[sub + 1] - 1; g >= sub_g0[sub]; g--) { // shallowest depth first
-        const int e0 = grp[g], nu = (grp[g + 1] - e0) * CG;
+        const int e0 = grp[g], nu = (grp[g + 1] - e0) * NCH;
         for (int u = warp; u < nu; u += nw) {
-            const int id = order[e0 + u / CG], c = (u % CG) * 32 + lane;
-            if (c >= CS) continue;
+            const int id = order[e0 + u / NCH], ch = u % NCH;
             const HmNestNode nd = nodes[id];
-            double out[R];
-            double *o = LAMp + (size_t)id * R * CS + c;
+            double acc[3][NBW][2];
+            double *o = LAMp + (size_t)id * R * CS + ch * (NBW * 8) + 2 * tig;
 #pragma unroll
-            for (int p = 0; p < R; p++) out[p] = o[(size_t)p * CS];
-            if (nd.parent >= 0) {
-                // out[p] += sum_{q >= p} M[q][p] in[q]: one parent coefficient at a time (few live registers)
-                const double *lp = LAMp + (size_t)nd.parent * R * CS + c;
-                const double *__restrict__ Mw = sM[nd.which];
+            for (int a = 0; a < 3; a++) {
+                const int pr = min(8 * a + gid, R - 1);
 #pragma unroll
-                for (int q = 0; q < R; q++) {
-                    const double inq = lp[(size_t)q * CS];
+                for (int n = 0; n < NBW; n++) {
+                    const double2 v = *reinterpret_cast<const double2 *>(o + (size_t)pr * CS + n * 8);
+                    acc[a][n][0] = v.x;
+                    acc[a][n][1] = v.y;
+                }
+            }
+            if (nd.parent >= 0) { // (warp-uniform)
+                const double *B = LAMp + ((size_t)nd.parent * R + tig) * CS + ch * (NBW * 8) + gid;
+                const double(*A)[R] = sA[nd.which];
 #pragma unroll
-                    for (int p = 0; p <= q; p += 2) {
-                        const double2 m = *reinterpret_cast<const double2 *>(Mw + q * R + p);
-                        out[p] = fma(m.x, inq, out[p]);
-                        if (p + 1 <= q) out[p + 1] = fma(m.y, inq, out[p + 1]);
+                for (int j = 0; j < R / 4; j++) {
+                    double bf[NBW];
+#pragma unroll
+                    for (int n = 0; n < NBW; n++) bf[n] = B[(size_t)(4 * j) * CS + n * 8];
+                    // row block a (p = 8 a ..) meets q >= p: active iff 4 j + 3 >= 8 a
+                    {
+                        const double a0 = A[gid][4 * j + tig];
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) dmma884(acc[0][n][0], acc[0][n][1], a0, bf[n]);
+                    }
+                    if (j >= 2) {
+                        const double a1 = A[8 + gid][4 * j + tig];
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) dmma884(acc[1][n][0], acc[1][n][1], a1, bf[n]);
+                    }
+                    if (j >= 4) {
+                        const double a2 = A[16 + gid][4 * j + tig];
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) dmma884(acc[2][n][0], acc[2][n][1], a2, bf[n]);
                     }
                 }
             }
             const int f = fin[id];
-            if (f >= 0) {
 #pragma unroll
-                for (int p = 0; p < R; p++) Sp[hm_panel_blocked_index((int64_t)f * R + p, c, NB)] = out[p];
-            } else {
+            for (int a = 0; a < 3; a++) {
+                const int pr = 8 * a + gid;
+                if (pr < R) {
 #pragma unroll
-                for (int p = 0; p < R; p++) o[(size_t)p * CS] = out[p];
+                    for (int n = 0; n < NBW; n++) {
+                        if (f >= 0) {
+                            const int c = ch * (NBW * 8) + n * 8 + 2 * tig;
+                            Sp[hm_panel_blocked_index((int64_t)f * R + pr, c, NB)] = acc[a][n][0];
+                            Sp[hm_panel_blocked_index((int64_t)f * R + pr, c + 1, NB)] = acc[a][n][1];
+                        } else {
+                            *reinterpret_cast<double2 *>(o + (size_t)pr * CS + n * 8) =
+                                make_double2(acc[a][n][0], acc[a][n][1]);
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
@@ -285,7 +334,7 @@ cudaError_t run_up(const HmNestDev &T, const double *pts, const double *Xt, cons
     for (int k = 0; k < T.ntiers; k++) {
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
         if (n <= 0) continue;
-        hm_nest_up_panel_kernel<NB * 8><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], M,
+        hm_nest_up_panel_kernel<NB><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], M,
                                                                     MUp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -299,7 +348,7 @@ cudaError_t run_down(const HmNestDev &T, const int32_t *fin, const double *M, do
     for (int k = T.ntiers - 1; k >= 0; k--) {
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
         if (n <= 0) continue;
-        hm_nest_down_panel_kernel<CS><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], fin, M,
+        hm_nest_down_panel_kernel<CS / 8><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], fin, M,
                                                                  LAMp, Sp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -172,8 +172,11 @@ HM_API int32_t hm_assemble_kernel_fn(const double *x, int64_t nx, const double *
  * applying it (the arithmetic of src/BarycentricMatrix.jl:248-297 and src/KernelMatrix.jl:57-60).
  * The plan holds the r x r cores and the planner tables only, so an operator whose packed form
  * exceeds the GPU memory still fits; the apply is bound by the FP64 pipe instead of HBM.
- * hm_matmat works (panel kernels that generate the entries in tensor-core fragment layout);
- * hm_matvec_adjoint, hm_plan_scale and hm_plan_read_leaf return HM_ERR_UNSUPPORTED.
+ * hm_matmat works (panel kernels that generate the entries in tensor-core fragment layout), and so does
+ * hm_matvec_adjoint on a whole operator (nparts = 1): the adjoint of a kernel operator is the kernel
+ * operator of the transposed leaves with the point sets exchanged -- a second matrix-free plan built on
+ * first use, applied to -x for the odd kernels.  hm_plan_scale and hm_plan_read_leaf return
+ * HM_ERR_UNSUPPORTED.
  * When the points are in descending order (as KernelMatrix's indsplit assumes) the plan takes its
  * nested-basis form: all leaves interpolate on dyadic halves of the root boxes with the same 20 nodes,
  * so column moments are formed once at the finest boxes and translated up the box tree, coefficients are
@@ -282,7 +285,7 @@ HM_API int32_t hm_dist_matvec(hm_plan *p, const double *x, int64_t incx, double 
  * entries, y with ncols.  The reference has no adjoint of its hierarchical types; the
  * leaf rules are those of its Transpose/Adjoint leaf methods (src/algebra.jl:52-82,
  * 138-159).  For a row part the result is the contribution of the owned rows (sum the
- * parts to get H'x). */
+ * parts to get H'x); matrix-free plans: whole operators only. */
 HM_API int32_t hm_matvec_adjoint(hm_plan *p, const double *x, int64_t incx, double *y, int64_t incy,
                                  int32_t accumulate);
 HM_API int32_t hm_matvec_adjoint_device(hm_plan *p, const double *dx, double *dy, int32_t accumulate,

@@ -958,11 +958,45 @@ def test_matrix_free_parts_determinism_and_unsupported(hm, O):
     assert relinf(res, u1) <= 1e-13
     P = full.plan()
     with pytest.raises(hm.HmError):
-        P.rmatvec(v, np.zeros(N))
+        part.plan().rmatvec(v, np.zeros(N))                         # the adjoint needs the whole operator
     with pytest.raises(hm.HmError):
         P.scale(np.ones(N), 0)
     with pytest.raises(hm.HmError):
         P.read_leaf(0, 3 if P.leaf_info(0)["kind"] == 3 else 0)
+
+
+@pytest.mark.parametrize("kernel,dist,N", [("cauchykernel", "cheb", 4096), ("cauchykernel", "unif", 3000),
+                                           ("coulombkernel", "quad", 1000), ("logkernel", "cheb", 77 * 2),
+                                           ("coulombprimekernel", "unif", 20011), ("logkernel", "unif", 9000)])
+def test_matrix_free_adjoint(hm, O, kernel, dist, N):
+    """y (+)= K'w on a matrix-free plan: the matrix-free plan of the transposed leaves with the point sets
+    exchanged (odd kernels through -w).  Against the oracle's adjoint restatement, the stored plan's adjoint,
+    and <w, K v> = <K'w, v>; both forms of the matrix-free apply."""
+    x, y, (a, b, c, d) = O.example_points(N, dist)
+    ref = O.kernelmatrix(getattr(O, kernel[:-6].upper()), x, y, a, b, c, d)
+    w, v = _vec(N, 21), _vec(N, 22)
+    want = ref.rmatvec(w)
+    Ks = hm.KernelMatrix(getattr(hm, kernel), x, y, a, b, c, d, device=0)
+    ys = np.zeros(N)
+    Ks.plan().rmatvec(w, ys, accumulate=False)
+    for env in (None, "cheb"):
+        if env:
+            os.environ["HMB200_FREE_FORM"] = env
+        try:
+            Kf = hm.KernelMatrix(getattr(hm, kernel), x, y, a, b, c, d, device=0, matrix_free=True)
+            P = Kf.plan()
+            got = np.zeros(N)
+            P.rmatvec(w, got, accumulate=False)
+        finally:
+            os.environ.pop("HMB200_FREE_FORM", None)
+        assert relinf(got, want) <= TOL
+        assert relinf(got, ys) <= 1e-12
+        y0 = _vec(N, 23)
+        acc = y0.copy()
+        P.rmatvec(w, acc, accumulate=True)                           # accumulate, twice the same answer
+        assert relinf(acc - y0, got) <= 1e-12
+        Kv = Kf * v
+        assert abs(np.dot(w, Kv) - np.dot(got, v)) <= 1e-11 * np.linalg.norm(w) * np.linalg.norm(Kv)
 
 
 @pytest.mark.parametrize("nrhs", [2, 16, 17, 33, 64, 70])

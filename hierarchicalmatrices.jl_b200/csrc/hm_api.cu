@@ -956,6 +956,10 @@ static int32_t build_nested(hm_plan *P, const double *x, int64_t nx, const doubl
     HM_CUDA(P->n_frunp.upload(N.frunp, st));
     P->n_fin_rows = (int64_t)N.rows.base.size() * HM_NEST_R;
     P->n_fused_eval = N.fused_eval;
+    {
+        const char *eo = getenv("HMB200_NEST_OVERLAP");
+        P->n_overlap = !(eo && eo[0] == '0');
+    }
     HM_CUDA(P->n_rleaf_begin.upload(N.rleaf_begin, st));
     HM_CUDA(P->n_rleaf.upload(N.rleaf, st));
     HM_CUDA(P->n_cores.upload(N.cores, st));
@@ -1144,6 +1148,45 @@ int32_t hm_matvec_device_peers(hm_plan *p, const double *dx, double *dy, int32_t
             // nested-basis form: moments up the column boxes, cores, coefficients down the row boxes and
             // their evaluation (writes every owned row), then the dense leaves on top
             const double *M = p->n_M.p, *Mt = p->n_M.p + 2 * HM_NEST_R * HM_NEST_R;
+            // The dense leaves (FP64-bound, 0.12 ms at N = 2^20) do not depend on the tree passes (short,
+            // latency-bound launches that leave most SMs idle): the passes run beside them on a second,
+            // high-priority stream (fork / join by events, so the call is still one unit of work on the
+            // caller's stream and can be captured into a graph), and the finest tier of the downward pass
+            // adds the series to the rows the dense kernel wrote.  HMB200_NEST_OVERLAP=0: one stream,
+            // evaluation fused into the dense pass.
+            if (p->n_fused_eval && !peers && p->n_overlap && p->n_round_begin.size() == 2) {
+                if (!p->side_stream) {
+                    // the tree passes get the highest priority: their few CTAs take the slots the dense kernel's
+                    // retiring CTAs free, ahead of its pending ones
+                    int lo = 0, hi = 0;
+                    HM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                    HM_CUDA(cudaStreamCreateWithPriority(&p->side_stream, cudaStreamNonBlocking, hi));
+                    HM_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+                    HM_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+                    HM_CUDA(cudaEventCreateWithFlags(&p->ev_dense, cudaEventDisableTiming));
+                }
+                cudaStream_t hs = p->side_stream;
+                HM_CUDA(cudaEventRecord(p->ev_fork, st));
+                HM_CUDA(cudaStreamWaitEvent(hs, p->ev_fork, 0));
+                HM_CUDA(hm_launch_nest_up(p->n_cols, p->f_py.p, dx, Mt, p->n_MU.p, hs));
+                HM_CUDA(hm_launch_nest_dense(p->n_items3.p, p->n_round_begin[1], p->n_runs.p, p->n_frun.p, p->f_px.p,
+                                             p->f_py.p, dx, dy, accumulate != 0, p->kernel_id, nullptr, p->nr_nodes.p,
+                                             p->n_LAM.p, nullptr, st));
+                HM_CUDA(cudaEventRecord(p->ev_dense, st));
+                if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
+                HM_CUDA(hm_launch_nest_core(p->n_rows.nnodes, p->n_rleaf_begin.p, p->n_rleaf.p, p->n_cores.p, p->n_MU.p,
+                                            p->n_LAM.p, hs));
+                if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
+                HM_CUDA(hm_launch_nest_down(p->n_rows, p->f_px.p, M, p->n_LAM.p, dy, 1, L.row_begin, L.row_end, true, hs,
+                                            p->ev_dense));
+                HM_CUDA(cudaEventRecord(p->ev_join, hs));
+                HM_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
+                if (ev) {
+                    HM_CUDA(cudaEventRecord(ev[3], st));
+                    p->tcount++;
+                }
+                return HM_OK;
+            }
             HM_CUDA(hm_launch_nest_up(p->n_cols, p->f_py.p, dx, Mt, p->n_MU.p, st));
             if (ev) HM_CUDA(cudaEventRecord(ev[1], st));
             HM_CUDA(hm_launch_nest_core(p->n_rows.nnodes, p->n_rleaf_begin.p, p->n_rleaf.p, p->n_cores.p, p->n_MU.p,

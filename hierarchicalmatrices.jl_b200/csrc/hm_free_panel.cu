@@ -201,7 +201,7 @@ __device__ __forceinline__ double selp(double a, double b, bool p)
 __device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 
 template <int NB, int KID> // KID: kernel id 0..3 of the dense entries (hm_assemble_kernel)
-__global__ void __launch_bounds__(FT, 2)
+__global__ void __launch_bounds__(FT, 3)
 hm_free3_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict__ runs,
                       const HmFreeRun *__restrict__ frun, const double *__restrict__ px,
                       const double *__restrict__ py, const double *__restrict__ Xt,
@@ -270,21 +270,7 @@ hm_free3_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict_
                 // (Sp and Xt are fragment-major: hm_panel_blocked_index)
                 const int64_t row0 = (int64_t)(~src) - k0 + tig; // row of rank k = tig
                 const double *__restrict__ bp = Sp + ((row0 >> 2) * NB + cb0) * 32 + gid * 4 + (row0 & 3);
-                double b[5][NBW];
-                if (k0 == 0 && kn == R) {
-#pragma unroll
-                    for (int j = 0; j < 5; j++)
-#pragma unroll
-                        for (int n = 0; n < NBW; n++) b[j][n] = __ldg(bp + (j * NB + n) * 32);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 5; j++) {
-                        const int k = 4 * j + tig;
-                        const bool v = k >= k0 && k < k0 + kn;
-#pragma unroll
-                        for (int n = 0; n < NBW; n++) b[j][n] = v ? __ldg(bp + (j * NB + n) * 32) : 0.0;
-                    }
-                }
+                const bool whole = k0 == 0 && kn == R;
                 const double2 box = rbox[r];
                 double cur[2], prev[2], t4x2[2];
 #pragma unroll
@@ -298,10 +284,16 @@ hm_free3_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict_
                 }
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
+                    // (fragments loaded step by step: all five at once cost 40 registers and a third CTA per SM)
+                    const int k = 4 * j + tig;
+                    const bool v = whole || (k >= k0 && k < k0 + kn);
+                    double b[NBW];
+#pragma unroll
+                    for (int n = 0; n < NBW; n++) b[n] = v ? __ldg(bp + (j * NB + n) * 32) : 0.0;
 #pragma unroll
                     for (int n = 0; n < NBW; n++) {
-                        dmma884(acc[0][n][0], acc[0][n][1], cur[0], b[j][n]);
-                        if (two_blocks) dmma884(acc[1][n][0], acc[1][n][1], cur[1], b[j][n]);
+                        dmma884(acc[0][n][0], acc[0][n][1], cur[0], b[n]);
+                        if (two_blocks) dmma884(acc[1][n][0], acc[1][n][1], cur[1], b[n]);
                     }
                     if (j < 4) {
 #pragma unroll
@@ -318,17 +310,28 @@ hm_free3_panel_kernel(const HmItem *__restrict__ items, const HmRun *__restrict_
                 const double *__restrict__ bp = Xt + ((row0 >> 2) * NB + cb0) * 32 + gid * 4 + (row0 & 3);
                 const double *__restrict__ yc = py + ryo[r] + tig;
                 int j0 = 0;
-                for (; j0 + 4 <= kn; j0 += 4) {
-                    const double yv = yc[j0];
+                if (kn >= 4) {
+                    // the next step's column point and B fragments are in flight during this step's MMAs
+                    double yv = yc[0];
                     double b[NBW];
 #pragma unroll
-                    for (int n = 0; n < NBW; n++) b[n] = __ldg(bp + ((j0 >> 2) * NB + n) * 32);
-                    const double a0 = kernel_eval_fast(KID, p0, yv);
-                    const double a1 = kernel_eval_fast(KID, p1, yv);
+                    for (int n = 0; n < NBW; n++) b[n] = __ldg(bp + n * 32);
+                    for (; j0 + 4 <= kn; j0 += 4) {
+                        const int jn = j0 + 8 <= kn ? j0 + 4 : j0; // (last full step: reload, unused)
+                        const double yn = yc[jn];
+                        double bn[NBW];
 #pragma unroll
-                    for (int n = 0; n < NBW; n++) {
-                        dmma884(acc[0][n][0], acc[0][n][1], a0, b[n]);
-                        if (two_blocks) dmma884(acc[1][n][0], acc[1][n][1], a1, b[n]);
+                        for (int n = 0; n < NBW; n++) bn[n] = __ldg(bp + ((jn >> 2) * NB + n) * 32);
+                        const double a0 = kernel_eval_fast(KID, p0, yv);
+                        const double a1 = kernel_eval_fast(KID, p1, yv);
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) {
+                            dmma884(acc[0][n][0], acc[0][n][1], a0, b[n]);
+                            if (two_blocks) dmma884(acc[1][n][0], acc[1][n][1], a1, b[n]);
+                        }
+                        yv = yn;
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) b[n] = bn[n];
                     }
                 }
                 if (j0 < kn) {

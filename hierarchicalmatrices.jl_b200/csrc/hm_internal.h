@@ -128,6 +128,9 @@ struct hm_plan {
     DevBuf<HmNestNode> nr_nodes, nc_nodes;
     DevBuf<int32_t> nr_order, nr_grp, nr_sub, nc_order, nc_grp, nc_sub, n_rleaf_begin, nr_base, nc_base, n_item_box;
     bool n_fused_eval = false;
+    bool n_overlap = true; // dense leaves on side_stream beside the tree passes (HMB200_NEST_OVERLAP=0: off)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_dense = nullptr;
     // many right-hand sides in nested form: items with the coefficient run, per-box panels
     DevBuf<int32_t> n_fin;
     DevBuf<HmItem> n_items3p;
@@ -206,6 +209,10 @@ struct hm_plan {
         }
         if (ev_y0) cudaEventDestroy(ev_y0);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_dense) cudaEventDestroy(ev_dense);
+        if (side_stream) cudaStreamDestroy(side_stream);
         if (hx) cudaFreeHost(hx);
         if (hy) cudaFreeHost(hy);
         if (stream) cudaStreamDestroy(stream);

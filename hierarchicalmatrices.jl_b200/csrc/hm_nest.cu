@@ -14,26 +14,23 @@
 #include "hm_device.cuh"
 #include "hm_kernels.cuh"
 #include "hm_nest.h"
+#include "hm_nest_dev.cuh"
 
 namespace {
 
 constexpr int R = HM_NEST_R;
 constexpr int NT = 256; // threads of a subtree CTA
 
+
 // ---------------------------------------------------------------------------
 // upward pass: MU[box][q] = sum over the box's columns of T_q(eta_s) x_s
 //   finest boxes from the points (flat kernel, a warp per box), the others from their two halves
 //   (M0, M1), subtree by subtree
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT)
-hm_nest_base_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ base, int nbase,
-                    const double *__restrict__ pts, const double *__restrict__ x, double *__restrict__ MU)
+// moments of one finest box from its points (a warp)
+__device__ __forceinline__ void base_moments(const HmNestNode &nd, int id, int lane, const double *__restrict__ pts,
+                                             const double *__restrict__ x, double *MU)
 {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-    if (b >= nbase) return;
-    const int id = base[b];
-    const HmNestNode nd = nodes[id];
     double acc[R];
 #pragma unroll
     for (int k = 0; k < R; k++) acc[k] = 0.0;
@@ -64,20 +61,52 @@ hm_nest_base_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restr
 }
 
 __global__ void __launch_bounds__(NT)
+hm_nest_base_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ base, int nbase,
+                    const double *__restrict__ pts, const double *__restrict__ x, double *__restrict__ MU)
+{
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (b >= nbase) return;
+    const int id = base[b];
+    base_moments(nodes[id], id, lane, pts, x, MU);
+}
+
+// BASE (measured slower than the separate flat launch above -- 71 vs 28 + 35 us at N = 2^20: subtrees with
+// many finest boxes hold up their CTA -- and not used): the CTA first forms the moments of
+// the subtree's finest boxes from the points, then translates upwards -- no separate base launch.
+// NTH: 256 threads for the many small subtrees of the finest tier, 1024 for the few of the upper tiers,
+// whose depths are latency-bound (a warp per box, so a level of 32 boxes is one round instead of four).
+template <int NTH, bool BASE>
+__global__ void __launch_bounds__(NTH)
 hm_nest_up_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
                   const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
-                  const double *__restrict__ Mt, double *MU)
+                  const double *__restrict__ Mt, const double *__restrict__ pts, const double *__restrict__ x,
+                  double *MU)
 {
     __shared__ double sMt[2][R * R]; // transposed maps: [p][q]
+    __shared__ HmSubSched S;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    const int sub = sub0 + blockIdx.x;
+    const int g0 = sub_g0[sub], g1 = sub_g0[sub + 1];
+    hm_stage_schedule<false>(S, nodes, order, grp, nullptr, g0, g1);
     for (int i = t; i < 2 * R * R; i += blockDim.x) sMt[0][i] = Mt[i];
     __syncthreads();
-    const int sub = sub0 + blockIdx.x;
-    for (int g = sub_g0[sub]; g < sub_g0[sub + 1]; g++) {
-        const int e0 = grp[g], e1 = grp[g + 1];
+    const bool cached = S.cached;
+    const int eb = cached ? S.grp[0] : 0;
+    if (BASE) {
+        const int ea = grp[g0], ez = grp[g1];
+        for (int e = ea + warp; e < ez; e += nw) {
+            const int id = cached ? S.id[e - eb] : order[e];
+            const int c0 = cached ? S.aux[e - eb] : nodes[id].child0;
+            if (c0 < 0) base_moments(nodes[id], id, lane, pts, x, MU); // (warp-uniform)
+        }
+        __syncthreads();
+    }
+    for (int g = g0; g < g1; g++) {
+        const int e0 = cached ? S.grp[g - g0] : grp[g], e1 = cached ? S.grp[g - g0 + 1] : grp[g + 1];
         for (int e = e0 + warp; e < e1; e += nw) {
-            const int id = order[e];
-            const int c0 = nodes[id].child0;
+            const int id = cached ? S.id[e - eb] : order[e];
+            const int c0 = cached ? S.aux[e - eb] : nodes[id].child0;
             if (c0 >= 0 && lane < R) {
                 const double *m0 = MU + (size_t)c0 * R, *m1 = m0 + R;
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0; // four short chains instead of one of 40
@@ -104,20 +133,31 @@ hm_nest_core_kernel(int nboxes, const int32_t *__restrict__ rleaf_begin, const H
 {
     const int lane = threadIdx.x & 31;
     const int box = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-    if (box >= nboxes || lane >= R) return;
+    if (box >= nboxes) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int l = rleaf_begin[box]; l < rleaf_begin[box + 1]; l++) {
-        const HmNestLeaf lf = rleaf[l];
-        const double *__restrict__ G = cores + (size_t)lf.core * (R * R) + lane;
-        const double *__restrict__ mu = MU + (size_t)lf.cnode * R;
+    const int l0 = rleaf_begin[box], l1 = rleaf_begin[box + 1];
+    const int q = min(lane, R - 1); // lanes 20 .. 31 shadow lane 19 (they take part in the shuffles)
+    for (int lb = l0; lb < l1; lb += 32) {
+        // the records of up to 32 leaves in one load (a box has a handful), handed out by shuffles: the
+        // loads of consecutive leaves are independent of each other
+        const int nl = min(32, l1 - lb);
+        HmNestLeaf mine{0, 0};
+        if (lane < nl) mine = rleaf[lb + lane];
+#pragma unroll 2
+        for (int l = 0; l < nl; l++) {
+            const int core = __shfl_sync(0xffffffffu, mine.core, l), cnode = __shfl_sync(0xffffffffu, mine.cnode, l);
+            const double *__restrict__ G = cores + (size_t)core * (R * R) + q;
+            const double *__restrict__ mu = MU + (size_t)cnode * R;
 #pragma unroll
-        for (int p = 0; p < R; p += 4) {
-            s0 = fma(__ldg(G + p * R), mu[p], s0);
-            s1 = fma(__ldg(G + (p + 1) * R), mu[p + 1], s1);
-            s2 = fma(__ldg(G + (p + 2) * R), mu[p + 2], s2);
-            s3 = fma(__ldg(G + (p + 3) * R), mu[p + 3], s3);
+            for (int p = 0; p < R; p += 4) {
+                s0 = fma(__ldg(G + p * R), mu[p], s0);
+                s1 = fma(__ldg(G + (p + 1) * R), mu[p + 1], s1);
+                s2 = fma(__ldg(G + (p + 2) * R), mu[p + 2], s2);
+                s3 = fma(__ldg(G + (p + 3) * R), mu[p + 3], s3);
+            }
         }
     }
+    if (lane >= R) return;
     LAM[(size_t)box * R + lane] = (s0 + s1) + (s2 + s3);
 }
 
@@ -125,27 +165,38 @@ hm_nest_core_kernel(int nboxes, const int32_t *__restrict__ rleaf_begin, const H
 // downward pass: LAM[box] += M_which' LAM[parent]; at a finest box the series is evaluated at its
 // rows (Clenshaw):  y_i = (accumulate ? y_i : 0) + sum_q LAM[box][q] T_q(xi_i)
 // ---------------------------------------------------------------------------
-template <bool EVAL>
-__global__ void __launch_bounds__(NT)
+template <int NTH, bool EVAL>
+__global__ void __launch_bounds__(NTH)
 hm_nest_down_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
                     const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
                     const double *__restrict__ pts, const double *__restrict__ M, double *LAM, double *y,
                     int accumulate, int row_begin, int row_end)
 {
     __shared__ double sM[2][R * R]; // maps: [q][p]
+    __shared__ HmSubSched S;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    const int sub = sub0 + blockIdx.x;
+    const int g0 = sub_g0[sub], g1 = sub_g0[sub + 1];
+    hm_stage_schedule<true>(S, nodes, order, grp, nullptr, g0, g1);
     for (int i = t; i < 2 * R * R; i += blockDim.x) sM[0][i] = M[i];
     __syncthreads();
-    const int sub = sub0 + blockIdx.x;
-    for (int g = sub_g0[sub + 1] - 1; g >= sub_g0[sub]; g--) { // shallowest depth first
-        const int e0 = grp[g], e1 = grp[g + 1];
+    const bool cached = S.cached;
+    const int eb = cached ? S.grp[0] : 0;
+    for (int g = g1 - 1; g >= g0; g--) { // shallowest depth first
+        const int e0 = cached ? S.grp[g - g0] : grp[g], e1 = cached ? S.grp[g - g0 + 1] : grp[g + 1];
         for (int e = e0 + warp; e < e1; e += nw) {
-            const int id = order[e];
-            const HmNestNode nd = nodes[id];
+            const int id = cached ? S.id[e - eb] : order[e];
+            int pw;
+            if (cached) {
+                pw = S.aux[e - eb];
+            } else {
+                const int par = nodes[id].parent;
+                pw = par >= 0 ? par * 2 + nodes[id].which : -1;
+            }
             double *lam = LAM + (size_t)id * R;
-            if (nd.parent >= 0 && lane < R) {
-                const double *lp = LAM + (size_t)nd.parent * R;
-                const double *m = sM[nd.which];
+            if (pw >= 0 && lane < R) {
+                const double *lp = LAM + (size_t)(pw >> 1) * R;
+                const double *m = sM[pw & 1];
                 double s0 = lam[lane], s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
                 for (int q = 0; q < R; q += 4) {
@@ -156,6 +207,8 @@ hm_nest_down_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restr
                 }
                 lam[lane] = (s0 + s1) + (s2 + s3);
             }
+            HmNestNode nd;
+            if (EVAL) nd = nodes[id];
             if (EVAL && nd.child0 < 0) {
                 __syncwarp();
                 double cf[R];
@@ -351,10 +404,16 @@ cudaError_t hm_launch_nest_up(const HmNestDev &T, const double *pts, const doubl
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
+    constexpr int NTU = 512; // (16 K registers: fits beside three resident CTAs of the dense kernel)
     for (int k = 0; k < T.ntiers; k++) { // finest tier first
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
         if (n <= 0) continue;
-        hm_nest_up_kernel<<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], Mt, MU);
+        if (k == 0)
+            hm_nest_up_kernel<NT, false><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], Mt, pts,
+                                                                   x, MU);
+        else
+            hm_nest_up_kernel<NTU, false><<<(unsigned)n, NTU, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], Mt,
+                                                                      pts, x, MU);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -373,17 +432,28 @@ cudaError_t hm_launch_nest_core(int nboxes, const int32_t *rleaf_begin, const Hm
 // eval: the finest boxes also evaluate their series into y (otherwise hm_launch_nest_dense does, fused
 // with the dense leaves)
 cudaError_t hm_launch_nest_down(const HmNestDev &T, const double *pts, const double *M, double *LAM, double *y,
-                                int accumulate, int64_t row_begin, int64_t row_end, bool eval, cudaStream_t st)
+                                int accumulate, int64_t row_begin, int64_t row_end, bool eval, cudaStream_t st,
+                                cudaEvent_t before_finest)
 {
+    constexpr int NTU = 512; // (16 K registers: fits beside three resident CTAs of the dense kernel)
     for (int k = T.ntiers - 1; k >= 0; k--) { // coarsest tier first
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
+        if (k == 0 && before_finest) { // the finest tier evaluates into y: after whoever else writes y
+            cudaError_t e = cudaStreamWaitEvent(st, before_finest, 0);
+            if (e != cudaSuccess) return e;
+        }
         if (n <= 0) continue;
-        if (eval)
-            hm_nest_down_kernel<true><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], pts, M,
-                                                                 LAM, y, accumulate, (int)row_begin, (int)row_end);
-        else
-            hm_nest_down_kernel<false><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], pts, M,
-                                                                  LAM, y, accumulate, (int)row_begin, (int)row_end);
+        const int sub0 = T.tier_sub0[k];
+        if (k > 0) { // (no finest box up here: nothing to evaluate)
+            hm_nest_down_kernel<NTU, false><<<(unsigned)n, NTU, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M, LAM, y,
+                                                                        accumulate, (int)row_begin, (int)row_end);
+        } else if (eval) {
+            hm_nest_down_kernel<NT, true><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M, LAM, y,
+                                                                     accumulate, (int)row_begin, (int)row_end);
+        } else {
+            hm_nest_down_kernel<NT, false><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M, LAM, y,
+                                                                      accumulate, (int)row_begin, (int)row_end);
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

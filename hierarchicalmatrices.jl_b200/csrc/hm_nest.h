@@ -106,8 +106,10 @@ cudaError_t hm_launch_nest_up(const HmNestDev &T, const double *pts, const doubl
                               cudaStream_t st);
 cudaError_t hm_launch_nest_core(int nboxes, const int32_t *rleaf_begin, const HmNestLeaf *rleaf, const double *cores,
                                 const double *MU, double *LAM, cudaStream_t st);
+// before_finest: an event the launch of the finest tier (the one that evaluates into y) waits for
 cudaError_t hm_launch_nest_down(const HmNestDev &T, const double *pts, const double *M, double *LAM, double *y,
-                                int accumulate, int64_t row_begin, int64_t row_end, bool eval, cudaStream_t st);
+                                int accumulate, int64_t row_begin, int64_t row_end, bool eval, cudaStream_t st,
+                                cudaEvent_t before_finest = nullptr);
 // the dense leaves (items with dense runs only, F <= 128 rows): y (+)= K(rows, columns of the runs) x;
 // with ibox (finest row box of every item) the low-rank part is evaluated in the same pass
 struct HmPeers;

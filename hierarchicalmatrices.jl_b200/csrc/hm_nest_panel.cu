@@ -16,6 +16,7 @@
 
 #include "hm_kernels.cuh"
 #include "hm_nest.h"
+#include "hm_nest_dev.cuh"
 
 namespace {
 
@@ -117,8 +118,8 @@ hm_nest_base_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *_
 // ---------------------------------------------------------------------------
 constexpr int UPITCH = 44; // [q][20 w + p], 40 + 4
 
-template <int NB>
-__global__ void __launch_bounds__(NT)
+template <int NB, int NTH> // NTH: 256 threads in the finest tier, 512 in the few latency-bound subtrees above
+__global__ void __launch_bounds__(NTH)
 hm_nest_up_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
                         const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
                         const double *__restrict__ M, double *MUp)
@@ -131,13 +132,20 @@ hm_nest_up_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__r
         const int q = i / UPITCH, k = i - q * UPITCH;
         sA[q][k] = (q < R && k < 2 * R) ? M[(k / R) * (R * R) + q * R + (k % R)] : 0.0;
     }
-    __syncthreads();
+    __shared__ HmSubSched S;
     const int sub = sub0 + blockIdx.x;
-    for (int g = sub_g0[sub]; g < sub_g0[sub + 1]; g++) {
-        const int e0 = grp[g], nu = (grp[g + 1] - e0) * NCH;
+    const int g0 = sub_g0[sub], g1 = sub_g0[sub + 1];
+    hm_stage_schedule<false>(S, nodes, order, grp, nullptr, g0, g1);
+    __syncthreads();
+    const bool cached = S.cached;
+    const int eb = cached ? S.grp[0] : 0;
+    for (int g = g0; g < g1; g++) {
+        const int e0 = cached ? S.grp[g - g0] : grp[g];
+        const int nu = ((cached ? S.grp[g - g0 + 1] : grp[g + 1]) - e0) * NCH;
         for (int u = warp; u < nu; u += nw) {
-            const int id = order[e0 + u / NCH], ch = u % NCH;
-            const int c0 = nodes[id].child0;
+            const int e = e0 + u / NCH, ch = u % NCH;
+            const int id = cached ? S.id[e - eb] : order[e];
+            const int c0 = cached ? S.aux[e - eb] : nodes[id].child0;
             if (c0 < 0) continue; // (warp-uniform)
             double acc[3][NBW][2];
 #pragma unroll
@@ -146,26 +154,32 @@ hm_nest_up_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__r
                 for (int n = 0; n < NBW; n++) acc[a][n][0] = acc[a][n][1] = 0.0;
             const double *B = MUp + ((size_t)c0 * R + tig) * CS + ch * (NBW * 8) + gid; // 40 rows: both halves
 #pragma unroll
-            for (int j = 0; j < 2 * R / 4; j++) {
-                const int jj = j % (R / 4); // k-step inside its map: columns p = 4 jj .. 4 jj + 3
-                double bf[NBW];
+            for (int w = 0; w < 2; w++) {
+                // the five B fragment rows of one half in flight together (one L2 round trip, not five)
+                double bf[R / 4][NBW];
 #pragma unroll
-                for (int n = 0; n < NBW; n++) bf[n] = B[(size_t)(4 * j) * CS + n * 8];
-                // row block a (q = 8 a ..) meets columns p <= q: active iff 4 jj <= 8 a + 7
-                if (jj <= 1) {
-                    const double a0 = sA[gid][4 * j + tig];
+                for (int jj = 0; jj < R / 4; jj++)
 #pragma unroll
-                    for (int n = 0; n < NBW; n++) dmma884(acc[0][n][0], acc[0][n][1], a0, bf[n]);
-                }
-                if (jj <= 3) {
-                    const double a1 = sA[8 + gid][4 * j + tig];
+                    for (int n = 0; n < NBW; n++) bf[jj][n] = B[(size_t)(R * w + 4 * jj) * CS + n * 8];
 #pragma unroll
-                    for (int n = 0; n < NBW; n++) dmma884(acc[1][n][0], acc[1][n][1], a1, bf[n]);
-                }
-                {
-                    const double a2 = sA[16 + gid][4 * j + tig];
+                for (int jj = 0; jj < R / 4; jj++) { // k-step inside its map: columns p = 4 jj .. 4 jj + 3
+                    const int k = R * w + 4 * jj + tig;
+                    // row block a (q = 8 a ..) meets columns p <= q: active iff 4 jj <= 8 a + 7
+                    if (jj <= 1) {
+                        const double a0 = sA[gid][k];
 #pragma unroll
-                    for (int n = 0; n < NBW; n++) dmma884(acc[2][n][0], acc[2][n][1], a2, bf[n]);
+                        for (int n = 0; n < NBW; n++) dmma884(acc[0][n][0], acc[0][n][1], a0, bf[jj][n]);
+                    }
+                    if (jj <= 3) {
+                        const double a1 = sA[8 + gid][k];
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) dmma884(acc[1][n][0], acc[1][n][1], a1, bf[jj][n]);
+                    }
+                    {
+                        const double a2 = sA[16 + gid][k];
+#pragma unroll
+                        for (int n = 0; n < NBW; n++) dmma884(acc[2][n][0], acc[2][n][1], a2, bf[jj][n]);
+                    }
                 }
             }
             double *o = MUp + (size_t)id * R * CS + ch * (NBW * 8) + 2 * tig;
@@ -184,8 +198,8 @@ hm_nest_up_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__r
 }
 
 // fin[box] >= 0: a finest box; its completed coefficients go fragment-major into Sp at rows 20 fin[box] ..
-template <int NB>
-__global__ void __launch_bounds__(NT)
+template <int NB, int NTH>
+__global__ void __launch_bounds__(NTH)
 hm_nest_down_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ order,
                           const int32_t *__restrict__ grp, const int32_t *__restrict__ sub_g0, int sub0,
                           const int32_t *__restrict__ fin, const double *__restrict__ M, double *LAMp,
@@ -199,13 +213,28 @@ hm_nest_down_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *_
         const int w = i / (TROWS * R), pq = i - w * (TROWS * R), pr = pq / R, q = pq - pr * R;
         sA[w][pr][q] = pr < R ? M[w * (R * R) + q * R + pr] : 0.0;
     }
-    __syncthreads();
+    __shared__ HmSubSched S;
     const int sub = sub0 + blockIdx.x;
-    for (int g = sub_g0[sub + 1] - 1; g >= sub_g0[sub]; g--) { // shallowest depth first
-        const int e0 = grp[g], nu = (grp[g + 1] - e0) * NCH;
+    const int g0 = sub_g0[sub], g1 = sub_g0[sub + 1];
+    hm_stage_schedule<true>(S, nodes, order, grp, fin, g0, g1);
+    __syncthreads();
+    const bool cached = S.cached;
+    const int eb = cached ? S.grp[0] : 0;
+    for (int g = g1 - 1; g >= g0; g--) { // shallowest depth first
+        const int e0 = cached ? S.grp[g - g0] : grp[g];
+        const int nu = ((cached ? S.grp[g - g0 + 1] : grp[g + 1]) - e0) * NCH;
         for (int u = warp; u < nu; u += nw) {
-            const int id = order[e0 + u / NCH], ch = u % NCH;
-            const HmNestNode nd = nodes[id];
+            const int e = e0 + u / NCH, ch = u % NCH;
+            const int id = cached ? S.id[e - eb] : order[e];
+            int pw, f;
+            if (cached) {
+                pw = S.aux[e - eb];
+                f = S.fin[e - eb];
+            } else {
+                const int par = nodes[id].parent;
+                pw = par >= 0 ? par * 2 + nodes[id].which : -1;
+                f = fin[id];
+            }
             double acc[3][NBW][2];
             double *o = LAMp + (size_t)id * R * CS + ch * (NBW * 8) + 2 * tig;
 #pragma unroll
@@ -218,33 +247,34 @@ hm_nest_down_panel_kernel(const HmNestNode *__restrict__ nodes, const int32_t *_
                     acc[a][n][1] = v.y;
                 }
             }
-            if (nd.parent >= 0) { // (warp-uniform)
-                const double *B = LAMp + ((size_t)nd.parent * R + tig) * CS + ch * (NBW * 8) + gid;
-                const double(*A)[R] = sA[nd.which];
+            if (pw >= 0) { // (warp-uniform)
+                const double *B = LAMp + ((size_t)(pw >> 1) * R + tig) * CS + ch * (NBW * 8) + gid;
+                const double(*A)[R] = sA[pw & 1];
+                double bf[R / 4][NBW];
+#pragma unroll
+                for (int j = 0; j < R / 4; j++)
+#pragma unroll
+                    for (int n = 0; n < NBW; n++) bf[j][n] = B[(size_t)(4 * j) * CS + n * 8];
 #pragma unroll
                 for (int j = 0; j < R / 4; j++) {
-                    double bf[NBW];
-#pragma unroll
-                    for (int n = 0; n < NBW; n++) bf[n] = B[(size_t)(4 * j) * CS + n * 8];
                     // row block a (p = 8 a ..) meets q >= p: active iff 4 j + 3 >= 8 a
                     {
                         const double a0 = A[gid][4 * j + tig];
 #pragma unroll
-                        for (int n = 0; n < NBW; n++) dmma884(acc[0][n][0], acc[0][n][1], a0, bf[n]);
+                        for (int n = 0; n < NBW; n++) dmma884(acc[0][n][0], acc[0][n][1], a0, bf[j][n]);
                     }
                     if (j >= 2) {
                         const double a1 = A[8 + gid][4 * j + tig];
 #pragma unroll
-                        for (int n = 0; n < NBW; n++) dmma884(acc[1][n][0], acc[1][n][1], a1, bf[n]);
+                        for (int n = 0; n < NBW; n++) dmma884(acc[1][n][0], acc[1][n][1], a1, bf[j][n]);
                     }
                     if (j >= 4) {
                         const double a2 = A[16 + gid][4 * j + tig];
 #pragma unroll
-                        for (int n = 0; n < NBW; n++) dmma884(acc[2][n][0], acc[2][n][1], a2, bf[n]);
+                        for (int n = 0; n < NBW; n++) dmma884(acc[2][n][0], acc[2][n][1], a2, bf[j][n]);
                     }
                 }
             }
-            const int f = fin[id];
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 const int pr = 8 * a + gid;
@@ -334,8 +364,10 @@ cudaError_t run_up(const HmNestDev &T, const double *pts, const double *Xt, cons
     for (int k = 0; k < T.ntiers; k++) {
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
         if (n <= 0) continue;
-        hm_nest_up_panel_kernel<NB><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], M,
-                                                                    MUp);
+        if (k == 0)
+            hm_nest_up_panel_kernel<NB, NT><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], M, MUp);
+        else
+            hm_nest_up_panel_kernel<NB, 512><<<(unsigned)n, 512, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], M, MUp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -348,8 +380,12 @@ cudaError_t run_down(const HmNestDev &T, const int32_t *fin, const double *M, do
     for (int k = T.ntiers - 1; k >= 0; k--) {
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
         if (n <= 0) continue;
-        hm_nest_down_panel_kernel<CS / 8><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], fin, M,
-                                                                 LAMp, Sp);
+        if (k == 0)
+            hm_nest_down_panel_kernel<CS / 8, NT><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k],
+                                                                             fin, M, LAMp, Sp);
+        else
+            hm_nest_down_panel_kernel<CS / 8, 512><<<(unsigned)n, 512, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k],
+                                                                               fin, M, LAMp, Sp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

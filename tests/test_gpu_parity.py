@@ -999,6 +999,60 @@ def test_matrix_free_adjoint(hm, O, kernel, dist, N):
         assert abs(np.dot(w, Kv) - np.dot(got, v)) <= 1e-11 * np.linalg.norm(w) * np.linalg.norm(Kv)
 
 
+def test_matrix_free_nested_overlap_and_graph(hm, O):
+    """Nested-basis matvec: the dense leaves run on the plan's second stream beside the tree passes
+    (fork / join by events).  Same result as the single-stream form (HMB200_NEST_OVERLAP=0), with
+    accumulate, back to back on one stream, and captured into a CUDA graph and replayed."""
+    import torch
+    N = 12000   # (even: no first-kind point coincides with a second-kind one)
+    x, y, (a, b, c, d) = O.example_points(N, "cheb")
+    v, y0 = _vec(N, 31), _vec(N, 32)
+    ref = O.kernelmatrix(O.CAUCHY, x, y, a, b, c, d).matvec(v)
+    outs = []
+    for env in ("0", None):
+        if env:
+            os.environ["HMB200_NEST_OVERLAP"] = env
+        try:
+            K = hm.KernelMatrix(hm.cauchykernel, x, y, a, b, c, d, device=0, matrix_free=True)
+        finally:
+            os.environ.pop("HMB200_NEST_OVERLAP", None)
+        assert K.plan().form == 3
+        u = K * v
+        acc = y0.copy()
+        K.plan().matvec(v, acc, accumulate=True)
+        assert relinf(u, ref) <= TOL and relinf(acc - y0, ref) <= 1e-12
+        outs.append(u)
+    assert relinf(outs[0], outs[1]) <= 1e-13
+    # device pointers: dependent chain on one stream, eager and as a replayed graph
+    P = K.plan()
+    dev = torch.device("cuda", 0)
+    xd = torch.from_numpy(v).to(dev)
+    bufs = [torch.zeros(N, dtype=torch.float64, device=dev) for _ in range(3)]
+    st = torch.cuda.Stream(device=dev)
+
+    def chain():
+        src = xd
+        for bb in bufs:
+            P.matvec_device(src.data_ptr(), bb.data_ptr(), accumulate=False, stream=st.cuda_stream)
+            src = bb
+
+    with torch.cuda.stream(st):
+        chain()
+    st.synchronize()
+    eager = [bb.clone() for bb in bufs]
+    assert relinf(eager[0].cpu().numpy(), ref) <= TOL
+    for bb in bufs:
+        bb.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        chain()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    for e, bb in zip(eager, bufs):
+        assert torch.equal(e, bb)
+
+
 @pytest.mark.parametrize("nrhs", [2, 16, 17, 33, 64, 70])
 @pytest.mark.parametrize("kernel,dist,N", [("cauchykernel", "cheb", 4096), ("cauchykernel", "unif", 3000),
                                            ("coulombkernel", "quad", 1000), ("logkernel", "cheb", 77 * 2),

@@ -64,11 +64,14 @@ __global__ void __launch_bounds__(NT)
 hm_nest_base_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ base, int nbase,
                     const double *__restrict__ pts, const double *__restrict__ x, double *__restrict__ MU)
 {
+    hm_pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     if (b >= nbase) return;
     const int id = base[b];
-    base_moments(nodes[id], id, lane, pts, x, MU);
+    const HmNestNode nd = nodes[id];
+    hm_pdl_wait(); // (x may be the previous kernel's output; MU may still be read by it)
+    base_moments(nd, id, lane, pts, x, MU);
 }
 
 // BASE (measured slower than the separate flat launch above -- 71 vs 28 + 35 us at N = 2^20: subtrees with
@@ -88,9 +91,11 @@ hm_nest_up_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restric
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
     const int sub = sub0 + blockIdx.x;
     const int g0 = sub_g0[sub], g1 = sub_g0[sub + 1];
+    hm_pdl_launch_dependents();
     hm_stage_schedule<false>(S, nodes, order, grp, nullptr, g0, g1);
     for (int i = t; i < 2 * R * R; i += blockDim.x) sMt[0][i] = Mt[i];
     __syncthreads();
+    hm_pdl_wait();
     const bool cached = S.cached;
     const int eb = cached ? S.grp[0] : 0;
     if (BASE) {
@@ -131,11 +136,13 @@ __global__ void __launch_bounds__(NT)
 hm_nest_core_kernel(int nboxes, const int32_t *__restrict__ rleaf_begin, const HmNestLeaf *__restrict__ rleaf,
                     const double *__restrict__ cores, const double *__restrict__ MU, double *__restrict__ LAM)
 {
+    hm_pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int box = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     if (box >= nboxes) return;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const int l0 = rleaf_begin[box], l1 = rleaf_begin[box + 1];
+    hm_pdl_wait();
     const int q = min(lane, R - 1); // lanes 20 .. 31 shadow lane 19 (they take part in the shuffles)
     for (int lb = l0; lb < l1; lb += 32) {
         // the records of up to 32 leaves in one load (a box has a handful), handed out by shuffles: the
@@ -177,9 +184,11 @@ hm_nest_down_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restr
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
     const int sub = sub0 + blockIdx.x;
     const int g0 = sub_g0[sub], g1 = sub_g0[sub + 1];
+    hm_pdl_launch_dependents();
     hm_stage_schedule<true>(S, nodes, order, grp, nullptr, g0, g1);
     for (int i = t; i < 2 * R * R; i += blockDim.x) sM[0][i] = M[i];
     __syncthreads();
+    hm_pdl_wait();
     const bool cached = S.cached;
     const int eb = cached ? S.grp[0] : 0;
     for (int g = g1 - 1; g >= g0; g--) { // shallowest depth first
@@ -399,22 +408,18 @@ cudaError_t hm_launch_nest_up(const HmNestDev &T, const double *pts, const doubl
                               cudaStream_t st)
 {
     if (T.nbase > 0) {
-        hm_nest_base_kernel<<<(unsigned)((T.nbase + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(T.nodes, T.base, T.nbase, pts, x,
-                                                                                         MU);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = hm_launch_pdl(hm_nest_base_kernel, (unsigned)((T.nbase + NT / 32 - 1) / (NT / 32)), NT, st, T.nodes,
+                                      T.base, T.nbase, pts, x, MU);
         if (e != cudaSuccess) return e;
     }
     constexpr int NTU = 512; // (16 K registers: fits beside three resident CTAs of the dense kernel)
     for (int k = 0; k < T.ntiers; k++) { // finest tier first
         const int n = T.tier_sub0[k + 1] - T.tier_sub0[k];
         if (n <= 0) continue;
-        if (k == 0)
-            hm_nest_up_kernel<NT, false><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], Mt, pts,
-                                                                   x, MU);
-        else
-            hm_nest_up_kernel<NTU, false><<<(unsigned)n, NTU, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, T.tier_sub0[k], Mt,
-                                                                      pts, x, MU);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = k == 0 ? hm_launch_pdl(hm_nest_up_kernel<NT, false>, (unsigned)n, NT, st, T.nodes, T.order, T.grp,
+                                               T.sub_g0, T.tier_sub0[k], Mt, pts, x, MU)
+                               : hm_launch_pdl(hm_nest_up_kernel<NTU, false>, (unsigned)n, NTU, st, T.nodes, T.order, T.grp,
+                                               T.sub_g0, T.tier_sub0[k], Mt, pts, x, MU);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -424,9 +429,8 @@ cudaError_t hm_launch_nest_core(int nboxes, const int32_t *rleaf_begin, const Hm
                                 const double *MU, double *LAM, cudaStream_t st)
 {
     if (nboxes <= 0) return cudaSuccess;
-    hm_nest_core_kernel<<<(unsigned)((nboxes + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(nboxes, rleaf_begin, rleaf, cores,
-                                                                                   MU, LAM);
-    return cudaGetLastError();
+    return hm_launch_pdl(hm_nest_core_kernel, (unsigned)((nboxes + NT / 32 - 1) / (NT / 32)), NT, st, nboxes, rleaf_begin,
+                         rleaf, cores, MU, LAM);
 }
 
 // eval: the finest boxes also evaluate their series into y (otherwise hm_launch_nest_dense does, fused
@@ -444,17 +448,16 @@ cudaError_t hm_launch_nest_down(const HmNestDev &T, const double *pts, const dou
         }
         if (n <= 0) continue;
         const int sub0 = T.tier_sub0[k];
-        if (k > 0) { // (no finest box up here: nothing to evaluate)
-            hm_nest_down_kernel<NTU, false><<<(unsigned)n, NTU, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M, LAM, y,
-                                                                        accumulate, (int)row_begin, (int)row_end);
-        } else if (eval) {
-            hm_nest_down_kernel<NT, true><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M, LAM, y,
-                                                                     accumulate, (int)row_begin, (int)row_end);
-        } else {
-            hm_nest_down_kernel<NT, false><<<(unsigned)n, NT, 0, st>>>(T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M, LAM, y,
-                                                                      accumulate, (int)row_begin, (int)row_end);
-        }
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e;
+        if (k > 0) // (no finest box up here: nothing to evaluate)
+            e = hm_launch_pdl(hm_nest_down_kernel<NTU, false>, (unsigned)n, NTU, st, T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M,
+                              LAM, y, accumulate, (int)row_begin, (int)row_end);
+        else if (eval)
+            e = hm_launch_pdl(hm_nest_down_kernel<NT, true>, (unsigned)n, NT, st, T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M,
+                              LAM, y, accumulate, (int)row_begin, (int)row_end);
+        else
+            e = hm_launch_pdl(hm_nest_down_kernel<NT, false>, (unsigned)n, NT, st, T.nodes, T.order, T.grp, T.sub_g0, sub0, pts, M,
+                              LAM, y, accumulate, (int)row_begin, (int)row_end);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;

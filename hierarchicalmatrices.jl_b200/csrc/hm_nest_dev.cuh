@@ -43,3 +43,39 @@ __device__ __forceinline__ void hm_stage_schedule(HmSubSched &S, const HmNestNod
     }
     if (threadIdx.x == 0) S.cached = ok;
 }
+
+// Programmatic dependent launch (as in hm_kernels.cu): a kernel launched with the attribute may start while
+// its predecessor in the stream still runs; hm_pdl_wait() blocks until the predecessor has completed and its
+// writes are visible.  The tree passes are chains of short dependent launches: each kernel stages its
+// schedule and maps (plan-time tables nobody writes) before it waits, under the tail of the previous one.
+__device__ __forceinline__ void hm_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void hm_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#include <cstdlib>
+inline bool hm_pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HMB200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// only kernels that call hm_pdl_wait() before they touch what the predecessor wrote (and before their own
+// first global write) may be launched through this
+template <class... KArgs, class... Args>
+inline cudaError_t hm_launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = hm_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}

@@ -999,6 +999,39 @@ def test_matrix_free_adjoint(hm, O, kernel, dist, N):
         assert abs(np.dot(w, Kv) - np.dot(got, v)) <= 1e-11 * np.linalg.norm(w) * np.linalg.norm(Kv)
 
 
+@pytest.mark.parametrize("N", [1, 2, 39, 80, 81, 161, 257, 1281])
+def test_matrix_free_small_and_ragged(hm, O, N):
+    """Matrix-free plans on the sizes where the tree degenerates (one dense leaf, one split, ragged halves):
+    matvec, accumulate, 3 and 17 right-hand sides and the adjoint against the oracle; rectangular operators
+    (more rows than columns and the other way round)."""
+    for nx, ny in ((N, N), (N, max(1, (2 * N) // 3)), (max(1, N // 2), N)):
+        i = np.arange(1, nx + 1, dtype=np.float64)
+        j = np.arange(1, ny + 1, dtype=np.float64)
+        x, y = 1.0 - 2.0 * (i - 0.5) / nx, 1.0 - 2.0 * (j - 0.25) / ny - 1e-3
+        ref = O.kernelmatrix(O.CAUCHY, x, y, 1.0, -1.0, 1.0, -1.0)
+        K = hm.KernelMatrix(hm.cauchykernel, x, y, 1.0, -1.0, 1.0, -1.0, device=0, matrix_free=True)
+        P = K.plan()
+        v, w, y0 = _vec(ny, 41), _vec(nx, 42), _vec(nx, 43)
+        want = ref.matvec(v)
+        scale = max(np.max(np.abs(want)), 1e-300)
+        got = np.zeros(nx)
+        P.matvec(v, got, accumulate=False)
+        assert np.max(np.abs(got - want)) <= TOL * scale
+        acc = y0.copy()
+        P.matvec(v, acc, accumulate=True)
+        assert np.max(np.abs(acc - y0 - want)) <= 1e-12 * max(scale, np.max(np.abs(y0)))
+        for nrhs in (3, 17):
+            X = np.asfortranarray(np.random.default_rng(nrhs).standard_normal((ny, nrhs)))
+            Y = K * X
+            for c in range(nrhs):
+                wc = ref.matvec(np.ascontiguousarray(X[:, c]))
+                assert np.max(np.abs(Y[:, c] - wc)) <= TOL * max(np.max(np.abs(wc)), 1e-300)
+        wt = ref.rmatvec(w)
+        gt = np.zeros(ny)
+        P.rmatvec(w, gt, accumulate=False)
+        assert np.max(np.abs(gt - wt)) <= TOL * max(np.max(np.abs(wt)), 1e-300)
+
+
 def test_matrix_free_nested_overlap_and_graph(hm, O):
     """Nested-basis matvec: the dense leaves run on the plan's second stream beside the tree passes
     (fork / join by events).  Same result as the single-stream form (HMB200_NEST_OVERLAP=0), with

@@ -12,6 +12,8 @@
 #include "hm_layout.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <new>
 #include <numeric>
@@ -535,8 +537,24 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         const int NC = HM_NCHUNK;
         L.xchunk.assign((size_t)NC + 1, ncols);
         L.ychunk.assign((size_t)NC + 1, rhi);
+        // Unequal chunks: only the first upload and the last download are exposed (nothing computes beside
+        // them), so x goes up as 1/16, 3/16, 4/16, 8/16 of the columns and y comes down as 8/16, 4/16, 3/16,
+        // 1/16 of the rows; every later copy is shorter than the kernels it hides behind.
+        // (HMB200_CHUNKS=equal: four quarters, the round-1 form.)
+        static_assert(HM_NCHUNK == 4, "chunk fractions are written for four chunks");
+        const char *ce = getenv("HMB200_CHUNKS");
+        const bool equal = ce && ce[0] == 'e';
+        int64_t xcum[5] = {0, equal ? 16 : 4, equal ? 32 : 16, equal ? 48 : 32, 64};
+        int64_t ycum[5] = {0, equal ? 16 : 32, equal ? 32 : 48, equal ? 48 : 60, 64};
+        if (ce && ce[0] >= '0' && ce[0] <= '9') { // experiment: "a,b,c" = cumulative 64ths of x; y mirrored
+            int a = 0, b = 0, c = 0;
+            if (sscanf(ce, "%d,%d,%d", &a, &b, &c) == 3 && 0 < a && a < b && b < c && c < 64) {
+                xcum[1] = a, xcum[2] = b, xcum[3] = c;
+                ycum[1] = 64 - c, ycum[2] = 64 - b, ycum[3] = 64 - a;
+            }
+        }
         for (int k = 0; k < NC; k++) {
-            L.xchunk[(size_t)k] = (ncols * k / NC) & ~(int64_t)511;
+            L.xchunk[(size_t)k] = (ncols * xcum[k] / 64) & ~(int64_t)511;
             L.ychunk[(size_t)k] = rlo;
         }
         auto chunk_of = [&](const std::vector<int64_t> &bnd, int64_t pos) {
@@ -565,7 +583,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
             size_t pos = 0;
             std::vector<std::vector<size_t>> groups((size_t)NC);
             for (int k = 0; k < NC; k++) {
-                const int64_t target = rlo + rows * (k + 1) / NC;
+                const int64_t target = rlo + rows * ycum[k + 1] / 64;
                 L.ychunk[(size_t)k] = pos < order.size() ? L.items3[order[pos]].out : rhi;
                 while (pos < order.size() && (k == NC - 1 || L.items3[order[pos]].out < target)) groups[(size_t)k].push_back(order[pos++]);
             }

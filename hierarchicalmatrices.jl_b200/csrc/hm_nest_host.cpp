@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -81,7 +83,7 @@ struct Trie {
     }
 };
 
-// Boxes are grouped into tiers by their point count (tier k: at most HM_NEST_TIER0 * 32^k points) and
+// Boxes are grouped into tiers by their point count (tier k: at most HM_NEST_TIER0 * HM_NEST_GROWTH^k points) and
 // every maximal connected set of boxes of one tier is a subtree handled by one CTA.  A box's halves
 // are in its own subtree (deeper, so earlier in the upward order) or in a lower tier (an earlier
 // launch).  Cutting by points rather than depth keeps the subtrees balanced on graded point sets
@@ -92,11 +94,20 @@ void schedule(const Trie &T, HmNestTree &out)
     const size_t nn = T.nodes.size();
     std::vector<int32_t> tier(nn);
     int ntiers = 1;
+    // (HMB200_NEST_TIERS="points of the finest tier,growth per tier": tuning experiments)
+    int64_t tier0 = HM_NEST_TIER0, growth = HM_NEST_GROWTH;
+    if (const char *e = getenv("HMB200_NEST_TIERS")) {
+        long a = 0, b = 0;
+        if (sscanf(e, "%ld,%ld", &a, &b) == 2 && a >= HM_NEST_BASE && b >= 2) {
+            tier0 = a;
+            growth = b;
+        }
+    }
     for (size_t i = 0; i < nn; i++) {
         int k = 0;
-        int64_t cap = HM_NEST_TIER0;
+        int64_t cap = tier0;
         while (T.nodes[i].np > cap) {
-            cap *= 32;
+            cap *= growth;
             k++;
         }
         tier[i] = k;

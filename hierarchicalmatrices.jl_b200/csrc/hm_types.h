@@ -101,6 +101,3 @@ struct HmFreeEnt {
     int64_t fofs;     // offset of the leaf's ranks inside the item's partial sums
 };
 
-struct HmLaunchParams {
-    int threads = 256;
-};

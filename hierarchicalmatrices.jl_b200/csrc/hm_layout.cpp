@@ -12,6 +12,16 @@
 #include "hm_layout.h"
 
 #include <algorithm>
+#include <chrono>
+static void hm_trace_point(const char *name)
+{
+    static std::chrono::steady_clock::time_point t_prev = std::chrono::steady_clock::now();
+    if (!getenv("HMB200_PLAN_TRACE")) return;
+    auto t_now = std::chrono::steady_clock::now();
+    fprintf(stderr, "plan %s: +%.3f s\n", name, std::chrono::duration<double>(t_now - t_prev).count());
+    t_prev = t_now;
+}
+#define HM_TRACE_POINT(name) hm_trace_point(name)
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -211,6 +221,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
     L.part = part;
     L.nparts = nparts;
 
+    HM_TRACE_POINT("0");
     // ---- accounting over the whole operator (SURVEY 8d formula) ----
     for (const HmLeaf &l : all) {
         if (l.kind == HM_LEAF_DENSE) {
@@ -229,6 +240,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
     L.row_begin = rlo;
     L.row_end = rhi;
 
+    HM_TRACE_POINT("1");
     // ---- leaves of this part ----
     for (size_t i = 0; i < all.size(); i++) {
         const HmLeaf &l = all[i];
@@ -241,6 +253,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
     const size_t nl = lv.size();
     if (nl >= ((size_t)1 << 31)) return "too many leaves";
 
+    HM_TRACE_POINT("2");
     // ---- stage 2 tables ----
     std::vector<int32_t> core_of(nl, -1);
     for (size_t i = 0; i < nl; i++) {
@@ -282,6 +295,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
     std::vector<AdjCol> adj_cols;
     std::vector<AdjQ> adj_q;
 
+    HM_TRACE_POINT("3");
     // ---- stage 3: row segments ----
     {
         std::vector<int64_t> b{rlo, rhi};
@@ -306,6 +320,11 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         };
         std::vector<Tmp> tmp;
         tmp.reserve(np);
+        // one run / fill entry (and one adjoint entry) per (piece, covering leaf) pair, a few more where a
+        // leaf's columns are cut: reserved up front, these vectors hold millions of records at N = 2^22
+        L.runs.reserve(L.runs.size() + cov.idx.size() + np);
+        L.fill3.reserve(L.fill3.size() + cov.idx.size() + np);
+        adj_q.reserve(adj_q.size() + cov.idx.size());
         int64_t slab = 0;
         int maxround = 0;
         int64_t qwords = 0;
@@ -391,6 +410,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         for (size_t r = 1; r < L.round_begin.size(); r++) L.round_begin[r] += L.round_begin[r - 1];
     }
 
+    HM_TRACE_POINT("4");
     // ---- stage 1: column segments ----
     hm_fault_checkpoint();
     {
@@ -422,6 +442,9 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
                 hi = l.col0 + l.n;
                 return true;
             });
+            L.fill1.reserve(L.fill1.size() + cov.idx.size());
+            L.s1ent.reserve(L.s1ent.size() + cov.idx.size());
+            pend.reserve(pend.size() + cov.idx.size());
             for (size_t p = 0; p < np; p++) {
                 if (cov.ptr[p + 1] == cov.ptr[p]) continue;
                 int64_t ps = starts[p], pe = starts[p + 1];
@@ -532,6 +555,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         }
     }
 
+    HM_TRACE_POINT("5");
     // ---- chunked orderings for the host-pointer path ----
     {
         const int NC = HM_NCHUNK;
@@ -600,6 +624,7 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         }
     }
 
+    HM_TRACE_POINT("6");
     // ---- adjoint tables ----
     {
         if (L.pq_words >= ((int64_t)1 << 31) - 64) return "adjoint work buffer too long";
@@ -651,5 +676,6 @@ std::string hm_build_layout(const std::vector<HmLeaf> &all, int64_t nrows, int64
         if ((int64_t)it.Fp * it.S >= ((int64_t)1 << 31)) return "stage-1 item too large";
     for (const HmItem &it : L.items3)
         if ((int64_t)it.Fp * it.S >= ((int64_t)1 << 31)) return "stage-3 item too large";
+    HM_TRACE_POINT("end");
     return "";
 }

@@ -95,6 +95,45 @@ def test_kernel_tree_reference_error(hm, O):
     assert rc == 0 and s.nrows == 200
 
 
+def test_kernel_tree_bisection_equals_linear_scan(hm, O):
+    """indsplit (BarycentricMatrix.jl:299-307) is a linear scan; on point sets verified to be non-increasing
+    the planner bisects instead.  Same leaves -- ranges, offsets, boxes, error returns -- as the literal scan
+    (HMB200_TREE_LINEAR=1) on graded, uniform, tied, rectangular and ill-fitting inputs and on the sizes where
+    ranges become empty."""
+    dp = C.POINTER(C.c_double)
+
+    def leaves(x, y, a, b, c, d):
+        cnt = C.c_int64()
+        rc = hm.lib().hm_kernel_tree_leaves(x.ctypes.data_as(dp), len(x), y.ctypes.data_as(dp), len(y), a, b, c, d,
+                                            None, 0, C.byref(cnt))
+        if rc:
+            return ("error", rc)
+        arr = (hm._lib.TreeLeaf * max(cnt.value, 1))()
+        hm._lib.check(hm.lib().hm_kernel_tree_leaves(x.ctypes.data_as(dp), len(x), y.ctypes.data_as(dp), len(y),
+                                                     a, b, c, d, arr, cnt.value, C.byref(cnt)))
+        return [(l.kind, l.rank, l.row0, l.col0, l.m, l.n, l.xi0, l.yj0, l.a, l.b, l.c, l.d) for l in arr[:cnt.value]]
+
+    cases = [O.example_points(N, dist) for N in (1, 2, 3, 39, 79, 80, 81, 160, 161, 257, 1000, 4096, 20011)
+             for dist in ("cheb", "unif", "quad")]
+    rng = np.random.default_rng(1)
+    for N in (500, 5000):
+        x = np.sort(np.round(rng.uniform(-1, 1, N), 3))[::-1].copy()      # ties
+        y = np.sort(rng.uniform(-1, 1, N // 2))[::-1].copy()              # rectangular
+        cases.append((x, y, (1.0, -1.0, 1.0, -1.0)))
+        cases.append((x, y, (0.5, -0.5, 2.0, -2.0)))                      # boxes that do not fit the points
+    xs = np.linspace(1.0, -1.0, 3000)
+    xs[10], xs[11] = xs[11], xs[10]                                       # not monotone: literal scan either way
+    cases.append((xs, xs.copy(), (1.0, -1.0, 1.0, -1.0)))
+    try:
+        for x, y, (a, b, c, d) in cases:
+            os.environ.pop("HMB200_TREE_LINEAR", None)
+            fast = leaves(x, y, a, b, c, d)
+            os.environ["HMB200_TREE_LINEAR"] = "1"
+            assert leaves(x, y, a, b, c, d) == fast
+    finally:
+        os.environ.pop("HMB200_TREE_LINEAR", None)
+
+
 def test_layout_stats_match_survey(hm, O):
     """leaf counts and algorithmic bytes (the roofline numerator)."""
     for dist, nd, nl in (("cheb", 274, 510), ("unif", 190, 342)):

@@ -1029,13 +1029,16 @@ static int32_t assemble_kernel_impl(const double *x, int64_t nx, const double *y
             cudaGetLastError();
             return fail(HM_ERR_CUDA, "point upload failed: %s", cudaGetErrorString(e));
         }
+        hm_trace_point("assemble: tree + layout + point upload");
         int32_t st = materialize(P, P->f_px.p, P->f_py.p);
+        hm_trace_point("assemble: materialize");
         if (st != HM_OK) {
             delete P;
             return st;
         }
         if (matrix_free && P->free_cheb) {
             st = build_nested(P, x, nx, y, ny, a, b, c, d);
+            hm_trace_point("assemble: nested form");
             if (st != HM_OK) {
                 delete P;
                 return st;

@@ -13,7 +13,7 @@
 
 #include <algorithm>
 #include <chrono>
-static void hm_trace_point(const char *name)
+void hm_trace_point(const char *name)
 {
     static std::chrono::steady_clock::time_point t_prev = std::chrono::steady_clock::now();
     if (!getenv("HMB200_PLAN_TRACE")) return;

@@ -85,3 +85,6 @@ void hm_fault_checkpoint();
 // Returns "" on success, else an error message.
 std::string hm_build_layout(const std::vector<HmLeaf> &all_leaves, int64_t nrows, int64_t ncols,
                             int part, int nparts, const HmLayoutParams &prm, HmLayout &out);
+
+// HMB200_PLAN_TRACE=1: time since the previous trace point, on stderr (plan-time diagnostics)
+void hm_trace_point(const char *name);

@@ -254,12 +254,14 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
     }
     if (L.core_words) HM_CUDA(cudaMemsetAsync(P->core.p, 0, (size_t)L.core_words * 8, st));
     HM_CUDA(cudaMemsetAsync(P->partial.p, 0, P->partial.n * 8, st));
+    hm_trace_point("materialize: allocations");
     HM_CUDA(P->items1.upload(L.items1, st));
     HM_CUDA(P->items3.upload(L.items3, st));
     HM_CUDA(P->runs.upload(L.runs, st));
     HM_CUDA(P->cores.upload(L.cores, st));
     HM_CUDA(P->plist.upload(L.plist, st));
     HM_CUDA(P->s1ent.upload(L.s1ent, st));
+    hm_trace_point("materialize: item / run / core tables uploaded");
     HM_CUDA(P->counters.alloc(std::max<size_t>(L.cores.size(), 1)));
     HM_CUDA(cudaMemsetAsync(P->counters.p, 0, P->counters.n * sizeof(int), st));
     {
@@ -290,6 +292,7 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
         int zcap = 2;
         for (const HmItem &it : L.items3) zcap = std::max(zcap, (int)it.S);
         P->free3_zcap = (zcap + 1) & ~1;
+        hm_trace_point("materialize: limits");
         std::vector<HmFreeEnt> ent1(L.fill1.size());
         for (const HmItem &it : L.items1)
             for (int32_t e = it.run0; e < it.run0 + it.nrun; e++) {
@@ -303,12 +306,14 @@ int32_t materialize(hm_plan *P, const double *dpx, const double *dpy)
             const HmLeaf &l = L.leaves[(size_t)f.leaf];
             run3[i] = HmFreeRun{0.5 * (l.a + l.b), 0.5 * (l.b - l.a), l.xi0 + f.off, l.yj0 + f.k0, f.k0, f.kn};
         }
+        hm_trace_point("materialize: free tables built");
         DevBuf<HmLeaf> dleaves;
         DevBuf<int32_t> dcore_leaf;
         HM_CUDA(dleaves.upload(L.leaves, st));
         HM_CUDA(P->f_ent1.upload(ent1, st));
         HM_CUDA(P->f_run3.upload(run3, st));
         HM_CUDA(dcore_leaf.upload(L.core_leaf, st));
+        hm_trace_point("materialize: free tables uploaded");
         HM_CUDA(hm_launch_fillcore(P->cores.p, dcore_leaf.p, (int64_t)L.cores.size(), dleaves.p, P->core.p,
                                    P->cheb, P->kernel_id, st));
         {

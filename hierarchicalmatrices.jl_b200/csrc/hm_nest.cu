@@ -132,40 +132,56 @@ hm_nest_up_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restric
 // ---------------------------------------------------------------------------
 // the leaves: LAM[row box][q] = sum over the box's leaves of G_leaf[q][:] . MU[column box of the leaf]
 // ---------------------------------------------------------------------------
+// Lanes (r, j) = (lane / 10, lane % 10), r < 3: lane (r, j) multiplies the rows p = r, r + 3, r + 6, ... of the
+// core (stored [p][q], q fastest: 160 bytes per row) with 16-byte loads of (G[p][2j], G[p][2j + 1]) -- one load
+// instruction of the warp covers three rows, seven cover the core -- against mu[p], which the warp fetches with
+// one coalesced load and hands round by shuffles: 8 memory requests per leaf instead of 40 (the kernel is bound
+// by outstanding requests, not by bytes or flops).  The three partial sums of a coefficient pair are added in
+// the order r = 0, 1, 2: deterministic.
 __global__ void __launch_bounds__(NT)
 hm_nest_core_kernel(int nboxes, const int32_t *__restrict__ rleaf_begin, const HmNestLeaf *__restrict__ rleaf,
                     const double *__restrict__ cores, const double *__restrict__ MU, double *__restrict__ LAM)
 {
+    static_assert(R == 20, "lane mapping of hm_nest_core_kernel is written for rank 20");
     hm_pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int box = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     if (box >= nboxes) return;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const int l0 = rleaf_begin[box], l1 = rleaf_begin[box + 1];
     hm_pdl_wait();
-    const int q = min(lane, R - 1); // lanes 20 .. 31 shadow lane 19 (they take part in the shuffles)
+    const int r = lane / 10, j = lane - 10 * r; // lanes 30, 31: r = 3, idle
+    const bool act = r < 3;
+    double ax = 0.0, ay = 0.0;
     for (int lb = l0; lb < l1; lb += 32) {
-        // the records of up to 32 leaves in one load (a box has a handful), handed out by shuffles: the
-        // loads of consecutive leaves are independent of each other
         const int nl = min(32, l1 - lb);
         HmNestLeaf mine{0, 0};
         if (lane < nl) mine = rleaf[lb + lane];
-#pragma unroll 2
+#pragma unroll 1
         for (int l = 0; l < nl; l++) {
             const int core = __shfl_sync(0xffffffffu, mine.core, l), cnode = __shfl_sync(0xffffffffu, mine.cnode, l);
-            const double *__restrict__ G = cores + (size_t)core * (R * R) + q;
-            const double *__restrict__ mu = MU + (size_t)cnode * R;
+            const double2 *__restrict__ G2 = reinterpret_cast<const double2 *>(cores + (size_t)core * (R * R)) + j;
+            const double mv = MU[(size_t)cnode * R + min(lane, R - 1)];
+            double2 g[7];
 #pragma unroll
-            for (int p = 0; p < R; p += 4) {
-                s0 = fma(__ldg(G + p * R), mu[p], s0);
-                s1 = fma(__ldg(G + (p + 1) * R), mu[p + 1], s1);
-                s2 = fma(__ldg(G + (p + 2) * R), mu[p + 2], s2);
-                s3 = fma(__ldg(G + (p + 3) * R), mu[p + 3], s3);
+            for (int i = 0; i < 7; i++) {
+                const int p = min(3 * i + (act ? r : 0), R - 1);
+                g[i] = __ldg(G2 + p * (R / 2));
+            }
+#pragma unroll
+            for (int i = 0; i < 7; i++) {
+                const int p = 3 * i + r;
+                const double m = __shfl_sync(0xffffffffu, mv, min(p, R - 1));
+                if (act && p < R) {
+                    ax = fma(g[i].x, m, ax);
+                    ay = fma(g[i].y, m, ay);
+                }
             }
         }
     }
-    if (lane >= R) return;
-    LAM[(size_t)box * R + lane] = (s0 + s1) + (s2 + s3);
+    const double bx = __shfl_sync(0xffffffffu, ax, min(lane + 10, 31)), by = __shfl_sync(0xffffffffu, ay, min(lane + 10, 31));
+    const double cx = __shfl_sync(0xffffffffu, ax, min(lane + 20, 31)), cy = __shfl_sync(0xffffffffu, ay, min(lane + 20, 31));
+    if (lane < 10)
+        reinterpret_cast<double2 *>(LAM + (size_t)box * R)[lane] = make_double2((ax + bx) + cx, (ay + by) + cy);
 }
 
 // ---------------------------------------------------------------------------

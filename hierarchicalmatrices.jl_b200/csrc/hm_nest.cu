@@ -112,17 +112,21 @@ hm_nest_up_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restric
         for (int e = e0 + warp; e < e1; e += nw) {
             const int id = cached ? S.id[e - eb] : order[e];
             const int c0 = cached ? S.aux[e - eb] : nodes[id].child0;
-            if (c0 >= 0 && lane < R) {
-                const double *m0 = MU + (size_t)c0 * R, *m1 = m0 + R;
+            if (c0 >= 0) { // (warp-uniform)
+                // the 40 moments of the two halves in two coalesced loads, handed round by shuffles (40
+                // broadcast loads are 40 memory requests; the pass is bound by requests in flight)
+                const int q = min(lane, R - 1);
+                const double *m0 = MU + (size_t)c0 * R;
+                const double v0 = m0[q], v1 = m0[R + q];
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0; // four short chains instead of one of 40
 #pragma unroll
                 for (int p = 0; p < R; p += 2) {
-                    s0 = fma(sMt[0][p * R + lane], m0[p], s0);
-                    s1 = fma(sMt[0][(p + 1) * R + lane], m0[p + 1], s1);
-                    s2 = fma(sMt[1][p * R + lane], m1[p], s2);
-                    s3 = fma(sMt[1][(p + 1) * R + lane], m1[p + 1], s3);
+                    s0 = fma(sMt[0][p * R + q], __shfl_sync(0xffffffffu, v0, p), s0);
+                    s1 = fma(sMt[0][(p + 1) * R + q], __shfl_sync(0xffffffffu, v0, p + 1), s1);
+                    s2 = fma(sMt[1][p * R + q], __shfl_sync(0xffffffffu, v1, p), s2);
+                    s3 = fma(sMt[1][(p + 1) * R + q], __shfl_sync(0xffffffffu, v1, p + 1), s3);
                 }
-                MU[(size_t)id * R + lane] = (s0 + s1) + (s2 + s3);
+                if (lane < R) MU[(size_t)id * R + lane] = (s0 + s1) + (s2 + s3);
             }
         }
         __syncthreads();
@@ -219,18 +223,19 @@ hm_nest_down_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restr
                 pw = par >= 0 ? par * 2 + nodes[id].which : -1;
             }
             double *lam = LAM + (size_t)id * R;
-            if (pw >= 0 && lane < R) {
-                const double *lp = LAM + (size_t)(pw >> 1) * R;
+            if (pw >= 0) { // (warp-uniform)
+                const int ql = min(lane, R - 1);
+                const double pv = LAM[(size_t)(pw >> 1) * R + ql]; // the parent's coefficients: one coalesced load
                 const double *m = sM[pw & 1];
-                double s0 = lam[lane], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                double s0 = lam[ql], s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
                 for (int q = 0; q < R; q += 4) {
-                    s0 = fma(m[q * R + lane], lp[q], s0);
-                    s1 = fma(m[(q + 1) * R + lane], lp[q + 1], s1);
-                    s2 = fma(m[(q + 2) * R + lane], lp[q + 2], s2);
-                    s3 = fma(m[(q + 3) * R + lane], lp[q + 3], s3);
+                    s0 = fma(m[q * R + ql], __shfl_sync(0xffffffffu, pv, q), s0);
+                    s1 = fma(m[(q + 1) * R + ql], __shfl_sync(0xffffffffu, pv, q + 1), s1);
+                    s2 = fma(m[(q + 2) * R + ql], __shfl_sync(0xffffffffu, pv, q + 2), s2);
+                    s3 = fma(m[(q + 3) * R + ql], __shfl_sync(0xffffffffu, pv, q + 3), s3);
                 }
-                lam[lane] = (s0 + s1) + (s2 + s3);
+                if (lane < R) lam[lane] = (s0 + s1) + (s2 + s3);
             }
             HmNestNode nd;
             if (EVAL) nd = nodes[id];

@@ -1185,8 +1185,11 @@ int32_t hm_matvec_device_peers(hm_plan *p, const double *dx, double *dy, int32_t
                 HM_CUDA(hm_launch_nest_core(p->n_rows.nnodes, p->n_rleaf_begin.p, p->n_rleaf.p, p->n_cores.p, p->n_MU.p,
                                             p->n_LAM.p, hs));
                 if (ev) HM_CUDA(cudaEventRecord(ev[2], st));
-                HM_CUDA(hm_launch_nest_down(p->n_rows, p->f_px.p, M, p->n_LAM.p, dy, 1, L.row_begin, L.row_end, true, hs,
-                                            p->ev_dense));
+                // translations of every tier without waiting for the dense kernel; only the evaluation adds to
+                // the rows it wrote
+                HM_CUDA(hm_launch_nest_down(p->n_rows, p->f_px.p, M, p->n_LAM.p, dy, 1, L.row_begin, L.row_end, false, hs));
+                HM_CUDA(cudaStreamWaitEvent(hs, p->ev_dense, 0));
+                HM_CUDA(hm_launch_nest_eval(p->n_rows, p->f_px.p, p->n_LAM.p, dy, 1, L.row_begin, L.row_end, hs));
                 HM_CUDA(cudaEventRecord(p->ev_join, hs));
                 HM_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
                 if (ev) {

@@ -266,6 +266,42 @@ hm_nest_down_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restr
 }
 
 // ---------------------------------------------------------------------------
+// evaluation alone: y_i (+)= sum_q LAM[box][q] T_q(xi_i) over the rows of every finest box (a warp per box).
+// When the dense leaves run beside the tree passes, the translations of the finest tier need not wait for
+// them -- only this short kernel does, so the tail after the dense kernel is the evaluation, not the tier.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+hm_nest_eval_kernel(const HmNestNode *__restrict__ nodes, const int32_t *__restrict__ base, int nbase,
+                    const double *__restrict__ pts, const double *__restrict__ LAM, double *y, int accumulate,
+                    int row_begin, int row_end)
+{
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    if (b >= nbase) return;
+    const int id = base[b];
+    const HmNestNode nd = nodes[id];
+    const double mine = LAM[(size_t)id * R + min(lane, R - 1)]; // the 20 coefficients: one coalesced load
+    double cf[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) cf[k] = __shfl_sync(0xffffffffu, mine, k);
+    const double *__restrict__ pp = pts + nd.p0;
+    for (int i = lane; i < nd.np; i += 32) {
+        const int row = nd.p0 + i;
+        if (row < row_begin || row >= row_end) continue;
+        const double xi = (pp[i] - nd.mid) * nd.ih, two = xi + xi;
+        double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+        for (int k = R - 1; k >= 1; k--) {
+            const double nb = fma(two, b1, cf[k]) - b2;
+            b2 = b1;
+            b1 = nb;
+        }
+        const double v = fma(xi, b1, cf[0]) - b2;
+        y[row] = (accumulate ? y[row] : 0.0) + v;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // dense leaves: y[rows of the item] += sum over its dense runs of K(x_i, y_j) v_j, entries evaluated on
 // the fly (src/KernelMatrix.jl:57-60, src/algebra.jl:37-48).  A warp owns an item (a row segment of at
 // most 128 rows, up to four rows per lane) and walks the columns of its runs; the column point and the
@@ -482,4 +518,13 @@ cudaError_t hm_launch_nest_down(const HmNestDev &T, const double *pts, const dou
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+cudaError_t hm_launch_nest_eval(const HmNestDev &T, const double *pts, const double *LAM, double *y, int accumulate,
+                                int64_t row_begin, int64_t row_end, cudaStream_t st)
+{
+    if (T.nbase <= 0) return cudaSuccess;
+    hm_nest_eval_kernel<<<(unsigned)((T.nbase + NT / 32 - 1) / (NT / 32)), NT, 0, st>>>(T.nodes, T.base, T.nbase, pts, LAM, y,
+                                                                                     accumulate, (int)row_begin, (int)row_end);
+    return cudaGetLastError();
 }

@@ -111,6 +111,9 @@ cudaError_t hm_launch_nest_core(int nboxes, const int32_t *rleaf_begin, const Hm
 cudaError_t hm_launch_nest_down(const HmNestDev &T, const double *pts, const double *M, double *LAM, double *y,
                                 int accumulate, int64_t row_begin, int64_t row_end, bool eval, cudaStream_t st,
                                 cudaEvent_t before_finest = nullptr);
+// evaluation of the finished series of every finest box at its rows (after hm_launch_nest_down(..., eval = false))
+cudaError_t hm_launch_nest_eval(const HmNestDev &T, const double *pts, const double *LAM, double *y, int accumulate,
+                                int64_t row_begin, int64_t row_end, cudaStream_t st);
 // the dense leaves (items with dense runs only, F <= 128 rows): y (+)= K(rows, columns of the runs) x;
 // with ibox (finest row box of every item) the low-rank part is evaluated in the same pass
 struct HmPeers;

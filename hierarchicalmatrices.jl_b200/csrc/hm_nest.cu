@@ -392,6 +392,77 @@ __device__ __forceinline__ void nest_dense_rows(const HmItem &it, int lane, cons
     for (int k = 0; k < NRL; k++) out[k] = acc[k][0] + acc[k][1];
 }
 
+// The same with 16-lane groups: lane (h, l) = (lane >> 4, lane & 15) holds rows l, l + 16, ... and the two halves
+// of the warp split the columns of every run (h takes columns h, h + 2, ...).  Used when it wastes fewer lanes:
+// a segment of 40 rows occupies 48 row slots this way instead of 64, one of 70 rows 80 instead of 96 (segments of
+// graded point sets have 40 .. 79 rows).  The halves' sums are added in the order h = 0, 1.
+template <int KID, int NRH> // NRH = ceil(F / 16) rows per lane
+__device__ __forceinline__ void nest_dense_rows16(const HmItem &it, int lane, const HmRun *__restrict__ runs,
+                                                  const HmFreeRun *__restrict__ frun, const double *__restrict__ px,
+                                                  const double *__restrict__ py, const double *__restrict__ x,
+                                                  const int32_t *__restrict__ ibox, int idx,
+                                                  const HmNestNode *__restrict__ nodes, const double *__restrict__ LAM,
+                                                  double (&out)[8])
+{
+    const int F = it.F, h = lane >> 4, hl = lane & 15;
+    double acc[NRH][2];
+#pragma unroll
+    for (int k = 0; k < NRH; k++) acc[k][0] = acc[k][1] = 0.0;
+    if (ibox) { // (warp-uniform) the series of the segment's finest box, counted once: by half 0
+        const int box = ibox[idx];
+        const HmNestNode nd = nodes[box];
+        const double *__restrict__ lam = LAM + (size_t)box * R;
+        double cf[R];
+#pragma unroll
+        for (int k = 0; k < R; k++) cf[k] = lam[k];
+        const double *__restrict__ pp = px + it.out;
+#pragma unroll
+        for (int k = 0; k < NRH; k++) {
+            const double xi = (pp[min(hl + 16 * k, F - 1)] - nd.mid) * nd.ih, two = xi + xi;
+            double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+            for (int q = R - 1; q >= 1; q--) {
+                const double nb = fma(two, b1, cf[q]) - b2;
+                b2 = b1;
+                b1 = nb;
+            }
+            acc[k][0] = h == 0 ? fma(xi, b1, cf[0]) - b2 : 0.0;
+        }
+    }
+    int64_t xo_prev = -1;
+    double p[NRH];
+#pragma unroll
+    for (int k = 0; k < NRH; k++) p[k] = 0.0;
+    for (int r = 0; r < it.nrun; r++) {
+        const HmRun rr = runs[it.run0 + r];
+        const HmFreeRun fr = frun[it.run0 + r];
+        if (fr.xoff != xo_prev) {
+            xo_prev = fr.xoff;
+#pragma unroll
+            for (int k = 0; k < NRH; k++) p[k] = px[fr.xoff + min(hl + 16 * k, F - 1)];
+        }
+        const double *__restrict__ yc = py + fr.yoff;
+        const double *__restrict__ xs = x + rr.src;
+        const int kn = fr.kn;
+        // this half's columns h, h + 2, ...: two per step (an odd one out gets a zero vector entry)
+        for (int j = h; j < kn; j += 4) {
+            const int j1 = j + 2 < kn ? j + 2 : j;
+            const double y0 = yc[j], v0 = xs[j], y1 = yc[j1], v1 = j + 2 < kn ? xs[j1] : 0.0;
+#pragma unroll
+            for (int k = 0; k < NRH; k++) {
+                acc[k][0] = fma(kernel_eval_fast(KID, p[k], y0), v0, acc[k][0]);
+                acc[k][1] = fma(kernel_eval_fast(KID, p[k], y1), v1, acc[k][1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NRH; k++) {
+        const double mine = acc[k][0] + acc[k][1];
+        const double other = __shfl_xor_sync(0xffffffffu, mine, 16);
+        out[k] = h == 0 ? mine + other : other + mine;
+    }
+}
+
 template <int KID, bool PEERS>
 __global__ void __launch_bounds__(NT)
 hm_nest_dense_kernel(const HmItem *__restrict__ items, int nitems, const HmRun *__restrict__ runs,
@@ -405,18 +476,34 @@ hm_nest_dense_kernel(const HmItem *__restrict__ items, int nitems, const HmRun *
     if (idx >= nitems) return;
     const HmItem it = items[idx];
     const int F = it.F;
-    double out[4] = {0.0, 0.0, 0.0, 0.0};
+    double out[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     const int nrl = __shfl_sync(0xffffffffu, (F + 31) >> 5, 0); // warp-uniform, and the compiler knows it
-    switch (nrl) {
-    case 1: nest_dense_rows<KID, 1>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
-    case 2: nest_dense_rows<KID, 2>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
-    case 3: nest_dense_rows<KID, 3>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
-    default: nest_dense_rows<KID, 4>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
-    }
+    const int nrh = __shfl_sync(0xffffffffu, (F + 15) >> 4, 0);
+    // 16-lane groups occupy fewer row slots when F mod 32 is in 1 .. 16 (33 .. 48 and 65 .. 80 rows; longer segments
+    // would cost registers and are rare)
+    const bool half = nrh == 3 || nrh == 5;
+    if (half) {
+        switch (nrh) {
+        case 3: nest_dense_rows16<KID, 3>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
+        default: nest_dense_rows16<KID, 5>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, out); break;
+        }
+    } else {
+        double o4[4] = {0.0, 0.0, 0.0, 0.0};
+        switch (nrl) {
+        case 1: nest_dense_rows<KID, 1>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, o4); break;
+        case 2: nest_dense_rows<KID, 2>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, o4); break;
+        case 3: nest_dense_rows<KID, 3>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, o4); break;
+        default: nest_dense_rows<KID, 4>(it, lane, runs, frun, px, py, x, ibox, idx, nodes, LAM, o4); break;
+        }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int f = lane + 32 * k;
-        if (f < F) {
+        for (int k = 0; k < 4; k++) out[k] = o4[k];
+    }
+    const int stride = half ? 16 : 32, first = half ? (lane & 15) : lane;
+    const bool writer = !half || lane < 16;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int f = first + stride * k;
+        if (writer && f < F && (half || k < 4)) {
             double *o = y + it.out + f;
             const double v = (accumulate ? *o : 0.0) + out[k];
             if (PEERS) {

@@ -348,6 +348,15 @@ std::string hm_nest_build(const HmLayout &L, const double *x, int64_t nx, const 
             out.zcap = std::max(out.zcap, (int)pos);
             out.items3.push_back(ni);
         }
+        // longest items first (the layout's order is by stored words, low-rank runs included): the hardware
+        // hands out CTAs in order, so the launch ends on its cheapest items
+        auto work = [](const HmItem &it) {
+            const int nrh = (it.F + 15) >> 4;
+            const int slots = (nrh == 3 || nrh == 5) ? 8 * nrh : 32 * ((it.F + 31) >> 5); // per column, as the kernel maps rows
+            return (int64_t)slots * it.S;
+        };
+        std::stable_sort(out.items3.begin() + out.round_begin[r], out.items3.end(),
+                         [&](const HmItem &a, const HmItem &b) { return work(a) > work(b); });
     }
     if (!out.round_begin.empty()) out.round_begin.back() = (int64_t)out.items3.size();
 
